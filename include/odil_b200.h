@@ -1,0 +1,156 @@
+/*
+ * odil_b200.h -- C ABI of libodil_b200.so, the B200-native (sm_100a) residual-and-gradient engine
+ * behind the ODIL Python API.
+ *
+ * The reference (cselab/odil) has NO native code and NO FFI: its per-iteration hot path is a
+ * jitted XLA/TF program reached through `Problem._eval_loss_grad` (reference
+ * src/odil/core.py:1027-1036 picks the backend, :1076-1111 is the JAX program) and the jitted
+ * Adam step (src/odil/optimizer.py:311-326).  This header is the seam a maintainer binds with
+ * ctypes to replace those programs.  Every entry point cites the reference
+ * lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; odil_b200_last_error() gives the message
+ *     (thread-local).  Nothing throws, nothing synchronises the device, nothing allocates after
+ *     plan creation (so calls are CUDA-graph capturable).
+ *   - all data pointers are DEVICE pointers owned by the caller, C-order (axis 0 slowest),
+ *     16-byte aligned; `stream` is a cudaStream_t passed as void*.
+ *   - dtype: 0 = float32, 1 = float64.  Scalars cross the ABI as double and are rounded to the
+ *     array dtype inside.
+ *   - slabs (multi-GPU, axis-0 decomposition): an array argument points at the FIRST OWNED plane;
+ *     `halo` planes exist physically before and after the owned planes (0 => none; neighbours
+ *     along axis 0 then wrap periodically inside the owned range, i.e. single-GPU semantics).
+ */
+#ifndef ODIL_B200_H
+#define ODIL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODIL_B200_MAX_NDIM 4
+#define ODIL_B200_MAX_OFFSETS 32
+#define ODIL_B200_F32 0
+#define ODIL_B200_F64 1
+
+typedef struct odil_b200_plan odil_b200_plan; /* opaque */
+
+int odil_b200_version(void);
+const char* odil_b200_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench `gpu_launches`). */
+int64_t odil_b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Region-typed affine stencil  F = A U + c.
+ *
+ * Replaces: ctx.field() = roll(U, -shift) (core.py:910-975, :963), the operator's elementwise
+ * arithmetic incl. where(index-mask, ...) boundary rows (examples/poisson/poisson.py:57-68,
+ * :100-113; examples/wave/wave.py:29-75), the loss reduction mean(square(F)) (core.py:1093) and
+ * the reverse-mode gradient (2/n) A^T F (core.py:1100-1101).
+ *
+ *   shape[ndim]    GLOBAL grid shape of U and F.
+ *   offsets        noff x ndim stencil shifts, same sign convention as ctx.field(key, *shift):
+ *                  F[x] uses U[(x + off) mod N].
+ *   rwidth[ndim]   region half-width r_a: per axis the classes are rows 0..r_a-1, interior,
+ *                  rows N-r_a..N-1  (2 r_a + 1 classes); requires N_a >= 2 r_a.
+ *   table          prod_a(2 r_a + 1) x noff coefficients, class index row-major over axes.
+ * ------------------------------------------------------------------------------------------- */
+int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int noff, const int32_t* offsets,
+                                  const int32_t* rwidth, const double* table, odil_b200_plan** plan);
+int odil_b200_stencil_plan_destroy(odil_b200_plan* plan);
+
+/* Slab geometry for one call: n0 owned planes starting at global plane z0; halo as above.
+ * Single GPU: n0 = shape[0], z0 = 0, halo = 0. */
+typedef struct {
+    int64_t n0;
+    int64_t z0;
+    int32_t halo;
+} odil_b200_slab;
+
+/* F_out = A U + F_in      (F_in nullable => 0; F_in may alias F_out). Owned planes only.
+ * U needs halo >= max|off_0| when slab.halo > 0. */
+int odil_b200_stencil_forward(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* U,
+                              const void* F_in, void* F_out, void* stream);
+
+/* G_out = scale * A^T F + G_in   (G_in nullable; may alias G_out). F needs halo >= max|off_0|. */
+int odil_b200_stencil_adjoint(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* F, double scale,
+                              const void* G_in, void* G_out, void* stream);
+
+/* Fused single sweep:  F = A U + c (never written to HBM),  sumsq_out[0] = sum_owned F^2 (double,
+ * deterministic two-stage reduction),  G_out = scale * A^T F.
+ * c nullable (=> 0).  With slab.halo > 0: U needs halo >= 2 r0, c needs halo >= r0
+ * (r0 = max|off_0|).  F_out nullable: when given, F is also stored (owned planes). */
+int odil_b200_stencil_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* U, const void* c,
+                            double scale, void* G_out, void* F_out, double* sumsq_out, void* stream);
+
+/* Which kernel the plan dispatches the fused sweep to: 0 = generic per-cell, 1 = tiled 3-D star. */
+int odil_b200_stencil_plan_kind(const odil_b200_plan* plan);
+/* Tuning knobs of the tiled kernel (0 keeps the default): planes per z-chunk. */
+int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant);
+
+/* sumsq_out[0] = sum x^2 (double accumulate).  Replaces mean(square(f)) of a materialised F
+ * (core.py:1093) and the norm used by optimizers. `count` elements. */
+int odil_b200_sum_squares(const void* x, int64_t count, int dtype, double* sumsq_out, void* stream);
+/* out[0] = sum x*y (double). */
+int odil_b200_dot(const void* x, const void* y, int64_t count, int dtype, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multigrid transfers (core.py:245-263 synthesis, :606-700 interp_to_finer, :703-755
+ * restrict_to_coarser).  `loc` is one char per axis: 'c' cell, 'n' node, '.' axis not coarsened.
+ * `cshape` is the coarse ARRAY shape (global); the fine array shape follows from loc
+ * ('c': 2n, 'n': 2(n-1)+1, '.': n).
+ *
+ * interp_add:  out = ffac * fine_term + cfac * I(coarse)      (fine_term nullable => pure interp)
+ *   Slabs: computes fine planes [fz_begin, fz_end) (GLOBAL indices). `out`/`fine_term` point at
+ *   global fine plane out_z0; `coarse` points at global coarse plane coarse_z0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t fz_begin, fz_end; /* fine planes to produce (global) */
+    int64_t out_z0;           /* global fine plane index at the out / fine_term pointer */
+    int64_t coarse_z0;        /* global coarse plane index at the coarse pointer */
+} odil_b200_mg_range;
+
+int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* coarse,
+                            double cfac, const void* fine_term, double ffac, void* out,
+                            const odil_b200_mg_range* range /* NULL => whole array */, void* stream);
+
+/* g_coarse = scale * I^T g_fine  (exact transpose of interp incl. the joint 2*symmetric-reflect
+ * pad; this is what AD of core.py:606-700 produces, NOT restrict_to_coarser).
+ * Slabs: computes coarse planes [cz_begin, cz_end) (global); g_fine points at global fine plane
+ * fine_z0 and must hold planes 2*cz_begin-1 .. 2*cz_end (clipped to the domain). */
+typedef struct {
+    int64_t cz_begin, cz_end;
+    int64_t out_z0;  /* global coarse plane at the g_coarse pointer */
+    int64_t fine_z0; /* global fine plane at the g_fine pointer */
+} odil_b200_mg_adj_range;
+
+int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* g_fine,
+                                double scale, void* g_coarse, const odil_b200_mg_adj_range* range, void* stream);
+
+/* out = restrict_to_coarser(in)  (core.py:703-755). `fshape` = fine ARRAY shape. Single GPU. */
+int odil_b200_mg_restrict(int ndim, const int64_t* fshape, const char* loc, int dtype, const void* in, void* out,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer updates.
+ * adam_step replaces AdamNativeOptimizer._step (optimizer.py:311-319) for all tensors at once:
+ *   m += (g - m) * one_minus_beta1;  v += (g*g - v) * one_minus_beta2;
+ *   x -= (m * alpha) / (sqrt(v) + epsilon)
+ * `alpha`, `one_minus_beta*` are computed by the host IN THE ARRAY DTYPE (optimizer.py:307-314)
+ * and passed as doubles holding exactly representable values.
+ * gd_step replaces GdOptimizer (optimizer.py:269-270): x -= g * lr.
+ * ------------------------------------------------------------------------------------------- */
+int odil_b200_adam_step(int ntensors, void* const* x, void* const* m, void* const* v, const void* const* g,
+                        const int64_t* counts, int dtype, double alpha, double one_minus_beta1,
+                        double one_minus_beta2, double epsilon, void* stream);
+int odil_b200_gd_step(int ntensors, void* const* x, const void* const* g, const int64_t* counts, int dtype,
+                      double lr, void* stream);
+/* y = a*x + b*y  (L-BFGS building block; also used for scaling). */
+int odil_b200_axpby(int64_t count, int dtype, double a, const void* x, double b, void* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODIL_B200_H */

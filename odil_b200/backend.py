@@ -1,0 +1,646 @@
+"""
+Array namespace `mod` of the B200 backend (the op seam of the reference: src/odil/backend.py:12-279).
+
+The user-written `operator(ctx)` is executed ONCE, exactly as it is under `jax.jit` in the reference
+(core.py:1106-1107).  Here the arrays it sees are not device arrays but two kinds of symbolic values:
+
+  Known   a value that does not depend on the unknowns (index masks, coordinates, right-hand sides,
+          boundary data).  Stored as a torch tensor in *compact broadcast form* (size-1 axes are kept
+          size 1), so `ctx.indices()` costs N elements per axis instead of N^d.
+  Affine  sum_s coef_s(x) * U_key[x + s] + const(x): an expression that is affine in the unknown
+          fields.  Coefficients are sums of compact Known terms.  `mod.roll`, `mod.where` on index
+          masks, + - * / by Known values keep an expression Affine.
+
+After the trace, `odil_b200.engine` lowers every Affine output to a region-typed stencil plan for the
+hand-written kernels.  Anything that would make an output non-affine in the unknowns raises
+NonAffineError (those operators are outside the hot path built so far).
+"""
+import math
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+
+class NonAffineError(NotImplementedError):
+    pass
+
+
+def default_device():
+    return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+
+
+_NP2T = {np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64, np.dtype("int32"): torch.int32,
+         np.dtype("int64"): torch.int64, np.dtype("bool"): torch.bool}
+_T2NP = {v: k for k, v in _NP2T.items()}
+
+
+def torch_dtype(dtype):
+    if isinstance(dtype, torch.dtype):
+        return dtype
+    if dtype is float:
+        return torch.float64
+    if dtype is int:
+        return torch.int64
+    return _NP2T[np.dtype(dtype)]
+
+
+def numpy_dtype(dtype):
+    if isinstance(dtype, torch.dtype):
+        return _T2NP[dtype]
+    return np.dtype(dtype)
+
+
+def _as_tensor(x, device=None, dtype=None):
+    """torch tensor from python scalar / numpy / torch, rounding python floats ONCE to `dtype`."""
+    device = device or default_device()
+    if torch.is_tensor(x):
+        t = x.to(device)
+    elif isinstance(x, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(x)).to(device)
+    elif isinstance(x, (bool, np.bool_)):
+        t = torch.tensor(bool(x), device=device)
+    elif isinstance(x, (int, np.integer)):
+        t = torch.tensor(int(x), device=device, dtype=torch_dtype(dtype) if dtype is not None else torch.int64)
+    elif isinstance(x, (float, np.floating)):
+        if dtype is None:
+            dtype = x.dtype if isinstance(x, np.floating) else np.float64
+        t = torch.tensor(float(x), device=device, dtype=torch_dtype(dtype))
+    else:
+        t = torch.from_numpy(np.asarray(x)).to(device)
+    if dtype is not None and t.dtype != torch_dtype(dtype):
+        t = t.to(torch_dtype(dtype))
+    return t
+
+
+class Lazy:
+    """Common operator plumbing of Known and Affine."""
+    __array_priority__ = 1000
+
+    def __add__(self, o):
+        return _binary("add", self, o)
+
+    def __radd__(self, o):
+        return _binary("add", o, self)
+
+    def __sub__(self, o):
+        return _binary("sub", self, o)
+
+    def __rsub__(self, o):
+        return _binary("sub", o, self)
+
+    def __mul__(self, o):
+        return _binary("mul", self, o)
+
+    def __rmul__(self, o):
+        return _binary("mul", o, self)
+
+    def __truediv__(self, o):
+        return _binary("div", self, o)
+
+    def __rtruediv__(self, o):
+        return _binary("div", o, self)
+
+    def __pow__(self, o):
+        return _binary("pow", self, o)
+
+    def __rpow__(self, o):
+        return _binary("pow", o, self)
+
+    def __neg__(self):
+        return _binary("mul", self, -1)
+
+    def __pos__(self):
+        return self
+
+    def __eq__(self, o):
+        return _binary("eq", self, o)
+
+    def __ne__(self, o):
+        return _binary("ne", self, o)
+
+    def __lt__(self, o):
+        return _binary("lt", self, o)
+
+    def __le__(self, o):
+        return _binary("le", self, o)
+
+    def __gt__(self, o):
+        return _binary("gt", self, o)
+
+    def __ge__(self, o):
+        return _binary("ge", self, o)
+
+    __hash__ = None
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+
+def _bshape(*shapes):
+    return tuple(np.broadcast_shapes(*shapes))
+
+
+class Known(Lazy):
+    """Value independent of the unknowns; `t` is compact (broadcastable to `shape`)."""
+
+    def __init__(self, t, shape=None):
+        self.t = t
+        self.shape = tuple(int(s) for s in (shape if shape is not None else t.shape))
+        if t.dim() < len(self.shape):
+            self.t = t.reshape((1,) * (len(self.shape) - t.dim()) + tuple(t.shape))
+
+    @property
+    def dtype(self):
+        return _T2NP[self.t.dtype]
+
+    def full(self):
+        """Materialised torch tensor of the logical shape."""
+        return self.t.expand(self.shape) if tuple(self.t.shape) != self.shape else self.t
+
+    def numpy(self):
+        return self.full().detach().cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def __getitem__(self, idx):
+        return Known(self.full()[idx])
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __iter__(self):
+        for i in range(self.shape[0]):
+            yield self[i]
+
+    def __float__(self):
+        return float(self.full().reshape(-1)[0].item()) if math.prod(self.shape) == 1 else float(self.numpy())
+
+    def __int__(self):
+        return int(float(self))
+
+    def __bool__(self):
+        if math.prod(self.shape) != 1:
+            raise ValueError("truth value of an array with more than one element is ambiguous")
+        return bool(self.full().reshape(-1)[0].item())
+
+    def __abs__(self):
+        return Known(torch.abs(self.t), self.shape)
+
+    def item(self):
+        return self.full().reshape(-1)[0].item()
+
+    def astype(self, dtype):
+        return Known(self.t.to(torch_dtype(dtype)), self.shape)
+
+    def flatten(self):
+        return Known(self.full().reshape(-1))
+
+    def __repr__(self):
+        return f"Known(shape={self.shape}, dtype={self.dtype}, compact={tuple(self.t.shape)})"
+
+
+def as_known(x, like=None):
+    """Wraps scalars / numpy / torch as Known. Python floats adopt the dtype of `like` (weak typing)."""
+    if isinstance(x, Known):
+        return x
+    if isinstance(x, Affine):
+        raise NonAffineError("expected a value independent of the unknown fields")
+    dtype = None
+    if like is not None and isinstance(x, (float, int)) and not isinstance(x, bool):
+        ldt = like.dtype
+        if np.issubdtype(ldt, np.floating):
+            dtype = ldt
+        elif isinstance(x, int):
+            dtype = ldt
+    return Known(_as_tensor(x, dtype=dtype))
+
+
+def _align(t, ndim):
+    return t.reshape((1,) * (ndim - t.dim()) + tuple(t.shape)) if t.dim() < ndim else t
+
+
+_TORCH_BIN = {
+    "add": torch.add, "sub": torch.sub, "mul": torch.mul, "div": torch.true_divide, "pow": torch.pow,
+    "eq": torch.eq, "ne": torch.ne, "lt": torch.lt, "le": torch.le, "gt": torch.gt, "ge": torch.ge,
+}
+
+
+def _known_binary(op, a, b):
+    if not isinstance(a, Known):
+        a = as_known(a, like=b)
+    if not isinstance(b, Known):
+        b = as_known(b, like=a)
+    nd = max(len(a.shape), len(b.shape))
+    ta, tb = _align(a.t, nd), _align(b.t, nd)
+    if ta.dtype != tb.dtype and ta.dtype.is_floating_point and tb.dtype.is_floating_point:
+        # numpy promotion (float32 op float64 -> float64)
+        pt = torch.promote_types(ta.dtype, tb.dtype)
+        ta, tb = ta.to(pt), tb.to(pt)
+    return Known(_TORCH_BIN[op](ta, tb), _bshape(a.shape, b.shape))
+
+
+class Coef:
+    """Sum of compact tensors (all with ndim == len(shape) of the owning expression)."""
+    __slots__ = ("terms",)
+
+    def __init__(self, terms=None):
+        self.terms = list(terms) if terms else []
+
+    def copy(self):
+        return Coef(self.terms)
+
+    def add_term(self, t):
+        for i, u in enumerate(self.terms):
+            if u.shape == t.shape:
+                self.terms[i] = u + t
+                return
+        self.terms.append(t)
+
+    def added(self, other, sign=1):
+        r = self.copy()
+        for t in other.terms:
+            r.add_term(t if sign == 1 else -t)
+        return r
+
+    def scaled(self, k, divide=False):
+        """Every term times (or divided by) compact tensor k."""
+        return Coef([(t / k) if divide else (t * k) for t in self.terms])
+
+    def masked(self, cond, keep_true):
+        z = None
+        out = []
+        for t in self.terms:
+            z = torch.zeros((), dtype=t.dtype, device=t.device)
+            out.append(torch.where(cond, t, z) if keep_true else torch.where(cond, z, t))
+        return Coef(out)
+
+    def rolled(self, shifts):
+        out = []
+        for t in self.terms:
+            sh, dims = [], []
+            for a, s in enumerate(shifts):
+                if s and t.shape[a] > 1:
+                    sh.append(int(s))
+                    dims.append(a)
+            out.append(torch.roll(t, sh, dims) if sh else t)
+        return Coef(out)
+
+    def is_zero(self):
+        return not self.terms
+
+    def dense(self, shape, dtype, device):
+        r = torch.zeros(shape, dtype=dtype, device=device)
+        for t in self.terms:
+            r += t.to(dtype)
+        return r
+
+
+class Affine(Lazy):
+    """sum_{(key, shift, frozen)} coef * U_key[x + shift] + const."""
+
+    def __init__(self, shape, dtype, lin=None, const=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.lin = lin if lin is not None else {}
+        self.const = const if const is not None else Coef()
+
+    @staticmethod
+    def symbol(key, shift, shape, dtype, frozen=False, device=None):
+        one = torch.ones((1,) * len(shape), dtype=torch_dtype(dtype), device=device or default_device())
+        return Affine(shape, dtype, {(key, tuple(int(s) for s in shift), bool(frozen)): Coef([one])})
+
+    def _coef_tensor(self, k):
+        """Known -> compact tensor aligned to this expression's rank and dtype family."""
+        nd = len(self.shape)
+        if k.t.dim() > nd:
+            raise NonAffineError(f"cannot broadcast shape {k.shape} into field expression of shape {self.shape}")
+        _bshape(self.shape, k.shape)  # raises on mismatch
+        if _bshape(self.shape, k.shape) != self.shape:
+            raise NonAffineError(f"broadcast of {k.shape} would change the field shape {self.shape}")
+        t = _align(k.t, nd)
+        if not t.dtype.is_floating_point:
+            t = t.to(torch_dtype(self.dtype))
+        return t
+
+    def __array__(self, dtype=None, copy=None):
+        raise NonAffineError("an expression of the unknown fields has no concrete value during tracing")
+
+    def __getitem__(self, idx):
+        raise NonAffineError("indexing an expression of the unknown fields is not supported on the fused path")
+
+    def __repr__(self):
+        return f"Affine(shape={self.shape}, symbols={list(self.lin)}, const_terms={len(self.const.terms)})"
+
+
+def _affine_binary(op, a, b):
+    if op in ("add", "sub"):
+        sign = 1 if op == "add" else -1
+        if isinstance(a, Affine) and isinstance(b, Affine):
+            if a.shape != b.shape:
+                raise NonAffineError(f"shape mismatch {a.shape} vs {b.shape}")
+            lin = {k: c.copy() for k, c in a.lin.items()}
+            for k, c in b.lin.items():
+                lin[k] = lin[k].added(c, sign) if k in lin else (c.copy() if sign == 1 else c.scaled(-1))
+            return Affine(a.shape, np.promote_types(a.dtype, b.dtype), lin, a.const.added(b.const, sign))
+        if isinstance(a, Affine):
+            k = a._coef_tensor(as_known(b, like=a))
+            return Affine(a.shape, a.dtype, {kk: c.copy() for kk, c in a.lin.items()},
+                          a.const.added(Coef([k]), sign))
+        k = b._coef_tensor(as_known(a, like=b))
+        lin = {kk: (c.copy() if sign == 1 else c.scaled(-1)) for kk, c in b.lin.items()}
+        return Affine(b.shape, b.dtype, lin, Coef([k]).added(b.const, sign))
+    if op == "mul":
+        if isinstance(a, Affine) and isinstance(b, Affine):
+            raise NonAffineError("product of two expressions of the unknown fields")
+        e, k = (a, b) if isinstance(a, Affine) else (b, a)
+        kt = e._coef_tensor(as_known(k, like=e))
+        return Affine(e.shape, e.dtype, {kk: c.scaled(kt) for kk, c in e.lin.items()}, e.const.scaled(kt))
+    if op == "div":
+        if isinstance(b, Affine):
+            raise NonAffineError("division by an expression of the unknown fields")
+        kt = a._coef_tensor(as_known(b, like=a))
+        return Affine(a.shape, a.dtype, {kk: c.scaled(kt, divide=True) for kk, c in a.lin.items()},
+                      a.const.scaled(kt, divide=True))
+    if op == "pow":
+        if isinstance(a, Affine) and isinstance(b, (int, float)) and b == 1:
+            return a
+        raise NonAffineError("power of an expression of the unknown fields")
+    raise NonAffineError(f"'{op}' on an expression of the unknown fields (data-dependent masks are not affine)")
+
+
+def _binary(op, a, b):
+    if isinstance(a, Affine) or isinstance(b, Affine):
+        return _affine_binary(op, a, b)
+    return _known_binary(op, a, b)
+
+
+def _unary_known(fn):
+    def f(x, *args, **kw):
+        if isinstance(x, Affine):
+            raise NonAffineError(f"{fn.__name__} of an expression of the unknown fields")
+        x = as_known(x)
+        t = x.t if x.t.dtype.is_floating_point else x.t.to(torch.float64)
+        return Known(fn(t), x.shape)
+
+    return f
+
+
+class ModB200:
+    """NumPy-like namespace handed to operators as `ctx.mod` / `domain.mod`."""
+    jax = None
+    tf = None
+    modsp = None
+    name = "b200"
+
+    def __init__(self, device=None):
+        self.device = device or default_device()
+        self.int32 = np.int32
+        self.float32 = np.float32
+        self.float64 = np.float64
+        self.ndarray = Known
+        self.random = Namespace(set_seed=self._set_seed, uniform=self._uniform, normal=self._normal)
+        self._gen = None
+        for name, fn in [("abs", torch.abs), ("cos", torch.cos), ("sin", torch.sin), ("exp", torch.exp),
+                         ("sqrt", torch.sqrt), ("square", torch.square), ("log", torch.log), ("tanh", torch.tanh),
+                         ("sigmoid", torch.sigmoid), ("floor", torch.floor), ("relu", torch.relu)]:
+            setattr(self, name, _unary_known(fn))
+
+    # -- creation -------------------------------------------------------------------------------
+    def _set_seed(self, seed):
+        self._gen = torch.Generator(device="cpu").manual_seed(int(seed))
+
+    def _uniform(self, shape, minval, maxval, dtype):
+        u = torch.rand(tuple(shape), generator=self._gen, dtype=torch.float64)
+        return Known((minval + (maxval - minval) * u).to(torch_dtype(dtype)).to(self.device))
+
+    def _normal(self, shape, mean=0, stddev=1, dtype=np.float32):
+        u = torch.randn(tuple(shape), generator=self._gen, dtype=torch.float64)
+        return Known((mean + stddev * u).to(torch_dtype(dtype)).to(self.device))
+
+    def cast(self, x, dtype):
+        if isinstance(x, Affine):
+            if np.dtype(numpy_dtype(dtype)) == x.dtype:
+                return x
+            raise NonAffineError("dtype cast of a field expression")
+        if isinstance(x, Known):
+            return x.astype(dtype)
+        return Known(_as_tensor(x, self.device, dtype=numpy_dtype(dtype)))
+
+    def array(self, x, dtype=None):
+        if isinstance(x, Lazy):
+            return x if dtype is None else self.cast(x, dtype)
+        return Known(_as_tensor(x, self.device, dtype=dtype))
+
+    constant = array
+    native = array
+
+    def numpy(self, x):
+        return np.asarray(x)
+
+    def variable(self, x, dtype=None):
+        """State storage: a plain device tensor (what the kernels and optimizers operate on)."""
+        if isinstance(x, Known):
+            x = x.full()
+        t = _as_tensor(x, self.device, dtype=dtype)
+        return t.contiguous().clone() if torch.is_tensor(x) else t.contiguous()
+
+    def is_tensor(self, x):
+        return torch.is_tensor(x) or isinstance(x, Lazy)
+
+    def zeros(self, shape, dtype=np.float32):
+        shape = (shape,) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
+        return Known(torch.zeros((1,) * len(shape), dtype=torch_dtype(dtype), device=self.device), shape)
+
+    def ones(self, shape, dtype=np.float32):
+        shape = (shape,) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
+        return Known(torch.ones((1,) * len(shape), dtype=torch_dtype(dtype), device=self.device), shape)
+
+    def full(self, shape, value, dtype=None):
+        return self.ones(shape, dtype or np.float32) * value
+
+    def zeros_like(self, x):
+        if torch.is_tensor(x):
+            return torch.zeros_like(x)
+        return self.zeros(x.shape, x.dtype)
+
+    def ones_like(self, x):
+        if torch.is_tensor(x):
+            return torch.ones_like(x)
+        return self.ones(x.shape, x.dtype)
+
+    def copy(self, x):
+        if torch.is_tensor(x):
+            return x.clone()
+        if isinstance(x, Known):
+            return Known(x.t.clone(), x.shape)
+        return x
+
+    def arange(self, *a, **k):
+        return Known(_as_tensor(np.arange(*a, **k), self.device))
+
+    def linspace(self, *a, **k):
+        return Known(_as_tensor(np.linspace(*a, **k), self.device))
+
+    def meshgrid(self, *xx, indexing="ij"):
+        """Sparse representation of numpy.meshgrid(..., indexing='ij'): each output is compact."""
+        assert indexing == "ij", "only indexing='ij' is supported"
+        n = len(xx)
+        shape = tuple(len(x) for x in xx)
+        res = []
+        for a, x in enumerate(xx):
+            t = as_known(x).full().reshape([-1 if b == a else 1 for b in range(n)])
+            res.append(Known(t, shape))
+        return tuple(res)
+
+    # -- elementwise / structural ---------------------------------------------------------------
+    def where(self, cond, a, b):
+        if isinstance(cond, Affine):
+            raise NonAffineError("where() on a condition that depends on the unknown fields")
+        cond = as_known(cond)
+        if isinstance(a, Affine) or isinstance(b, Affine):
+            e = a if isinstance(a, Affine) else b
+            if not isinstance(a, Affine):
+                a = Affine(e.shape, e.dtype, {}, Coef([e._coef_tensor(as_known(a, like=e))]))
+            if not isinstance(b, Affine):
+                b = Affine(e.shape, e.dtype, {}, Coef([e._coef_tensor(as_known(b, like=e))]))
+            if a.shape != b.shape:
+                raise NonAffineError(f"where(): shape mismatch {a.shape} vs {b.shape}")
+            c = _align(cond.t, len(e.shape)).to(torch.bool)
+            _bshape(e.shape, cond.shape)
+            lin = {}
+            for k, co in a.lin.items():
+                lin[k] = co.masked(c, True)
+            for k, co in b.lin.items():
+                m = co.masked(c, False)
+                lin[k] = lin[k].added(m) if k in lin else m
+            const = a.const.masked(c, True).added(b.const.masked(c, False))
+            return Affine(e.shape, e.dtype, lin, const)
+        like = a if isinstance(a, Known) else (b if isinstance(b, Known) else None)
+        a, b = as_known(a, like=like), as_known(b, like=like)
+        nd = max(len(cond.shape), len(a.shape), len(b.shape))
+        ta, tb = _align(a.t, nd), _align(b.t, nd)
+        if ta.dtype != tb.dtype:
+            pt = torch.promote_types(ta.dtype, tb.dtype)
+            ta, tb = ta.to(pt), tb.to(pt)
+        return Known(torch.where(_align(cond.t, nd).to(torch.bool), ta, tb), _bshape(cond.shape, a.shape, b.shape))
+
+    def roll(self, x, shift, axis=None):
+        if axis is None:
+            raise NotImplementedError("roll() without axis")
+        if np.ndim(shift) == 0:
+            shifts, axes = [int(shift)], [int(axis)]
+        else:
+            shifts, axes = [int(s) for s in shift], [int(a) for a in axis]
+        if isinstance(x, Affine):
+            nd = len(x.shape)
+            per_axis = [0] * nd
+            for s, a in zip(shifts, axes):
+                per_axis[a % nd] += s
+            lin = {}
+            for (key, off, frozen), co in x.lin.items():
+                noff = tuple(o - s for o, s in zip(off, per_axis))
+                k2 = (key, noff, frozen)
+                r = co.rolled(per_axis)
+                lin[k2] = lin[k2].added(r) if k2 in lin else r
+            return Affine(x.shape, x.dtype, lin, x.const.rolled(per_axis))
+        x = as_known(x)
+        nd = len(x.shape)
+        sh, dims = [], []
+        for s, a in zip(shifts, axes):
+            a %= nd
+            if x.t.shape[a] > 1:
+                sh.append(s)
+                dims.append(a)
+        return Known(torch.roll(x.t, sh, dims) if sh else x.t, x.shape)
+
+    def stop_gradient(self, x):
+        if isinstance(x, Affine):
+            return Affine(x.shape, x.dtype, {(k, o, True): c for (k, o, _), c in x.lin.items()}, x.const)
+        return x
+
+    def reshape(self, x, shape):
+        if isinstance(x, Affine):
+            raise NonAffineError("reshape of a field expression")
+        if torch.is_tensor(x):
+            return x.reshape(tuple(int(s) for s in shape))
+        return Known(as_known(x).full().reshape(tuple(int(s) for s in shape)))
+
+    def flatten(self, x):
+        return self.reshape(x, [-1])
+
+    def stack(self, xs, axis=0):
+        return Known(torch.stack([as_known(x).full() for x in xs], dim=axis))
+
+    def concatenate(self, xs, axis=0):
+        if all(torch.is_tensor(x) for x in xs):
+            return torch.cat(list(xs), dim=axis)
+        return Known(torch.cat([as_known(x).full() for x in xs], dim=axis))
+
+    hstack = concatenate
+
+    def split_by_sizes(self, x, sizes, axis=0):
+        if torch.is_tensor(x):
+            return list(torch.split(x, [int(s) for s in sizes], dim=axis))
+        return [Known(t) for t in torch.split(as_known(x).full(), [int(s) for s in sizes], dim=axis)]
+
+    def transpose(self, x, perm=None):
+        t = as_known(x).full()
+        return Known(t.permute(*[int(p) for p in perm]) if perm is not None else t.T)
+
+    def moveaxis(self, x, src, dst):
+        return Known(torch.movedim(as_known(x).full(), src, dst))
+
+    def broadcast_to(self, x, shape):
+        x = as_known(x)
+        return Known(x.t, _bshape(x.shape, tuple(shape)))
+
+    def pad(self, x, pad_width, mode="constant"):
+        if isinstance(x, Affine):
+            raise NonAffineError("pad of a field expression (loc change) is not on the fused path yet")
+        return Known(_as_tensor(np.pad(as_known(x).numpy(), pad_width, mode=mode), self.device))
+
+    def minimum(self, a, b):
+        a, b = as_known(a, like=b if isinstance(b, Known) else None), as_known(b, like=a if isinstance(a, Known) else None)
+        return Known(torch.minimum(*torch.broadcast_tensors(a.full(), b.full())))
+
+    def maximum(self, a, b):
+        a, b = as_known(a, like=b if isinstance(b, Known) else None), as_known(b, like=a if isinstance(a, Known) else None)
+        return Known(torch.maximum(*torch.broadcast_tensors(a.full(), b.full())))
+
+    def clip(self, x, lo, hi):
+        return Known(torch.clamp(as_known(x).full(), lo, hi))
+
+    def matmul(self, a, b):
+        return Known(torch.matmul(as_known(a).full(), as_known(b).full()))
+
+    def gather_nd(self, u, idx):
+        idx = as_known(idx).full().long()
+        return Known(as_known(u).full()[tuple(torch.movedim(idx, -1, 0))])
+
+    # -- reductions (Known only; reductions of field expressions are the loss, done by the engine) --
+    def _reduce(self, fn, x, axis=None):
+        if isinstance(x, Affine):
+            raise NonAffineError("reduction of a field expression inside the operator")
+        t = as_known(x).full()
+        if not t.dtype.is_floating_point and fn in (torch.mean,):
+            t = t.to(torch.float64)
+        return Known(fn(t) if axis is None else fn(t, dim=axis))
+
+    def sum(self, x, axis=None):
+        return self._reduce(torch.sum, x, axis)
+
+    def mean(self, x, axis=None):
+        return self._reduce(torch.mean, x, axis)
+
+    def max(self, x, axis=None):
+        return self._reduce(torch.amax if axis is not None else torch.max, x, axis)
+
+    def min(self, x, axis=None):
+        return self._reduce(torch.amin if axis is not None else torch.min, x, axis)
+
+    def norm(self, x):
+        return self._reduce(torch.linalg.vector_norm, x)

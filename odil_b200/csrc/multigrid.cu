@@ -1,0 +1,427 @@
+// Multigrid transfers (sm_100a): synthesis step  out = ffac*t + cfac*I(coarse), its exact transpose,
+// and restriction.  Restates reference core.py:245-263 (multigrid_to_regular), :606-700
+// (interp_to_finer, method "stack"/"conv" -- both pinned to the same answers) and :703-755
+// (restrict_to_coarser).  The boundary rule is the JOINT pad  P = 2*symmetric(u) - reflect(u)
+// (core.py:640-643): for an out-of-range tap q the value is 2*u[clamp(q)] - u[reflect(q)] with
+// clamp/reflect applied to all axes at once, so corners are not the tensor product of 1-D rules.
+#include "common.cuh"
+
+namespace odil {
+
+enum : int { LOC_C = 0, LOC_N = 1, LOC_DOT = 2 };
+
+struct MgGeom {
+    int ndim;
+    int loc[ODIL_B200_MAX_NDIM];
+    int64_t cn[ODIL_B200_MAX_NDIM];       // coarse global array shape
+    int64_t fn[ODIL_B200_MAX_NDIM];       // fine global array shape
+    int64_t cstride[ODIL_B200_MAX_NDIM];  // element strides (local == global except the axis-0 origin)
+    int64_t fstride[ODIL_B200_MAX_NDIM];
+};
+
+__device__ __forceinline__ int64_t clampi(int64_t q, int64_t n) { return q < 0 ? 0 : (q > n - 1 ? n - 1 : q); }
+__device__ __forceinline__ int64_t reflecti(int64_t q, int64_t n) {
+    if (n == 1) return 0;
+    return q < 0 ? 1 : (q > n - 1 ? n - 2 : q);
+}
+
+// Padded coarse value at global padded coords q (components in [-1, n]).
+template <typename T>
+__device__ __forceinline__ T padded_value(const MgGeom& g, const T* __restrict__ coarse, int64_t coarse_z0,
+                                          const int64_t* q) {
+    int64_t ls = 0, lr = 0;
+    bool outside = false;
+#pragma unroll
+    for (int a = 0; a < ODIL_B200_MAX_NDIM; ++a) {
+        if (a >= g.ndim) break;
+        const int64_t n = g.cn[a];
+        int64_t qs = clampi(q[a], n), qr = reflecti(q[a], n);
+        outside |= (qs != q[a]);
+        if (a == 0) {
+            qs -= coarse_z0;
+            qr -= coarse_z0;
+        }
+        ls += qs * g.cstride[a];
+        lr += qr * g.cstride[a];
+    }
+    if (!outside) return __ldg(coarse + ls);
+    return T(2) * __ldg(coarse + ls) - __ldg(coarse + lr);
+}
+
+// One thread per fine cell.
+template <typename T>
+__global__ void __launch_bounds__(256) k_interp_add(MgGeom g, const T* __restrict__ coarse, T cfac,
+                                                    const T* __restrict__ term, T ffac, T* __restrict__ out,
+                                                    int64_t fz_begin, int64_t nfz, int64_t out_z0, int64_t coarse_z0) {
+    int64_t total = nfz;
+    for (int a = 1; a < g.ndim; ++a) total *= g.fn[a];
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    int64_t f[ODIL_B200_MAX_NDIM] = {0, 0, 0, 0};
+    int64_t rem = gid;
+    for (int a = g.ndim - 1; a >= 1; --a) {
+        f[a] = rem % g.fn[a];
+        rem /= g.fn[a];
+    }
+    f[0] = fz_begin + rem;
+    // taps per axis: (index, integer weight); denominators multiply to `den`
+    int64_t q0[ODIL_B200_MAX_NDIM], q1[ODIL_B200_MAX_NDIM];
+    int w0[ODIL_B200_MAX_NDIM], w1[ODIL_B200_MAX_NDIM];
+    int den = 1;
+    int64_t lin = 0;
+#pragma unroll
+    for (int a = 0; a < ODIL_B200_MAX_NDIM; ++a) {
+        if (a >= g.ndim) break;
+        const int64_t i = f[a] >> 1;
+        const int par = (int)(f[a] & 1);
+        if (g.loc[a] == LOC_C) {
+            q0[a] = par ? i + 1 : i - 1;
+            w0[a] = 1;
+            q1[a] = i;
+            w1[a] = 3;
+            den *= 4;
+        } else if (g.loc[a] == LOC_N) {
+            q0[a] = i;
+            w0[a] = 1;
+            q1[a] = par ? i + 1 : i;
+            w1[a] = 1;
+            den *= 2;
+        } else {
+            q0[a] = f[a];
+            w0[a] = 1;
+            q1[a] = f[a];
+            w1[a] = 0;
+        }
+        lin += (a == 0 ? f[0] - out_z0 : f[a]) * g.fstride[a];
+    }
+    T acc = T(0);
+    const int ncombo = 1 << g.ndim;
+    for (int m = 0; m < ncombo; ++m) {
+        int64_t q[ODIL_B200_MAX_NDIM] = {0, 0, 0, 0};
+        int w = 1;
+        for (int a = 0; a < g.ndim; ++a) {
+            const bool second = (m >> a) & 1;
+            q[a] = second ? q1[a] : q0[a];
+            w *= second ? w1[a] : w0[a];
+        }
+        if (w == 0) continue;
+        acc += T(w) * padded_value<T>(g, coarse, coarse_z0, q);
+    }
+    T res = cfac * (acc / T(den));
+    if (term) res += ffac * __ldg(term + lin);
+    out[lin] = res;
+}
+
+// Gather of fine gradient onto the PADDED coarse index q (separable 4-tap / 3-tap rule, clipped to
+// the fine array), i.e. the plain transpose of the interpolation weights on the padded grid.
+template <typename T>
+__device__ __forceinline__ T gather_fine(const MgGeom& g, const T* __restrict__ gf, int64_t fine_z0,
+                                         const int64_t* q) {
+    // per-axis tap lists
+    int64_t fi[ODIL_B200_MAX_NDIM][4];
+    T fw[ODIL_B200_MAX_NDIM][4];
+    int nt[ODIL_B200_MAX_NDIM];
+#pragma unroll
+    for (int a = 0; a < ODIL_B200_MAX_NDIM; ++a) {
+        if (a >= g.ndim) {
+            nt[a] = 0;
+            continue;
+        }
+        int k = 0;
+        const int64_t n = g.fn[a];
+        if (g.loc[a] == LOC_C) {
+            const int64_t b = 2 * q[a];
+            const T ww[4] = {T(0.25), T(0.75), T(0.75), T(0.25)};
+            for (int t = 0; t < 4; ++t) {
+                const int64_t fidx = b - 1 + t;
+                if (fidx >= 0 && fidx < n) {
+                    fi[a][k] = fidx;
+                    fw[a][k] = ww[t];
+                    ++k;
+                }
+            }
+        } else if (g.loc[a] == LOC_N) {
+            const int64_t b = 2 * q[a];
+            const T ww[3] = {T(0.5), T(1), T(0.5)};
+            for (int t = 0; t < 3; ++t) {
+                const int64_t fidx = b - 1 + t;
+                if (fidx >= 0 && fidx < n) {
+                    fi[a][k] = fidx;
+                    fw[a][k] = ww[t];
+                    ++k;
+                }
+            }
+        } else {
+            fi[a][0] = q[a];
+            fw[a][0] = T(1);
+            k = 1;
+        }
+        nt[a] = k;
+    }
+    T acc = T(0);
+    const int n1 = g.ndim > 1 ? nt[1] : 1, n2 = g.ndim > 2 ? nt[2] : 1, n3 = g.ndim > 3 ? nt[3] : 1;
+    for (int t0 = 0; t0 < nt[0]; ++t0) {
+        const int64_t l0 = (fi[0][t0] - fine_z0) * g.fstride[0];
+        const T w0 = fw[0][t0];
+        for (int t1 = 0; t1 < n1; ++t1) {
+            const int64_t l1 = g.ndim > 1 ? l0 + fi[1][t1] * g.fstride[1] : l0;
+            const T w1 = g.ndim > 1 ? w0 * fw[1][t1] : w0;
+            for (int t2 = 0; t2 < n2; ++t2) {
+                const int64_t l2 = g.ndim > 2 ? l1 + fi[2][t2] * g.fstride[2] : l1;
+                const T w2 = g.ndim > 2 ? w1 * fw[2][t2] : w1;
+                for (int t3 = 0; t3 < n3; ++t3) {
+                    const int64_t l3 = g.ndim > 3 ? l2 + fi[3][t3] * g.fstride[3] : l2;
+                    const T w3 = g.ndim > 3 ? w2 * fw[3][t3] : w2;
+                    acc += w3 * __ldg(gf + l3);
+                }
+            }
+        }
+    }
+    return acc;
+}
+
+// One thread per coarse cell J:  g_c[J] = sum_{q: clamp(q)=J} 2 G(q) - sum_{q: reflect(q)=J} G(q).
+template <typename T>
+__global__ void __launch_bounds__(128) k_interp_adjoint(MgGeom g, const T* __restrict__ gf, T scale,
+                                                        T* __restrict__ gc, int64_t cz_begin, int64_t ncz,
+                                                        int64_t out_z0, int64_t fine_z0) {
+    int64_t total = ncz;
+    for (int a = 1; a < g.ndim; ++a) total *= g.cn[a];
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    int64_t J[ODIL_B200_MAX_NDIM] = {0, 0, 0, 0};
+    int64_t rem = gid;
+    for (int a = g.ndim - 1; a >= 1; --a) {
+        J[a] = rem % g.cn[a];
+        rem /= g.cn[a];
+    }
+    J[0] = cz_begin + rem;
+    // candidate padded indices per axis
+    int64_t cand[ODIL_B200_MAX_NDIM][3];
+    int nc[ODIL_B200_MAX_NDIM];
+    int64_t lin = 0;
+    bool boundary = false;
+    for (int a = 0; a < g.ndim; ++a) {
+        const int64_t n = g.cn[a];
+        int k = 0;
+        cand[a][k++] = J[a];
+        if (g.loc[a] == LOC_C) {
+            if (J[a] <= 1) cand[a][k++] = -1;
+            if (J[a] >= n - 2) cand[a][k++] = n;
+        }
+        nc[a] = k;
+        boundary |= k > 1;
+        lin += (a == 0 ? J[0] - out_z0 : J[a]) * g.cstride[a];
+    }
+    T acc;
+    if (!boundary) {
+        acc = gather_fine<T>(g, gf, fine_z0, J);
+    } else {
+        acc = T(0);
+        const int n1 = g.ndim > 1 ? nc[1] : 1, n2 = g.ndim > 2 ? nc[2] : 1, n3 = g.ndim > 3 ? nc[3] : 1;
+        for (int c0 = 0; c0 < nc[0]; ++c0)
+            for (int c1 = 0; c1 < n1; ++c1)
+                for (int c2 = 0; c2 < n2; ++c2)
+                    for (int c3 = 0; c3 < n3; ++c3) {
+                        int64_t q[ODIL_B200_MAX_NDIM] = {cand[0][c0], g.ndim > 1 ? cand[1][c1] : 0,
+                                                         g.ndim > 2 ? cand[2][c2] : 0, g.ndim > 3 ? cand[3][c3] : 0};
+                        bool mc = true, mr = true, outside = false;
+                        for (int a = 0; a < g.ndim; ++a) {
+                            mc = mc && clampi(q[a], g.cn[a]) == J[a];
+                            mr = mr && reflecti(q[a], g.cn[a]) == J[a];
+                            outside |= q[a] < 0 || q[a] > g.cn[a] - 1;
+                        }
+                        // in-range q is the plain value u[q]: coefficient 1 (=2-1) when q == J
+                        T coef = outside ? T((mc ? 2 : 0) - (mr ? 1 : 0)) : T(1);
+                        if (coef != T(0)) acc += coef * gather_fine<T>(g, gf, fine_z0, q);
+                    }
+    }
+    gc[lin] = scale * acc;
+}
+
+// One thread per coarse cell; joint pad on the fine array (only 'n' axes ever leave the range).
+template <typename T>
+__global__ void __launch_bounds__(256) k_restrict(MgGeom g /* cn = coarse(out), fn = fine(in) */,
+                                                  const T* __restrict__ fine, T* __restrict__ out) {
+    int64_t total = 1;
+    for (int a = 0; a < g.ndim; ++a) total *= g.cn[a];
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    int64_t J[ODIL_B200_MAX_NDIM] = {0, 0, 0, 0};
+    int64_t rem = gid;
+    for (int a = g.ndim - 1; a >= 0; --a) {
+        J[a] = rem % g.cn[a];
+        rem /= g.cn[a];
+    }
+    int64_t ti[ODIL_B200_MAX_NDIM][3];
+    T tw[ODIL_B200_MAX_NDIM][3];
+    int nt[ODIL_B200_MAX_NDIM] = {1, 1, 1, 1};
+    for (int a = 0; a < g.ndim; ++a) {
+        if (g.loc[a] == LOC_C) {
+            ti[a][0] = 2 * J[a];
+            ti[a][1] = 2 * J[a] + 1;
+            tw[a][0] = tw[a][1] = T(0.5);
+            nt[a] = 2;
+        } else if (g.loc[a] == LOC_N) {
+            ti[a][0] = 2 * J[a] - 1;
+            ti[a][1] = 2 * J[a];
+            ti[a][2] = 2 * J[a] + 1;
+            tw[a][0] = tw[a][2] = T(0.25);
+            tw[a][1] = T(0.5);
+            nt[a] = 3;
+        } else {
+            ti[a][0] = J[a];
+            tw[a][0] = T(1);
+            nt[a] = 1;
+        }
+    }
+    // geometry for padded_value expects "cn"/"cstride" to describe the array being read -> swap roles
+    MgGeom r = g;
+    for (int a = 0; a < g.ndim; ++a) {
+        r.cn[a] = g.fn[a];
+        r.cstride[a] = g.fstride[a];
+    }
+    T acc = T(0);
+    for (int t0 = 0; t0 < nt[0]; ++t0)
+        for (int t1 = 0; t1 < nt[1]; ++t1)
+            for (int t2 = 0; t2 < nt[2]; ++t2)
+                for (int t3 = 0; t3 < nt[3]; ++t3) {
+                    int64_t q[ODIL_B200_MAX_NDIM] = {ti[0][t0], g.ndim > 1 ? ti[1][t1] : 0, g.ndim > 2 ? ti[2][t2] : 0,
+                                                     g.ndim > 3 ? ti[3][t3] : 0};
+                    T w = tw[0][t0];
+                    if (g.ndim > 1) w *= tw[1][t1];
+                    if (g.ndim > 2) w *= tw[2][t2];
+                    if (g.ndim > 3) w *= tw[3][t3];
+                    acc += w * padded_value<T>(r, fine, 0, q);
+                }
+    out[gid] = acc;
+}
+
+static int make_geom(int ndim, const int64_t* cshape, const char* loc, MgGeom& g) {
+    ODIL_REQUIRE(ndim >= 1 && ndim <= ODIL_B200_MAX_NDIM, "ndim=%d unsupported", ndim);
+    ODIL_REQUIRE(loc != nullptr, "null loc");
+    g.ndim = ndim;
+    for (int a = 0; a < ndim; ++a) {
+        ODIL_REQUIRE(cshape[a] >= 1, "bad coarse shape");
+        g.cn[a] = cshape[a];
+        switch (loc[a]) {
+            case 'c': g.loc[a] = LOC_C; g.fn[a] = 2 * cshape[a]; break;
+            case 'n': g.loc[a] = LOC_N; g.fn[a] = 2 * (cshape[a] - 1) + 1; break;
+            case '.': g.loc[a] = LOC_DOT; g.fn[a] = cshape[a]; break;
+            default: return fail("loc[%d]='%c' invalid (expected c, n or .)", a, loc[a]);
+        }
+    }
+    int64_t cs = 1, fs = 1;
+    for (int a = ndim - 1; a >= 0; --a) {
+        g.cstride[a] = cs;
+        g.fstride[a] = fs;
+        cs *= g.cn[a];
+        fs *= g.fn[a];
+    }
+    for (int a = ndim; a < ODIL_B200_MAX_NDIM; ++a) {
+        g.loc[a] = LOC_DOT;
+        g.cn[a] = g.fn[a] = 1;
+        g.cstride[a] = g.fstride[a] = 0;
+    }
+    return 0;
+}
+
+}  // namespace odil
+
+using namespace odil;
+
+extern "C" {
+
+int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* coarse,
+                            double cfac, const void* fine_term, double ffac, void* out,
+                            const odil_b200_mg_range* range, void* stream) {
+    MgGeom g;
+    if (int rc = make_geom(ndim, cshape, loc, g)) return rc;
+    ODIL_REQUIRE(coarse && out, "null array");
+    odil_b200_mg_range r{0, g.fn[0], 0, 0};
+    if (range) r = *range;
+    ODIL_REQUIRE(r.fz_begin >= 0 && r.fz_end <= g.fn[0] && r.fz_begin <= r.fz_end, "bad fine plane range");
+    int64_t total = r.fz_end - r.fz_begin;
+    for (int a = 1; a < ndim; ++a) total *= g.fn[a];
+    if (total == 0) return 0;
+    const int64_t nb = (total + 255) / 256;
+    ODIL_REQUIRE(nb < (1ll << 31), "grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ODIL_B200_F32)
+        k_interp_add<float><<<(unsigned)nb, 256, 0, st>>>(g, (const float*)coarse, (float)cfac, (const float*)fine_term,
+                                                          (float)ffac, (float*)out, r.fz_begin, r.fz_end - r.fz_begin,
+                                                          r.out_z0, r.coarse_z0);
+    else if (dtype == ODIL_B200_F64)
+        k_interp_add<double><<<(unsigned)nb, 256, 0, st>>>(g, (const double*)coarse, cfac, (const double*)fine_term,
+                                                           ffac, (double*)out, r.fz_begin, r.fz_end - r.fz_begin,
+                                                           r.out_z0, r.coarse_z0);
+    else
+        return fail("dtype=%d unsupported", dtype);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* g_fine,
+                                double scale, void* g_coarse, const odil_b200_mg_adj_range* range, void* stream) {
+    MgGeom g;
+    if (int rc = make_geom(ndim, cshape, loc, g)) return rc;
+    ODIL_REQUIRE(g_fine && g_coarse, "null array");
+    odil_b200_mg_adj_range r{0, g.cn[0], 0, 0};
+    if (range) r = *range;
+    ODIL_REQUIRE(r.cz_begin >= 0 && r.cz_end <= g.cn[0] && r.cz_begin <= r.cz_end, "bad coarse plane range");
+    int64_t total = r.cz_end - r.cz_begin;
+    for (int a = 1; a < ndim; ++a) total *= g.cn[a];
+    if (total == 0) return 0;
+    const int64_t nb = (total + 127) / 128;
+    ODIL_REQUIRE(nb < (1ll << 31), "grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ODIL_B200_F32)
+        k_interp_adjoint<float><<<(unsigned)nb, 128, 0, st>>>(g, (const float*)g_fine, (float)scale, (float*)g_coarse,
+                                                              r.cz_begin, r.cz_end - r.cz_begin, r.out_z0, r.fine_z0);
+    else if (dtype == ODIL_B200_F64)
+        k_interp_adjoint<double><<<(unsigned)nb, 128, 0, st>>>(g, (const double*)g_fine, scale, (double*)g_coarse,
+                                                               r.cz_begin, r.cz_end - r.cz_begin, r.out_z0, r.fine_z0);
+    else
+        return fail("dtype=%d unsupported", dtype);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+int odil_b200_mg_restrict(int ndim, const int64_t* fshape, const char* loc, int dtype, const void* in, void* out,
+                          void* stream) {
+    ODIL_REQUIRE(ndim >= 1 && ndim <= ODIL_B200_MAX_NDIM && loc && fshape, "bad arguments");
+    int64_t cshape[ODIL_B200_MAX_NDIM];
+    for (int a = 0; a < ndim; ++a) {
+        if (loc[a] == 'c')
+            cshape[a] = fshape[a] / 2;
+        else if (loc[a] == 'n')
+            cshape[a] = (fshape[a] - 1) / 2 + 1;
+        else
+            cshape[a] = fshape[a];
+    }
+    MgGeom g;
+    if (int rc = make_geom(ndim, cshape, loc, g)) return rc;
+    // the fine array may be one larger than 2*coarse along odd-sized 'c' axes; take the given shape
+    int64_t fs = 1;
+    for (int a = ndim - 1; a >= 0; --a) {
+        g.fn[a] = fshape[a];
+        g.fstride[a] = fs;
+        fs *= fshape[a];
+    }
+    ODIL_REQUIRE(in && out, "null array");
+    int64_t total = 1;
+    for (int a = 0; a < ndim; ++a) total *= g.cn[a];
+    if (total == 0) return 0;
+    const int64_t nb = (total + 255) / 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ODIL_B200_F32)
+        k_restrict<float><<<(unsigned)nb, 256, 0, st>>>(g, (const float*)in, (float*)out);
+    else if (dtype == ODIL_B200_F64)
+        k_restrict<double><<<(unsigned)nb, 256, 0, st>>>(g, (const double*)in, (double*)out);
+    else
+        return fail("dtype=%d unsupported", dtype);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,228 @@
+// Optimizer updates and vector building blocks (sm_100a, HBM-bound, 128-bit accesses).
+// adam_step restates reference optimizer.py:311-319 (AdamNativeOptimizer._step), gd_step :269-270.
+#include "common.cuh"
+
+namespace odil {
+
+constexpr int kMaxTensors = 16;
+
+template <typename T>
+struct AdamBatch {
+    T* x[kMaxTensors];
+    T* m[kMaxTensors];
+    T* v[kMaxTensors];
+    const T* g[kMaxTensors];
+    int64_t n[kMaxTensors];
+    int vec[kMaxTensors];  // 1 if all four pointers are 16-byte aligned
+    T alpha, omb1, omb2, eps;
+};
+
+template <typename T>
+__device__ __forceinline__ void adam_one(T& x, T& m, T& v, const T g, const T alpha, const T omb1, const T omb2,
+                                         const T eps) {
+    // Same operation order as the reference; no FMA contraction across the rounding points that
+    // matter (m and v updates are written as the reference writes them).
+    m = m + (g - m) * omb1;
+    v = v + (g * g - v) * omb2;
+    x = x - (m * alpha) / (sqrt(v) + eps);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_adam(AdamBatch<T> b) {
+    const int t = blockIdx.y;
+    const int64_t n = b.n[t];
+    T* __restrict__ x = b.x[t];
+    T* __restrict__ m = b.m[t];
+    T* __restrict__ v = b.v[t];
+    const T* __restrict__ g = b.g[t];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b.vec[t]) {
+        const int64_t n4 = n / 4;
+        for (int64_t i = tid; i < n4; i += stride) {
+            Vec4<T> xx = reinterpret_cast<Vec4<T>*>(x)[i];
+            Vec4<T> mm = reinterpret_cast<Vec4<T>*>(m)[i];
+            Vec4<T> vv = reinterpret_cast<Vec4<T>*>(v)[i];
+            const Vec4<T> gg = reinterpret_cast<const Vec4<T>*>(g)[i];
+            adam_one(xx.x, mm.x, vv.x, gg.x, b.alpha, b.omb1, b.omb2, b.eps);
+            adam_one(xx.y, mm.y, vv.y, gg.y, b.alpha, b.omb1, b.omb2, b.eps);
+            adam_one(xx.z, mm.z, vv.z, gg.z, b.alpha, b.omb1, b.omb2, b.eps);
+            adam_one(xx.w, mm.w, vv.w, gg.w, b.alpha, b.omb1, b.omb2, b.eps);
+            reinterpret_cast<Vec4<T>*>(x)[i] = xx;
+            reinterpret_cast<Vec4<T>*>(m)[i] = mm;
+            reinterpret_cast<Vec4<T>*>(v)[i] = vv;
+        }
+        for (int64_t i = n4 * 4 + tid; i < n; i += stride) adam_one(x[i], m[i], v[i], g[i], b.alpha, b.omb1, b.omb2, b.eps);
+    } else {
+        for (int64_t i = tid; i < n; i += stride) adam_one(x[i], m[i], v[i], g[i], b.alpha, b.omb1, b.omb2, b.eps);
+    }
+}
+
+template <typename T>
+struct GdBatch {
+    T* x[kMaxTensors];
+    const T* g[kMaxTensors];
+    int64_t n[kMaxTensors];
+    T lr;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gd(GdBatch<T> b) {
+    const int t = blockIdx.y;
+    const int64_t n = b.n[t];
+    T* __restrict__ x = b.x[t];
+    const T* __restrict__ g = b.g[t];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = x[i] - g[i] * b.lr;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_axpby(int64_t n, T a, const T* __restrict__ x, T bb, T* __restrict__ y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T yi = bb == T(0) ? T(0) : bb * y[i];
+        y[i] = a * x[i] + yi;
+    }
+}
+
+template <typename T, bool DOT>
+__global__ void __launch_bounds__(256) k_dot_partial(const T* __restrict__ x, const T* __restrict__ y, int64_t n,
+                                                     double* __restrict__ partials) {
+    __shared__ double red[32];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double a = (double)x[i];
+        acc += DOT ? a * (double)y[i] : a * a;
+    }
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+static unsigned blocks_for(int64_t n, int per_thread) {
+    int64_t nb = (n + 256ll * per_thread - 1) / (256ll * per_thread);
+    if (nb < 1) nb = 1;
+    const int64_t cap = 148ll * 16;
+    return (unsigned)(nb > cap ? cap : nb);
+}
+
+template <typename T>
+static int run_adam(int nt, void* const* x, void* const* m, void* const* v, const void* const* g,
+                    const int64_t* counts, double alpha, double omb1, double omb2, double eps, cudaStream_t st) {
+    for (int base = 0; base < nt; base += kMaxTensors) {
+        AdamBatch<T> b;
+        const int k = nt - base < kMaxTensors ? nt - base : kMaxTensors;
+        int64_t nmax = 0;
+        for (int i = 0; i < k; ++i) {
+            b.x[i] = (T*)x[base + i];
+            b.m[i] = (T*)m[base + i];
+            b.v[i] = (T*)v[base + i];
+            b.g[i] = (const T*)g[base + i];
+            b.n[i] = counts[base + i];
+            ODIL_REQUIRE(b.n[i] >= 0 && (b.n[i] == 0 || (b.x[i] && b.m[i] && b.v[i] && b.g[i])), "adam: null tensor %d",
+                         base + i);
+            b.vec[i] = (((uintptr_t)b.x[i] | (uintptr_t)b.m[i] | (uintptr_t)b.v[i] | (uintptr_t)b.g[i]) % 16) == 0;
+            nmax = b.n[i] > nmax ? b.n[i] : nmax;
+        }
+        if (nmax == 0) continue;
+        b.alpha = (T)alpha;
+        b.omb1 = (T)omb1;
+        b.omb2 = (T)omb2;
+        b.eps = (T)eps;
+        dim3 grid(blocks_for(nmax, 8), k);
+        k_adam<T><<<grid, 256, 0, st>>>(b);
+        ODIL_LAUNCHED();
+    }
+    return 0;
+}
+
+template <typename T>
+static int run_gd(int nt, void* const* x, const void* const* g, const int64_t* counts, double lr, cudaStream_t st) {
+    for (int base = 0; base < nt; base += kMaxTensors) {
+        GdBatch<T> b;
+        const int k = nt - base < kMaxTensors ? nt - base : kMaxTensors;
+        int64_t nmax = 0;
+        for (int i = 0; i < k; ++i) {
+            b.x[i] = (T*)x[base + i];
+            b.g[i] = (const T*)g[base + i];
+            b.n[i] = counts[base + i];
+            nmax = b.n[i] > nmax ? b.n[i] : nmax;
+        }
+        if (nmax == 0) continue;
+        b.lr = (T)lr;
+        dim3 grid(blocks_for(nmax, 8), k);
+        k_gd<T><<<grid, 256, 0, st>>>(b);
+        ODIL_LAUNCHED();
+    }
+    return 0;
+}
+
+template <typename T, bool DOT>
+static int run_dot(const void* x, const void* y, int64_t n, double* out, cudaStream_t st) {
+    double* scratch = reduction_scratch(kMaxPartialBlocks);
+    ODIL_REQUIRE(scratch != nullptr, "reduction scratch allocation failed");
+    int nb = (int)blocks_for(n, 16);
+    if (nb > kMaxPartialBlocks) nb = kMaxPartialBlocks;
+    k_dot_partial<T, DOT><<<nb, 256, 0, st>>>((const T*)x, (const T*)y, n, scratch);
+    ODIL_LAUNCHED();
+    k_reduce_partials<<<1, 1024, 0, st>>>(scratch, nb, out);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+}  // namespace odil
+
+using namespace odil;
+
+extern "C" {
+
+int odil_b200_adam_step(int ntensors, void* const* x, void* const* m, void* const* v, const void* const* g,
+                        const int64_t* counts, int dtype, double alpha, double one_minus_beta1,
+                        double one_minus_beta2, double epsilon, void* stream) {
+    ODIL_REQUIRE(ntensors >= 0 && (ntensors == 0 || (x && m && v && g && counts)), "adam: bad arguments");
+    if (dtype == ODIL_B200_F32)
+        return run_adam<float>(ntensors, x, m, v, g, counts, alpha, one_minus_beta1, one_minus_beta2, epsilon,
+                               (cudaStream_t)stream);
+    if (dtype == ODIL_B200_F64)
+        return run_adam<double>(ntensors, x, m, v, g, counts, alpha, one_minus_beta1, one_minus_beta2, epsilon,
+                                (cudaStream_t)stream);
+    return fail("dtype=%d unsupported", dtype);
+}
+
+int odil_b200_gd_step(int ntensors, void* const* x, const void* const* g, const int64_t* counts, int dtype,
+                      double lr, void* stream) {
+    ODIL_REQUIRE(ntensors >= 0 && (ntensors == 0 || (x && g && counts)), "gd: bad arguments");
+    if (dtype == ODIL_B200_F32) return run_gd<float>(ntensors, x, g, counts, lr, (cudaStream_t)stream);
+    if (dtype == ODIL_B200_F64) return run_gd<double>(ntensors, x, g, counts, lr, (cudaStream_t)stream);
+    return fail("dtype=%d unsupported", dtype);
+}
+
+int odil_b200_axpby(int64_t count, int dtype, double a, const void* x, double b, void* y, void* stream) {
+    ODIL_REQUIRE(count >= 0 && (count == 0 || (x && y)), "axpby: bad arguments");
+    if (count == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ODIL_B200_F32)
+        k_axpby<float><<<blocks_for(count, 4), 256, 0, st>>>(count, (float)a, (const float*)x, (float)b, (float*)y);
+    else if (dtype == ODIL_B200_F64)
+        k_axpby<double><<<blocks_for(count, 4), 256, 0, st>>>(count, a, (const double*)x, b, (double*)y);
+    else
+        return fail("dtype=%d unsupported", dtype);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+int odil_b200_sum_squares(const void* x, int64_t count, int dtype, double* sumsq_out, void* stream) {
+    ODIL_REQUIRE(x && sumsq_out && count >= 0, "sum_squares: bad arguments");
+    if (dtype == ODIL_B200_F32) return run_dot<float, false>(x, x, count, sumsq_out, (cudaStream_t)stream);
+    if (dtype == ODIL_B200_F64) return run_dot<double, false>(x, x, count, sumsq_out, (cudaStream_t)stream);
+    return fail("dtype=%d unsupported", dtype);
+}
+
+int odil_b200_dot(const void* x, const void* y, int64_t count, int dtype, double* out, void* stream) {
+    ODIL_REQUIRE(x && y && out && count >= 0, "dot: bad arguments");
+    if (dtype == ODIL_B200_F32) return run_dot<float, true>(x, y, count, out, (cudaStream_t)stream);
+    if (dtype == ODIL_B200_F64) return run_dot<double, true>(x, y, count, out, (cudaStream_t)stream);
+    return fail("dtype=%d unsupported", dtype);
+}
+
+}  // extern "C"

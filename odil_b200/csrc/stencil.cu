@@ -1,0 +1,880 @@
+// Region-typed affine stencil  F = A U + c,  loss = sum F^2,  g = scale * A^T F   (sm_100a).
+//
+// Replaces, on the reference side: ctx.field()=roll (core.py:910-975), the example operators'
+// arithmetic (examples/poisson/poisson.py:57-68,100-113; examples/wave/wave.py:29-75), the loss
+// reduction (core.py:1093) and the AD gradient (core.py:1100-1101).
+//
+// Two kernels:
+//   k_generic  - any ndim<=4, any offsets, per-cell class lookup; works on a list of boxes.  Used for
+//                (a) whole-domain evaluation of stencils the tiled kernel does not cover and
+//                (b) the boundary SHELL (cells within 2r of a face) after the tiled kernel.
+//   k_star3d   - the hot kernel: 3-D (or 2-D) star stencil with the INTERIOR coefficient row only,
+//                2.5-D marching along axis 0, F staged in a 4-slot shared-memory ring, forward
+//                residual + squared-loss partial + adjoint gradient in ONE sweep (U and c read once,
+//                g written once; F never touches HBM).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace odil {
+
+std::string& last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+std::atomic<int64_t>& launch_counter() {
+    static std::atomic<int64_t> c{0};
+    return c;
+}
+
+double* reduction_scratch(int nslots) {
+    static double* buf[64] = {nullptr};
+    static int cap[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (cap[dev] < nslots) {
+        if (buf[dev]) cudaFree(buf[dev]);
+        int n = std::max(nslots, 4 * kMaxPartialBlocks);
+        if (cudaMalloc(&buf[dev], sizeof(double) * n) != cudaSuccess) return nullptr;
+        cap[dev] = n;
+    }
+    return buf[dev];
+}
+
+constexpr int kMaxBoxes = 8;
+constexpr int kPartialCapacity = 1 << 16;
+
+struct BoxList {
+    int nbox;
+    int64_t lo[kMaxBoxes][ODIL_B200_MAX_NDIM];  // local coords (axis 0 relative to first owned plane)
+    int64_t sz[kMaxBoxes][ODIL_B200_MAX_NDIM];
+    int64_t start[kMaxBoxes + 1];  // prefix sums of cell counts
+};
+
+struct GenParams {
+    int ndim, noff;
+    int64_t shape[ODIL_B200_MAX_NDIM];   // global shape
+    int64_t stride[ODIL_B200_MAX_NDIM];  // element strides of the local arrays
+    int64_t n0, z0;
+    int halo;
+    int off[ODIL_B200_MAX_OFFSETS][ODIL_B200_MAX_NDIM];
+    int R[ODIL_B200_MAX_NDIM];
+    int cstride[ODIL_B200_MAX_NDIM];  // class-index strides
+    int zero_off;                     // index of the all-zero offset, or -1
+    int count_mode;                   // 0: every cell counts toward the loss; 1: only cells with a non-interior class
+};
+
+}  // namespace odil
+
+using namespace odil;
+
+struct odil_b200_plan {
+    int ndim, dtype, noff;
+    int64_t shape[ODIL_B200_MAX_NDIM];
+    int off[ODIL_B200_MAX_OFFSETS][ODIL_B200_MAX_NDIM];
+    int R[ODIL_B200_MAX_NDIM];
+    int ncls;
+    std::vector<double> table;  // host copy [ncls][noff]
+    void* table_dev;            // typed copy
+    double* partials;           // device, kPartialCapacity doubles
+    int device;
+    // tiled-kernel eligibility
+    int kind;      // 0 generic, 1 star tiled
+    double w[7];   // interior weights: c, zm, zp, ym, yp, xm, xp  (3-D naming; 2-D uses y,x)
+    int zchunk;    // 0 => auto
+    int variant;   // tile shape variant
+    int rmax0;     // max |off| along axis 0
+};
+
+namespace odil {
+
+// ------------------------------------------------------------------------------------------------
+// Generic kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int axis_class(int64_t i, int64_t n, int r) {
+    if (i < r) return (int)i;
+    const int64_t d = n - 1 - i;
+    if (d < r) return 2 * r - (int)d;
+    return r;
+}
+
+template <typename T>
+struct GenIO {
+    const T* U;     // forward/fused: input field; adjoint: F
+    const T* c;     // fused: constant term (nullable); forward: F_in; adjoint: G_in
+    T* out;         // forward: F_out; adjoint/fused: G_out
+    T* Fout;        // fused: optional F store
+    const T* table;
+    double* partials;
+    T scale;
+};
+
+// Resolves the local element offset and class index of the cell `x + sgn*off` given local coords.
+struct CellRef {
+    int64_t lin;
+    int cls;
+};
+
+__device__ __forceinline__ CellRef neighbour(const GenParams& p, const int64_t* xc /*local coords*/, const int* off,
+                                             int sgn) {
+    CellRef r;
+    r.lin = 0;
+    r.cls = 0;
+#pragma unroll
+    for (int a = 0; a < ODIL_B200_MAX_NDIM; ++a) {
+        if (a >= p.ndim) break;
+        const int s = sgn * off[a];
+        const int64_t n = p.shape[a];
+        int64_t il, ig;
+        if (a == 0) {
+            ig = p.z0 + xc[0] + s;
+            if (ig < 0) ig += n;
+            if (ig >= n) ig -= n;
+            if (p.halo > 0) {
+                il = xc[0] + s;  // physical halo plane
+            } else {
+                il = xc[0] + s;
+                if (il < 0) il += p.n0;
+                if (il >= p.n0) il -= p.n0;
+            }
+        } else {
+            il = xc[a] + s;
+            if (il < 0) il += n;
+            if (il >= n) il -= n;
+            ig = il;
+        }
+        r.lin += il * p.stride[a];
+        r.cls += axis_class(ig, n, p.R[a]) * p.cstride[a];
+    }
+    return r;
+}
+
+template <typename T, int MODE>  // 0 forward, 1 adjoint, 2 fused
+__global__ void __launch_bounds__(256) k_generic(GenParams p, BoxList boxes, GenIO<T> io) {
+    __shared__ double red[32];
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc2 = 0.0;
+    if (gid < boxes.start[boxes.nbox]) {
+        int b = 0;
+        while (gid >= boxes.start[b + 1]) ++b;
+        int64_t rem = gid - boxes.start[b];
+        int64_t xc[ODIL_B200_MAX_NDIM] = {0, 0, 0, 0};
+        for (int a = p.ndim - 1; a >= 0; --a) {
+            const int64_t s = boxes.sz[b][a];
+            xc[a] = boxes.lo[b][a] + rem % s;
+            rem /= s;
+        }
+        const int zero[ODIL_B200_MAX_NDIM] = {0, 0, 0, 0};
+        const CellRef self = neighbour(p, xc, zero, 0);
+        if (MODE == 0) {
+            T f = io.c ? io.c[self.lin] : T(0);
+            for (int o = 0; o < p.noff; ++o) {
+                const CellRef nb = neighbour(p, xc, p.off[o], +1);
+                f += io.table[self.cls * p.noff + o] * io.U[nb.lin];
+            }
+            io.out[self.lin] = f;
+        } else if (MODE == 1) {
+            T g = T(0);
+            for (int o = 0; o < p.noff; ++o) {
+                const CellRef nb = neighbour(p, xc, p.off[o], -1);
+                g += io.table[nb.cls * p.noff + o] * io.U[nb.lin];
+            }
+            g *= io.scale;
+            if (io.c) g += io.c[self.lin];
+            io.out[self.lin] = g;
+        } else {
+            // F at a cell y (given by local coords yc): sum_p table[cls(y)][p] * U[y + off_p] + c[y]
+            auto eval_F = [&](const int64_t* yc, const CellRef& yref) -> T {
+                T f = io.c ? io.c[yref.lin] : T(0);
+                for (int q = 0; q < p.noff; ++q) {
+                    const CellRef nb = neighbour(p, yc, p.off[q], +1);
+                    f += io.table[yref.cls * p.noff + q] * io.U[nb.lin];
+                }
+                return f;
+            };
+            T g = T(0);
+            T fself = T(0);
+            bool have_self = false;
+            for (int o = 0; o < p.noff; ++o) {
+                // y = x - off_o, in local coords with the same wrapping rule as `neighbour`
+                int64_t yc[ODIL_B200_MAX_NDIM] = {0, 0, 0, 0};
+                for (int a = 0; a < p.ndim; ++a) {
+                    int64_t v = xc[a] - p.off[o][a];
+                    if (a == 0) {
+                        if (p.halo == 0) {
+                            if (v < 0) v += p.n0;
+                            if (v >= p.n0) v -= p.n0;
+                        }
+                    } else {
+                        if (v < 0) v += p.shape[a];
+                        if (v >= p.shape[a]) v -= p.shape[a];
+                    }
+                    yc[a] = v;
+                }
+                const CellRef yref = neighbour(p, yc, zero, 0);
+                const T fy = eval_F(yc, yref);
+                if (o == p.zero_off) {
+                    fself = fy;
+                    have_self = true;
+                }
+                g += io.table[yref.cls * p.noff + o] * fy;
+            }
+            if (!have_self) fself = eval_F(xc, self);
+            io.out[self.lin] = g * io.scale;
+            if (io.Fout) io.Fout[self.lin] = fself;
+            bool count = true;
+            if (p.count_mode == 1) {
+                // interior class index = sum_a R[a]*cstride[a]
+                int cint = 0;
+                for (int a = 0; a < p.ndim; ++a) cint += p.R[a] * p.cstride[a];
+                count = self.cls != cint;
+            }
+            if (count) acc2 = (double)fself * (double)fself;
+        }
+    }
+    if (MODE == 2) {
+        const double s = block_sum(acc2, red);
+        if (threadIdx.x == 0) io.partials[blockIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiled star kernel
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct StarParams {
+    const T* U;
+    const T* c;
+    T* G;
+    T* Fout;
+    double* partials;
+    int64_t n0, N0g, z0;
+    int halo;
+    int N1, N2;
+    T wc, wzm, wzp, wym, wyp, wxm, wxp;
+    T scale;
+    int R0, R1, R2;
+    int zchunk;
+    int has_z;
+};
+
+template <typename T, int TY, int TX, int NT, bool VEC>
+__global__ void __launch_bounds__(NT) k_star3d(StarParams<T> p) {
+    constexpr int FH = TY + 2;
+    constexpr int FW = TX + 2;
+    constexpr int PITCH = TX + 8;
+    constexpr int NC = FH * FW;
+    constexpr int NCOL = (NC + NT - 1) / NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Fs = reinterpret_cast<T*>(smem_raw);  // [4][FH][PITCH]
+    __shared__ double red[32];
+
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * TX;
+    const int ty0 = blockIdx.y * TY;
+    const int64_t zs = (int64_t)blockIdx.z * p.zchunk;
+    const int64_t ze = min(zs + (int64_t)p.zchunk, p.n0);
+    const int64_t plane = (int64_t)p.N1 * p.N2;
+
+    // Per-column precomputation (columns are fixed while marching along axis 0).
+    int offc[NCOL], oym[NCOL], oyp[NCOL], oxm[NCOL], oxp[NCOL], sidx[NCOL];
+    unsigned valid = 0, counted = 0, inner = 0;
+    T um[NCOL], uc[NCOL];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+        const int i = tid + j * NT;
+        offc[j] = oym[j] = oyp[j] = oxm[j] = oxp[j] = 0;
+        sidx[j] = 0;
+        um[j] = uc[j] = T(0);
+        if (i < NC) {
+            valid |= 1u << j;
+            const int fy = i / FW, fx = i - fy * FW;
+            const int y = ty0 - 1 + fy, x = tx0 - 1 + fx;
+            const int yw = ((y % p.N1) + p.N1) % p.N1;
+            const int xw = ((x % p.N2) + p.N2) % p.N2;
+            const int ym = yw == 0 ? p.N1 - 1 : yw - 1;
+            const int yp = yw == p.N1 - 1 ? 0 : yw + 1;
+            const int xm = xw == 0 ? p.N2 - 1 : xw - 1;
+            const int xp = xw == p.N2 - 1 ? 0 : xw + 1;
+            offc[j] = yw * p.N2 + xw;
+            oym[j] = ym * p.N2 + xw;
+            oyp[j] = yp * p.N2 + xw;
+            oxm[j] = yw * p.N2 + xm;
+            oxp[j] = yw * p.N2 + xp;
+            sidx[j] = fy * PITCH + fx + 3;
+            const bool in_tile = fy >= 1 && fy <= TY && fx >= 1 && fx <= TX && y < p.N1 && x < p.N2;
+            if (in_tile) inner |= 1u << j;
+            if (in_tile && y >= p.R1 && y < p.N1 - p.R1 && x >= p.R2 && x < p.N2 - p.R2) counted |= 1u << j;
+        }
+    }
+
+    auto zoff = [&](int64_t k) -> int64_t {
+        if (p.halo == 0) {
+            k %= p.n0;
+            if (k < 0) k += p.n0;
+        }
+        return k * plane;
+    };
+
+    const int64_t kf_begin = p.has_z ? zs - 1 : zs;
+    const int64_t kf_end = p.has_z ? ze + 1 : ze;
+    if (p.has_z) {
+        const T* Um = p.U + zoff(kf_begin - 1);
+        const T* Uc = p.U + zoff(kf_begin);
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j)
+            if (valid >> j & 1) {
+                um[j] = __ldg(Um + offc[j]);
+                uc[j] = __ldg(Uc + offc[j]);
+            }
+    } else {
+        const T* Uc = p.U + zoff(kf_begin);
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j)
+            if (valid >> j & 1) uc[j] = __ldg(Uc + offc[j]);
+    }
+
+    double acc2 = 0.0;
+    for (int64_t kf = kf_begin; kf < kf_end; ++kf) {
+        const int slot = (int)((kf - kf_begin) & 3);
+        const int64_t zo = zoff(kf);
+        const T* Uc = p.U + zo;
+        const T* Up = p.U + zoff(kf + 1);
+        const T* cp = p.c ? p.c + zo : nullptr;
+        T* Fslot = Fs + slot * (FH * PITCH);
+        const int64_t zg = p.z0 + kf;
+        const bool zcount = kf >= zs && kf < ze && zg >= p.R0 && zg < p.N0g - p.R0;
+        const bool zown = kf >= zs && kf < ze;
+        T acc = T(0);
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            if (valid >> j & 1) {
+                T up = T(0);
+                if (p.has_z) up = __ldg(Up + offc[j]);
+                T f = cp ? __ldg(cp + offc[j]) : T(0);
+                f += p.wc * uc[j];
+                f += p.wzm * um[j];
+                f += p.wzp * up;
+                f += p.wym * __ldg(Uc + oym[j]);
+                f += p.wyp * __ldg(Uc + oyp[j]);
+                f += p.wxm * __ldg(Uc + oxm[j]);
+                f += p.wxp * __ldg(Uc + oxp[j]);
+                Fslot[sidx[j]] = f;
+                if (zcount && (counted >> j & 1)) acc += f * f;
+                if (p.Fout && zown && (inner >> j & 1)) p.Fout[kf * plane + offc[j]] = f;
+                um[j] = uc[j];
+                uc[j] = up;
+            }
+        }
+        acc2 += (double)acc;
+        __syncthreads();
+        const int64_t kg = p.has_z ? kf - 1 : kf;
+        if (!p.has_z || kf >= zs + 1) {
+            const T* Fc = Fs + (int)((kg - kf_begin) & 3) * (FH * PITCH);
+            const T* Fm = p.has_z ? Fs + (int)((kg - 1 - kf_begin) & 3) * (FH * PITCH) : Fc;
+            const T* Fp = p.has_z ? Fs + (int)((kg + 1 - kf_begin) & 3) * (FH * PITCH) : Fc;
+            T* Gp = p.G + kg * plane;
+            if (VEC) {
+                constexpr int GX = TX / 4;
+                for (int t = tid; t < TY * GX; t += NT) {
+                    const int gy = t / GX, gx = (t - gy * GX) * 4;
+                    const int y = ty0 + gy, x = tx0 + gx;
+                    if (y < p.N1 && x < p.N2) {
+                        const T* r0 = Fc + (gy + 1) * PITCH + gx + 4;
+                        const Vec4<T> fc = *reinterpret_cast<const Vec4<T>*>(r0);
+                        const T fl = r0[-1], fr = r0[4];
+                        const Vec4<T> fym = *reinterpret_cast<const Vec4<T>*>(r0 - PITCH);
+                        const Vec4<T> fyp = *reinterpret_cast<const Vec4<T>*>(r0 + PITCH);
+                        Vec4<T> g;
+                        g.x = p.wc * fc.x + p.wxm * fc.y + p.wxp * fl + p.wym * fyp.x + p.wyp * fym.x;
+                        g.y = p.wc * fc.y + p.wxm * fc.z + p.wxp * fc.x + p.wym * fyp.y + p.wyp * fym.y;
+                        g.z = p.wc * fc.z + p.wxm * fc.w + p.wxp * fc.y + p.wym * fyp.z + p.wyp * fym.z;
+                        g.w = p.wc * fc.w + p.wxm * fr + p.wxp * fc.z + p.wym * fyp.w + p.wyp * fym.w;
+                        if (p.has_z) {
+                            const Vec4<T> fzm = *reinterpret_cast<const Vec4<T>*>(Fm + (gy + 1) * PITCH + gx + 4);
+                            const Vec4<T> fzp = *reinterpret_cast<const Vec4<T>*>(Fp + (gy + 1) * PITCH + gx + 4);
+                            g.x += p.wzm * fzp.x + p.wzp * fzm.x;
+                            g.y += p.wzm * fzp.y + p.wzp * fzm.y;
+                            g.z += p.wzm * fzp.z + p.wzp * fzm.z;
+                            g.w += p.wzm * fzp.w + p.wzp * fzm.w;
+                        }
+                        g.x *= p.scale;
+                        g.y *= p.scale;
+                        g.z *= p.scale;
+                        g.w *= p.scale;
+                        *reinterpret_cast<Vec4<T>*>(Gp + (int64_t)y * p.N2 + x) = g;
+                    }
+                }
+            } else {
+                for (int t = tid; t < TY * TX; t += NT) {
+                    const int gy = t / TX, gx = t - gy * TX;
+                    const int y = ty0 + gy, x = tx0 + gx;
+                    if (y < p.N1 && x < p.N2) {
+                        const T* r0 = Fc + (gy + 1) * PITCH + gx + 4;
+                        T g = p.wc * r0[0] + p.wxm * r0[1] + p.wxp * r0[-1] + p.wym * r0[PITCH] + p.wyp * r0[-PITCH];
+                        if (p.has_z)
+                            g += p.wzm * Fp[(gy + 1) * PITCH + gx + 4] + p.wzp * Fm[(gy + 1) * PITCH + gx + 4];
+                        Gp[(int64_t)y * p.N2 + x] = g * p.scale;
+                    }
+                }
+            }
+        }
+    }
+    const double s = block_sum(acc2, red);
+    if (tid == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+static void fill_gen_params(const odil_b200_plan* plan, const odil_b200_slab* slab, GenParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.ndim = plan->ndim;
+    p.noff = plan->noff;
+    int64_t st = 1;
+    for (int a = plan->ndim - 1; a >= 0; --a) {
+        p.shape[a] = plan->shape[a];
+        p.stride[a] = st;
+        st *= plan->shape[a];
+    }
+    int cs = 1;
+    for (int a = plan->ndim - 1; a >= 0; --a) {
+        p.R[a] = plan->R[a];
+        p.cstride[a] = cs;
+        cs *= 2 * plan->R[a] + 1;
+    }
+    p.n0 = slab->n0;
+    p.z0 = slab->z0;
+    p.halo = slab->halo;
+    p.zero_off = -1;
+    for (int o = 0; o < plan->noff; ++o) {
+        bool z = true;
+        for (int a = 0; a < plan->ndim; ++a) {
+            p.off[o][a] = plan->off[o][a];
+            z = z && plan->off[o][a] == 0;
+        }
+        if (z) p.zero_off = o;
+    }
+}
+
+static void whole_box(const odil_b200_plan* plan, const odil_b200_slab* slab, BoxList& b) {
+    memset(&b, 0, sizeof(b));
+    b.nbox = 1;
+    int64_t cnt = 1;
+    for (int a = 0; a < plan->ndim; ++a) {
+        b.lo[0][a] = 0;
+        b.sz[0][a] = a == 0 ? slab->n0 : plan->shape[a];
+        cnt *= b.sz[0][a];
+    }
+    b.start[0] = 0;
+    b.start[1] = cnt;
+}
+
+// Boxes covering every owned cell within `thick[a]` of a domain face along some axis, disjoint.
+static void shell_boxes(const odil_b200_plan* plan, const odil_b200_slab* slab, const int* thick, BoxList& b) {
+    memset(&b, 0, sizeof(b));
+    const int nd = plan->ndim;
+    // global [lo, hi) ranges per axis: face-low, face-high, interior
+    int64_t flo[ODIL_B200_MAX_NDIM][2], fhi[ODIL_B200_MAX_NDIM][2], inner[ODIL_B200_MAX_NDIM][2];
+    bool has_hi[ODIL_B200_MAX_NDIM];
+    for (int a = 0; a < nd; ++a) {
+        const int64_t n = plan->shape[a];
+        const int64_t t = thick[a];
+        if (t <= 0) {
+            flo[a][0] = flo[a][1] = 0;
+            fhi[a][0] = fhi[a][1] = 0;
+            has_hi[a] = false;
+            inner[a][0] = 0;
+            inner[a][1] = n;
+        } else if (2 * t >= n) {
+            flo[a][0] = 0;
+            flo[a][1] = n;
+            has_hi[a] = false;
+            fhi[a][0] = fhi[a][1] = 0;
+            inner[a][0] = inner[a][1] = 0;
+        } else {
+            flo[a][0] = 0;
+            flo[a][1] = t;
+            fhi[a][0] = n - t;
+            fhi[a][1] = n;
+            has_hi[a] = true;
+            inner[a][0] = t;
+            inner[a][1] = n - t;
+        }
+    }
+    auto clip0 = [&](int64_t& lo, int64_t& hi) {  // global -> local along axis 0
+        lo = std::max(lo, slab->z0) - slab->z0;
+        hi = std::min(hi, slab->z0 + slab->n0) - slab->z0;
+    };
+    int nb = 0;
+    int64_t total = 0;
+    b.start[0] = 0;
+    for (int a = 0; a < nd; ++a) {
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && !has_hi[a]) continue;
+            int64_t lo[ODIL_B200_MAX_NDIM], hi[ODIL_B200_MAX_NDIM];
+            bool empty = false;
+            for (int c = 0; c < nd; ++c) {
+                if (c == a) {
+                    lo[c] = side ? fhi[a][0] : flo[a][0];
+                    hi[c] = side ? fhi[a][1] : flo[a][1];
+                } else if (c < a) {
+                    lo[c] = inner[c][0];
+                    hi[c] = inner[c][1];
+                } else {
+                    lo[c] = 0;
+                    hi[c] = plan->shape[c];
+                }
+                if (c == 0) clip0(lo[c], hi[c]);
+                if (hi[c] <= lo[c]) empty = true;
+            }
+            if (empty) continue;
+            int64_t cnt = 1;
+            for (int c = 0; c < nd; ++c) {
+                b.lo[nb][c] = lo[c];
+                b.sz[nb][c] = hi[c] - lo[c];
+                cnt *= hi[c] - lo[c];
+            }
+            total += cnt;
+            ++nb;
+            b.start[nb] = total;
+        }
+    }
+    b.nbox = nb;
+}
+
+template <typename T, int MODE>
+static int launch_generic(const odil_b200_plan* plan, const GenParams& p, const BoxList& boxes, GenIO<T> io,
+                          cudaStream_t st, int* nblocks_out) {
+    const int64_t total = boxes.start[boxes.nbox];
+    if (nblocks_out) *nblocks_out = 0;
+    if (total == 0) return 0;
+    const int64_t nb = (total + 255) / 256;
+    ODIL_REQUIRE(nb < (1ll << 31), "generic stencil grid too large");
+    if (MODE == 2) ODIL_REQUIRE(nb <= kPartialCapacity, "generic fused grid exceeds the partials workspace");
+    k_generic<T, MODE><<<(unsigned)nb, 256, 0, st>>>(p, boxes, io);
+    ODIL_LAUNCHED();
+    if (nblocks_out) *nblocks_out = (int)nb;
+    return 0;
+}
+
+template <typename T, int TY, int TX, int NT>
+static int launch_star_cfg(const StarParams<T>& sp, dim3 grid, bool vec, cudaStream_t st) {
+    const size_t smem = (size_t)4 * (TY + 2) * (TX + 8) * sizeof(T);
+    static bool attr_set[2] = {false, false};  // per template instantiation
+    if (!attr_set[vec ? 1 : 0]) {
+        if (vec)
+            ODIL_CUDA(cudaFuncSetAttribute(k_star3d<T, TY, TX, NT, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+            ODIL_CUDA(cudaFuncSetAttribute(k_star3d<T, TY, TX, NT, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[vec ? 1 : 0] = true;
+    }
+    if (vec)
+        k_star3d<T, TY, TX, NT, true><<<grid, NT, smem, st>>>(sp);
+    else
+        k_star3d<T, TY, TX, NT, false><<<grid, NT, smem, st>>>(sp);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+static void star_tile(int variant, int& TY, int& TX) {
+    switch (variant) {
+        case 1: TY = 16; TX = 64; break;
+        case 2: TY = 16; TX = 128; break;
+        case 3: TY = 4; TX = 128; break;
+        default: TY = 8; TX = 128; break;
+    }
+}
+
+template <typename T>
+static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* U, const void* c,
+                     double scale, void* G, void* Fout, double* sumsq, cudaStream_t st) {
+    GenParams gp;
+    fill_gen_params(plan, slab, gp);
+    GenIO<T> io;
+    io.U = (const T*)U;
+    io.c = (const T*)c;
+    io.out = (T*)G;
+    io.Fout = (T*)Fout;
+    io.table = (const T*)plan->table_dev;
+    io.scale = (T)scale;
+    int nparts = 0;
+    const bool slab_mode = slab->halo > 0 || slab->n0 != plan->shape[0] || slab->z0 != 0;
+    bool tiled = plan->kind == 1 && !(plan->ndim == 2 && slab_mode);
+    if (tiled) {
+        StarParams<T> sp;
+        sp.U = io.U;
+        sp.c = io.c;
+        sp.G = io.out;
+        sp.Fout = io.Fout;
+        sp.partials = plan->partials;
+        if (plan->ndim == 3) {
+            sp.n0 = slab->n0;
+            sp.N0g = plan->shape[0];
+            sp.z0 = slab->z0;
+            sp.halo = slab->halo;
+            sp.N1 = (int)plan->shape[1];
+            sp.N2 = (int)plan->shape[2];
+            sp.R0 = plan->R[0];
+            sp.R1 = plan->R[1];
+            sp.R2 = plan->R[2];
+            sp.has_z = plan->w[1] != 0.0 || plan->w[2] != 0.0;
+        } else {
+            sp.n0 = 1;
+            sp.N0g = 1;
+            sp.z0 = 0;
+            sp.halo = 0;
+            sp.N1 = (int)plan->shape[0];
+            sp.N2 = (int)plan->shape[1];
+            sp.R0 = 0;
+            sp.R1 = plan->R[0];
+            sp.R2 = plan->R[1];
+            sp.has_z = 0;
+        }
+        sp.wc = (T)plan->w[0];
+        sp.wzm = (T)plan->w[1];
+        sp.wzp = (T)plan->w[2];
+        sp.wym = (T)plan->w[3];
+        sp.wyp = (T)plan->w[4];
+        sp.wxm = (T)plan->w[5];
+        sp.wxp = (T)plan->w[6];
+        sp.scale = (T)scale;
+        int TY, TX;
+        star_tile(plan->variant, TY, TX);
+        const int gx = (sp.N2 + TX - 1) / TX, gy = (sp.N1 + TY - 1) / TY;
+        int zchunk = plan->zchunk;
+        if (zchunk <= 0) {
+            // aim for >= ~8 waves of 148 SMs x 4 CTAs, but keep the z-redundancy (2 extra planes) small
+            zchunk = 64;
+            while (zchunk > 16 && (int64_t)gx * gy * ((sp.n0 + zchunk - 1) / zchunk) < 148 * 4 * 6) zchunk /= 2;
+        }
+        if (zchunk > sp.n0) zchunk = (int)sp.n0;
+        if (zchunk < 1) zchunk = 1;
+        sp.zchunk = zchunk;
+        const int gz = (int)((sp.n0 + zchunk - 1) / zchunk);
+        ODIL_REQUIRE((int64_t)gx * gy * gz <= kPartialCapacity / 2, "star grid exceeds the partials workspace");
+        dim3 grid(gx, gy, gz);
+        const bool vec = (sp.N2 % 4 == 0) && ((uintptr_t)G % 16 == 0);
+        int rc = 0;
+        switch (plan->variant) {
+            case 1: rc = launch_star_cfg<T, 16, 64, 256>(sp, grid, vec, st); break;
+            case 2: rc = launch_star_cfg<T, 16, 128, 512>(sp, grid, vec, st); break;
+            case 3: rc = launch_star_cfg<T, 4, 128, 128>(sp, grid, vec, st); break;
+            default: rc = launch_star_cfg<T, 8, 128, 256>(sp, grid, vec, st); break;
+        }
+        if (rc) return rc;
+        nparts = gx * gy * gz;
+        // Boundary shell: per-cell class lookup, overwrites g within 2r of a face, adds the loss
+        // of the cells whose own row is a boundary row.
+        BoxList shell;
+        int thick[ODIL_B200_MAX_NDIM];
+        for (int a = 0; a < plan->ndim; ++a) thick[a] = 2 * plan->R[a];
+        shell_boxes(plan, slab, thick, shell);
+        gp.count_mode = 1;
+        io.partials = plan->partials + nparts;
+        int nb = 0;
+        rc = launch_generic<T, 2>(plan, gp, shell, io, st, &nb);
+        if (rc) return rc;
+        ODIL_REQUIRE(nparts + nb <= kPartialCapacity, "partials workspace overflow");
+        nparts += nb;
+    } else {
+        BoxList all;
+        whole_box(plan, slab, all);
+        gp.count_mode = 0;
+        io.partials = plan->partials;
+        int nb = 0;
+        int rc = launch_generic<T, 2>(plan, gp, all, io, st, &nb);
+        if (rc) return rc;
+        nparts = nb;
+    }
+    k_reduce_partials<<<1, 1024, 0, st>>>(plan->partials, nparts, sumsq);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+}  // namespace odil
+
+extern "C" {
+
+int odil_b200_version(void) { return 100; }
+const char* odil_b200_last_error(void) { return last_error_ref().c_str(); }
+int64_t odil_b200_launch_count(void) { return launch_counter().load(); }
+
+int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int noff, const int32_t* offsets,
+                                  const int32_t* rwidth, const double* table, odil_b200_plan** out) {
+    ODIL_REQUIRE(out != nullptr, "plan out pointer is null");
+    *out = nullptr;
+    ODIL_REQUIRE(ndim >= 1 && ndim <= ODIL_B200_MAX_NDIM, "ndim=%d unsupported (1..%d)", ndim, ODIL_B200_MAX_NDIM);
+    ODIL_REQUIRE(noff >= 1 && noff <= ODIL_B200_MAX_OFFSETS, "noff=%d unsupported (1..%d)", noff,
+                 ODIL_B200_MAX_OFFSETS);
+    ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    odil_b200_plan* p = new odil_b200_plan();
+    p->ndim = ndim;
+    p->dtype = dtype;
+    p->noff = noff;
+    p->ncls = 1;
+    p->zchunk = 0;
+    p->variant = 0;
+    p->table_dev = nullptr;
+    p->partials = nullptr;
+    int64_t total = 1;
+    for (int a = 0; a < ndim; ++a) {
+        p->shape[a] = shape[a];
+        p->R[a] = rwidth[a];
+        if (shape[a] < 1 || rwidth[a] < 0 || 2 * (int64_t)rwidth[a] > shape[a]) {
+            delete p;
+            return fail("axis %d: shape=%lld rwidth=%d invalid (need shape >= 2*rwidth)", a, (long long)shape[a],
+                        rwidth[a]);
+        }
+        p->ncls *= 2 * rwidth[a] + 1;
+        total *= shape[a];
+    }
+    p->rmax0 = 0;
+    for (int o = 0; o < noff; ++o)
+        for (int a = 0; a < ndim; ++a) {
+            p->off[o][a] = offsets[o * ndim + a];
+            if (std::abs(p->off[o][a]) >= shape[a] && shape[a] > 1 && p->off[o][a] != 0) {
+                delete p;
+                return fail("offset %d axis %d = %d exceeds the grid size", o, a, p->off[o][a]);
+            }
+            if (a == 0) p->rmax0 = std::max(p->rmax0, std::abs(p->off[o][a]));
+        }
+    p->table.assign(table, table + (size_t)p->ncls * noff);
+    // Tiled eligibility: 2-D / 3-D, every offset a unit star arm, grid not degenerate.
+    p->kind = 0;
+    for (int i = 0; i < 7; ++i) p->w[i] = 0.0;
+    if ((ndim == 3 || ndim == 2) && total >= 512) {
+        bool ok = true;
+        int cint = 0, cs = 1;
+        for (int a = ndim - 1; a >= 0; --a) {
+            cint += p->R[a] * cs;
+            cs *= 2 * p->R[a] + 1;
+            if (shape[a] < 4 * p->R[a] + 1 || shape[a] < 4) ok = false;
+        }
+        double w[7] = {0, 0, 0, 0, 0, 0, 0};
+        const int base = ndim == 3 ? 0 : 1;  // axis a of the plan maps to tiled axis base + a
+        for (int o = 0; o < noff && ok; ++o) {
+            int nz = 0, ax = -1, sg = 0;
+            for (int a = 0; a < ndim; ++a)
+                if (p->off[o][a] != 0) {
+                    ++nz;
+                    ax = a;
+                    sg = p->off[o][a];
+                }
+            const double v = p->table[(size_t)cint * noff + o];
+            if (nz == 0)
+                w[0] += v;
+            else if (nz == 1 && (sg == 1 || sg == -1))
+                w[1 + 2 * (base + ax) + (sg > 0 ? 1 : 0)] += v;
+            else
+                ok = false;
+        }
+        if (ok) {
+            p->kind = 1;
+            for (int i = 0; i < 7; ++i) p->w[i] = w[i];
+        }
+    }
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e == cudaSuccess) {
+        const size_t esz = dtype == ODIL_B200_F32 ? 4 : 8;
+        e = cudaMalloc(&p->table_dev, esz * p->table.size());
+        if (e == cudaSuccess) {
+            if (dtype == ODIL_B200_F32) {
+                std::vector<float> tf(p->table.begin(), p->table.end());
+                e = cudaMemcpy(p->table_dev, tf.data(), esz * tf.size(), cudaMemcpyHostToDevice);
+            } else {
+                e = cudaMemcpy(p->table_dev, p->table.data(), esz * p->table.size(), cudaMemcpyHostToDevice);
+            }
+        }
+        if (e == cudaSuccess) e = cudaMalloc((void**)&p->partials, sizeof(double) * kPartialCapacity);
+    }
+    if (e != cudaSuccess) {
+        if (p->table_dev) cudaFree(p->table_dev);
+        if (p->partials) cudaFree(p->partials);
+        delete p;
+        return fail("plan_create: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return 0;
+}
+
+int odil_b200_stencil_plan_destroy(odil_b200_plan* plan) {
+    if (!plan) return 0;
+    if (plan->table_dev) cudaFree(plan->table_dev);
+    if (plan->partials) cudaFree(plan->partials);
+    delete plan;
+    return 0;
+}
+
+int odil_b200_stencil_plan_kind(const odil_b200_plan* plan) { return plan ? plan->kind : -1; }
+
+int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant) {
+    ODIL_REQUIRE(plan != nullptr, "null plan");
+    ODIL_REQUIRE(variant >= 0 && variant <= 3, "variant=%d unknown", variant);
+    plan->zchunk = zchunk;
+    plan->variant = variant;
+    return 0;
+}
+
+static int check_slab(const odil_b200_plan* plan, const odil_b200_slab* slab, int need_halo) {
+    ODIL_REQUIRE(plan && slab, "null plan/slab");
+    ODIL_REQUIRE(slab->n0 >= 1 && slab->z0 >= 0 && slab->z0 + slab->n0 <= plan->shape[0],
+                 "slab [%lld,+%lld) outside axis 0 of size %lld", (long long)slab->z0, (long long)slab->n0,
+                 (long long)plan->shape[0]);
+    if (slab->halo == 0)
+        ODIL_REQUIRE(slab->n0 == plan->shape[0], "halo=0 requires the whole axis 0 (single-GPU semantics)");
+    else
+        ODIL_REQUIRE(slab->halo >= need_halo, "halo=%d too small, need %d", slab->halo, need_halo);
+    return 0;
+}
+
+int odil_b200_stencil_forward(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* U,
+                              const void* F_in, void* F_out, void* stream) {
+    if (int rc = check_slab(plan, slab, plan ? plan->rmax0 : 0)) return rc;
+    ODIL_REQUIRE(U && F_out, "null array");
+    GenParams gp;
+    fill_gen_params(plan, slab, gp);
+    BoxList all;
+    whole_box(plan, slab, all);
+    if (plan->dtype == ODIL_B200_F32) {
+        GenIO<float> io{(const float*)U, (const float*)F_in, (float*)F_out, nullptr, (const float*)plan->table_dev,
+                        nullptr, 1.f};
+        return launch_generic<float, 0>(plan, gp, all, io, (cudaStream_t)stream, nullptr);
+    }
+    GenIO<double> io{(const double*)U, (const double*)F_in, (double*)F_out, nullptr, (const double*)plan->table_dev,
+                     nullptr, 1.0};
+    return launch_generic<double, 0>(plan, gp, all, io, (cudaStream_t)stream, nullptr);
+}
+
+int odil_b200_stencil_adjoint(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* F, double scale,
+                              const void* G_in, void* G_out, void* stream) {
+    if (int rc = check_slab(plan, slab, plan ? plan->rmax0 : 0)) return rc;
+    ODIL_REQUIRE(F && G_out, "null array");
+    GenParams gp;
+    fill_gen_params(plan, slab, gp);
+    BoxList all;
+    whole_box(plan, slab, all);
+    if (plan->dtype == ODIL_B200_F32) {
+        GenIO<float> io{(const float*)F, (const float*)G_in, (float*)G_out, nullptr, (const float*)plan->table_dev,
+                        nullptr, (float)scale};
+        return launch_generic<float, 1>(plan, gp, all, io, (cudaStream_t)stream, nullptr);
+    }
+    GenIO<double> io{(const double*)F, (const double*)G_in, (double*)G_out, nullptr, (const double*)plan->table_dev,
+                     nullptr, scale};
+    return launch_generic<double, 1>(plan, gp, all, io, (cudaStream_t)stream, nullptr);
+}
+
+int odil_b200_stencil_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* U, const void* c,
+                            double scale, void* G_out, void* F_out, double* sumsq_out, void* stream) {
+    if (int rc = check_slab(plan, slab, plan ? 2 * plan->rmax0 : 0)) return rc;
+    ODIL_REQUIRE(U && G_out && sumsq_out, "null array");
+    if (plan->dtype == ODIL_B200_F32)
+        return run_fused<float>(plan, slab, U, c, scale, G_out, F_out, sumsq_out, (cudaStream_t)stream);
+    return run_fused<double>(plan, slab, U, c, scale, G_out, F_out, sumsq_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

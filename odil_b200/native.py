@@ -1,0 +1,278 @@
+"""
+ctypes binding of libodil_b200.so (see include/odil_b200.h).  This is the ONLY compute path of the
+package: there is no CPU or eager fallback -- if the library cannot be loaded, every entry point
+raises.  Arguments are torch CUDA tensors (device memory plumbing) and Python scalars; work is
+enqueued on torch's current stream.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libodil_b200.so")
+
+F32, F64 = 0, 1
+MAX_NDIM = 4
+MAX_OFFSETS = 32
+
+EXPORTS = [
+    "odil_b200_version", "odil_b200_last_error", "odil_b200_launch_count",
+    "odil_b200_stencil_plan_create", "odil_b200_stencil_plan_destroy", "odil_b200_stencil_forward",
+    "odil_b200_stencil_adjoint", "odil_b200_stencil_fused", "odil_b200_stencil_plan_kind",
+    "odil_b200_stencil_plan_tune", "odil_b200_sum_squares", "odil_b200_dot", "odil_b200_mg_interp_add",
+    "odil_b200_mg_interp_adjoint", "odil_b200_mg_restrict", "odil_b200_adam_step", "odil_b200_gd_step",
+    "odil_b200_axpby",
+]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class Slab(ctypes.Structure):
+    _fields_ = [("n0", ctypes.c_int64), ("z0", ctypes.c_int64), ("halo", ctypes.c_int32)]
+
+
+class MgRange(ctypes.Structure):
+    _fields_ = [("fz_begin", ctypes.c_int64), ("fz_end", ctypes.c_int64), ("out_z0", ctypes.c_int64),
+                ("coarse_z0", ctypes.c_int64)]
+
+
+class MgAdjRange(ctypes.Structure):
+    _fields_ = [("cz_begin", ctypes.c_int64), ("cz_end", ctypes.c_int64), ("out_z0", ctypes.c_int64),
+                ("fine_z0", ctypes.c_int64)]
+
+
+_lib = None
+
+
+def load(build_if_missing=False):
+    """Loads the shared library (once). Raises NativeError if it is absent or lacks a symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            from . import build as _build
+
+            _build.build()
+        else:
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -m odil_b200.build` "
+                "(there is no CPU fallback for the ODIL hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise NativeError(f"{LIB_PATH} does not export {name}")
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    P = ctypes.POINTER
+    lib.odil_b200_version.restype = ctypes.c_int
+    lib.odil_b200_last_error.restype = ctypes.c_char_p
+    lib.odil_b200_launch_count.restype = i64
+    lib.odil_b200_stencil_plan_create.argtypes = [ctypes.c_int, P(i64), ctypes.c_int, ctypes.c_int, P(i32), P(i32),
+                                                  P(dbl), P(vp)]
+    lib.odil_b200_stencil_plan_destroy.argtypes = [vp]
+    lib.odil_b200_stencil_forward.argtypes = [vp, P(Slab), vp, vp, vp, vp]
+    lib.odil_b200_stencil_adjoint.argtypes = [vp, P(Slab), vp, dbl, vp, vp, vp]
+    lib.odil_b200_stencil_fused.argtypes = [vp, P(Slab), vp, vp, dbl, vp, vp, vp, vp]
+    lib.odil_b200_stencil_plan_kind.argtypes = [vp]
+    lib.odil_b200_stencil_plan_tune.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    lib.odil_b200_sum_squares.argtypes = [vp, i64, ctypes.c_int, vp, vp]
+    lib.odil_b200_dot.argtypes = [vp, vp, i64, ctypes.c_int, vp, vp]
+    lib.odil_b200_mg_interp_add.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, dbl, vp, dbl, vp,
+                                            P(MgRange), vp]
+    lib.odil_b200_mg_interp_adjoint.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, dbl, vp,
+                                                P(MgAdjRange), vp]
+    lib.odil_b200_mg_restrict.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, vp, vp]
+    lib.odil_b200_adam_step.argtypes = [ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), ctypes.c_int, dbl, dbl,
+                                        dbl, dbl, vp]
+    lib.odil_b200_gd_step.argtypes = [ctypes.c_int, P(vp), P(vp), P(i64), ctypes.c_int, dbl, vp]
+    lib.odil_b200_axpby.argtypes = [i64, ctypes.c_int, dbl, vp, dbl, vp, vp]
+    for name in EXPORTS:
+        if name not in ("odil_b200_last_error", "odil_b200_launch_count", "odil_b200_version"):
+            getattr(lib, name).restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def is_loaded():
+    return _lib is not None
+
+
+def _check(rc):
+    if rc != 0:
+        raise NativeError(_lib.odil_b200_last_error().decode())
+
+
+def dtype_code(dtype):
+    if dtype in (torch.float32, np.float32) or (not isinstance(dtype, torch.dtype) and np.dtype(dtype) == np.float32):
+        return F32
+    if dtype in (torch.float64, np.float64) or (not isinstance(dtype, torch.dtype) and np.dtype(dtype) == np.float64):
+        return F64
+    raise NativeError(f"unsupported dtype {dtype}")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, what="array"):
+    if t is None:
+        return None
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise NativeError(f"{what}: expected a CUDA tensor (the ODIL hot path has no CPU fallback)")
+    if not t.is_contiguous():
+        raise NativeError(f"{what}: tensor must be C-contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _plane_ptr(t, halo):
+    """Pointer to the first OWNED plane of a slab tensor that carries `halo` planes on both sides."""
+    if t is None:
+        return None
+    p = _ptr(t)
+    if halo:
+        plane = t.stride(0) * t.element_size()
+        return ctypes.c_void_p(p.value + halo * plane)
+    return p
+
+
+def launch_count():
+    return int(load().odil_b200_launch_count())
+
+
+class StencilPlan:
+    """Region-typed affine stencil (include/odil_b200.h: odil_b200_stencil_plan_create)."""
+
+    def __init__(self, shape, dtype, offsets, rwidth, table):
+        lib = load()
+        self.shape = tuple(int(s) for s in shape)
+        self.ndim = len(self.shape)
+        self.dtype = dtype
+        self.code = dtype_code(dtype)
+        offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int32).reshape(-1, self.ndim))
+        self.offsets = offsets
+        self.noff = offsets.shape[0]
+        self.rwidth = tuple(int(r) for r in rwidth)
+        ncls = int(np.prod([2 * r + 1 for r in self.rwidth]))
+        table = np.ascontiguousarray(np.asarray(table, dtype=np.float64).reshape(ncls, self.noff))
+        self.table = table
+        self.rmax0 = int(np.abs(offsets[:, 0]).max()) if self.noff else 0
+        shp = (ctypes.c_int64 * self.ndim)(*self.shape)
+        rw = (ctypes.c_int32 * self.ndim)(*self.rwidth)
+        h = ctypes.c_void_p()
+        _check(lib.odil_b200_stencil_plan_create(
+            self.ndim, shp, self.code, self.noff, offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), rw,
+            table.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                _lib.odil_b200_stencil_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def kind(self):
+        return int(_lib.odil_b200_stencil_plan_kind(self.handle))
+
+    def tune(self, zchunk=0, variant=0):
+        _check(_lib.odil_b200_stencil_plan_tune(self.handle, int(zchunk), int(variant)))
+
+    def _slab(self, slab):
+        if slab is None:
+            return Slab(self.shape[0], 0, 0)
+        return Slab(int(slab[0]), int(slab[1]), int(slab[2]))
+
+    def forward(self, U, F_in, F_out, slab=None):
+        s = self._slab(slab)
+        _check(_lib.odil_b200_stencil_forward(self.handle, ctypes.byref(s), _plane_ptr(U, s.halo),
+                                              _plane_ptr(F_in, s.halo), _plane_ptr(F_out, s.halo), _stream()))
+
+    def adjoint(self, F, scale, G_in, G_out, slab=None):
+        s = self._slab(slab)
+        _check(_lib.odil_b200_stencil_adjoint(self.handle, ctypes.byref(s), _plane_ptr(F, s.halo), float(scale),
+                                              _plane_ptr(G_in, s.halo), _plane_ptr(G_out, s.halo), _stream()))
+
+    def fused(self, U, c, scale, G_out, sumsq_out, F_out=None, slab=None):
+        s = self._slab(slab)
+        _check(_lib.odil_b200_stencil_fused(self.handle, ctypes.byref(s), _plane_ptr(U, s.halo),
+                                            _plane_ptr(c, s.halo), float(scale), _plane_ptr(G_out, s.halo),
+                                            _plane_ptr(F_out, s.halo), _ptr(sumsq_out), _stream()))
+
+
+def sum_squares(x, out):
+    load()
+    _check(_lib.odil_b200_sum_squares(_ptr(x), x.numel(), dtype_code(x.dtype), _ptr(out), _stream()))
+
+
+def dot(x, y, out):
+    load()
+    _check(_lib.odil_b200_dot(_ptr(x), _ptr(y), x.numel(), dtype_code(x.dtype), _ptr(out), _stream()))
+
+
+def _cshape(shape):
+    return (ctypes.c_int64 * len(shape))(*[int(s) for s in shape])
+
+
+def mg_interp_add(cshape, loc, coarse, cfac, fine_term, ffac, out, rng=None):
+    """out = ffac*fine_term + cfac*I(coarse). `cshape` = GLOBAL coarse array shape."""
+    load()
+    r = ctypes.byref(MgRange(*[int(v) for v in rng])) if rng is not None else None
+    _check(_lib.odil_b200_mg_interp_add(len(cshape), _cshape(cshape), loc.encode(), dtype_code(out.dtype), _ptr(coarse),
+                                        float(cfac), _ptr(fine_term), float(ffac), _ptr(out), r, _stream()))
+
+
+def mg_interp_adjoint(cshape, loc, g_fine, scale, g_coarse, rng=None):
+    load()
+    r = ctypes.byref(MgAdjRange(*[int(v) for v in rng])) if rng is not None else None
+    _check(_lib.odil_b200_mg_interp_adjoint(len(cshape), _cshape(cshape), loc.encode(), dtype_code(g_fine.dtype),
+                                            _ptr(g_fine), float(scale), _ptr(g_coarse), r, _stream()))
+
+
+def mg_restrict(fshape, loc, fine, out):
+    load()
+    _check(_lib.odil_b200_mg_restrict(len(fshape), _cshape(fshape), loc.encode(), dtype_code(fine.dtype), _ptr(fine),
+                                      _ptr(out), _stream()))
+
+
+def _ptr_array(tensors, dtype=None, counts=None):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        if dtype is not None and t.dtype != dtype:
+            raise NativeError(f"tensor {i}: dtype {t.dtype} does not match {dtype}")
+        if counts is not None and t.numel() != counts[i]:
+            raise NativeError(f"tensor {i}: {t.numel()} elements, expected {counts[i]}")
+        arr[i] = _ptr(t).value
+    return arr
+
+
+def adam_step(x, m, v, g, alpha, omb1, omb2, eps):
+    load()
+    n = len(x)
+    cnt = [t.numel() for t in x]
+    counts = (ctypes.c_int64 * n)(*cnt)
+    dt = x[0].dtype
+    _check(_lib.odil_b200_adam_step(n, _ptr_array(x, dt), _ptr_array(m, dt, cnt), _ptr_array(v, dt, cnt),
+                                    _ptr_array(g, dt, cnt), counts,
+                                    dtype_code(x[0].dtype), float(alpha), float(omb1), float(omb2), float(eps),
+                                    _stream()))
+
+
+def gd_step(x, g, lr):
+    load()
+    n = len(x)
+    cnt = [t.numel() for t in x]
+    counts = (ctypes.c_int64 * n)(*cnt)
+    _check(_lib.odil_b200_gd_step(n, _ptr_array(x, x[0].dtype), _ptr_array(g, x[0].dtype, cnt), counts,
+                                  dtype_code(x[0].dtype), float(lr),
+                                  _stream()))
+
+
+def axpby(a, x, b, y):
+    load()
+    _check(_lib.odil_b200_axpby(x.numel(), dtype_code(x.dtype), float(a), _ptr(x), float(b), _ptr(y), _stream()))

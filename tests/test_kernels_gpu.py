@@ -1,0 +1,407 @@
+"""
+GPU parity tests of the CUDA kernels, called through the C ABI (odil_b200.native -> libodil_b200.so),
+against the CPU oracle and the golden vectors generated from the unmodified reference.
+"""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import odil_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from odil_b200 import native
+    native.load()
+
+DT = {"f32": (np.float32, torch.float32), "f64": (np.float64, torch.float64)}
+TOL = {"f32": 2e-5, "f64": 1e-12}
+
+
+def dev(a, td=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    return t.to(td) if td is not None else t
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+LOCS = ["cccc", "nnnn", "cnnn", "nccc", "c.cn"]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("ndim", [1, 2, 3, 4])
+@pytest.mark.parametrize("loc4", LOCS)
+def test_interp_golden(golden, prec, ndim, loc4):
+    nd, td = DT[prec]
+    g = golden("transfers")
+    loc = loc4[:ndim]
+    u = g[f"interp_{ndim}_{loc}_in"].astype(nd)
+    ref = g[f"interp_{ndim}_{loc}_out"]
+    out = torch.empty(ref.shape, dtype=td, device="cuda")
+    native.mg_interp_add(u.shape, loc, dev(u), 1.0, None, 0.0, out)
+    assert relerr(out.cpu().numpy(), ref) < (100 * np.finfo(nd).eps)
+    # fused synthesis step: out = 0.5*t + 2*I(u)
+    t = np.random.default_rng(0).standard_normal(ref.shape).astype(nd)
+    native.mg_interp_add(u.shape, loc, dev(u), 2.0, dev(t), 0.5, out)
+    assert relerr(out.cpu().numpy(), 0.5 * t.astype(np.float64) + 2 * ref) < (100 * np.finfo(nd).eps)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("ndim", [1, 2, 3, 4])
+@pytest.mark.parametrize("loc4", LOCS)
+def test_interp_adjoint(golden, prec, ndim, loc4):
+    nd, td = DT[prec]
+    g = golden("transfers")
+    loc = loc4[:ndim]
+    cshape = g[f"interp_{ndim}_{loc}_in"].shape
+    fshape = g[f"interp_{ndim}_{loc}_out"].shape
+    w = np.random.default_rng(5).standard_normal(fshape).astype(nd)
+    ref = orc.interp_adjoint(w.astype(np.float64), loc, cshape)
+    out = torch.empty(cshape, dtype=td, device="cuda")
+    native.mg_interp_adjoint(cshape, loc, dev(w), 1.0, out)
+    assert relerr(out.cpu().numpy(), ref) < (200 * np.finfo(nd).eps)
+
+
+def test_interp_adjoint_small_levels():
+    """Coarse sizes 2 and 3 (deepest multigrid levels): every cell is a boundary cell."""
+    for cshape in [(2,), (3,), (2, 2), (2, 3, 2), (3, 2, 2)]:
+        loc = "c" * len(cshape)
+        fshape = tuple(2 * n for n in cshape)
+        w = np.random.default_rng(1).standard_normal(fshape)
+        ref = orc.interp_adjoint(w, loc, cshape)
+        out = torch.empty(cshape, dtype=torch.float64, device="cuda")
+        native.mg_interp_adjoint(cshape, loc, dev(w), 1.0, out)
+        assert relerr(out.cpu().numpy(), ref) < 1e-13
+        u = np.random.default_rng(2).standard_normal(cshape)
+        o2 = torch.empty(fshape, dtype=torch.float64, device="cuda")
+        native.mg_interp_add(cshape, loc, dev(u), 1.0, None, 0.0, o2)
+        assert relerr(o2.cpu().numpy(), orc.interp_to_finer(u, loc)) < 1e-13
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("ndim", [1, 2, 3, 4])
+@pytest.mark.parametrize("loc4", LOCS[:4])
+def test_restrict_golden(golden, prec, ndim, loc4):
+    nd, td = DT[prec]
+    g = golden("transfers")
+    loc = loc4[:ndim]
+    u = g[f"restrict_{ndim}_{loc}_in"].astype(nd)
+    ref = g[f"restrict_{ndim}_{loc}_out"]
+    out = torch.empty(ref.shape, dtype=td, device="cuda")
+    native.mg_restrict(u.shape, loc, dev(u), out)
+    assert relerr(out.cpu().numpy(), ref) < (100 * np.finfo(nd).eps)
+
+
+def random_plan(rng, shape, offsets, rr):
+    ncls = int(np.prod([2 * r + 1 for r in rr]))
+    return rng.standard_normal((ncls, len(offsets)))
+
+
+STENCIL_CASES = [
+    # shape, offsets, rwidth
+    ((37,), [(0,), (-1,), (1,), (2,)], (2,)),
+    ((16, 12), [(0, 0), (-1, 0), (-2, 0), (-1, -1), (-1, 1)], (2, 1)),       # wave footprint
+    ((9, 10), [(0, 0), (1, 1), (-1, 1)], (1, 1)),                            # non-star -> generic
+    ((12, 12, 12), None, (1, 1, 1)),                                         # 3-D star -> tiled
+    ((16, 8, 12), None, (1, 1, 1)),
+    ((10, 7, 20), None, (1, 0, 1)),                                          # periodic axis 1
+    ((24, 40), None, (1, 1)),                                                # 2-D star -> tiled
+    ((33, 130), None, (2, 1)),                                               # 2-D star, scalar g path, r=2
+    ((5, 6, 4, 7), None, (1, 1, 0, 1)),                                      # 4-D star -> generic
+]
+
+
+def star_offsets(ndim):
+    offs = [(0,) * ndim]
+    for a in range(ndim):
+        for s in (-1, 1):
+            offs.append(tuple(s if b == a else 0 for b in range(ndim)))
+    return offs
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("case", range(len(STENCIL_CASES)))
+def test_stencil_random_tables(prec, case):
+    nd, td = DT[prec]
+    shape, offsets, rr = STENCIL_CASES[case]
+    offsets = offsets or star_offsets(len(shape))
+    rng = np.random.default_rng(100 + case)
+    table = random_plan(rng, shape, offsets, rr)
+    tshape = tuple(2 * r + 1 for r in rr) + (len(offsets),)
+    U = rng.standard_normal(shape).astype(nd)
+    c = rng.standard_normal(shape).astype(nd)
+    plan = native.StencilPlan(shape, td, offsets, rr, table)
+    F_ref = orc.stencil_forward(U.astype(np.float64), offsets, table.reshape(tshape), rr, c.astype(np.float64))
+    scale = 2.0 / U.size
+    g_ref = orc.stencil_adjoint(F_ref, offsets, table.reshape(tshape), rr, scale)
+    dU, dc = dev(U), dev(c)
+    # forward
+    F = torch.empty_like(dU)
+    plan.forward(dU, dc, F)
+    tol = TOL[prec] * 10
+    assert relerr(F.cpu().numpy(), F_ref) < tol
+    # adjoint of the device F
+    G = torch.empty_like(dU)
+    plan.adjoint(F, scale, None, G)
+    assert relerr(G.cpu().numpy(), g_ref) < tol
+    # fused (tiled when eligible)
+    G2 = torch.full_like(dU, float("nan"))
+    F2 = torch.full_like(dU, float("nan"))
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    plan.fused(dU, dc, scale, G2, ss, F_out=F2)
+    assert relerr(F2.cpu().numpy(), F_ref) < tol
+    assert relerr(G2.cpu().numpy(), g_ref) < tol
+    assert abs(ss.item() - np.sum(F_ref ** 2)) < tol * np.sum(F_ref ** 2)
+    # fused without c and without F_out
+    plan.fused(dU, None, scale, G2, ss)
+    F0 = orc.stencil_forward(U.astype(np.float64), offsets, table.reshape(tshape), rr, None)
+    assert abs(ss.item() - np.sum(F0 ** 2)) < tol * np.sum(F0 ** 2)
+    assert relerr(G2.cpu().numpy(), orc.stencil_adjoint(F0, offsets, table.reshape(tshape), rr, scale)) < tol
+
+
+def test_star_plans_use_tiled_kernel():
+    kinds = []
+    for shape, offsets, rr in STENCIL_CASES:
+        offsets = offsets or star_offsets(len(shape))
+        ncls = int(np.prod([2 * r + 1 for r in rr]))
+        plan = native.StencilPlan(shape, torch.float32, offsets, rr, np.ones((ncls, len(offsets))))
+        kinds.append(plan.kind)
+    assert kinds == [0, 0, 0, 1, 1, 1, 1, 1, 0]
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("zchunk", [0, 1, 5, 64])
+def test_star_variants(variant, zchunk):
+    shape, rr = (20, 18, 36), (1, 1, 1)
+    offsets = star_offsets(3)
+    rng = np.random.default_rng(7)
+    table = rng.standard_normal((27, 7))
+    U = rng.standard_normal(shape)
+    c = rng.standard_normal(shape)
+    plan = native.StencilPlan(shape, torch.float64, offsets, rr, table)
+    plan.tune(zchunk=zchunk, variant=variant)
+    F_ref = orc.stencil_forward(U, offsets, table.reshape(3, 3, 3, 7), rr, c)
+    g_ref = orc.stencil_adjoint(F_ref, offsets, table.reshape(3, 3, 3, 7), rr, 0.5)
+    G = torch.empty(shape, dtype=torch.float64, device="cuda")
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    plan.fused(dev(U), dev(c), 0.5, G, ss)
+    assert relerr(G.cpu().numpy(), g_ref) < 1e-12
+    assert abs(ss.item() - np.sum(F_ref ** 2)) < 1e-12 * np.sum(F_ref ** 2)
+
+
+POISSON_CASES = {
+    "p1d_16_L0": ((16,), 0), "p1d_16_L3": ((16,), 3), "p2d_16_L3": ((16, 16), 3), "p2d_12x8_L0": ((12, 8), 0),
+    "p3d_8_L3": ((8, 8, 8), 3), "p3d_16x8x12_L2": ((16, 8, 12), 2), "p3d_12_L0": ((12, 12, 12), 0),
+}
+
+
+def device_eval_loss_grad(terms, loc, plan, c, td):
+    """Multigrid synthesis -> fused stencil -> multigrid adjoint, all on the device."""
+    L = len(terms)
+    dterms = [dev(t) for t in terms]
+    V = dterms[-1]
+    for l in range(L - 2, -1, -1):
+        out = torch.empty_like(dterms[l])
+        native.mg_interp_add(dterms[l + 1].shape, loc, V, 1.0, dterms[l], 1.0, out)
+        V = out
+    U = V
+    G = torch.empty_like(U)
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    n = U.numel()
+    plan.fused(U, c, 2.0 / n, G, ss)
+    grads = [G]
+    for l in range(1, L):
+        gc = torch.empty_like(dterms[l])
+        native.mg_interp_adjoint(dterms[l].shape, loc, grads[-1], 1.0, gc)
+        grads.append(gc)
+    return ss.item() / n, [x.cpu().numpy() for x in grads], U.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(POISSON_CASES))
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_poisson_golden(golden, name, prec):
+    """Loss and gradient w.r.t. every multigrid term vs the reference (core.py + poisson.py under autograd)."""
+    nd, td = DT[prec]
+    g = golden("poisson")
+    cshape, nlvl = POISSON_CASES[name]
+    tag = f"{name}_{prec}"
+    terms, grads = [], []
+    i = 0
+    while f"{tag}_term{i}" in g.files:
+        terms.append(g[f"{tag}_term{i}"])
+        grads.append(g[f"{tag}_grad{i}"])
+        i += 1
+    ndim = len(cshape)
+    steps = [nd(1) / nd(n) for n in cshape]
+    offsets, table, rr = orc.poisson_plan(ndim, steps)
+    plan = native.StencilPlan(cshape, td, offsets, rr, table)
+    loss, gr, U = device_eval_loss_grad(terms, "c" * ndim, plan, dev(-g[tag + "_rhs"]), td)
+    tol = 1e-11 if prec == "f64" else 2e-4
+    assert relerr(U, g[tag + "_U"]) < (1e-13 if prec == "f64" else 1e-5)
+    assert abs(loss - g[tag + "_loss"]) < tol * abs(g[tag + "_loss"])
+    for a, b in zip(gr, grads):
+        assert a.shape == b.shape
+        assert relerr(a, b) < tol
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_adam_gd(prec):
+    nd, td = DT[prec]
+    rng = np.random.default_rng(3)
+    shapes = [(33, 7), (1000,), (5,), (16, 16, 16)]
+    x = [rng.standard_normal(s).astype(nd) for s in shapes]
+    m = [np.zeros(s, nd) for s in shapes]
+    v = [np.zeros(s, nd) for s in shapes]
+    dx, dm, dv = [dev(a) for a in x], [dev(a) for a in m], [dev(a) for a in v]
+    for t in range(1, 6):
+        g = [(rng.standard_normal(s) * 10.0 ** rng.integers(-6, 2)).astype(nd) for s in shapes]
+        alpha, omb1, omb2 = orc.adam_scalars(0.01, 0.9, 0.999, t, nd)
+        native.adam_step(dx, dm, dv, [dev(a) for a in g], alpha, omb1, omb2, 1e-7)
+        for i in range(len(x)):
+            x[i], m[i], v[i] = orc.adam_step(x[i], m[i], v[i], g[i], 0.01, t)
+    tol = 1e-13 if prec == "f64" else 3e-6
+    for i in range(len(x)):
+        assert relerr(dx[i].cpu().numpy(), x[i]) < tol
+        assert relerr(dm[i].cpu().numpy(), m[i]) < tol
+        assert relerr(dv[i].cpu().numpy(), v[i]) < tol
+    g = [rng.standard_normal(s).astype(nd) for s in shapes]
+    native.gd_step(dx, [dev(a) for a in g], 0.125)
+    for i in range(len(x)):
+        assert relerr(dx[i].cpu().numpy(), orc.gd_step(x[i], g[i], 0.125)) < tol
+
+
+def test_adam_trajectory_golden(golden):
+    """20 Adam epochs of 2-D Poisson 16^2 / 3 levels: loss trajectory vs the reference's own optimizer."""
+    for prec in ["f64", "f32"]:
+        nd, td = DT[prec]
+        g = golden("optim")
+        tag = f"adam_p2d_16_L3_{prec}"
+        steps = [nd(1) / nd(16)] * 2
+        offsets, table, rr = orc.poisson_plan(2, steps)
+        plan = native.StencilPlan((16, 16), td, offsets, rr, table)
+        c = dev(-g[tag + "_rhs"])
+        shapes = [(16, 16), (8, 8), (4, 4)]
+        x = [torch.zeros(s, dtype=td, device="cuda") for s in shapes]
+        m = [torch.zeros_like(a) for a in x]
+        v = [torch.zeros_like(a) for a in x]
+        losses = []
+        for t in range(1, 21):
+            V = x[2]
+            for l in (1, 0):
+                out = torch.empty_like(x[l])
+                native.mg_interp_add(shapes[l + 1], "cc", V, 1.0, x[l], 1.0, out)
+                V = out
+            G = torch.empty_like(V)
+            ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+            plan.fused(V, c, 2.0 / 256, G, ss)
+            grads = [G]
+            for l in (1, 2):
+                gc = torch.empty_like(x[l])
+                native.mg_interp_adjoint(shapes[l], "cc", grads[-1], 1.0, gc)
+                grads.append(gc)
+            losses.append(ss.item() / 256)
+            alpha, omb1, omb2 = orc.adam_scalars(0.005, 0.9, 0.999, t, nd)
+            native.adam_step(x, m, v, grads, alpha, omb1, omb2, 1e-7)
+        tol = 1e-9 if prec == "f64" else 1e-4
+        assert np.max(np.abs(np.array(losses) / g[tag + "_losses"] - 1)) < tol
+        for i in range(3):
+            assert relerr(x[i].cpu().numpy(), g[f"{tag}_x{i}"]) < (1e-8 if prec == "f64" else 2e-3)
+
+
+def test_reductions():
+    rng = np.random.default_rng(9)
+    for n in [1, 31, 4097, 1 << 20]:
+        for prec in ["f32", "f64"]:
+            nd, td = DT[prec]
+            a = rng.standard_normal(n).astype(nd)
+            b = rng.standard_normal(n).astype(nd)
+            out = torch.zeros(1, dtype=torch.float64, device="cuda")
+            native.sum_squares(dev(a), out)
+            assert abs(out.item() - np.sum(a.astype(np.float64) ** 2)) < 1e-12 * n
+            native.dot(dev(a), dev(b), out)
+            assert abs(out.item() - np.dot(a.astype(np.float64), b.astype(np.float64))) < 1e-10 * n
+            y = dev(b)
+            native.axpby(2.0, dev(a), -0.5, y)
+            assert relerr(y.cpu().numpy(), 2.0 * a - 0.5 * b) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# Full-size property checks (BASELINE.json sizes): no CPU oracle at this size, so use identities.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,prec", [((512, 512, 512), "f32"), ((256, 256, 256), "f64"), ((1024, 1024), "f32")])
+def test_fullsize_properties(shape, prec):
+    nd, td = DT[prec]
+    ndim = len(shape)
+    steps = [nd(1) / nd(n) for n in shape]
+    offsets, table, rr = orc.poisson_plan(ndim, steps)
+    plan = native.StencilPlan(shape, td, offsets, rr, table)
+    assert plan.kind == 1
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    U = torch.randn(shape, dtype=td, device="cuda", generator=gen)
+    c = torch.randn(shape, dtype=td, device="cuda", generator=gen)
+    n = U.numel()
+    G = torch.empty_like(U)
+    F = torch.empty_like(U)
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    plan.fused(U, c, 2.0 / n, G, ss, F_out=F)
+    # (1) fused F equals the unfused generic forward kernel; loss equals sum of squares of F
+    F2 = torch.empty_like(U)
+    plan.forward(U, c, F2)
+    scaleF = F2.abs().max().item()
+    assert (F - F2).abs().max().item() < (1e-5 if prec == "f32" else 1e-12) * scaleF
+    s2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    native.sum_squares(F2, s2)
+    assert abs(ss.item() - s2.item()) < (1e-6 if prec == "f32" else 1e-12) * s2.item()
+    # (2) fused G equals the unfused generic adjoint kernel
+    G2 = torch.empty_like(U)
+    plan.adjoint(F2, 2.0 / n, None, G2)
+    assert (G - G2).abs().max().item() < (2e-5 if prec == "f32" else 1e-12) * G2.abs().max().item()
+    # (3) adjoint identity  <A W, F> == <W, A^T F>
+    W = torch.randn(shape, dtype=td, device="cuda", generator=gen)
+    AW = torch.empty_like(U)
+    plan.forward(W, None, AW)
+    d1 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    d2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    native.dot(AW, F2, d1)
+    ATF = torch.empty_like(U)
+    plan.adjoint(F2, 1.0, None, ATF)
+    native.dot(W, ATF, d2)
+    assert abs(d1.item() - d2.item()) < (1e-4 if prec == "f32" else 1e-11) * max(abs(d1.item()), 1.0)
+    # (4) boundary rows: a field that is exactly the zero-Dirichlet quadratic in x along the last
+    #     axis has the analytic second derivative in the first/last cell (poisson.py:57-68)
+    del G, G2, AW, ATF, W
+
+
+@pytest.mark.parametrize("cshape", [(256, 256, 256), (512, 512)])
+def test_fullsize_mg_transpose(cshape):
+    """<I u, w> == <u, I^T w> at full size, fp64."""
+    ndim = len(cshape)
+    loc = "c" * ndim
+    fshape = tuple(2 * n for n in cshape)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    u = torch.randn(cshape, dtype=torch.float64, device="cuda", generator=gen)
+    w = torch.randn(fshape, dtype=torch.float64, device="cuda", generator=gen)
+    Iu = torch.empty(fshape, dtype=torch.float64, device="cuda")
+    native.mg_interp_add(cshape, loc, u, 1.0, None, 0.0, Iu)
+    Itw = torch.empty(cshape, dtype=torch.float64, device="cuda")
+    native.mg_interp_adjoint(cshape, loc, w, 1.0, Itw)
+    d1 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    d2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    native.dot(Iu, w, d1)
+    native.dot(u, Itw, d2)
+    assert abs(d1.item() - d2.item()) < 1e-10 * max(abs(d1.item()), 1.0)
+    # linear functions are reproduced exactly by I (reference tests/test_mg_interp.py)
+    xs = [torch.arange(n, dtype=torch.float64, device="cuda") + 0.5 for n in cshape]
+    lin = sum((i + 1.0) * x.reshape([-1 if a == i else 1 for a in range(ndim)]) / cshape[i] for i, x in enumerate(xs))
+    lin = lin.expand(cshape).contiguous()
+    native.mg_interp_add(cshape, loc, lin, 1.0, None, 0.0, Iu)
+    xf = [torch.arange(2 * n, dtype=torch.float64, device="cuda") + 0.5 for n in cshape]
+    linf = sum((i + 1.0) * x.reshape([-1 if a == i else 1 for a in range(ndim)]) / (2 * cshape[i])
+               for i, x in enumerate(xf))
+    assert (Iu - linf).abs().max().item() < 1e-12
