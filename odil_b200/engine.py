@@ -1,0 +1,379 @@
+"""
+ResidualEngine: traces the user operator once, lowers every output to region-typed stencil plans and
+evaluates loss + gradient with the CUDA kernels.  This is what `Problem._eval_loss_grad_b200` calls;
+it replaces the jitted XLA program of the reference (core.py:1076-1111):
+
+    reference                                      here
+    ---------------------------------------------  ---------------------------------------------
+    multigrid_to_regular / interp_to_finer         odil_b200_mg_interp_add      (one launch / level)
+    operator(ctx): roll, where, arithmetic         odil_b200_stencil_fused      (one sweep: F, sum F^2,
+    mean(square(F)), jax.value_and_grad                                           g_U = (2/n) A^T F)
+    AD through interp_to_finer                     odil_b200_mg_interp_adjoint  (one launch / level)
+
+Outputs that are affine in the unknown fields with coefficients that are piecewise constant per
+boundary region (Poisson, wave, identity-type data terms) are supported; anything else raises
+NonAffineError at trace time (no silent fallback).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import native
+from .backend import Affine, Known, NonAffineError, as_known, torch_dtype
+from .core import Array, Context, Field, MultigridField, NeuralNet
+
+MAX_REGION_WIDTH = 8
+
+
+class _Fetch:
+    """One device->host copy shared by all scalars of an evaluation, done on first use."""
+
+    def __init__(self, sums, counts, dtype):
+        self.sums = sums
+        self.counts = counts
+        self.dtype = dtype
+        self._terms = None
+
+    def terms(self):
+        if self._terms is None:
+            host = self.sums.detach().cpu().numpy()
+            self._terms = [self.dtype.type(s / n) for s, n in zip(host, self.counts)]
+            self.sums = None
+        return self._terms
+
+
+class LazyScalar:
+    """Device-resident scalar (loss / term / norm). Converts on np.array(), float(), format()."""
+    __array_priority__ = 1000
+
+    def __init__(self, fetch, kind, index=None):
+        self._fetch, self._kind, self._index = fetch, kind, index
+
+    def value(self):
+        t = self._fetch.terms()
+        if self._kind == "loss":
+            return self._fetch.dtype.type(sum(t))
+        if self._kind == "term":
+            return t[self._index]
+        return np.sqrt(t[self._index])
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.array(self.value())
+        return a.astype(dtype) if dtype is not None else a
+
+    def __float__(self):
+        return float(self.value())
+
+    def item(self):
+        return self.value().item()
+
+    def __format__(self, spec):
+        return format(self.value(), spec)
+
+    def __repr__(self):
+        return repr(self.value())
+
+    def _bin(self, other, op):
+        return op(self.value(), other.value() if isinstance(other, LazyScalar) else other)
+
+    def __add__(self, o):
+        return self._bin(o, lambda a, b: a + b)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self._bin(o, lambda a, b: a - b)
+
+    def __rsub__(self, o):
+        return self._bin(o, lambda a, b: b - a)
+
+    def __mul__(self, o):
+        return self._bin(o, lambda a, b: a * b)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return self._bin(o, lambda a, b: a / b)
+
+    def __lt__(self, o):
+        return self._bin(o, lambda a, b: a < b)
+
+    def __gt__(self, o):
+        return self._bin(o, lambda a, b: a > b)
+
+
+# --------------------------------------------------------------------------------------------------
+# Lowering: Affine expression -> region-typed table
+# --------------------------------------------------------------------------------------------------
+def axis_region_width(t, axis, n):
+    """Smallest r such that compact tensor `t` is constant along `axis` on [r, n - r)."""
+    if t.shape[axis] == 1 or n <= 1:
+        return 0
+    diff = t.narrow(axis, 1, n - 1) != t.narrow(axis, 0, n - 1)
+    other = [a for a in range(t.dim()) if a != axis]
+    if other:
+        diff = diff.sum(dim=other) > 0
+    idx = torch.nonzero(diff.reshape(-1)).reshape(-1)
+    if idx.numel() == 0:
+        return 0
+    idx = idx.to(torch.int64)
+    return int(torch.minimum(idx + 1, (n - 1) - idx).max().item())
+
+
+def representative_indices(n, r):
+    mid = min(r, n - 1)
+    return list(range(r)) + [mid] + list(range(n - r, n))
+
+
+def lower_block(shape, coefs):
+    """
+    coefs: {offset tuple: Coef}.  Returns (offsets [noff, ndim], rwidth [ndim], table [ncls, noff]).
+    Raises NonAffineError if some coefficient varies in the interior (not region-typed).
+    """
+    nd = len(shape)
+    offsets = sorted(coefs.keys())
+    rr = [0] * nd
+    for off in offsets:
+        for t in coefs[off].terms:
+            for a in range(nd):
+                rr[a] = max(rr[a], axis_region_width(t, a, shape[a]))
+    for a in range(nd):
+        if rr[a] > MAX_REGION_WIDTH or 2 * rr[a] > shape[a]:
+            raise NonAffineError(
+                f"stencil coefficients vary inside the domain along axis {a} (region width {rr[a]}): per-cell "
+                "coefficient arrays are not supported on the fused path yet")
+    reps = [representative_indices(shape[a], rr[a]) for a in range(nd)]
+    cls_shape = tuple(2 * r + 1 for r in rr)
+    table = np.zeros(cls_shape + (len(offsets),), dtype=np.float64)
+    for o, off in enumerate(offsets):
+        acc = torch.zeros(cls_shape, dtype=torch.float64, device=coefs[off].terms[0].device if coefs[off].terms
+                          else "cpu")
+        for t in coefs[off].terms:
+            s = t.to(torch.float64)
+            for a in range(nd):
+                if s.shape[a] != 1:
+                    s = s.index_select(a, torch.as_tensor(reps[a], device=s.device))
+            acc = acc + s
+        table[..., o] = acc.cpu().numpy()
+    keep = [o for o in range(len(offsets)) if np.any(table[..., o] != 0)]
+    if not keep:
+        keep = [0]
+    offsets = [offsets[o] for o in keep]
+    table = table[..., keep]
+    return np.asarray(offsets, dtype=np.int32).reshape(len(offsets), nd), rr, table.reshape(-1, len(offsets))
+
+
+class _Block:
+    def __init__(self, key, frozen, plan):
+        self.key, self.frozen, self.plan = key, frozen, plan
+
+
+class _Output:
+    def __init__(self, name, shape, const, blocks):
+        self.name, self.shape, self.const, self.blocks = name, shape, const, blocks
+        self.n = math.prod(shape)
+        self.fused = False
+
+
+class _Unknown:
+    """How one state entry maps to arrays of the flat unknown list."""
+
+    def __init__(self, key, field, first):
+        self.key, self.first = key, first
+        self.kind = type(field).__name__
+        if isinstance(field, MultigridField):
+            self.narrays = len(field.terms)
+            self.loc = field.loc
+            self.shapes = [tuple(t.array.shape) for t in field.terms]
+        elif isinstance(field, (Field, Array)):
+            self.narrays = 1
+            self.shapes = [tuple(field.array.shape)]
+        elif isinstance(field, NeuralNet):
+            self.narrays = len(field.weights) + len(field.biases)
+            self.shapes = [tuple(a.shape) for a in list(field.weights) + list(field.biases)]
+        else:
+            raise TypeError("Unknown field type '{}'".format(type(field).__name__))
+        self.shape = self.shapes[0]
+
+
+class ResidualEngine:
+
+    def __init__(self, problem, state, trace_only=False):
+        """trace_only=True stops after lowering (no CUDA needed): used to inspect / test the plans."""
+        self.trace_only = trace_only
+        if not trace_only:
+            native.load()
+            if not torch.cuda.is_available():
+                raise native.NativeError("the ODIL B200 engine needs a CUDA device (no CPU fallback)")
+        self.problem = problem
+        self.domain = domain = problem.domain
+        self.dtype = np.dtype(domain.dtype)
+        self.tdtype = torch_dtype(self.dtype)
+        self.device = domain.mod.device
+        # unknown layout
+        self.unknowns = {}
+        first = 0
+        for key, field in state.fields.items():
+            u = _Unknown(key, field, first)
+            if isinstance(field, MultigridField):
+                u.mgloc = domain._mg_loc(field)
+                u.factors = [float(f) for f in (field.factors or domain.mg_factors or [1] * len(field.terms))]
+            self.unknowns[key] = u
+            first += u.narrays
+        self.narrays = first
+        self._trace(state)
+        self._buffers = {}
+
+    # ----------------------------------------------------------------------------------------------
+    def _trace(self, state):
+        problem, domain = self.problem, self.domain
+        ctx = Context(domain, state, extra=problem.extra, tracers=problem.tracers)
+        ff = problem.operator(ctx)
+        assert isinstance(ff, (tuple, list)) and len(ff), "Operator must return a non-empty list"
+        names = [f[0] if isinstance(f, tuple) else "" for f in ff]
+        nonempty = [n for n in names if n]
+        assert len(nonempty) == len(set(nonempty)), "Name of fields must be unique, got {}".format(nonempty)
+        values = [f[1] if isinstance(f, tuple) else f for f in ff]
+        self.names = names
+        self.outputs = []
+        use_count = {}
+        for name, v in zip(names, values):
+            if isinstance(v, Context.Raw):
+                raise NonAffineError("Context.Raw loss terms are not on the fused path yet")
+            if not isinstance(v, Affine):
+                v = as_known(v)
+                const = v.full().to(self.tdtype).contiguous()
+                self.outputs.append(_Output(name, tuple(v.shape), const, []))
+                continue
+            groups = {}
+            for (key, off, frozen), coef in v.lin.items():
+                groups.setdefault((key, frozen), {})[off] = coef
+            blocks = []
+            for (key, frozen), coefs in groups.items():
+                unk = self.unknowns[key]
+                if tuple(unk.shape) != tuple(v.shape):
+                    raise NonAffineError(f"output shape {v.shape} differs from field '{key}' shape {unk.shape}")
+                offsets, rr, table = lower_block(v.shape, coefs)
+                blk = _Block(key, frozen, None)
+                blk.spec = dict(shape=tuple(v.shape), offsets=offsets, rwidth=tuple(rr), table=table)
+                if not self.trace_only:
+                    blk.plan = native.StencilPlan(v.shape, self.tdtype, offsets, rr, table)
+                blocks.append(blk)
+                if not frozen:
+                    use_count[key] = use_count.get(key, 0) + 1
+            const = None
+            if not v.const.is_zero():
+                const = v.const.dense(v.shape, self.tdtype, self.device).contiguous()
+            self.outputs.append(_Output(name, tuple(v.shape), const, blocks))
+        for out in self.outputs:
+            out.fused = (len(out.blocks) == 1 and not out.blocks[0].frozen and use_count.get(out.blocks[0].key) == 1)
+        self.used_keys = set(use_count)
+
+    # ----------------------------------------------------------------------------------------------
+    def _buf(self, name, shape):
+        b = self._buffers.get(name)
+        if b is None or tuple(b.shape) != tuple(shape):
+            b = torch.empty(shape, dtype=self.tdtype, device=self.device)
+            self._buffers[name] = b
+        return b
+
+    def _check_arrays(self, arrays):
+        if len(arrays) != self.narrays:
+            raise ValueError(f"expected {self.narrays} arrays, got {len(arrays)}")
+        for a in arrays:
+            if not (torch.is_tensor(a) and a.is_cuda and a.dtype == self.tdtype and a.is_contiguous()):
+                raise native.NativeError(
+                    "state arrays must be contiguous CUDA tensors of the domain dtype; use domain.init_state() "
+                    "(the ODIL hot path has no CPU fallback)")
+
+    def _regular(self, unk, arrays):
+        """Regular field U of one unknown (multigrid synthesis when needed)."""
+        a = arrays[unk.first: unk.first + unk.narrays]
+        if unk.kind != "MultigridField":
+            return a[0]
+        L = unk.narrays
+        if L == 1:
+            return a[0] if unk.factors[0] == 1 else a[0] * unk.factors[0]
+        res, cfac = a[L - 1], unk.factors[L - 1]
+        for lvl in range(L - 2, -1, -1):
+            out = self._buf(("V", unk.key, lvl), unk.shapes[lvl])
+            native.mg_interp_add(unk.shapes[lvl + 1], unk.mgloc, res, cfac, a[lvl], unk.factors[lvl], out)
+            res, cfac = out, 1.0
+        return res
+
+    def _scatter_grad(self, unk, gU, grads):
+        """Gradient of the regular field -> gradients of the stored arrays."""
+        if unk.kind != "MultigridField":
+            grads[unk.first] = gU
+            return
+        g = gU
+        for lvl in range(unk.narrays):
+            if lvl > 0:
+                gc = self._buf(("gV", unk.key, lvl), unk.shapes[lvl])
+                native.mg_interp_adjoint(unk.shapes[lvl], unk.mgloc, g, 1.0, gc)
+                g = gc
+            f = unk.factors[lvl]
+            grads[unk.first + lvl] = g if f == 1 else g * f
+
+    # ----------------------------------------------------------------------------------------------
+    def loss_grad(self, arrays):
+        self._check_arrays(arrays)
+        K = len(self.outputs)
+        sums = torch.empty(K, dtype=torch.float64, device=self.device)
+        U = {key: self._regular(self.unknowns[key], arrays) for key in self.used_keys | self._frozen_keys()}
+        gU = {}
+        for k, out in enumerate(self.outputs):
+            if out.fused:
+                blk = out.blocks[0]
+                g = self._buf(("gU", blk.key), out.shape)
+                blk.plan.fused(U[blk.key], out.const, 2.0 / out.n, g, sums[k:k + 1])
+                gU[blk.key] = g
+                continue
+            if not out.blocks:
+                native.sum_squares(out.const, sums[k:k + 1])
+                continue
+            F = self._buf(("F", k), out.shape)
+            src = out.const
+            for blk in out.blocks:
+                blk.plan.forward(U[blk.key], src, F)
+                src = F
+            native.sum_squares(F, sums[k:k + 1])
+            for blk in out.blocks:
+                if blk.frozen:
+                    continue
+                g = self._buf(("gU", blk.key), out.shape)
+                blk.plan.adjoint(F, 2.0 / out.n, g if blk.key in gU else None, g)
+                gU[blk.key] = g
+        grads = [None] * self.narrays
+        for key, unk in self.unknowns.items():
+            if key in gU:
+                self._scatter_grad(unk, gU[key], grads)
+        for i in range(self.narrays):
+            if grads[i] is None:
+                grads[i] = torch.zeros_like(arrays[i])
+        fetch = _Fetch(sums, [o.n for o in self.outputs], self.dtype)
+        loss = LazyScalar(fetch, "loss")
+        terms = [LazyScalar(fetch, "term", k) for k in range(K)]
+        norms = [LazyScalar(fetch, "norm", k) for k in range(K)]
+        return loss, grads, terms, norms
+
+    def _frozen_keys(self):
+        return {b.key for o in self.outputs for b in o.blocks if b.frozen}
+
+    def operator_values(self, arrays):
+        """Materialised operator outputs F_k (Problem.eval_operator, core.py:1298-1311)."""
+        self._check_arrays(arrays)
+        U = {key: self._regular(self.unknowns[key], arrays) for key in self.used_keys | self._frozen_keys()}
+        res = []
+        for out in self.outputs:
+            if not out.blocks:
+                res.append(Known(out.const.clone()))
+                continue
+            F = torch.empty(out.shape, dtype=self.tdtype, device=self.device)
+            src = out.const
+            for blk in out.blocks:
+                blk.plan.forward(U[blk.key], src, F)
+                src = F
+            res.append(Known(F))
+        return res

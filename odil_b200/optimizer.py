@@ -1,0 +1,155 @@
+"""
+Optimizers behind the reference's optimizer seam (src/odil/optimizer.py): `make_optimizer(name)` returns
+an object with `.run(x0, loss_grad, epochs, callback, epoch_start, lr, **kw) -> (arrays, optinfo)`.
+
+  adam / adamn   device-resident Adam: one multi-tensor CUDA launch per epoch
+                 (odil_b200_adam_step; reference AdamNativeOptimizer, optimizer.py:280-341)
+  gd             device-resident gradient descent (odil_b200_gd_step; optimizer.py:256-277)
+  lbfgsb / lbfgs SciPy L-BFGS-B driving the device loss/gradient, exactly the reference's arrangement
+                 (optimizer.py:29-117): the flat fp64 unknown vector lives on the host.
+  adam_tf, tfp lbfgs: TensorFlow-only wrappers of the reference, not provided.
+"""
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+from . import native
+
+
+class Optimizer:
+
+    def __init__(self, name=None, displayname=None, dtype=None):
+        self.name = name
+        self.displayname = displayname if displayname is not None else name
+        self.dtype = dtype
+        self.pinfo = None
+        self.evals = 0
+
+    def run(self, x0, loss_grad, epochs, callback=None, epoch_start=0, **kwargs):
+        return x0, Namespace(evals=0, epochs=0)
+
+
+class EarlyStopError(Exception):
+
+    def __init__(self, msg, optinfo):
+        super().__init__(msg)
+        self.optinfo = optinfo
+
+
+def adam_scalars(lr, beta_1, beta_2, local_epoch, dtype):
+    """Bias-corrected step size and (1 - beta) factors, evaluated IN `dtype` like optimizer.py:307-314."""
+    d = np.dtype(dtype).type
+    lr, b1, b2, t = d(lr), d(beta_1), d(beta_2), d(local_epoch)
+    alpha = lr * np.sqrt(d(1) - b2 ** t) / (d(1) - b1 ** t)
+    return float(d(alpha)), float(d(d(1) - b1)), float(d(d(1) - b2))
+
+
+def _device_copy(arrays):
+    out = []
+    for a in arrays:
+        if not (torch.is_tensor(a) and a.is_cuda):
+            raise native.NativeError("optimizer state must be CUDA tensors (use domain.init_state)")
+        out.append(a.clone().contiguous())
+    return out
+
+
+class AdamNativeOptimizer(Optimizer):
+
+    def __init__(self, dtype=None, mod=None, **kwargs):
+        super().__init__(name="adamn", displayname="AdamNative", dtype=dtype)
+        self.mod = mod
+
+    def run(self, x0, loss_grad, epochs=None, callback=None, lr=1e-3, epoch_start=0, beta_1=0.9, beta_2=0.999,
+            epsilon=1e-7, jit=True, **kwargs):
+        dtype = np.dtype(self.dtype if self.dtype is not None else np.float32)
+        x = _device_copy(x0)
+        m = [torch.zeros_like(e) for e in x]
+        v = [torch.zeros_like(e) for e in x]
+        eps = float(dtype.type(epsilon))
+        for epoch in range(epoch_start + 1, epoch_start + epochs + 1):
+            self.evals += 1
+            loss, grads, pinfo = loss_grad(x)
+            alpha, omb1, omb2 = adam_scalars(lr, beta_1, beta_2, epoch - epoch_start, dtype)
+            native.adam_step(x, m, v, grads, alpha, omb1, omb2, eps)
+            if epoch > 0 and callback is not None:
+                callback(x, epoch, pinfo)
+        return x, Namespace(epochs=epochs, evals=self.evals)
+
+
+class GdOptimizer(Optimizer):
+
+    def __init__(self, dtype=None, mod=None, **kwargs):
+        super().__init__(name="gd", displayname="GD", dtype=dtype)
+        self.mod = mod
+
+    def run(self, x0, loss_grad, epochs=None, callback=None, lr=1e-3, epoch_start=0, **kwargs):
+        x = _device_copy(x0)
+        for epoch in range(epoch_start + 1, epoch_start + epochs + 1):
+            self.evals += 1
+            loss, grads, pinfo = loss_grad(x)
+            native.gd_step(x, grads, lr)
+            if epoch > 0 and callback is not None:
+                callback(x, epoch, pinfo)
+        return x, Namespace(epochs=epochs, evals=self.evals)
+
+
+class LbfgsbOptimizer(Optimizer):
+
+    def __init__(self, pgtol=1e-16, m=50, maxls=50, factr=0, dtype=None, mod=None, **kwargs):
+        """
+        pgtol: projected-gradient tolerance; m: number of correction pairs; maxls: line-search steps per
+        iteration; factr: relative-reduction stop factor (0 disables) -- as scipy.optimize.fmin_l_bfgs_b.
+        """
+        super().__init__(name="lbfgsb", displayname="L-BFGS-B", dtype=dtype)
+        self.mod = mod
+        self.pgtol, self.m, self.maxls, self.factr = pgtol, m, maxls, factr
+
+    def run(self, x0, loss_grad, epochs=None, callback=None, epoch_start=0, **kwargs):
+        from scipy import optimize
+
+        self.epoch = epoch_start
+        tdtype = x0[0].dtype
+        device = x0[0].device
+        shapes = [tuple(a.shape) for a in x0]
+        sizes = [int(np.prod(s)) for s in shapes]
+        bounds = np.cumsum([0] + sizes)
+
+        def to_arrays(flat):
+            t = torch.from_numpy(np.ascontiguousarray(flat)).to(device=device, dtype=tdtype)
+            return [t[bounds[i]:bounds[i + 1]].reshape(shapes[i]).contiguous() for i in range(len(sizes))]
+
+        def to_flat(arrays):
+            return torch.cat([a.reshape(-1) for a in arrays]).to(torch.float64).cpu().numpy()
+
+        def func(flat):
+            self.evals += 1
+            loss, grads, pinfo = loss_grad(to_arrays(flat))
+            self.pinfo = pinfo
+            return float(loss), to_flat(grads)
+
+        def on_iteration(flat):
+            self.epoch += 1
+            if callback:
+                callback(to_arrays(flat), self.epoch, self.pinfo)
+
+        x, f, info = optimize.fmin_l_bfgs_b(func=func, x0=to_flat(x0), maxiter=epochs, pgtol=self.pgtol, m=self.m,
+                                            maxls=self.maxls, factr=self.factr, maxfun=np.inf,
+                                            callback=on_iteration)
+        optinfo = Namespace(warnflag=info["warnflag"], task=info["task"], evals=info["funcalls"], epochs=info["nit"])
+        if optinfo.warnflag not in [0, 1] or optinfo.epochs < epochs:
+            raise EarlyStopError(", ".join("{:}={:}".format(k, info.get(k, ""))
+                                           for k in ["warnflag", "task", "funcalls", "nit"]), optinfo)
+        return to_arrays(x), optinfo
+
+
+def make_optimizer(name, dtype=None, mod=None, **kwargs):
+    if name in ("lbfgsb", "lbfgs"):
+        return LbfgsbOptimizer(dtype=dtype, mod=mod, **kwargs)
+    if name in ("adam", "adamn"):
+        return AdamNativeOptimizer(dtype=dtype, mod=mod, **kwargs)
+    if name == "gd":
+        return GdOptimizer(dtype=dtype, mod=mod, **kwargs)
+    if name == "adam_tf":
+        raise ValueError("Optimizer 'adam_tf' wraps Keras and is not provided by the B200 backend; use 'adam'")
+    raise ValueError("Unknown optimizer '{}'".format(name))

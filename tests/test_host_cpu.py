@@ -1,0 +1,236 @@
+"""
+CPU tests (no GPU): the tracing front-end and its lowering to stencil plans, the host-side API mirror,
+and the C-ABI library surface.  The plans are checked by interpreting them with the CPU oracle.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import odil
+from odil_b200.engine import ResidualEngine
+from oracle import odil_oracle as orc
+from tests import operators as ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def plan_apply(spec, U, const):
+    shape = spec["shape"]
+    tshape = tuple(2 * r + 1 for r in spec["rwidth"]) + (len(spec["offsets"]),)
+    return orc.stencil_forward(U, [tuple(o) for o in spec["offsets"]], spec["table"].reshape(tshape),
+                               spec["rwidth"], const)
+
+
+@pytest.mark.parametrize("cshape", [(16,), (12, 8), (8, 6, 10), (4, 6, 4, 6)])
+def test_trace_poisson_matches_direct_operator(cshape):
+    problem, state = ops.make_poisson(cshape)
+    eng = ResidualEngine(problem, state, trace_only=True)
+    assert len(eng.outputs) == 1 and eng.outputs[0].fused
+    spec = eng.outputs[0].blocks[0].spec
+    assert spec["rwidth"] == (1,) * len(cshape)
+    assert len(spec["offsets"]) == 2 * len(cshape) + 1
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal(cshape)
+    F = plan_apply(spec, U, eng.outputs[0].const.cpu().numpy())
+    rhs = np.asarray(problem.extra.rhs)
+    F_ref = orc.poisson_residual(U, rhs, [1.0 / n for n in cshape])
+    assert np.max(np.abs(F - F_ref)) < 1e-9 * np.max(np.abs(F_ref))
+    # the table is exactly the one written down in SURVEY.md Appendix A
+    offsets, table, rr = orc.poisson_plan(len(cshape), [1.0 / n for n in cshape])
+    mine = {tuple(o): spec["table"][:, i] for i, o in enumerate(spec["offsets"])}
+    ref = {tuple(o): table.reshape(-1, len(offsets))[:, i] for i, o in enumerate(offsets)}
+    assert set(mine) == set(ref)
+    for k in ref:
+        assert np.max(np.abs(mine[k] - ref[k])) < 1e-9 * np.max(np.abs(ref[k]))
+
+
+def test_trace_poisson_rhs_matches_golden(golden):
+    """discrete rhs computed through ModB200 (host side) equals the reference's (poisson.py:71-86)."""
+    problem, state = ops.make_poisson((16, 16))
+    g = golden("poisson")
+    assert np.max(np.abs(np.asarray(problem.extra.rhs) - g["p2d_16_L3_f64_rhs"])) < 1e-11
+
+
+@pytest.mark.parametrize("cshape,nlvl", [((16, 12), 0), ((16, 8), 2)])
+def test_trace_wave_matches_direct_operator(golden, cshape, nlvl):
+    problem, state = ops.make_wave(cshape, nlvl)
+    eng = ResidualEngine(problem, state, trace_only=True)
+    out = eng.outputs[0]
+    assert eng.names == ["fu"] and out.fused
+    spec = out.blocks[0].spec
+    assert spec["rwidth"] == (2, 1)  # rows it==0 and it==1 differ from the interior (wave.py:63,71)
+    assert sorted(map(tuple, spec["offsets"])) == sorted([(0, 0), (-1, 0), (-2, 0), (-1, -1), (-1, 1)])
+    rng = np.random.default_rng(1)
+    U = rng.standard_normal(cshape)
+    e = problem.extra
+    F = plan_apply(spec, U, out.const.cpu().numpy())
+    F_ref = orc.wave_residual(U, 1.0 / cshape[0], 2.0 / cshape[1], e.left_u, e.right_u, e.init_u, e.init_ut, 1.0)
+    assert np.max(np.abs(F - F_ref)) < 1e-10 * np.max(np.abs(F_ref))
+    # and against the reference itself
+    g = golden("wave")
+    tag = ("w_16x12_L0" if nlvl == 0 else "w_16x8_L2") + "_f64"
+    terms = []
+    i = 0
+    while f"{tag}_term{i}" in g.files:
+        terms.append(g[f"{tag}_term{i}"])
+        i += 1
+    Ug = orc.mg_synthesize(terms, "cc") if len(terms) > 1 else terms[0]
+    Fg = plan_apply(spec, Ug, out.const.cpu().numpy())
+    assert np.max(np.abs(Fg - g[tag + "_F"])) < 1e-10 * np.max(np.abs(g[tag + "_F"]))
+
+
+def test_trace_multiple_fields_and_array():
+    """Operator in the style of reference tests/test_optimize.py: several fields at c/n locations + Array."""
+    domain = odil.Domain(cshape=(8, 4), dimnames=["x", "y"], lower=(0, 0), upper=(2, 1), multigrid=True, mg_nlvl=2,
+                         dtype=np.float64)
+    ref = {}
+    for key, loc in [("uc", "cc"), ("un", "nn"), ("ufx", "nc"), ("ufy", "cn")]:
+        x, y = domain.points(loc=loc)
+        ref[key] = np.asarray(x) * 0.25 + np.asarray(y) * 0.5
+    ref["a"] = np.arange(5, dtype=np.float64)
+
+    def operator(ctx):
+        res = [(key, ctx.field(key) - ctx.extra[key]) for key in ["uc", "un", "ufx", "ufy"]]
+        res += [("a", ctx.field("a") - ctx.extra["a"])]
+        return res
+
+    state = odil.State(fields={
+        "uc": odil.Field(np.zeros(domain.size(loc="cc")), loc="cc"),
+        "un": odil.Field(np.zeros(domain.size(loc="nn")), loc="nn"),
+        "ufx": odil.Field(np.zeros(domain.size(loc="nc")), loc="nc"),
+        "ufy": odil.Field(np.zeros(domain.size(loc="cn")), loc="cn"),
+        "a": odil.Array(np.zeros(5)),
+    })
+    state = domain.init_state(state)
+    assert isinstance(state.fields["un"], odil.MultigridField)  # mg_convert_all
+    assert [tuple(t.array.shape) for t in state.fields["ufx"].terms] == [(9, 4), (5, 2)]
+    eng = ResidualEngine(odil.Problem(operator, domain, ref), state, trace_only=True)
+    assert eng.names == ["uc", "un", "ufx", "ufy", "a"]
+    assert all(o.fused for o in eng.outputs)
+    for o, key in zip(eng.outputs, eng.names):
+        spec = o.blocks[0].spec
+        assert spec["rwidth"] == (0,) * len(o.shape) and spec["table"].tolist() == [[1.0]]
+        assert np.allclose(o.const.cpu().numpy(), -ref[key])
+    assert eng.narrays == 2 * 4 + 1
+
+
+def test_nonaffine_operators_fail_loudly():
+    problem, state = ops.make_poisson((32, 8))
+
+    def op_square(ctx):
+        u = ctx.field("u")
+        return [u * u]
+
+    def op_mask(ctx):
+        u = ctx.field("u")
+        return [ctx.mod.where(u > 0, u, 0 * u)]
+
+    def op_varcoef(ctx):
+        x, y = ctx.points()
+        return [ctx.field("u", 1, 0) * x - ctx.field("u")]
+
+    for op in (op_square, op_mask, op_varcoef):
+        p = odil.Problem(op, problem.domain, problem.extra)
+        with pytest.raises(odil.NonAffineError):
+            ResidualEngine(p, state, trace_only=True)
+
+
+def test_roll_and_stop_gradient_of_expressions():
+    problem, state = ops.make_poisson((8, 6))
+
+    def operator(ctx):
+        mod = ctx.mod
+        u = ctx.field("u")
+        d = (mod.roll(u, -1, 0) - u) * 3.0          # forward difference via roll of an expression
+        d2 = mod.roll(d, [1, 0], [0, 1])            # shift back: (u - roll(u, 1))*3
+        return [d2 + mod.stop_gradient(ctx.field("u", 0, 1))]
+
+    eng = ResidualEngine(odil.Problem(operator, problem.domain, problem.extra), state, trace_only=True)
+    out = eng.outputs[0]
+    blocks = {b.frozen: b.spec for b in out.blocks}
+    live = {tuple(o): blocks[False]["table"][0, i] for i, o in enumerate(blocks[False]["offsets"])}
+    assert live == {(0, 0): 3.0, (-1, 0): -3.0}
+    assert [tuple(o) for o in blocks[True]["offsets"]] == [(0, 1)]
+    assert not out.fused
+
+
+def test_domain_geometry_and_state_roundtrip():
+    domain = odil.Domain(cshape=(4, 6), dimnames=["x", "y"], lower=(0, -1), upper=(2, 1), dtype=np.float64,
+                         multigrid=True, mg_convert_all=False)
+    x, y = domain.points()
+    assert x.shape == (4, 6) and np.allclose(np.asarray(x)[:, 0], [0.25, 0.75, 1.25, 1.75])
+    xn = domain.points("x", loc="nn")
+    assert xn.shape == (5, 7) and np.allclose(np.asarray(xn)[:, 0], [0, 0.5, 1, 1.5, 2])
+    ix, iy = domain.indices()
+    assert np.array_equal(np.asarray(iy)[0], np.arange(6))
+    assert domain.size() == [4, 6] and domain.size("y", loc="cn") == 7
+    assert np.allclose(domain.step(), (0.5, 1 / 3))
+    assert domain.mg_cshapes == [(4, 6), (2, 3)]
+    state = odil.State(fields={
+        "field": np.random.rand(4, 6),
+        "mgfield": domain.regular_to_multigrid(np.random.rand(4, 6)),
+        "net": domain.make_neural_net([3, 3]),
+        "array": [1, 2, 3],
+    })
+    state = domain.init_state(state)
+    arrays = domain.arrays_from_state(state)
+    assert [tuple(a.shape) for a in arrays] == [(4, 6), (4, 6), (2, 3), (3, 3), (3,), (3,)]
+    packed = domain.pack_state(state)
+    assert packed.shape == (24 + 24 + 6 + 9 + 3 + 3,)
+    domain.unpack_state(packed + 1, state)
+    after = domain.arrays_from_state(state)
+    for a, b in zip(arrays, after):
+        assert torch.equal(a + 1, b)
+    with pytest.raises(ValueError):
+        odil.Domain(cshape=(6, 6), multigrid=True, mg_nlvl=3)  # 6 -> 3 -> 1 is not a halving chain
+
+
+def test_adam_scalars_follow_dtype():
+    from odil_b200.optimizer import adam_scalars
+
+    for dt in (np.float32, np.float64):
+        for t in (1, 2, 17, 1000):
+            a, o1, o2 = adam_scalars(0.005, 0.9, 0.999, t, dt)
+            ra, ro1, ro2 = orc.adam_scalars(0.005, 0.9, 0.999, t, dt)
+            assert (a, o1, o2) == (float(ra), float(ro1), float(ro2))
+    assert adam_scalars(0.1, 0.9, 0.999, 1, np.float32)[1] == float(np.float32(1) - np.float32(0.9))
+
+
+def test_history_csv(tmp_path):
+    h = odil.History(csvpath=str(tmp_path / "train.csv"), warmup=1)
+    for e in range(3):
+        h.append("epoch", e)
+        h.append("loss", np.float32(1.0 / (e + 1)))
+        if e > 0:
+            h.append("late", 2.0 * e)
+        h.write()
+    lines = open(tmp_path / "train.csv").read().strip().split("\n")
+    assert lines[0] == "epoch,loss,late" and len(lines) == 4 and lines[1].startswith("0,1.0,0.0")
+
+
+def test_cabi_exports_match_header():
+    """Every function declared in include/odil_b200.h is exported by the built library."""
+    from odil_b200 import build, native
+
+    lib_path = build.build()
+    header = open(os.path.join(ROOT, "include", "odil_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(odil_b200_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 18
+    import ctypes
+
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(native.EXPORTS) == declared
+    assert lib.odil_b200_version() == 100
+
+
+def test_engine_refuses_cpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    problem, state = ops.make_poisson((8, 8))
+    with pytest.raises(odil.native.NativeError):
+        problem.eval_loss_grad(state)
