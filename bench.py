@@ -1,0 +1,361 @@
+#!/usr/bin/env python3
+"""
+bench.py -- headline benchmark of the ODIL residual-and-gradient hot path on B200.
+
+Metric (BASELINE.json): Mcells/s = prod(domain.cshape) / (time per epoch) / 1e6, one epoch = one
+loss+gradient evaluation (multigrid synthesis -> fused stencil residual/loss/adjoint -> multigrid adjoint)
+plus the Adam update of every multigrid term -- the reference's own throughput definition
+(src/odil/util.py:383-386, :408-419), callback time excluded.
+
+Workload at N=1: 3-D Poisson 512^3, 4-level multigrid, Adam, fp32 (BASELINE.json configs[3] on one GPU;
+the configuration the metric is quoted on).  At N>1 the grid is slab-decomposed along axis 0
+(weak scaling: 512^3 cells per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size 512] [--levels 4]
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    p.add_argument("--size", type=int, default=512, help="cells per axis (per GPU along axis 0)")
+    p.add_argument("--levels", type=int, default=4)
+    p.add_argument("--dtype", type=str, default="f32", choices=["f32", "f64"])
+    p.add_argument("--lr", type=float, default=0.005)
+    p.add_argument("--e2e_steps", type=int, default=5)
+    p.add_argument("--cpu_size", type=int, default=192, help="cells per axis of the bounded CPU sample")
+    p.add_argument("--cpu_steps", type=int, default=3)
+    p.add_argument("--no_cpu_baseline", action="store_true")
+    return p.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# Reference arm / CPU baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_epoch_rate(size, levels, steps, warmup, dtype):
+    import torch
+
+    from oracle import ref_port_torch as port
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    tdt = torch.float32 if dtype == "f32" else torch.float64
+    ep = port.PoissonAdamEpoch((size,) * 3, levels, dtype=tdt)
+    for _ in range(warmup):
+        ep.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ep.step()
+    dt = (time.perf_counter() - t0) / steps
+    return size ** 3 / dt / 1e6, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    value, dt, cores = cpu_epoch_rate(args.cpu_size, args.levels, args.steps, args.warmup, args.dtype)
+    sample = (f"3-D Poisson {args.cpu_size}^3 (bounded sample of the {args.size}^3 workload), {args.levels}-level "
+              f"multigrid, Adam, {args.dtype}: oracle/ref_port_torch.py = the reference's per-epoch array ops "
+              f"(interp 'stack', roll, where, mean(square), reverse-mode AD, Adam) on torch-CPU, {cores} threads; "
+              "JAX-CPU itself is not installable in this image")
+    line = {
+        "impl": "reference", "metric": "Mcells/s (residual+grad+Adam epoch), 3D Poisson, 4-level multigrid",
+        "value": value, "unit": "Mcells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"3D Poisson {args.size}^3/GPU, {args.levels}-level multigrid, Adam, {args.dtype}; "
+                               f"timed on a {args.cpu_size}^3 sample"},
+        "cpu_baseline": {"value": value, "unit": "Mcells/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def poisson_operator(ctx):
+    """Zero-Dirichlet Poisson residual, written against the ODIL API like the reference example
+    (examples/poisson/poisson.py:57-68, :89-123)."""
+    import odil
+
+    mod, ndim = ctx.mod, ctx.domain.ndim
+    h, idx, n = ctx.step(), ctx.indices(), ctx.size()
+    u = ctx.field("u")
+    zero = mod.cast(0, u.dtype)
+    ex = odil.core.extrap_quadh
+    res = -ctx.extra.rhs
+    for a in range(ndim):
+        e = [1 if b == a else 0 for b in range(ndim)]
+        um, up = ctx.field("u", *[-s for s in e]), ctx.field("u", *e)
+        um2 = mod.where(idx[a] == 0, ex(up, u, zero), um)
+        up2 = mod.where(idx[a] == n[a] - 1, ex(um, u, zero), up)
+        res = res + (up2 - 2 * u + um2) / h[a] ** 2
+    return [res]
+
+
+def run_b200(args):
+    import torch
+
+    import odil
+    from odil_b200 import native
+    from odil_b200.optimizer import adam_scalars
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    native.load()
+    npdt = np.float32 if args.dtype == "f32" else np.float64
+    tdt = torch.float32 if args.dtype == "f32" else torch.float64
+    es = 4 if args.dtype == "f32" else 8
+    N = args.size
+    if world > 1:
+        from odil_b200.slab import SlabProblem
+
+        prob = SlabProblem.poisson((N * world, N, N), args.levels, npdt, rank, world, seed=0)
+        return run_b200_slab(args, prob, dist, rank, world)
+
+    cshape = (N, N, N)
+    domain = odil.Domain(cshape=cshape, dimnames=["x", "y", "z"], multigrid=True, mg_nlvl=args.levels, dtype=npdt)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    rhs = odil.backend.Known(torch.randn(cshape, dtype=tdt, device="cuda", generator=gen))
+    state = odil.State()
+    state.fields["u"] = None
+    state = domain.init_state(state)
+    problem = odil.Problem(poisson_operator, domain, argparse.Namespace(rhs=rhs))
+    x = domain.arrays_from_state(state)
+    m = [torch.zeros_like(a) for a in x]
+    v = [torch.zeros_like(a) for a in x]
+    eps = float(npdt(1e-7))
+    ncells = int(np.prod(cshape))
+    nunk = sum(a.numel() for a in x)
+
+    # per-op event timers (kernel-level roofline, measured live in the timed region)
+    timers = {}
+
+    def timed(name, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        timers.setdefault(name, []).append((e0, e1))
+        return r
+
+    def epoch(t):
+        domain.arrays_to_state(x, state)
+        loss, grads, terms, names, norms = problem.eval_loss_grad(state)
+        alpha, omb1, omb2 = adam_scalars(args.lr, 0.9, 0.999, t, npdt)
+        native.adam_step(x, m, v, grads, alpha, omb1, omb2, eps)
+        return loss
+
+    native.set_timer_hook(timed)
+
+    t = 0
+    for _ in range(args.warmup):
+        t += 1
+        epoch(t)
+    torch.cuda.synchronize()
+    timers.clear()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        t += 1
+        loss = epoch(t)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = native.launch_count() - launches0
+    loss_val = float(loss)
+
+    peak, peak_src = measured_peak()
+    kern = {}
+    alg_bytes = {"stencil_fused": 3 * es * ncells, "adam_step": 7 * es * nunk}
+    for name, evs in timers.items():
+        total = sum(a.elapsed_time(b) for a, b in evs)
+        per_step = total / args.steps
+        kern[name] = {"ms_per_step": per_step, "launch_groups_per_step": len(evs) / args.steps}
+        if name in alg_bytes:
+            gbs = alg_bytes[name] / (per_step * 1e-3) / 1e9
+            kern[name].update({"achieved_GBs": gbs, "frac": gbs / peak})
+    fused = kern.get("stencil_fused", {})
+    roofline = {
+        "bound": "hbm", "kernel": "odil_b200_stencil_fused (k_star3d + boundary-shell k_generic + reduce)",
+        "achieved": fused.get("achieved_GBs"), "peak": peak, "unit": "GB/s", "frac": fused.get("frac"),
+        "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes["stencil_fused"], "ms_per_launch": fused.get("ms_per_step"),
+    }
+
+    # e2e: every step the unknowns arrive from pinned host memory and the loss goes back to the host
+    host = [torch.empty(a.shape, dtype=a.dtype, pin_memory=True).copy_(a) for a in x]
+    h2d = sum(a.numel() * a.element_size() for a in host)
+    native.set_timer_hook(None)
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        t += 1
+        for d, h in zip(x, host):
+            d.copy_(h, non_blocking=True)
+        loss = epoch(t)
+        _ = float(loss)  # device -> host read of the step's result
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - w0) / args.e2e_steps * 1e3
+    e2e = {"value": ncells / (e2e_ms * 1e-3) / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms,
+           "note": "per step: H2D of all multigrid terms from pinned host memory + epoch + D2H of the loss"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cv, cdt, cores = cpu_epoch_rate(args.cpu_size, args.levels, args.cpu_steps, 1, args.dtype)
+        cpu = {"value": cv, "unit": "Mcells/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_steps} epochs of 3-D Poisson {args.cpu_size}^3, {args.levels}-level multigrid, "
+                         f"Adam, {args.dtype}, oracle/ref_port_torch.py on torch-CPU ({cores} threads)"}
+
+    line = {
+        "metric": "Mcells/s (residual+grad+Adam epoch), 3D Poisson, 4-level multigrid",
+        "value": ncells / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"3D Poisson {N}^3, {args.levels}-level multigrid, Adam lr={args.lr}, {args.dtype}, "
+                               "zero-Dirichlet BC, rhs ~ N(0,1), unknowns start at 0",
+                   "l2": f"inputs exceed L2 ({ncells * es / 2**20:.0f} MiB per field vs 126 MB L2); no explicit flush",
+                   "api": "odil.Domain / odil.Problem(operator) / eval_loss_grad + odil_b200_adam_step"},
+        "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks, "final_loss": loss_val,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200_slab(args, prob, dist, rank, world):
+    import torch
+
+    for _ in range(args.warmup):
+        prob.epoch()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+    if rank == 0:
+        sampler.start()
+    from odil_b200 import native
+
+    launches0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        prob.epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    launches = native.launch_count() - launches0
+    loss = prob.loss_value()
+    if rank == 0:
+        clocks = sampler.stop()
+        ncells = int(np.prod(prob.global_shape))
+        line = {
+            "metric": "Mcells/s (residual+grad+Adam epoch), 3D Poisson, 4-level multigrid",
+            "value": ncells / (ms.item() * 1e-3) / 1e6, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms.item(), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"3D Poisson {prob.global_shape}, slabs of {args.size} planes along axis 0, "
+                                   f"{args.levels}-level multigrid, Adam, {args.dtype}; NCCL halo exchange"},
+            "gpu_launches": launches, "clocks": clocks, "final_loss": loss,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

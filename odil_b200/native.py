@@ -46,6 +46,17 @@ class MgAdjRange(ctypes.Structure):
 
 
 _lib = None
+_timer_hook = None
+
+
+def set_timer_hook(hook):
+    """hook(name, thunk) -> result: lets bench.py bracket each C-ABI call with CUDA events."""
+    global _timer_hook
+    _timer_hook = hook
+
+
+def _call(name, thunk):
+    return _timer_hook(name, thunk) if _timer_hook is not None else thunk()
 
 
 def load(build_if_missing=False):
@@ -200,9 +211,9 @@ class StencilPlan:
 
     def fused(self, U, c, scale, G_out, sumsq_out, F_out=None, slab=None):
         s = self._slab(slab)
-        _check(_lib.odil_b200_stencil_fused(self.handle, ctypes.byref(s), _plane_ptr(U, s.halo),
-                                            _plane_ptr(c, s.halo), float(scale), _plane_ptr(G_out, s.halo),
-                                            _plane_ptr(F_out, s.halo), _ptr(sumsq_out), _stream()))
+        _call("stencil_fused", lambda: _check(_lib.odil_b200_stencil_fused(
+            self.handle, ctypes.byref(s), _plane_ptr(U, s.halo), _plane_ptr(c, s.halo), float(scale),
+            _plane_ptr(G_out, s.halo), _plane_ptr(F_out, s.halo), _ptr(sumsq_out), _stream())))
 
 
 def sum_squares(x, out):
@@ -223,15 +234,17 @@ def mg_interp_add(cshape, loc, coarse, cfac, fine_term, ffac, out, rng=None):
     """out = ffac*fine_term + cfac*I(coarse). `cshape` = GLOBAL coarse array shape."""
     load()
     r = ctypes.byref(MgRange(*[int(v) for v in rng])) if rng is not None else None
-    _check(_lib.odil_b200_mg_interp_add(len(cshape), _cshape(cshape), loc.encode(), dtype_code(out.dtype), _ptr(coarse),
-                                        float(cfac), _ptr(fine_term), float(ffac), _ptr(out), r, _stream()))
+    _call("mg_interp_add", lambda: _check(_lib.odil_b200_mg_interp_add(
+        len(cshape), _cshape(cshape), loc.encode(), dtype_code(out.dtype), _ptr(coarse), float(cfac),
+        _ptr(fine_term), float(ffac), _ptr(out), r, _stream())))
 
 
 def mg_interp_adjoint(cshape, loc, g_fine, scale, g_coarse, rng=None):
     load()
     r = ctypes.byref(MgAdjRange(*[int(v) for v in rng])) if rng is not None else None
-    _check(_lib.odil_b200_mg_interp_adjoint(len(cshape), _cshape(cshape), loc.encode(), dtype_code(g_fine.dtype),
-                                            _ptr(g_fine), float(scale), _ptr(g_coarse), r, _stream()))
+    _call("mg_interp_adjoint", lambda: _check(_lib.odil_b200_mg_interp_adjoint(
+        len(cshape), _cshape(cshape), loc.encode(), dtype_code(g_fine.dtype), _ptr(g_fine), float(scale),
+        _ptr(g_coarse), r, _stream())))
 
 
 def mg_restrict(fshape, loc, fine, out):
@@ -257,10 +270,9 @@ def adam_step(x, m, v, g, alpha, omb1, omb2, eps):
     cnt = [t.numel() for t in x]
     counts = (ctypes.c_int64 * n)(*cnt)
     dt = x[0].dtype
-    _check(_lib.odil_b200_adam_step(n, _ptr_array(x, dt), _ptr_array(m, dt, cnt), _ptr_array(v, dt, cnt),
-                                    _ptr_array(g, dt, cnt), counts,
-                                    dtype_code(x[0].dtype), float(alpha), float(omb1), float(omb2), float(eps),
-                                    _stream()))
+    _call("adam_step", lambda: _check(_lib.odil_b200_adam_step(
+        n, _ptr_array(x, dt), _ptr_array(m, dt, cnt), _ptr_array(v, dt, cnt), _ptr_array(g, dt, cnt), counts,
+        dtype_code(x[0].dtype), float(alpha), float(omb1), float(omb2), float(eps), _stream())))
 
 
 def gd_step(x, g, lr):

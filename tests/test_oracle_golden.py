@@ -173,3 +173,28 @@ def test_gd(golden):
     assert np.max(np.abs(np.array(losses) / g[tag + "_losses"] - 1)) < 1e-11
     for i in range(3):
         assert relerr(x[i], g[f"{tag}_x{i}"]) < 1e-12
+
+
+def test_torch_port_matches_oracle():
+    """The torch-CPU port timed by bench.py computes the same epoch as the NumPy oracle."""
+    import torch
+
+    from oracle import ref_port_torch as port
+
+    for cshape, nlvl in [((16, 16), 3), ((8, 8, 8), 3)]:
+        ep = port.PoissonAdamEpoch(cshape, nlvl, dtype=torch.float64, lr=0.005, seed=1)
+        rng = np.random.default_rng(0)
+        for a in ep.x:
+            a.copy_(torch.from_numpy(rng.standard_normal(tuple(a.shape))))
+        x0 = [a.numpy().copy() for a in ep.x]
+        nd = len(cshape)
+        offsets, table, rr = orc.poisson_plan(nd, [1.0 / n for n in cshape])
+        loss_ref, grads_ref, _, _ = orc.eval_loss_grad_plan(x0, "c" * nd, offsets, table, rr, -ep.rhs.numpy())
+        loss, grads = ep.loss_grad()
+        assert abs(float(loss) - loss_ref) < 1e-12 * loss_ref
+        for a, b in zip(grads, grads_ref):
+            assert relerr(a.numpy(), b) < 1e-11
+        ep.step()
+        for i in range(nlvl):
+            xr, _, _ = orc.adam_step(x0[i], np.zeros_like(x0[i]), np.zeros_like(x0[i]), grads_ref[i], 0.005, 1)
+            assert relerr(ep.x[i].numpy(), xr) < 1e-11
