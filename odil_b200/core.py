@@ -202,6 +202,10 @@ class Domain:
         self.lower = (np.ones(ndim, dtype=dtype) * lower).astype(dtype)
         self.upper = (np.ones(ndim, dtype=dtype) * upper).astype(dtype)
         self.mod = mod
+        # Slab decomposition along axis 0 when launched with one process per GPU (odil_b200.slab).
+        from .slab import SlabInfo
+
+        self.slab = SlabInfo.from_environment()
         self.multigrid = multigrid
         if multigrid:
             self.mg_factors = mg_factors
@@ -318,10 +322,18 @@ class Domain:
         factors = mgfield.factors or self.mg_factors or [1] * len(mgfield.terms)
         assert_equal(len(factors), len(mgfield.terms))
         arrays = [_device_array(t.array, self.mod) for t in mgfield.terms]
-        res = synthesize_multigrid(arrays, factors, self._mg_loc(mgfield))
+        if self.slab is not None:
+            from .engine import synthesize_slab
+
+            shapes = [self._get_field_shape(t.cshape, mgfield.loc) for t in mgfield.terms]
+            res = self.slab.gather(synthesize_slab(self.slab, arrays, shapes, factors, self._mg_loc(mgfield)))
+        else:
+            res = synthesize_multigrid(arrays, factors, self._mg_loc(mgfield))
         return Field(Known(res), loc=mgfield.loc)
 
     def get_regular_array(self, field):
+        if isinstance(field, Field) and self.slab is not None and torch.is_tensor(field.array):
+            return Known(self.slab.gather(field.array))
         if isinstance(field, (Field, Array)):
             return field.array
         if isinstance(field, MultigridField):
@@ -341,12 +353,17 @@ class Domain:
         first = field.array if factors[0] == 1 else field.array / factors[0]
         terms = [Field(first, loc=field.loc, cshape=field.cshape)]
         for cshape in cshapes[1:]:
-            zero = mod.variable(mod.zeros(self._get_field_shape(cshape, loc=field.loc), dtype=self.dtype),
-                                dtype=self.dtype)
-            terms.append(Field(zero, loc=field.loc, cshape=cshape))
+            terms.append(Field(self._zeros_storage(self._get_field_shape(cshape, loc=field.loc)), loc=field.loc,
+                               cshape=cshape))
         return MultigridField(terms=terms, loc=field.loc, factors=factors, method=method)
 
     # -- state ----------------------------------------------------------------------------------
+    def _zeros_storage(self, shape):
+        """Zero state array of GLOBAL field shape `shape` (the local slab with halos when decomposed)."""
+        if self.slab is not None:
+            shape = self.slab.local_shape(shape)
+        return torch.zeros(tuple(shape), dtype=torch_dtype(self.dtype), device=self.mod.device)
+
     def init_field(self, field):
         """Moves a field description into backend storage, filling defaults (core.py:299-346)."""
         mod = self.mod
@@ -360,10 +377,17 @@ class Domain:
             assert_equal(len(loc), len(cshape))
             shape = self._get_field_shape(cshape, loc=loc)
             array = field.array
+            local = self.slab.local_shape(shape) if self.slab is not None else shape
             if array is None:
-                array = mod.zeros(shape, dtype=self.dtype)
-            array = mod.variable(array, dtype=self.dtype)
-            assert_equal(tuple(array.shape), shape)
+                array = self._zeros_storage(shape)
+            elif torch.is_tensor(array) and tuple(array.shape) == local and self.slab is not None:
+                array = mod.variable(array, dtype=self.dtype)  # already a local slab
+            else:
+                array = mod.variable(array, dtype=self.dtype)
+                assert_equal(tuple(array.shape), shape)
+                if self.slab is not None:
+                    array = self.slab.scatter(array)
+            assert_equal(tuple(array.shape), local)
             return Field(array, loc=loc, cshape=cshape)
         if isinstance(field, MultigridField):
             return MultigridField([self.init_field(t) for t in field.terms], loc=field.loc, factors=field.factors,

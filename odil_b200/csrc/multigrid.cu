@@ -48,27 +48,14 @@ __device__ __forceinline__ T padded_value(const MgGeom& g, const T* __restrict__
     return T(2) * __ldg(coarse + ls) - __ldg(coarse + lr);
 }
 
-// One thread per fine cell.
+// Interpolated value I(coarse) at the GLOBAL fine cell f (generic: any ndim <= 4, any loc).
 template <typename T>
-__global__ void __launch_bounds__(256) k_interp_add(MgGeom g, const T* __restrict__ coarse, T cfac,
-                                                    const T* __restrict__ term, T ffac, T* __restrict__ out,
-                                                    int64_t fz_begin, int64_t nfz, int64_t out_z0, int64_t coarse_z0) {
-    int64_t total = nfz;
-    for (int a = 1; a < g.ndim; ++a) total *= g.fn[a];
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    int64_t f[ODIL_B200_MAX_NDIM] = {0, 0, 0, 0};
-    int64_t rem = gid;
-    for (int a = g.ndim - 1; a >= 1; --a) {
-        f[a] = rem % g.fn[a];
-        rem /= g.fn[a];
-    }
-    f[0] = fz_begin + rem;
+__device__ __noinline__ T interp_cell_generic(const MgGeom& g, const T* __restrict__ coarse, int64_t coarse_z0,
+                                              const int64_t* f) {
     // taps per axis: (index, integer weight); denominators multiply to `den`
     int64_t q0[ODIL_B200_MAX_NDIM], q1[ODIL_B200_MAX_NDIM];
     int w0[ODIL_B200_MAX_NDIM], w1[ODIL_B200_MAX_NDIM];
     int den = 1;
-    int64_t lin = 0;
 #pragma unroll
     for (int a = 0; a < ODIL_B200_MAX_NDIM; ++a) {
         if (a >= g.ndim) break;
@@ -92,7 +79,6 @@ __global__ void __launch_bounds__(256) k_interp_add(MgGeom g, const T* __restric
             q1[a] = f[a];
             w1[a] = 0;
         }
-        lin += (a == 0 ? f[0] - out_z0 : f[a]) * g.fstride[a];
     }
     T acc = T(0);
     const int ncombo = 1 << g.ndim;
@@ -107,9 +93,156 @@ __global__ void __launch_bounds__(256) k_interp_add(MgGeom g, const T* __restric
         if (w == 0) continue;
         acc += T(w) * padded_value<T>(g, coarse, coarse_z0, q);
     }
-    T res = cfac * (acc / T(den));
+    return acc / T(den);
+}
+
+// One thread per fine cell (generic path).
+template <typename T>
+__global__ void __launch_bounds__(256) k_interp_add(MgGeom g, const T* __restrict__ coarse, T cfac,
+                                                    const T* __restrict__ term, T ffac, T* __restrict__ out,
+                                                    int64_t fz_begin, int64_t nfz, int64_t out_z0, int64_t coarse_z0) {
+    int64_t total = nfz;
+    for (int a = 1; a < g.ndim; ++a) total *= g.fn[a];
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    int64_t f[ODIL_B200_MAX_NDIM] = {0, 0, 0, 0};
+    int64_t rem = gid;
+    for (int a = g.ndim - 1; a >= 1; --a) {
+        f[a] = rem % g.fn[a];
+        rem /= g.fn[a];
+    }
+    f[0] = fz_begin + rem;
+    int64_t lin = 0;
+    for (int a = 0; a < g.ndim; ++a) lin += (a == 0 ? f[0] - out_z0 : f[a]) * g.fstride[a];
+    T res = cfac * interp_cell_generic<T>(g, coarse, coarse_z0, f);
     if (term) res += ffac * __ldg(term + lin);
     out[lin] = res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path for cell-centred fields: the last two axes are 'c', axis 0 is 'c' (CZ) or has size 1.
+// One thread per COARSE cell: loads its 3x3x3 neighbourhood once and produces the 2x2x2 fine cells
+// with separable integer weights (1,3) -- exact same weights as the reference, scaled by 1/64 at the
+// end (a power of two).  Cells on a single face use per-axis linear extrapolation (= the joint pad
+// when only one axis leaves the range); cells on an edge/corner take the generic per-cell path.
+// ------------------------------------------------------------------------------------------------
+struct Mg3 {
+    int n0, n1, n2;        // coarse global shape (n0 == 1 and CZ == false for 2-D)
+    int64_t cs0, cs1;      // coarse strides (elements); stride of axis 2 is 1
+    int64_t fs0, fs1;      // fine strides
+};
+
+template <typename T, bool CZ>
+__global__ void __launch_bounds__(128) k_interp_add3(MgGeom g, Mg3 m, const T* __restrict__ coarse, T cfac,
+                                                     const T* __restrict__ term, T ffac, T* __restrict__ out,
+                                                     int cz_begin, int ncz, int out_z0, int coarse_z0) {
+    const int K = blockIdx.x * blockDim.x + threadIdx.x;
+    const int J = blockIdx.y * blockDim.y + threadIdx.y;
+    const int I = cz_begin + blockIdx.z;
+    if (K >= m.n2 || J >= m.n1) return;
+    const bool bz = CZ && (I == 0 || I == m.n0 - 1);
+    const bool by = (J == 0 || J == m.n1 - 1);
+    const bool bx = (K == 0 || K == m.n2 - 1);
+    constexpr int NZ = CZ ? 2 : 1;
+    T res[NZ][2][2];
+    if ((int)bz + (int)by + (int)bx >= 2) {
+        for (int a = 0; a < NZ; ++a)
+            for (int b = 0; b < 2; ++b)
+                for (int c = 0; c < 2; ++c) {
+                    const int64_t f3[ODIL_B200_MAX_NDIM] = {CZ ? 2 * (int64_t)I + a : (int64_t)I, 2 * (int64_t)J + b,
+                                                            2 * (int64_t)K + c, 0};
+                    const int64_t f2[ODIL_B200_MAX_NDIM] = {2 * (int64_t)J + b, 2 * (int64_t)K + c, 0, 0};
+                    res[a][b][c] = interp_cell_generic<T>(g, coarse, coarse_z0, g.ndim == 3 ? f3 : f2);
+                }
+    } else {
+        constexpr int DZ = CZ ? 3 : 1;
+        T v[DZ][3][3];
+        const int km = max(K - 1, 0), kp = min(K + 1, m.n2 - 1);
+        const int jm = max(J - 1, 0), jp = min(J + 1, m.n1 - 1);
+#pragma unroll
+        for (int dz = 0; dz < DZ; ++dz) {
+            int ii = CZ ? min(max(I - 1 + dz, 0), m.n0 - 1) : I;
+            const T* pz = coarse + (int64_t)(ii - coarse_z0) * m.cs0;
+            const int jj[3] = {jm, J, jp};
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const T* py = pz + (int64_t)jj[dy] * m.cs1;
+                v[dz][dy][0] = __ldg(py + km);
+                v[dz][dy][1] = __ldg(py + K);
+                v[dz][dy][2] = __ldg(py + kp);
+            }
+        }
+        // single-face linear extrapolation of the out-of-range neighbour (2*u[clamp] - u[reflect])
+        if (bx) {
+#pragma unroll
+            for (int dz = 0; dz < DZ; ++dz)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    if (K == 0) v[dz][dy][0] = T(2) * v[dz][dy][1] - v[dz][dy][2];
+                    if (K == m.n2 - 1) v[dz][dy][2] = T(2) * v[dz][dy][1] - v[dz][dy][0];
+                }
+        }
+        if (by) {
+#pragma unroll
+            for (int dz = 0; dz < DZ; ++dz)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    if (J == 0) v[dz][0][dx] = T(2) * v[dz][1][dx] - v[dz][2][dx];
+                    if (J == m.n1 - 1) v[dz][2][dx] = T(2) * v[dz][1][dx] - v[dz][0][dx];
+                }
+        }
+        if (CZ && bz) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    if (I == 0) v[0][dy][dx] = T(2) * v[DZ > 1 ? 1 : 0][dy][dx] - v[DZ - 1][dy][dx];
+                    if (I == m.n0 - 1) v[DZ - 1][dy][dx] = T(2) * v[DZ > 1 ? 1 : 0][dy][dx] - v[0][dy][dx];
+                }
+        }
+        // separable accumulation with integer weights
+        T ax[DZ][3][2];
+#pragma unroll
+        for (int dz = 0; dz < DZ; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                ax[dz][dy][0] = v[dz][dy][0] + T(3) * v[dz][dy][1];
+                ax[dz][dy][1] = T(3) * v[dz][dy][1] + v[dz][dy][2];
+            }
+        T ay[DZ][2][2];
+#pragma unroll
+        for (int dz = 0; dz < DZ; ++dz)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                ay[dz][0][c] = ax[dz][0][c] + T(3) * ax[dz][1][c];
+                ay[dz][1][c] = T(3) * ax[dz][1][c] + ax[dz][2][c];
+            }
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (CZ) {
+                    res[0][b][c] = (ay[0][b][c] + T(3) * ay[DZ > 1 ? 1 : 0][b][c]) * T(1.0 / 64.0);
+                    res[NZ - 1][b][c] = (T(3) * ay[DZ > 1 ? 1 : 0][b][c] + ay[DZ - 1][b][c]) * T(1.0 / 64.0);
+                } else {
+                    res[0][b][c] = ay[0][b][c] * T(1.0 / 16.0);
+                }
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < NZ; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int64_t fz = CZ ? 2 * (int64_t)I + a : (int64_t)I;
+            const int64_t lin = (fz - out_z0) * m.fs0 + (int64_t)(2 * J + b) * m.fs1 + 2 * K;
+            T r0 = cfac * res[a][b][0], r1 = cfac * res[a][b][1];
+            if (term) {
+                r0 += ffac * __ldg(term + lin);
+                r1 += ffac * __ldg(term + lin + 1);
+            }
+            out[lin] = r0;
+            out[lin + 1] = r1;
+        }
 }
 
 // Gather of fine gradient onto the PADDED coarse index q (separable 4-tap / 3-tap rule, clipped to
@@ -180,7 +313,47 @@ __device__ __forceinline__ T gather_fine(const MgGeom& g, const T* __restrict__ 
     return acc;
 }
 
-// One thread per coarse cell J:  g_c[J] = sum_{q: clamp(q)=J} 2 G(q) - sum_{q: reflect(q)=J} G(q).
+// (I^T g_fine)[J] for the GLOBAL coarse cell J:  sum_{q: clamp(q)=J} 2 G(q) - sum_{q: reflect(q)=J} G(q).
+template <typename T>
+__device__ __noinline__ T adjoint_cell_generic(const MgGeom& g, const T* __restrict__ gf, int64_t fine_z0,
+                                               const int64_t* J) {
+    int64_t cand[ODIL_B200_MAX_NDIM][3];
+    int nc[ODIL_B200_MAX_NDIM];
+    bool boundary = false;
+    for (int a = 0; a < g.ndim; ++a) {
+        const int64_t n = g.cn[a];
+        int k = 0;
+        cand[a][k++] = J[a];
+        if (g.loc[a] == LOC_C) {
+            if (J[a] <= 1) cand[a][k++] = -1;
+            if (J[a] >= n - 2) cand[a][k++] = n;
+        }
+        nc[a] = k;
+        boundary |= k > 1;
+    }
+    if (!boundary) return gather_fine<T>(g, gf, fine_z0, J);
+    T acc = T(0);
+    const int n1 = g.ndim > 1 ? nc[1] : 1, n2 = g.ndim > 2 ? nc[2] : 1, n3 = g.ndim > 3 ? nc[3] : 1;
+    for (int c0 = 0; c0 < nc[0]; ++c0)
+        for (int c1 = 0; c1 < n1; ++c1)
+            for (int c2 = 0; c2 < n2; ++c2)
+                for (int c3 = 0; c3 < n3; ++c3) {
+                    int64_t q[ODIL_B200_MAX_NDIM] = {cand[0][c0], g.ndim > 1 ? cand[1][c1] : 0,
+                                                     g.ndim > 2 ? cand[2][c2] : 0, g.ndim > 3 ? cand[3][c3] : 0};
+                    bool mc = true, mr = true, outside = false;
+                    for (int a = 0; a < g.ndim; ++a) {
+                        mc = mc && clampi(q[a], g.cn[a]) == J[a];
+                        mr = mr && reflecti(q[a], g.cn[a]) == J[a];
+                        outside |= q[a] < 0 || q[a] > g.cn[a] - 1;
+                    }
+                    // in-range q is the plain value u[q]: coefficient 1 (=2-1) when q == J
+                    T coef = outside ? T((mc ? 2 : 0) - (mr ? 1 : 0)) : T(1);
+                    if (coef != T(0)) acc += coef * gather_fine<T>(g, gf, fine_z0, q);
+                }
+    return acc;
+}
+
+// One thread per coarse cell (generic path).
 template <typename T>
 __global__ void __launch_bounds__(128) k_interp_adjoint(MgGeom g, const T* __restrict__ gf, T scale,
                                                         T* __restrict__ gc, int64_t cz_begin, int64_t ncz,
@@ -196,46 +369,81 @@ __global__ void __launch_bounds__(128) k_interp_adjoint(MgGeom g, const T* __res
         rem /= g.cn[a];
     }
     J[0] = cz_begin + rem;
-    // candidate padded indices per axis
-    int64_t cand[ODIL_B200_MAX_NDIM][3];
-    int nc[ODIL_B200_MAX_NDIM];
     int64_t lin = 0;
-    bool boundary = false;
-    for (int a = 0; a < g.ndim; ++a) {
-        const int64_t n = g.cn[a];
-        int k = 0;
-        cand[a][k++] = J[a];
-        if (g.loc[a] == LOC_C) {
-            if (J[a] <= 1) cand[a][k++] = -1;
-            if (J[a] >= n - 2) cand[a][k++] = n;
-        }
-        nc[a] = k;
-        boundary |= k > 1;
-        lin += (a == 0 ? J[0] - out_z0 : J[a]) * g.cstride[a];
-    }
+    for (int a = 0; a < g.ndim; ++a) lin += (a == 0 ? J[0] - out_z0 : J[a]) * g.cstride[a];
+    gc[lin] = scale * adjoint_cell_generic<T>(g, gf, fine_z0, J);
+}
+
+// 1-D transposed-interpolation weights of coarse cell J (axis size n) on the SIX fine cells
+// 2J-2 .. 2J+3: interior [0,1,3,3,1,0]/4, clipped to the fine array, plus the pad corrections
+// (coarse 0: +2/4 on fine 0; coarse 1: -1/4 on fine 0; mirrored at the high end).  This is the
+// separable rule; it equals the joint rule unless two or more axes are at a boundary.
+template <typename T>
+__device__ __forceinline__ void adjoint_weights(int J, int n, T* w) {
+    const int nf = 2 * n;
+    const int f0 = 2 * J - 2;
+    const T base[6] = {T(0), T(0.25), T(0.75), T(0.75), T(0.25), T(0)};
+#pragma unroll
+    for (int t = 0; t < 6; ++t) w[t] = (f0 + t >= 0 && f0 + t < nf) ? base[t] : T(0);
+    if (J == 0) w[2] += T(0.5);
+    if (J == 1) w[0] -= T(0.25);
+    if (J == n - 1) w[3] += T(0.5);
+    if (J == n - 2) w[5] -= T(0.25);
+}
+
+// Fast transposed interpolation, cell-centred, one thread per coarse cell, 6x6(x6) window read as
+// aligned pairs along x.
+template <typename T, bool CZ>
+__global__ void __launch_bounds__(128) k_interp_adjoint3(MgGeom g, Mg3 m, const T* __restrict__ gf, T scale,
+                                                         T* __restrict__ gc, int cz_begin, int out_z0, int fine_z0) {
+    const int K = blockIdx.x * blockDim.x + threadIdx.x;
+    const int J = blockIdx.y * blockDim.y + threadIdx.y;
+    const int I = cz_begin + blockIdx.z;
+    if (K >= m.n2 || J >= m.n1) return;
+    const bool bz = CZ && (I <= 1 || I >= m.n0 - 2);
+    const bool by = (J <= 1 || J >= m.n1 - 2);
+    const bool bx = (K <= 1 || K >= m.n2 - 2);
     T acc;
-    if (!boundary) {
-        acc = gather_fine<T>(g, gf, fine_z0, J);
+    if ((int)bz + (int)by + (int)bx >= 2) {
+        const int64_t J3[ODIL_B200_MAX_NDIM] = {I, J, K, 0};
+        const int64_t J2[ODIL_B200_MAX_NDIM] = {J, K, 0, 0};
+        acc = adjoint_cell_generic<T>(g, gf, fine_z0, g.ndim == 3 ? J3 : J2);
     } else {
+        T wx[6], wy[6], wz[6];
+        adjoint_weights<T>(K, m.n2, wx);
+        adjoint_weights<T>(J, m.n1, wy);
+        if (CZ) adjoint_weights<T>(I, m.n0, wz);
+        const int nf1 = 2 * m.n1, nf2 = 2 * m.n2;
+        const int nf0 = CZ ? 2 * m.n0 : m.n0;
+        // clamp the x window into the array (weights of clipped cells are zero)
+        const int x0 = 2 * K - 2;
         acc = T(0);
-        const int n1 = g.ndim > 1 ? nc[1] : 1, n2 = g.ndim > 2 ? nc[2] : 1, n3 = g.ndim > 3 ? nc[3] : 1;
-        for (int c0 = 0; c0 < nc[0]; ++c0)
-            for (int c1 = 0; c1 < n1; ++c1)
-                for (int c2 = 0; c2 < n2; ++c2)
-                    for (int c3 = 0; c3 < n3; ++c3) {
-                        int64_t q[ODIL_B200_MAX_NDIM] = {cand[0][c0], g.ndim > 1 ? cand[1][c1] : 0,
-                                                         g.ndim > 2 ? cand[2][c2] : 0, g.ndim > 3 ? cand[3][c3] : 0};
-                        bool mc = true, mr = true, outside = false;
-                        for (int a = 0; a < g.ndim; ++a) {
-                            mc = mc && clampi(q[a], g.cn[a]) == J[a];
-                            mr = mr && reflecti(q[a], g.cn[a]) == J[a];
-                            outside |= q[a] < 0 || q[a] > g.cn[a] - 1;
-                        }
-                        // in-range q is the plain value u[q]: coefficient 1 (=2-1) when q == J
-                        T coef = outside ? T((mc ? 2 : 0) - (mr ? 1 : 0)) : T(1);
-                        if (coef != T(0)) acc += coef * gather_fine<T>(g, gf, fine_z0, q);
+        constexpr int TZ = CZ ? 6 : 1;
+#pragma unroll
+        for (int tz = 0; tz < TZ; ++tz) {
+            const int fz = CZ ? 2 * I - 2 + tz : I;
+            if (CZ && (wz[tz] == T(0) || fz < 0 || fz >= nf0)) continue;
+            const T* pz = gf + (int64_t)(fz - fine_z0) * m.fs0;
+            T accy = T(0);
+#pragma unroll
+            for (int ty = 0; ty < 6; ++ty) {
+                const int fy = 2 * J - 2 + ty;
+                if (wy[ty] == T(0) || fy < 0 || fy >= nf1) continue;
+                const T* py = pz + (int64_t)fy * m.fs1;
+                T accx = T(0);
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const int fx = x0 + 2 * p;
+                    if (fx >= 0 && fx + 1 < nf2) {
+                        accx += wx[2 * p] * __ldg(py + fx) + wx[2 * p + 1] * __ldg(py + fx + 1);
                     }
+                }
+                accy += wy[ty] * accx;
+            }
+            acc += CZ ? wz[tz] * accy : accy;
+        }
     }
+    const int64_t lin = (int64_t)(I - out_z0) * m.cs0 + (int64_t)J * m.cs1 + K;
     gc[lin] = scale * acc;
 }
 
@@ -326,6 +534,37 @@ static int make_geom(int ndim, const int64_t* cshape, const char* loc, MgGeom& g
     return 0;
 }
 
+// Fast-path eligibility: cell-centred last two axes; axis 0 cell-centred (3-D), untouched ('.') or absent (2-D).
+static bool fast3_geometry(const MgGeom& g, Mg3& m, bool& cz) {
+    if (g.ndim == 3) {
+        if (g.loc[1] != LOC_C || g.loc[2] != LOC_C) return false;
+        if (g.loc[0] == LOC_C)
+            cz = true;
+        else if (g.loc[0] == LOC_DOT)
+            cz = false;
+        else
+            return false;
+        m.n0 = (int)g.cn[0];
+        m.n1 = (int)g.cn[1];
+        m.n2 = (int)g.cn[2];
+    } else if (g.ndim == 2) {
+        if (g.loc[0] != LOC_C || g.loc[1] != LOC_C) return false;
+        cz = false;
+        m.n0 = 1;
+        m.n1 = (int)g.cn[0];
+        m.n2 = (int)g.cn[1];
+    } else {
+        return false;
+    }
+    if (m.n1 < 4 || m.n2 < 4 || (cz && m.n0 < 4)) return false;
+    if (g.cn[0] > (1 << 29) || g.cn[1] > (1 << 29) || (g.ndim > 2 && g.cn[2] > (1 << 29))) return false;
+    m.cs1 = m.n2;
+    m.cs0 = (int64_t)m.n1 * m.n2;
+    m.fs1 = 2 * (int64_t)m.n2;
+    m.fs0 = 4 * (int64_t)m.n1 * m.n2;
+    return true;
+}
+
 }  // namespace odil
 
 using namespace odil;
@@ -347,6 +586,44 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
     const int64_t nb = (total + 255) / 256;
     ODIL_REQUIRE(nb < (1ll << 31), "grid too large");
     cudaStream_t st = (cudaStream_t)stream;
+    ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    {
+        Mg3 m;
+        bool cz = false;
+        const bool pairs = (r.fz_begin % 2 == 0) && (r.fz_end % 2 == 0);
+        if (fast3_geometry(g, m, cz) && (!cz || pairs)) {
+            const int zb = (int)(ndim == 3 ? (cz ? r.fz_begin / 2 : r.fz_begin) : 0);
+            const int nz = (int)(ndim == 3 ? (cz ? (r.fz_end - r.fz_begin) / 2 : r.fz_end - r.fz_begin) : 1);
+            if (nz <= 65535) {
+                dim3 block(64, 2, 1);
+                dim3 grid((m.n2 + 63) / 64, (m.n1 + 1) / 2, nz);
+                const int oz0 = (int)(ndim == 3 ? r.out_z0 : 0), cz0 = (int)(ndim == 3 ? r.coarse_z0 : 0);
+                if (grid.y <= 65535) {
+                    if (dtype == ODIL_B200_F32) {
+                        if (cz)
+                            k_interp_add3<float, true><<<grid, block, 0, st>>>(g, m, (const float*)coarse, (float)cfac,
+                                                                             (const float*)fine_term, (float)ffac,
+                                                                             (float*)out, zb, nz, oz0, cz0);
+                        else
+                            k_interp_add3<float, false><<<grid, block, 0, st>>>(g, m, (const float*)coarse, (float)cfac,
+                                                                              (const float*)fine_term, (float)ffac,
+                                                                              (float*)out, zb, nz, oz0, cz0);
+                    } else {
+                        if (cz)
+                            k_interp_add3<double, true><<<grid, block, 0, st>>>(g, m, (const double*)coarse, cfac,
+                                                                              (const double*)fine_term, ffac,
+                                                                              (double*)out, zb, nz, oz0, cz0);
+                        else
+                            k_interp_add3<double, false><<<grid, block, 0, st>>>(g, m, (const double*)coarse, cfac,
+                                                                               (const double*)fine_term, ffac,
+                                                                               (double*)out, zb, nz, oz0, cz0);
+                    }
+                    ODIL_LAUNCHED();
+                    return 0;
+                }
+            }
+        }
+    }
     if (dtype == ODIL_B200_F32)
         k_interp_add<float><<<(unsigned)nb, 256, 0, st>>>(g, (const float*)coarse, (float)cfac, (const float*)fine_term,
                                                           (float)ffac, (float*)out, r.fz_begin, r.fz_end - r.fz_begin,
@@ -375,6 +652,38 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
     const int64_t nb = (total + 127) / 128;
     ODIL_REQUIRE(nb < (1ll << 31), "grid too large");
     cudaStream_t st = (cudaStream_t)stream;
+    ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    {
+        Mg3 m;
+        bool cz = false;
+        if (fast3_geometry(g, m, cz)) {
+            const int zb = (int)(ndim == 3 ? r.cz_begin : 0);
+            const int nz = (int)(ndim == 3 ? r.cz_end - r.cz_begin : 1);
+            dim3 block(64, 2, 1);
+            dim3 grid((m.n2 + 63) / 64, (m.n1 + 1) / 2, nz);
+            const int oz0 = (int)(ndim == 3 ? r.out_z0 : 0), fz0 = (int)(ndim == 3 ? r.fine_z0 : 0);
+            if (nz <= 65535 && grid.y <= 65535) {
+                if (dtype == ODIL_B200_F32) {
+                    if (cz)
+                        k_interp_adjoint3<float, true><<<grid, block, 0, st>>>(g, m, (const float*)g_fine, (float)scale,
+                                                                             (float*)g_coarse, zb, oz0, fz0);
+                    else
+                        k_interp_adjoint3<float, false><<<grid, block, 0, st>>>(g, m, (const float*)g_fine,
+                                                                              (float)scale, (float*)g_coarse, zb, oz0,
+                                                                              fz0);
+                } else {
+                    if (cz)
+                        k_interp_adjoint3<double, true><<<grid, block, 0, st>>>(g, m, (const double*)g_fine, scale,
+                                                                              (double*)g_coarse, zb, oz0, fz0);
+                    else
+                        k_interp_adjoint3<double, false><<<grid, block, 0, st>>>(g, m, (const double*)g_fine, scale,
+                                                                               (double*)g_coarse, zb, oz0, fz0);
+                }
+                ODIL_LAUNCHED();
+                return 0;
+            }
+        }
+    }
     if (dtype == ODIL_B200_F32)
         k_interp_adjoint<float><<<(unsigned)nb, 128, 0, st>>>(g, (const float*)g_fine, (float)scale, (float*)g_coarse,
                                                               r.cz_begin, r.cz_end - r.cz_begin, r.out_z0, r.fine_z0);

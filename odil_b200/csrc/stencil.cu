@@ -86,6 +86,9 @@ struct odil_b200_plan {
     int zchunk;    // 0 => auto
     int variant;   // tile shape variant
     int rmax0;     // max |off| along axis 0
+    void* star_table;  // device, typed [ncls][7] (c, zm, zp, ym, yp, xm, xp) when kind == 1
+    int star_has_z;    // some class row couples axis 0 (even if the interior row does not)
+    int use_v3;        // 1: column-group kernel (default when N2 % 4 == 0), 0: v2 tile kernel + shell
 };
 
 namespace odil {
@@ -426,6 +429,249 @@ __global__ void __launch_bounds__(NT) k_star3d(StarParams<T> p) {
     if (tid == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Star kernel v3: one thread per float4 COLUMN GROUP of the F region (tile + 1-cell ring), marching
+// along axis 0 with U[k-1], U[k], U[k+1] and F[k-2], F[k-1], F[k] of its own column in registers.
+// Per plane and thread: 2 x LDG.128 (next U plane, c), 2 x STS.128 (own U[k], own F[k-1]),
+// one __syncthreads, 4 x LDS.128 + 4 x LDS.32 (in-plane neighbours of U and F), 1 x STG.128.
+// Boundary rows (non-interior region classes) are handled in the same sweep by a per-cell table
+// lookup on the few threads/planes that touch them -- no separate shell pass.
+// Requires N2 % 4 == 0 (16-byte column groups).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct StarV3Params {
+    const T* U;
+    const T* c;
+    T* G;
+    T* Fout;
+    double* partials;
+    const T* table;  // [C0*C1*C2][7] in star order: c, zm, zp, ym, yp, xm, xp
+    int64_t n0, N0g, z0;
+    int halo;
+    int N1, N2;
+    int R0, R1, R2;
+    T w[7];
+    T scale;
+    int zchunk;
+    int has_z;
+};
+
+__device__ __forceinline__ int wrapi(int i, int n) {
+    i %= n;
+    return i < 0 ? i + n : i;
+}
+
+template <typename T>
+__device__ __forceinline__ Vec4<T> ldg4(const T* p) {
+    return __ldg(reinterpret_cast<const Vec4<T>*>(p));
+}
+template <>
+__device__ __forceinline__ Vec4<float> ldg4<float>(const float* p) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return Vec4<float>{v.x, v.y, v.z, v.w};
+}
+template <>
+__device__ __forceinline__ Vec4<double> ldg4<double>(const double* p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return Vec4<double>{a.x, a.y, b.x, b.y};
+}
+
+template <typename T, int TY, int TX>
+__global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Params<T> p) {
+    constexpr int GXN = TX / 4 + 2;
+    constexpr int FH = TY + 2;
+    constexpr int PITCH = GXN * 4 + 8;
+    constexpr int NT = GXN * FH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Us = reinterpret_cast<T*>(smem_raw);  // [2][FH][PITCH]
+    T* Fs = Us + 2 * FH * PITCH;             // [2][FH][PITCH]
+    __shared__ double red[32];
+
+    const int tid = threadIdx.x;
+    const int fy = tid / GXN, gx = tid - fy * GXN;
+    const int tx0 = blockIdx.x * TX, ty0 = blockIdx.y * TY;
+    const int y = ty0 - 1 + fy, x0 = tx0 - 4 + 4 * gx;
+    const int yw = wrapi(y, p.N1), x0w = wrapi(x0, p.N2);
+    const int64_t zs = (int64_t)blockIdx.z * p.zchunk;
+    const int64_t ze = min(zs + (int64_t)p.zchunk, p.n0);
+    const int64_t plane = (int64_t)p.N1 * p.N2;
+    const int col = yw * p.N2 + x0w;
+    const bool interior = fy >= 1 && fy <= TY && gx >= 1 && gx <= GXN - 2 && y < p.N1 && x0 < p.N2;
+    // in-plane neighbour row needed from global memory by the two edge rows of the F region
+    const bool edge_lo = fy == 0, edge_hi = fy == FH - 1;
+    const int ecol = (edge_lo ? wrapi(y - 1, p.N1) : wrapi(y + 1, p.N1)) * p.N2 + x0w;
+    const int soff = fy * PITCH + 4 + 4 * gx;
+
+    // boundary-class bookkeeping (per thread: y and the 4 x cells; per plane: z)
+    const int C1 = 2 * p.R1 + 1, C2 = 2 * p.R2 + 1;
+    auto cls1 = [&](int i, int n, int r) -> int {
+        if (i < r) return i;
+        const int d = n - 1 - i;
+        return d < r ? 2 * r - d : r;
+    };
+    const int cy = cls1(yw, p.N1, p.R1);
+    const int cym = cls1(wrapi(yw - 1, p.N1), p.N1, p.R1), cyp = cls1(wrapi(yw + 1, p.N1), p.N1, p.R1);
+    bool fwd_slow_yx = cy != p.R1, adj_slow_yx = cy != p.R1 || cym != p.R1 || cyp != p.R1;
+#pragma unroll
+    for (int i = -1; i <= 4; ++i) {
+        const bool b = cls1(wrapi(x0w + i, p.N2), p.N2, p.R2) != p.R2;
+        if (i >= 0 && i <= 3) fwd_slow_yx |= b;
+        adj_slow_yx |= b;
+    }
+
+    auto zoff = [&](int64_t k) -> int64_t {
+        if (p.halo == 0) {
+            k %= p.n0;
+            if (k < 0) k += p.n0;
+        }
+        return k * plane;
+    };
+    auto zcls = [&](int64_t k) -> int {  // class of local plane k (global index wraps periodically)
+        int64_t zg = (p.z0 + k) % p.N0g;
+        if (zg < 0) zg += p.N0g;
+        return cls1((int)zg, (int)p.N0g, p.R0);
+    };
+
+    const Vec4<T> zero4{T(0), T(0), T(0), T(0)};
+    Vec4<T> um = zero4, uc = zero4, up = zero4, un = zero4;  // U[kf-1], U[kf], U[kf+1], prefetch U[kf+2]
+    Vec4<T> ex = zero4, exn = zero4;                         // edge rows: U[kf] / U[kf+1] at the row outside
+    Vec4<T> cc = zero4, cn = zero4;                          // c[kf], c[kf+1]
+    Vec4<T> fm = zero4, fc = zero4;                          // F[kf-2], F[kf-1]
+    const bool has_z = p.has_z != 0;
+    const bool edge = edge_lo || edge_hi;
+    const int64_t kf0 = has_z ? zs - 1 : zs;
+    if (has_z) {
+        um = ldg4<T>(p.U + zoff(kf0 - 1) + col);
+        up = ldg4<T>(p.U + zoff(kf0 + 1) + col);
+    }
+    uc = ldg4<T>(p.U + zoff(kf0) + col);
+    if (edge) ex = ldg4<T>(p.U + zoff(kf0) + ecol);
+    if (p.c) cc = ldg4<T>(p.c + zoff(kf0) + col);
+
+    double acc2 = 0.0;
+    for (int64_t kf = kf0; kf <= ze; ++kf) {
+        const int pb = (int)((kf - kf0) & 1);
+        T* Ub = Us + pb * (FH * PITCH);
+        T* Fb = Fs + pb * (FH * PITCH);
+        // (a) prefetch the next plane's inputs
+        if (kf < ze) {
+            if (has_z) un = ldg4<T>(p.U + zoff(kf + 2) + col);
+            if (edge) exn = ldg4<T>(p.U + zoff(kf + 1) + ecol);
+            if (p.c) cn = ldg4<T>(p.c + zoff(kf + 1) + col);
+            if (!has_z) un = ldg4<T>(p.U + zoff(kf + 1) + col);
+        }
+        // (b) publish own U[kf] and F[kf-1]
+        *reinterpret_cast<Vec4<T>*>(Ub + soff) = uc;
+        *reinterpret_cast<Vec4<T>*>(Fb + soff) = fc;
+        __syncthreads();
+        // (d) F[kf] for the own column group
+        Vec4<T> fp = zero4;
+        const bool do_f = has_z ? true : (kf < ze);
+        if (do_f) {
+            const Vec4<T> uym = edge_lo ? ex : *reinterpret_cast<const Vec4<T>*>(Ub + soff - PITCH);
+            const Vec4<T> uyp = edge_hi ? ex : *reinterpret_cast<const Vec4<T>*>(Ub + soff + PITCH);
+            const T ul = Ub[soff - 1], ur = Ub[soff + 4];
+            const int cz = has_z || p.R0 > 0 ? zcls(kf) : 0;
+            if (!(fwd_slow_yx || cz != p.R0)) {
+                fp.x = cc.x + p.w[0] * uc.x + p.w[1] * um.x + p.w[2] * up.x + p.w[3] * uym.x + p.w[4] * uyp.x +
+                       p.w[5] * ul + p.w[6] * uc.y;
+                fp.y = cc.y + p.w[0] * uc.y + p.w[1] * um.y + p.w[2] * up.y + p.w[3] * uym.y + p.w[4] * uyp.y +
+                       p.w[5] * uc.x + p.w[6] * uc.z;
+                fp.z = cc.z + p.w[0] * uc.z + p.w[1] * um.z + p.w[2] * up.z + p.w[3] * uym.z + p.w[4] * uyp.z +
+                       p.w[5] * uc.y + p.w[6] * uc.w;
+                fp.w = cc.w + p.w[0] * uc.w + p.w[1] * um.w + p.w[2] * up.w + p.w[3] * uym.w + p.w[4] * uyp.w +
+                       p.w[5] * uc.z + p.w[6] * ur;
+            } else {
+                const T ucv[6] = {ul, uc.x, uc.y, uc.z, uc.w, ur};
+                const T umv[4] = {um.x, um.y, um.z, um.w}, upv[4] = {up.x, up.y, up.z, up.w};
+                const T uymv[4] = {uym.x, uym.y, uym.z, uym.w}, uypv[4] = {uyp.x, uyp.y, uyp.z, uyp.w};
+                const T ccv[4] = {cc.x, cc.y, cc.z, cc.w};
+                T fv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int cx = cls1(wrapi(x0w + i, p.N2), p.N2, p.R2);
+                    const T* row = p.table + ((cz * C1 + cy) * C2 + cx) * 7;
+                    fv[i] = ccv[i] + __ldg(row + 0) * ucv[i + 1] + __ldg(row + 1) * umv[i] + __ldg(row + 2) * upv[i] +
+                            __ldg(row + 3) * uymv[i] + __ldg(row + 4) * uypv[i] + __ldg(row + 5) * ucv[i] +
+                            __ldg(row + 6) * ucv[i + 2];
+                }
+                fp = Vec4<T>{fv[0], fv[1], fv[2], fv[3]};
+            }
+            if (interior && kf >= zs && kf < ze) {
+                acc2 += (double)(fp.x * fp.x + fp.y * fp.y + fp.z * fp.z + fp.w * fp.w);
+                if (p.Fout) *reinterpret_cast<Vec4<T>*>(p.Fout + kf * plane + col) = fp;
+            }
+        }
+        // (e) g[kf-1] from F[kf-2], F[kf-1], F[kf] (own column) and the in-plane neighbours of F[kf-1]
+        const int64_t kg = kf - 1;
+        if (interior && kg >= zs && kg < ze) {
+            const Vec4<T> fym = *reinterpret_cast<const Vec4<T>*>(Fb + soff - PITCH);
+            const Vec4<T> fyp = *reinterpret_cast<const Vec4<T>*>(Fb + soff + PITCH);
+            const T fl = Fb[soff - 1], fr = Fb[soff + 4];
+            Vec4<T> g;
+            bool slow = adj_slow_yx;
+            int czm = 0, cz0 = 0, czp = 0;
+            if (has_z || p.R0 > 0) {
+                cz0 = zcls(kg);
+                czm = zcls(kg - 1);
+                czp = zcls(kg + 1);
+                slow |= cz0 != p.R0 || (has_z && (czm != p.R0 || czp != p.R0));
+            }
+            if (!slow) {
+                g.x = p.w[0] * fc.x + p.w[1] * fp.x + p.w[2] * fm.x + p.w[3] * fyp.x + p.w[4] * fym.x + p.w[5] * fc.y +
+                      p.w[6] * fl;
+                g.y = p.w[0] * fc.y + p.w[1] * fp.y + p.w[2] * fm.y + p.w[3] * fyp.y + p.w[4] * fym.y + p.w[5] * fc.z +
+                      p.w[6] * fc.x;
+                g.z = p.w[0] * fc.z + p.w[1] * fp.z + p.w[2] * fm.z + p.w[3] * fyp.z + p.w[4] * fym.z + p.w[5] * fc.w +
+                      p.w[6] * fc.y;
+                g.w = p.w[0] * fc.w + p.w[1] * fp.w + p.w[2] * fm.w + p.w[3] * fyp.w + p.w[4] * fym.w + p.w[5] * fr +
+                      p.w[6] * fc.z;
+            } else {
+                const T fcv[6] = {fl, fc.x, fc.y, fc.z, fc.w, fr};
+                const T fmv[4] = {fm.x, fm.y, fm.z, fm.w}, fpv[4] = {fp.x, fp.y, fp.z, fp.w};
+                const T fymv[4] = {fym.x, fym.y, fym.z, fym.w}, fypv[4] = {fyp.x, fyp.y, fyp.z, fyp.w};
+                T gv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int cx = cls1(wrapi(x0w + i, p.N2), p.N2, p.R2);
+                    const int cxm = cls1(wrapi(x0w + i - 1, p.N2), p.N2, p.R2);
+                    const int cxp = cls1(wrapi(x0w + i + 1, p.N2), p.N2, p.R2);
+                    auto tab = [&](int z, int yy, int xx, int o) -> T {
+                        return __ldg(p.table + ((z * C1 + yy) * C2 + xx) * 7 + o);
+                    };
+                    T gi = tab(cz0, cy, cx, 0) * fcv[i + 1];
+                    if (has_z) gi += tab(czp, cy, cx, 1) * fpv[i] + tab(czm, cy, cx, 2) * fmv[i];
+                    gi += tab(cz0, cyp, cx, 3) * fypv[i] + tab(cz0, cym, cx, 4) * fymv[i];
+                    gi += tab(cz0, cy, cxp, 5) * fcv[i + 2] + tab(cz0, cy, cxm, 6) * fcv[i];
+                    gv[i] = gi;
+                }
+                g = Vec4<T>{gv[0], gv[1], gv[2], gv[3]};
+            }
+            g.x *= p.scale;
+            g.y *= p.scale;
+            g.z *= p.scale;
+            g.w *= p.scale;
+            *reinterpret_cast<Vec4<T>*>(p.G + kg * plane + col) = g;
+        }
+        // (f) rotate
+        fm = fc;
+        fc = fp;
+        if (has_z) {
+            um = uc;
+            uc = up;
+            up = un;
+        } else {
+            uc = un;
+        }
+        ex = exn;
+        cc = cn;
+    }
+    const double sum = block_sum(acc2, red);
+    if (tid == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sum;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
@@ -581,6 +827,29 @@ static int launch_star_cfg(const StarParams<T>& sp, dim3 grid, bool vec, cudaStr
     return 0;
 }
 
+template <typename T, int TY, int TX>
+static int launch_star_v3(const StarV3Params<T>& sp, dim3 grid, cudaStream_t st) {
+    constexpr int NT = (TX / 4 + 2) * (TY + 2);
+    const size_t smem = (size_t)4 * (TY + 2) * ((TX / 4 + 2) * 4 + 8) * sizeof(T);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ODIL_CUDA(cudaFuncSetAttribute(k_star_v3<T, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_star_v3<T, TY, TX><<<grid, NT, smem, st>>>(sp);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+static void star_v3_tile(int variant, int& TY, int& TX) {
+    switch (variant) {
+        case 1: TY = 8; TX = 128; break;
+        case 2: TY = 14; TX = 128; break;
+        case 3: TY = 8; TX = 64; break;
+        default: TY = 16; TX = 128; break;
+    }
+}
+
 static void star_tile(int variant, int& TY, int& TX) {
     switch (variant) {
         case 1: TY = 16; TX = 64; break;
@@ -605,7 +874,66 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     int nparts = 0;
     const bool slab_mode = slab->halo > 0 || slab->n0 != plan->shape[0] || slab->z0 != 0;
     bool tiled = plan->kind == 1 && !(plan->ndim == 2 && slab_mode);
-    if (tiled) {
+    const int64_t n2 = plan->shape[plan->ndim - 1];
+    const bool v3 = tiled && plan->use_v3 && (n2 % 4 == 0) && ((uintptr_t)U % 16 == 0) && ((uintptr_t)G % 16 == 0) &&
+                    ((uintptr_t)c % 16 == 0) && ((uintptr_t)Fout % 16 == 0);
+    if (v3) {
+        StarV3Params<T> sp;
+        sp.U = io.U;
+        sp.c = io.c;
+        sp.G = io.out;
+        sp.Fout = io.Fout;
+        sp.partials = plan->partials;
+        sp.table = (const T*)plan->star_table;
+        if (plan->ndim == 3) {
+            sp.n0 = slab->n0;
+            sp.N0g = plan->shape[0];
+            sp.z0 = slab->z0;
+            sp.halo = slab->halo;
+            sp.N1 = (int)plan->shape[1];
+            sp.N2 = (int)plan->shape[2];
+            sp.R0 = plan->R[0];
+            sp.R1 = plan->R[1];
+            sp.R2 = plan->R[2];
+            sp.has_z = plan->w[1] != 0.0 || plan->w[2] != 0.0 || plan->star_has_z;
+        } else {
+            sp.n0 = 1;
+            sp.N0g = 1;
+            sp.z0 = 0;
+            sp.halo = 0;
+            sp.N1 = (int)plan->shape[0];
+            sp.N2 = (int)plan->shape[1];
+            sp.R0 = 0;
+            sp.R1 = plan->R[0];
+            sp.R2 = plan->R[1];
+            sp.has_z = 0;
+        }
+        for (int i = 0; i < 7; ++i) sp.w[i] = (T)plan->w[i];
+        sp.scale = (T)scale;
+        int TY, TX;
+        star_v3_tile(plan->variant, TY, TX);
+        const int gx = (sp.N2 + TX - 1) / TX, gy = (sp.N1 + TY - 1) / TY;
+        int zchunk = plan->zchunk;
+        if (zchunk <= 0) {
+            zchunk = 128;
+            while (zchunk > 16 && (int64_t)gx * gy * ((sp.n0 + zchunk - 1) / zchunk) < 148 * 2 * 4) zchunk /= 2;
+        }
+        if (zchunk > sp.n0) zchunk = (int)sp.n0;
+        if (zchunk < 1) zchunk = 1;
+        sp.zchunk = zchunk;
+        const int gz = (int)((sp.n0 + zchunk - 1) / zchunk);
+        ODIL_REQUIRE((int64_t)gx * gy * gz <= kPartialCapacity, "star grid exceeds the partials workspace");
+        dim3 grid(gx, gy, gz);
+        int rc = 0;
+        switch (plan->variant) {
+            case 1: rc = launch_star_v3<T, 8, 128>(sp, grid, st); break;
+            case 2: rc = launch_star_v3<T, 14, 128>(sp, grid, st); break;
+            case 3: rc = launch_star_v3<T, 8, 64>(sp, grid, st); break;
+            default: rc = launch_star_v3<T, 16, 128>(sp, grid, st); break;
+        }
+        if (rc) return rc;
+        nparts = gx * gy * gz;
+    } else if (tiled) {
         StarParams<T> sp;
         sp.U = io.U;
         sp.c = io.c;
@@ -746,6 +1074,10 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
     p->table.assign(table, table + (size_t)p->ncls * noff);
     // Tiled eligibility: 2-D / 3-D, every offset a unit star arm, grid not degenerate.
     p->kind = 0;
+    p->star_table = nullptr;
+    p->star_has_z = 0;
+    p->use_v3 = 1;
+    std::vector<double> star;
     for (int i = 0; i < 7; ++i) p->w[i] = 0.0;
     if ((ndim == 3 || ndim == 2) && total >= 512) {
         bool ok = true;
@@ -776,6 +1108,16 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
         if (ok) {
             p->kind = 1;
             for (int i = 0; i < 7; ++i) p->w[i] = w[i];
+            star.assign((size_t)p->ncls * 7, 0.0);
+            for (int o = 0; o < noff; ++o) {
+                int slot = 0;
+                for (int a = 0; a < ndim; ++a)
+                    if (p->off[o][a] != 0) slot = 1 + 2 * (base + a) + (p->off[o][a] > 0 ? 1 : 0);
+                for (int cl = 0; cl < p->ncls; ++cl) {
+                    star[(size_t)cl * 7 + slot] += p->table[(size_t)cl * noff + o];
+                    if ((slot == 1 || slot == 2) && p->table[(size_t)cl * noff + o] != 0.0) p->star_has_z = 1;
+                }
+            }
         }
     }
     cudaError_t e = cudaGetDevice(&p->device);
@@ -791,10 +1133,22 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
             }
         }
         if (e == cudaSuccess) e = cudaMalloc((void**)&p->partials, sizeof(double) * kPartialCapacity);
+        if (e == cudaSuccess && !star.empty()) {
+            e = cudaMalloc(&p->star_table, esz * star.size());
+            if (e == cudaSuccess) {
+                if (dtype == ODIL_B200_F32) {
+                    std::vector<float> tf(star.begin(), star.end());
+                    e = cudaMemcpy(p->star_table, tf.data(), esz * tf.size(), cudaMemcpyHostToDevice);
+                } else {
+                    e = cudaMemcpy(p->star_table, star.data(), esz * star.size(), cudaMemcpyHostToDevice);
+                }
+            }
+        }
     }
     if (e != cudaSuccess) {
         if (p->table_dev) cudaFree(p->table_dev);
         if (p->partials) cudaFree(p->partials);
+        if (p->star_table) cudaFree(p->star_table);
         delete p;
         return fail("plan_create: %s", cudaGetErrorString(e));
     }
@@ -806,6 +1160,7 @@ int odil_b200_stencil_plan_destroy(odil_b200_plan* plan) {
     if (!plan) return 0;
     if (plan->table_dev) cudaFree(plan->table_dev);
     if (plan->partials) cudaFree(plan->partials);
+    if (plan->star_table) cudaFree(plan->star_table);
     delete plan;
     return 0;
 }
@@ -814,9 +1169,10 @@ int odil_b200_stencil_plan_kind(const odil_b200_plan* plan) { return plan ? plan
 
 int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant) {
     ODIL_REQUIRE(plan != nullptr, "null plan");
-    ODIL_REQUIRE(variant >= 0 && variant <= 3, "variant=%d unknown", variant);
+    ODIL_REQUIRE((variant >= 0 && variant <= 3) || (variant >= 10 && variant <= 13), "variant=%d unknown", variant);
     plan->zchunk = zchunk;
-    plan->variant = variant;
+    plan->use_v3 = variant < 10;  // 0..3: column-group kernel tiles; 10..13: v2 tile kernel + shell pass
+    plan->variant = variant % 10;
     return 0;
 }
 

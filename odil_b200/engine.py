@@ -164,6 +164,61 @@ def lower_block(shape, coefs):
     return np.asarray(offsets, dtype=np.int32).reshape(len(offsets), nd), rr, table.reshape(-1, len(offsets))
 
 
+def wraps_axis0(shape, offsets, rwidth, table):
+    """True if some row of the region table multiplies a neighbour that lies across the axis-0
+    boundary (i.e. the stencil really is periodic along axis 0, not overridden by boundary rows)."""
+    n0, r0 = shape[0], rwidth[0]
+    ncls0 = 2 * r0 + 1
+    t = np.asarray(table).reshape((ncls0, -1, len(offsets)))
+    rows = list(range(r0)) + [min(r0, n0 - 1)] + list(range(n0 - r0, n0))   # representative index per class
+    interior_lo, interior_hi = r0, n0 - r0 - 1                               # index range of the interior class
+    for o, off in enumerate(offsets):
+        d = int(off[0])
+        if d == 0:
+            continue
+        for cl, i in enumerate(rows):
+            if cl == r0:
+                out = (interior_lo + d < 0) or (interior_hi + d > n0 - 1) if interior_hi >= interior_lo else False
+            else:
+                out = (i + d < 0) or (i + d > n0 - 1)
+            if out and np.any(t[cl, :, o] != 0):
+                return True
+    return False
+
+
+def synthesize_slab(slab, arrays, shapes, factors, loc, buffers=None, exchanged=False):
+    """
+    Multigrid synthesis on local slabs: every level is produced on its EXTENDED range (owned planes
+    plus the halo, clipped to the domain) from the level below, after one batched halo exchange of
+    all terms.  `shapes` are the GLOBAL array shapes per level.  Returns the local U (with halos).
+    """
+    L = len(arrays)
+    if not exchanged:
+        slab.exchange(list(arrays), width=slab.halo)
+    if L == 1:
+        return arrays[0] if factors[0] == 1 else arrays[0] * factors[0]
+    H = slab.halo
+    res, cfac = arrays[L - 1], float(factors[L - 1])
+    for lvl in range(L - 2, -1, -1):
+        fshape, cshape = shapes[lvl], shapes[lvl + 1]
+        zf, nf = slab.owned_range(fshape)
+        zc, _ = slab.owned_range(cshape)
+        key = ("V", lvl)
+        out = None if buffers is None else buffers.get(key)
+        if out is None or tuple(out.shape) != tuple(arrays[lvl].shape):
+            out = torch.zeros_like(arrays[lvl])
+            if buffers is not None:
+                buffers[key] = out
+        lo, hi = max(zf - H, 0), min(zf + nf + H, fshape[0])
+        if loc[0] == "c":
+            lo -= lo % 2
+            hi += hi % 2
+        native.mg_interp_add(cshape, loc, res, cfac, arrays[lvl], float(factors[lvl]), out,
+                             rng=(lo, hi, zf - H, zc - H))
+        res, cfac = out, 1.0
+    return res
+
+
 class _Block:
     def __init__(self, key, frozen, plan):
         self.key, self.frozen, self.plan = key, frozen, plan
@@ -179,14 +234,17 @@ class _Output:
 class _Unknown:
     """How one state entry maps to arrays of the flat unknown list."""
 
-    def __init__(self, key, field, first):
+    def __init__(self, key, field, first, domain):
         self.key, self.first = key, first
         self.kind = type(field).__name__
         if isinstance(field, MultigridField):
             self.narrays = len(field.terms)
             self.loc = field.loc
-            self.shapes = [tuple(t.array.shape) for t in field.terms]
-        elif isinstance(field, (Field, Array)):
+            self.shapes = [domain._get_field_shape(t.cshape, field.loc) for t in field.terms]  # GLOBAL shapes
+        elif isinstance(field, Field):
+            self.narrays = 1
+            self.shapes = [domain._get_field_shape(field.cshape or domain.cshape, field.loc)]
+        elif isinstance(field, Array):
             self.narrays = 1
             self.shapes = [tuple(field.array.shape)]
         elif isinstance(field, NeuralNet):
@@ -215,15 +273,18 @@ class ResidualEngine:
         self.unknowns = {}
         first = 0
         for key, field in state.fields.items():
-            u = _Unknown(key, field, first)
+            u = _Unknown(key, field, first, domain)
             if isinstance(field, MultigridField):
                 u.mgloc = domain._mg_loc(field)
                 u.factors = [float(f) for f in (field.factors or domain.mg_factors or [1] * len(field.terms))]
             self.unknowns[key] = u
             first += u.narrays
         self.narrays = first
+        self.slab = getattr(domain, "slab", None)
         self._trace(state)
         self._buffers = {}
+        if self.slab is not None and not trace_only:
+            self._prepare_slabs()
 
     # ----------------------------------------------------------------------------------------------
     def _trace(self, state):
@@ -270,15 +331,81 @@ class ResidualEngine:
             out.fused = (len(out.blocks) == 1 and not out.blocks[0].frozen and use_count.get(out.blocks[0].key) == 1)
         self.used_keys = set(use_count)
 
+    def _prepare_slabs(self):
+        """Slices the constant terms into local slabs and decides which fields need a U halo exchange."""
+        slab = self.slab
+        self.periodic_keys = set()
+        for out in self.outputs:
+            if not out.fused:
+                raise NonAffineError("multi-GPU slabs support single-field fused outputs only (so far)")
+            blk = out.blocks[0]
+            if self.unknowns[blk.key].kind == "Array":
+                raise NonAffineError("non-grid Array unknowns are not decomposed into slabs yet")
+            out.const_local = slab.scatter(out.const) if out.const is not None else None
+            sp = blk.spec
+            if wraps_axis0(sp["shape"], sp["offsets"], sp["rwidth"], sp["table"]):
+                self.periodic_keys.add(blk.key)
+            out.const = None  # the global copy is no longer needed
+
     # ----------------------------------------------------------------------------------------------
-    def _buf(self, name, shape):
+    def _loss_grad_slab(self, arrays):
+        slab, H = self.slab, self.slab.halo
+        K = len(self.outputs)
+        sums = torch.empty(K, dtype=torch.float64, device=self.device)
+        used = [self.unknowns[k] for k in self.unknowns if k in self.used_keys]
+        # one batched halo exchange of every array of every used unknown
+        slab.exchange([arrays[u.first + i] for u in used for i in range(u.narrays)], width=H)
+        U = {}
+        for u in used:
+            a = arrays[u.first: u.first + u.narrays]
+            if u.kind == "MultigridField":
+                bufs = self._buffers.setdefault(("slabV", u.key), {})
+                U[u.key] = synthesize_slab(slab, a, u.shapes, u.factors, u.mgloc, bufs, exchanged=True)
+                if u.key in self.periodic_keys:
+                    slab.exchange([U[u.key]], width=H)
+            else:
+                U[u.key] = a[0]
+        grads = [None] * self.narrays
+        for k, out in enumerate(self.outputs):
+            blk = out.blocks[0]
+            u = self.unknowns[blk.key]
+            z0, n0 = slab.owned_range(out.shape)
+            g = self._buf(("gU", blk.key), slab.local_shape(out.shape), zero=True)
+            blk.plan.fused(U[blk.key], out.const_local, 2.0 / out.n, g, sums[k:k + 1], slab=(n0, z0, H))
+            if u.kind != "MultigridField":
+                grads[u.first] = g
+                continue
+            gl = g
+            for lvl in range(u.narrays):
+                if lvl > 0:
+                    slab.exchange([gl], width=1)
+                    zc, nc = slab.owned_range(u.shapes[lvl])
+                    zf, _ = slab.owned_range(u.shapes[lvl - 1])
+                    gc = self._buf(("gV", u.key, lvl), slab.local_shape(u.shapes[lvl]), zero=True)
+                    native.mg_interp_adjoint(u.shapes[lvl], u.mgloc, gl, 1.0, gc, rng=(zc, zc + nc, zc - H, zf - H))
+                    gl = gc
+                f = u.factors[lvl]
+                grads[u.first + lvl] = gl if f == 1 else gl * f
+        for i in range(self.narrays):
+            if grads[i] is None:
+                grads[i] = torch.zeros_like(arrays[i])
+        slab.all_reduce_sum(sums)
+        fetch = _Fetch(sums, [o.n for o in self.outputs], self.dtype)
+        return (LazyScalar(fetch, "loss"), grads, [LazyScalar(fetch, "term", k) for k in range(K)],
+                [LazyScalar(fetch, "norm", k) for k in range(K)])
+
+    # ----------------------------------------------------------------------------------------------
+    def _buf(self, name, shape, zero=False):
         b = self._buffers.get(name)
         if b is None or tuple(b.shape) != tuple(shape):
-            b = torch.empty(shape, dtype=self.tdtype, device=self.device)
+            alloc = torch.zeros if zero else torch.empty
+            b = alloc(tuple(shape), dtype=self.tdtype, device=self.device)
             self._buffers[name] = b
         return b
 
     def _check_arrays(self, arrays):
+        if self.trace_only:
+            raise native.NativeError("engine was built with trace_only=True")
         if len(arrays) != self.narrays:
             raise ValueError(f"expected {self.narrays} arrays, got {len(arrays)}")
         for a in arrays:
@@ -319,6 +446,8 @@ class ResidualEngine:
     # ----------------------------------------------------------------------------------------------
     def loss_grad(self, arrays):
         self._check_arrays(arrays)
+        if self.slab is not None:
+            return self._loss_grad_slab(arrays)
         K = len(self.outputs)
         sums = torch.empty(K, dtype=torch.float64, device=self.device)
         U = {key: self._regular(self.unknowns[key], arrays) for key in self.used_keys | self._frozen_keys()}
@@ -364,6 +493,8 @@ class ResidualEngine:
     def operator_values(self, arrays):
         """Materialised operator outputs F_k (Problem.eval_operator, core.py:1298-1311)."""
         self._check_arrays(arrays)
+        if self.slab is not None:
+            raise NotImplementedError("eval_operator on slab-decomposed grids")
         U = {key: self._regular(self.unknowns[key], arrays) for key in self.used_keys | self._frozen_keys()}
         res = []
         for out in self.outputs:

@@ -175,7 +175,7 @@ def test_star_plans_use_tiled_kernel():
     assert kinds == [0, 0, 0, 1, 1, 1, 1, 1, 0]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 10, 11, 12, 13])
 @pytest.mark.parametrize("zchunk", [0, 1, 5, 64])
 def test_star_variants(variant, zchunk):
     shape, rr = (20, 18, 36), (1, 1, 1)
