@@ -313,12 +313,14 @@ __global__ void __launch_bounds__(NT) k_star3d(StarParams<T> p) {
         }
     }
 
-    auto zoff = [&](int64_t k) -> int64_t {
+    const int n0i = (int)p.n0;
+    auto zoff = [&](int64_t k64) -> int64_t {
+        int k = (int)k64;
         if (p.halo == 0) {
-            k %= p.n0;
-            if (k < 0) k += p.n0;
+            while (k < 0) k += n0i;
+            while (k >= n0i) k -= n0i;
         }
-        return k * plane;
+        return (int64_t)k * plane;
     };
 
     const int64_t kf_begin = p.has_z ? zs - 1 : zs;
@@ -494,8 +496,8 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
     const int tx0 = blockIdx.x * TX, ty0 = blockIdx.y * TY;
     const int y = ty0 - 1 + fy, x0 = tx0 - 4 + 4 * gx;
     const int yw = wrapi(y, p.N1), x0w = wrapi(x0, p.N2);
-    const int64_t zs = (int64_t)blockIdx.z * p.zchunk;
-    const int64_t ze = min(zs + (int64_t)p.zchunk, p.n0);
+    const int zs = blockIdx.z * p.zchunk;
+    const int ze = min(zs + p.zchunk, (int)p.n0);
     const int64_t plane = (int64_t)p.N1 * p.N2;
     const int col = yw * p.N2 + x0w;
     const bool interior = fy >= 1 && fy <= TY && gx >= 1 && gx <= GXN - 2 && y < p.N1 && x0 < p.N2;
@@ -521,17 +523,20 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
         adj_slow_yx |= b;
     }
 
-    auto zoff = [&](int64_t k) -> int64_t {
+    // plane indices stay within a few planes of [0, n0): wrap by comparison (64-bit % is ~100 instructions)
+    const int n0i = (int)p.n0, N0gi = (int)p.N0g, z0i = (int)p.z0;
+    auto zoff = [&](int k) -> int64_t {
         if (p.halo == 0) {
-            k %= p.n0;
-            if (k < 0) k += p.n0;
+            while (k < 0) k += n0i;
+            while (k >= n0i) k -= n0i;
         }
-        return k * plane;
+        return (int64_t)k * plane;
     };
-    auto zcls = [&](int64_t k) -> int {  // class of local plane k (global index wraps periodically)
-        int64_t zg = (p.z0 + k) % p.N0g;
-        if (zg < 0) zg += p.N0g;
-        return cls1((int)zg, (int)p.N0g, p.R0);
+    auto zcls = [&](int k) -> int {  // class of local plane k (global index wraps periodically)
+        int zg = z0i + k;
+        while (zg < 0) zg += N0gi;
+        while (zg >= N0gi) zg -= N0gi;
+        return cls1(zg, N0gi, p.R0);
     };
 
     const Vec4<T> zero4{T(0), T(0), T(0), T(0)};
@@ -541,7 +546,7 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
     Vec4<T> fm = zero4, fc = zero4;                          // F[kf-2], F[kf-1]
     const bool has_z = p.has_z != 0;
     const bool edge = edge_lo || edge_hi;
-    const int64_t kf0 = has_z ? zs - 1 : zs;
+    const int kf0 = has_z ? zs - 1 : zs;
     if (has_z) {
         um = ldg4<T>(p.U + zoff(kf0 - 1) + col);
         up = ldg4<T>(p.U + zoff(kf0 + 1) + col);
@@ -551,7 +556,7 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
     if (p.c) cc = ldg4<T>(p.c + zoff(kf0) + col);
 
     double acc2 = 0.0;
-    for (int64_t kf = kf0; kf <= ze; ++kf) {
+    for (int kf = kf0; kf <= ze; ++kf) {
         const int pb = (int)((kf - kf0) & 1);
         T* Ub = Us + pb * (FH * PITCH);
         T* Fb = Fs + pb * (FH * PITCH);
@@ -601,11 +606,11 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
             }
             if (interior && kf >= zs && kf < ze) {
                 acc2 += (double)(fp.x * fp.x + fp.y * fp.y + fp.z * fp.z + fp.w * fp.w);
-                if (p.Fout) *reinterpret_cast<Vec4<T>*>(p.Fout + kf * plane + col) = fp;
+                if (p.Fout) *reinterpret_cast<Vec4<T>*>(p.Fout + (int64_t)kf * plane + col) = fp;
             }
         }
         // (e) g[kf-1] from F[kf-2], F[kf-1], F[kf] (own column) and the in-plane neighbours of F[kf-1]
-        const int64_t kg = kf - 1;
+        const int kg = kf - 1;
         if (interior && kg >= zs && kg < ze) {
             const Vec4<T> fym = *reinterpret_cast<const Vec4<T>*>(Fb + soff - PITCH);
             const Vec4<T> fyp = *reinterpret_cast<const Vec4<T>*>(Fb + soff + PITCH);
@@ -653,7 +658,7 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
             g.y *= p.scale;
             g.z *= p.scale;
             g.w *= p.scale;
-            *reinterpret_cast<Vec4<T>*>(p.G + kg * plane + col) = g;
+            *reinterpret_cast<Vec4<T>*>(p.G + (int64_t)kg * plane + col) = g;
         }
         // (f) rotate
         fm = fc;

@@ -25,9 +25,9 @@ HALO = 2
 
 class SlabInfo:
 
-    def __init__(self, rank, world, group=None):
+    def __init__(self, rank, world, group=None, halo=HALO):
         self.rank, self.world, self.group = int(rank), int(world), group
-        self.halo = HALO
+        self.halo = int(halo)
 
     @staticmethod
     def from_environment():
@@ -38,7 +38,8 @@ class SlabInfo:
             return None
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return None
-        return SlabInfo(dist.get_rank(), dist.get_world_size())
+        # ODIL_HALO: halo planes per side; must be >= 2 * (largest |shift| along axis 0), default 2.
+        return SlabInfo(dist.get_rank(), dist.get_world_size(), halo=int(os.environ.get("ODIL_HALO", HALO)))
 
     # -- geometry -----------------------------------------------------------------------------------
     def check(self, shape):
@@ -78,7 +79,7 @@ class SlabInfo:
         return torch.cat(parts, dim=0)
 
     # -- halo exchange ------------------------------------------------------------------------------
-    def exchange(self, locals_, width=HALO):
+    def exchange(self, locals_, width=None):
         """
         Fills the `width` innermost halo planes of every local array in `locals_` from the ring
         neighbours (rank 0's lower neighbour is rank world-1: periodic, which is what ctx.field's roll
@@ -87,6 +88,7 @@ class SlabInfo:
         """
         import torch.distributed as dist
 
+        width = self.halo if width is None else width
         if self.world == 1:
             for a in locals_:
                 n = a.shape[0] - 2 * self.halo
