@@ -150,6 +150,16 @@ int odil_b200_gd_step(int ntensors, void* const* x, const void* const* g, const 
 /* y = a*x + b*y  (L-BFGS building block; also used for scaling). */
 int odil_b200_axpby(int64_t count, int dtype, double a, const void* x, double b, void* y, void* stream);
 
+/* L-BFGS building blocks (compact form). V: row-major [k][ld] matrix holding the history vectors
+ * (k <= 256 rows of `count` elements).  Replaces the host vector algebra inside SciPy's
+ * fmin_l_bfgs_b that the reference calls (optimizer.py:95-105).
+ *   multi_dot:  out[r] = sum_i V[r][i] * g[i]            (device doubles, deterministic)
+ *   multi_axpy: d[i]   = a0 * g[i] + sum_r coef[r] * V[r][i]   (coef: k device doubles; g nullable) */
+int odil_b200_multi_dot(const void* V, int64_t ld, int k, const void* g, int64_t count, int dtype, double* out,
+                        void* stream);
+int odil_b200_multi_axpy(const void* V, int64_t ld, int k, const double* coef, double a0, const void* g, void* d,
+                         int64_t count, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

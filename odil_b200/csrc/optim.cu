@@ -1,5 +1,7 @@
 // Optimizer updates and vector building blocks (sm_100a, HBM-bound, 128-bit accesses).
 // adam_step restates reference optimizer.py:311-319 (AdamNativeOptimizer._step), gd_step :269-270.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace odil {
@@ -97,6 +99,69 @@ __global__ void __launch_bounds__(256) k_dot_partial(const T* __restrict__ x, co
     }
     const double s = block_sum(acc, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// L-BFGS building blocks (compact / Byrd-Nocedal-Schnabel form): one pass over the 2m history vectors
+// for all inner products [S Y]^T g, one pass for the direction d = a0*g + sum_r coef_r V_r.
+// Replaces the host-side SciPy L-BFGS-B vector algebra of the reference (optimizer.py:95-105).
+// V is a row-major [k][n] matrix (row stride `ld` elements).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMdChunk = 2048;     // elements of g staged per block iteration
+constexpr int kMdMaxRows = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_multi_dot(const T* __restrict__ V, int64_t ld, int k, const T* __restrict__ g,
+                                                   int64_t n, double* __restrict__ partials /*[k][gridDim.x]*/) {
+    __shared__ T gs[kMdChunk];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = 8;
+    double acc[kMdMaxRows / NW];
+#pragma unroll
+    for (int j = 0; j < kMdMaxRows / NW; ++j) acc[j] = 0.0;
+    for (int64_t base = (int64_t)blockIdx.x * kMdChunk; base < n; base += (int64_t)gridDim.x * kMdChunk) {
+        const int len = (int)min((int64_t)kMdChunk, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < len; i += blockDim.x) gs[i] = g[base + i];
+        __syncthreads();
+#pragma unroll 1
+        for (int j = 0; j * NW + warp < k; ++j) {
+            const T* row = V + (int64_t)(j * NW + warp) * ld + base;
+            double a = 0.0;
+            for (int i = lane; i < len; i += 32) a += (double)row[i] * (double)gs[i];
+            acc[j] += a;
+        }
+    }
+    for (int j = 0; j * NW + warp < k; ++j) {
+        const double a = warp_sum(acc[j]);
+        if (lane == 0) partials[(int64_t)(j * NW + warp) * gridDim.x + blockIdx.x] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_multi_dot_final(const double* __restrict__ partials, int nblocks,
+                                                         double* __restrict__ out) {
+    __shared__ double red[32];
+    const double* row = partials + (int64_t)blockIdx.x * nblocks;
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v += row[i];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_multi_axpy(const T* __restrict__ V, int64_t ld, int k,
+                                                    const double* __restrict__ coef /*[k] device*/, double a0,
+                                                    const T* __restrict__ g, T* __restrict__ d, int64_t n) {
+    __shared__ double cs[kMdMaxRows];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) cs[i] = coef[i];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double acc = g ? a0 * (double)g[i] : 0.0;
+        for (int r = 0; r < k; ++r) acc += cs[r] * (double)V[(int64_t)r * ld + i];
+        d[i] = (T)acc;
+    }
 }
 
 static unsigned blocks_for(int64_t n, int per_thread) {
@@ -223,6 +288,43 @@ int odil_b200_dot(const void* x, const void* y, int64_t count, int dtype, double
     if (dtype == ODIL_B200_F32) return run_dot<float, true>(x, y, count, out, (cudaStream_t)stream);
     if (dtype == ODIL_B200_F64) return run_dot<double, true>(x, y, count, out, (cudaStream_t)stream);
     return fail("dtype=%d unsupported", dtype);
+}
+
+
+int odil_b200_multi_dot(const void* V, int64_t ld, int k, const void* g, int64_t count, int dtype, double* out,
+                        void* stream) {
+    ODIL_REQUIRE(V && g && out && k >= 1 && k <= kMdMaxRows && count >= 0 && ld >= count, "multi_dot: bad arguments");
+    const int nb = (int)std::min<int64_t>(512, (count + kMdChunk - 1) / kMdChunk > 0 ? (count + kMdChunk - 1) / kMdChunk : 1);
+    double* scratch = reduction_scratch(kMdMaxRows * 512);
+    ODIL_REQUIRE(scratch != nullptr, "reduction scratch allocation failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ODIL_B200_F32)
+        k_multi_dot<float><<<nb, 256, 0, st>>>((const float*)V, ld, k, (const float*)g, count, scratch);
+    else if (dtype == ODIL_B200_F64)
+        k_multi_dot<double><<<nb, 256, 0, st>>>((const double*)V, ld, k, (const double*)g, count, scratch);
+    else
+        return fail("dtype=%d unsupported", dtype);
+    ODIL_LAUNCHED();
+    k_multi_dot_final<<<k, 256, 0, st>>>(scratch, nb, out);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+int odil_b200_multi_axpy(const void* V, int64_t ld, int k, const double* coef, double a0, const void* g, void* d,
+                         int64_t count, int dtype, void* stream) {
+    ODIL_REQUIRE(V && coef && d && k >= 1 && k <= kMdMaxRows && count >= 0 && ld >= count, "multi_axpy: bad arguments");
+    if (count == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ODIL_B200_F32)
+        k_multi_axpy<float><<<blocks_for(count, 2), 256, 0, st>>>((const float*)V, ld, k, coef, a0, (const float*)g,
+                                                                  (float*)d, count);
+    else if (dtype == ODIL_B200_F64)
+        k_multi_axpy<double><<<blocks_for(count, 2), 256, 0, st>>>((const double*)V, ld, k, coef, a0, (const double*)g,
+                                                                   (double*)d, count);
+    else
+        return fail("dtype=%d unsupported", dtype);
+    ODIL_LAUNCHED();
+    return 0;
 }
 
 }  // extern "C"

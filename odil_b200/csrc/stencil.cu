@@ -485,10 +485,11 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
     constexpr int GXN = TX / 4 + 2;
     constexpr int FH = TY + 2;
     constexpr int PITCH = GXN * 4 + 8;
-    constexpr int NT = GXN * FH;
+    constexpr int kTabSmem = 512;  // table entries kept in shared memory (27 classes x 7 = 189 for r = 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Us = reinterpret_cast<T*>(smem_raw);  // [2][FH][PITCH]
     T* Fs = Us + 2 * FH * PITCH;             // [2][FH][PITCH]
+    T* tab_s = Fs + 2 * FH * PITCH;          // [kTabSmem]
     __shared__ double red[32];
 
     const int tid = threadIdx.x;
@@ -496,35 +497,44 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
     const int tx0 = blockIdx.x * TX, ty0 = blockIdx.y * TY;
     const int y = ty0 - 1 + fy, x0 = tx0 - 4 + 4 * gx;
     const int yw = wrapi(y, p.N1), x0w = wrapi(x0, p.N2);
+    const int n0i = (int)p.n0, N0gi = (int)p.N0g, z0i = (int)p.z0;
     const int zs = blockIdx.z * p.zchunk;
-    const int ze = min(zs + p.zchunk, (int)p.n0);
+    const int ze = min(zs + p.zchunk, n0i);
     const int64_t plane = (int64_t)p.N1 * p.N2;
     const int col = yw * p.N2 + x0w;
     const bool interior = fy >= 1 && fy <= TY && gx >= 1 && gx <= GXN - 2 && y < p.N1 && x0 < p.N2;
     // in-plane neighbour row needed from global memory by the two edge rows of the F region
     const bool edge_lo = fy == 0, edge_hi = fy == FH - 1;
+    const bool edge = edge_lo || edge_hi;
     const int ecol = (edge_lo ? wrapi(y - 1, p.N1) : wrapi(y + 1, p.N1)) * p.N2 + x0w;
     const int soff = fy * PITCH + 4 + 4 * gx;
 
-    // boundary-class bookkeeping (per thread: y and the 4 x cells; per plane: z)
+    // Region classes of this thread's row and of the cells x0-1 .. x0+4 (computed once; columns are fixed).
     const int C1 = 2 * p.R1 + 1, C2 = 2 * p.R2 + 1;
-    auto cls1 = [&](int i, int n, int r) -> int {
+    auto cls1 = [](int i, int n, int r) -> int {
         if (i < r) return i;
         const int d = n - 1 - i;
         return d < r ? 2 * r - d : r;
     };
+    const int ncls = (2 * p.R0 + 1) * C1 * C2;
+    const bool tab_in_smem = ncls * 7 <= kTabSmem;
+    if (tab_in_smem)
+        for (int i = tid; i < ncls * 7; i += blockDim.x) tab_s[i] = p.table[i];
+    const T* __restrict__ tab = tab_in_smem ? tab_s : p.table;
     const int cy = cls1(yw, p.N1, p.R1);
     const int cym = cls1(wrapi(yw - 1, p.N1), p.N1, p.R1), cyp = cls1(wrapi(yw + 1, p.N1), p.N1, p.R1);
-    bool fwd_slow_yx = cy != p.R1, adj_slow_yx = cy != p.R1 || cym != p.R1 || cyp != p.R1;
+    int cxs[6];
 #pragma unroll
-    for (int i = -1; i <= 4; ++i) {
-        const bool b = cls1(wrapi(x0w + i, p.N2), p.N2, p.R2) != p.R2;
-        if (i >= 0 && i <= 3) fwd_slow_yx |= b;
-        adj_slow_yx |= b;
+    for (int i = 0; i < 6; ++i) cxs[i] = cls1(wrapi(x0w + i - 1, p.N2), p.N2, p.R2);
+    unsigned fmask = 0, amask = 0;  // cells whose F row / g row is not the interior row because of y or x
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (cy != p.R1 || cxs[i + 1] != p.R2) fmask |= 1u << i;
+        if (cy != p.R1 || cym != p.R1 || cyp != p.R1 || cxs[i] != p.R2 || cxs[i + 1] != p.R2 || cxs[i + 2] != p.R2)
+            amask |= 1u << i;
     }
 
     // plane indices stay within a few planes of [0, n0): wrap by comparison (64-bit % is ~100 instructions)
-    const int n0i = (int)p.n0, N0gi = (int)p.N0g, z0i = (int)p.z0;
     auto zoff = [&](int k) -> int64_t {
         if (p.halo == 0) {
             while (k < 0) k += n0i;
@@ -545,62 +555,62 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
     Vec4<T> cc = zero4, cn = zero4;                          // c[kf], c[kf+1]
     Vec4<T> fm = zero4, fc = zero4;                          // F[kf-2], F[kf-1]
     const bool has_z = p.has_z != 0;
-    const bool edge = edge_lo || edge_hi;
+    const bool zvar = has_z || p.R0 > 0;
     const int kf0 = has_z ? zs - 1 : zs;
+    const T* __restrict__ Ucol = p.U + col;
+    const T* __restrict__ Uecol = p.U + ecol;
+    const T* __restrict__ Ccol = p.c ? p.c + col : nullptr;
     if (has_z) {
-        um = ldg4<T>(p.U + zoff(kf0 - 1) + col);
-        up = ldg4<T>(p.U + zoff(kf0 + 1) + col);
+        um = ldg4<T>(Ucol + zoff(kf0 - 1));
+        up = ldg4<T>(Ucol + zoff(kf0 + 1));
     }
-    uc = ldg4<T>(p.U + zoff(kf0) + col);
-    if (edge) ex = ldg4<T>(p.U + zoff(kf0) + ecol);
-    if (p.c) cc = ldg4<T>(p.c + zoff(kf0) + col);
+    uc = ldg4<T>(Ucol + zoff(kf0));
+    if (edge) ex = ldg4<T>(Uecol + zoff(kf0));
+    if (Ccol) cc = ldg4<T>(Ccol + zoff(kf0));
+    const T w0 = p.w[0], w1 = p.w[1], w2 = p.w[2], w3 = p.w[3], w4 = p.w[4], w5 = p.w[5], w6 = p.w[6];
+    int czm = zvar ? zcls(kf0 - 2) : 0, cz0 = zvar ? zcls(kf0 - 1) : 0, czp = zvar ? zcls(kf0) : 0;
 
     double acc2 = 0.0;
     for (int kf = kf0; kf <= ze; ++kf) {
-        const int pb = (int)((kf - kf0) & 1);
+        const int pb = (kf - kf0) & 1;
         T* Ub = Us + pb * (FH * PITCH);
         T* Fb = Fs + pb * (FH * PITCH);
         // (a) prefetch the next plane's inputs
         if (kf < ze) {
-            if (has_z) un = ldg4<T>(p.U + zoff(kf + 2) + col);
-            if (edge) exn = ldg4<T>(p.U + zoff(kf + 1) + ecol);
-            if (p.c) cn = ldg4<T>(p.c + zoff(kf + 1) + col);
-            if (!has_z) un = ldg4<T>(p.U + zoff(kf + 1) + col);
+            const int64_t o1 = zoff(kf + 1);
+            un = ldg4<T>(Ucol + (has_z ? zoff(kf + 2) : o1));
+            if (edge) exn = ldg4<T>(Uecol + o1);
+            if (Ccol) cn = ldg4<T>(Ccol + o1);
         }
         // (b) publish own U[kf] and F[kf-1]
         *reinterpret_cast<Vec4<T>*>(Ub + soff) = uc;
         *reinterpret_cast<Vec4<T>*>(Fb + soff) = fc;
         __syncthreads();
-        // (d) F[kf] for the own column group
+        // (d) F[kf] for the own column group: interior row for all four cells, then patch boundary cells
         Vec4<T> fp = zero4;
-        const bool do_f = has_z ? true : (kf < ze);
-        if (do_f) {
+        if (has_z || kf < ze) {
             const Vec4<T> uym = edge_lo ? ex : *reinterpret_cast<const Vec4<T>*>(Ub + soff - PITCH);
             const Vec4<T> uyp = edge_hi ? ex : *reinterpret_cast<const Vec4<T>*>(Ub + soff + PITCH);
             const T ul = Ub[soff - 1], ur = Ub[soff + 4];
-            const int cz = has_z || p.R0 > 0 ? zcls(kf) : 0;
-            if (!(fwd_slow_yx || cz != p.R0)) {
-                fp.x = cc.x + p.w[0] * uc.x + p.w[1] * um.x + p.w[2] * up.x + p.w[3] * uym.x + p.w[4] * uyp.x +
-                       p.w[5] * ul + p.w[6] * uc.y;
-                fp.y = cc.y + p.w[0] * uc.y + p.w[1] * um.y + p.w[2] * up.y + p.w[3] * uym.y + p.w[4] * uyp.y +
-                       p.w[5] * uc.x + p.w[6] * uc.z;
-                fp.z = cc.z + p.w[0] * uc.z + p.w[1] * um.z + p.w[2] * up.z + p.w[3] * uym.z + p.w[4] * uyp.z +
-                       p.w[5] * uc.y + p.w[6] * uc.w;
-                fp.w = cc.w + p.w[0] * uc.w + p.w[1] * um.w + p.w[2] * up.w + p.w[3] * uym.w + p.w[4] * uyp.w +
-                       p.w[5] * uc.z + p.w[6] * ur;
-            } else {
+            fp.x = cc.x + w0 * uc.x + w1 * um.x + w2 * up.x + w3 * uym.x + w4 * uyp.x + w5 * ul + w6 * uc.y;
+            fp.y = cc.y + w0 * uc.y + w1 * um.y + w2 * up.y + w3 * uym.y + w4 * uyp.y + w5 * uc.x + w6 * uc.z;
+            fp.z = cc.z + w0 * uc.z + w1 * um.z + w2 * up.z + w3 * uym.z + w4 * uyp.z + w5 * uc.y + w6 * uc.w;
+            fp.w = cc.w + w0 * uc.w + w1 * um.w + w2 * up.w + w3 * uym.w + w4 * uyp.w + w5 * uc.z + w6 * ur;
+            const unsigned fmk = (czp != p.R0) ? 0xFu : fmask;  // czp == class of plane kf here
+            if (fmk) {
                 const T ucv[6] = {ul, uc.x, uc.y, uc.z, uc.w, ur};
                 const T umv[4] = {um.x, um.y, um.z, um.w}, upv[4] = {up.x, up.y, up.z, up.w};
                 const T uymv[4] = {uym.x, uym.y, uym.z, uym.w}, uypv[4] = {uyp.x, uyp.y, uyp.z, uyp.w};
                 const T ccv[4] = {cc.x, cc.y, cc.z, cc.w};
-                T fv[4];
+                T fv[4] = {fp.x, fp.y, fp.z, fp.w};
+                const int rbase = (czp * C1 + cy) * C2;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int cx = cls1(wrapi(x0w + i, p.N2), p.N2, p.R2);
-                    const T* row = p.table + ((cz * C1 + cy) * C2 + cx) * 7;
-                    fv[i] = ccv[i] + __ldg(row + 0) * ucv[i + 1] + __ldg(row + 1) * umv[i] + __ldg(row + 2) * upv[i] +
-                            __ldg(row + 3) * uymv[i] + __ldg(row + 4) * uypv[i] + __ldg(row + 5) * ucv[i] +
-                            __ldg(row + 6) * ucv[i + 2];
+                    if (fmk >> i & 1) {
+                        const T* row = tab + (rbase + cxs[i + 1]) * 7;
+                        fv[i] = ccv[i] + row[0] * ucv[i + 1] + row[1] * umv[i] + row[2] * upv[i] + row[3] * uymv[i] +
+                                row[4] * uypv[i] + row[5] * ucv[i] + row[6] * ucv[i + 2];
+                    }
                 }
                 fp = Vec4<T>{fv[0], fv[1], fv[2], fv[3]};
             }
@@ -616,41 +626,32 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
             const Vec4<T> fyp = *reinterpret_cast<const Vec4<T>*>(Fb + soff + PITCH);
             const T fl = Fb[soff - 1], fr = Fb[soff + 4];
             Vec4<T> g;
-            bool slow = adj_slow_yx;
-            int czm = 0, cz0 = 0, czp = 0;
-            if (has_z || p.R0 > 0) {
-                cz0 = zcls(kg);
-                czm = zcls(kg - 1);
-                czp = zcls(kg + 1);
-                slow |= cz0 != p.R0 || (has_z && (czm != p.R0 || czp != p.R0));
-            }
-            if (!slow) {
-                g.x = p.w[0] * fc.x + p.w[1] * fp.x + p.w[2] * fm.x + p.w[3] * fyp.x + p.w[4] * fym.x + p.w[5] * fc.y +
-                      p.w[6] * fl;
-                g.y = p.w[0] * fc.y + p.w[1] * fp.y + p.w[2] * fm.y + p.w[3] * fyp.y + p.w[4] * fym.y + p.w[5] * fc.z +
-                      p.w[6] * fc.x;
-                g.z = p.w[0] * fc.z + p.w[1] * fp.z + p.w[2] * fm.z + p.w[3] * fyp.z + p.w[4] * fym.z + p.w[5] * fc.w +
-                      p.w[6] * fc.y;
-                g.w = p.w[0] * fc.w + p.w[1] * fp.w + p.w[2] * fm.w + p.w[3] * fyp.w + p.w[4] * fym.w + p.w[5] * fr +
-                      p.w[6] * fc.z;
-            } else {
+            g.x = w0 * fc.x + w1 * fp.x + w2 * fm.x + w3 * fyp.x + w4 * fym.x + w5 * fc.y + w6 * fl;
+            g.y = w0 * fc.y + w1 * fp.y + w2 * fm.y + w3 * fyp.y + w4 * fym.y + w5 * fc.z + w6 * fc.x;
+            g.z = w0 * fc.z + w1 * fp.z + w2 * fm.z + w3 * fyp.z + w4 * fym.z + w5 * fc.w + w6 * fc.y;
+            g.w = w0 * fc.w + w1 * fp.w + w2 * fm.w + w3 * fyp.w + w4 * fym.w + w5 * fr + w6 * fc.z;
+            // plane classes here: czm = class(kg-1), cz0 = class(kg), czp = class(kg+1)
+            const bool zslow = cz0 != p.R0 || (has_z && (czm != p.R0 || czp != p.R0));
+            const unsigned amk = zslow ? 0xFu : amask;
+            if (amk) {
                 const T fcv[6] = {fl, fc.x, fc.y, fc.z, fc.w, fr};
                 const T fmv[4] = {fm.x, fm.y, fm.z, fm.w}, fpv[4] = {fp.x, fp.y, fp.z, fp.w};
                 const T fymv[4] = {fym.x, fym.y, fym.z, fym.w}, fypv[4] = {fyp.x, fyp.y, fyp.z, fyp.w};
-                T gv[4];
+                T gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int cx = cls1(wrapi(x0w + i, p.N2), p.N2, p.R2);
-                    const int cxm = cls1(wrapi(x0w + i - 1, p.N2), p.N2, p.R2);
-                    const int cxp = cls1(wrapi(x0w + i + 1, p.N2), p.N2, p.R2);
-                    auto tab = [&](int z, int yy, int xx, int o) -> T {
-                        return __ldg(p.table + ((z * C1 + yy) * C2 + xx) * 7 + o);
-                    };
-                    T gi = tab(cz0, cy, cx, 0) * fcv[i + 1];
-                    if (has_z) gi += tab(czp, cy, cx, 1) * fpv[i] + tab(czm, cy, cx, 2) * fmv[i];
-                    gi += tab(cz0, cyp, cx, 3) * fypv[i] + tab(cz0, cym, cx, 4) * fymv[i];
-                    gi += tab(cz0, cy, cxp, 5) * fcv[i + 2] + tab(cz0, cy, cxm, 6) * fcv[i];
-                    gv[i] = gi;
+                    if (amk >> i & 1) {
+                        const int cx = cxs[i + 1], cxm = cxs[i], cxp = cxs[i + 2];
+                        T gi = tab[((cz0 * C1 + cy) * C2 + cx) * 7 + 0] * fcv[i + 1];
+                        if (has_z)
+                            gi += tab[((czp * C1 + cy) * C2 + cx) * 7 + 1] * fpv[i] +
+                                  tab[((czm * C1 + cy) * C2 + cx) * 7 + 2] * fmv[i];
+                        gi += tab[((cz0 * C1 + cyp) * C2 + cx) * 7 + 3] * fypv[i] +
+                              tab[((cz0 * C1 + cym) * C2 + cx) * 7 + 4] * fymv[i];
+                        gi += tab[((cz0 * C1 + cy) * C2 + cxp) * 7 + 5] * fcv[i + 2] +
+                              tab[((cz0 * C1 + cy) * C2 + cxm) * 7 + 6] * fcv[i];
+                        gv[i] = gi;
+                    }
                 }
                 g = Vec4<T>{gv[0], gv[1], gv[2], gv[3]};
             }
@@ -672,6 +673,11 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
         }
         ex = exn;
         cc = cn;
+        if (zvar) {
+            czm = cz0;
+            cz0 = czp;
+            czp = zcls(kf + 1);
+        }
     }
     const double sum = block_sum(acc2, red);
     if (tid == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sum;
@@ -835,7 +841,7 @@ static int launch_star_cfg(const StarParams<T>& sp, dim3 grid, bool vec, cudaStr
 template <typename T, int TY, int TX>
 static int launch_star_v3(const StarV3Params<T>& sp, dim3 grid, cudaStream_t st) {
     constexpr int NT = (TX / 4 + 2) * (TY + 2);
-    const size_t smem = (size_t)4 * (TY + 2) * ((TX / 4 + 2) * 4 + 8) * sizeof(T);
+    const size_t smem = ((size_t)4 * (TY + 2) * ((TX / 4 + 2) * 4 + 8) + 512) * sizeof(T);
     static bool attr_set = false;
     if (!attr_set) {
         ODIL_CUDA(cudaFuncSetAttribute(k_star_v3<T, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -23,7 +23,7 @@ EXPORTS = [
     "odil_b200_stencil_adjoint", "odil_b200_stencil_fused", "odil_b200_stencil_plan_kind",
     "odil_b200_stencil_plan_tune", "odil_b200_sum_squares", "odil_b200_dot", "odil_b200_mg_interp_add",
     "odil_b200_mg_interp_adjoint", "odil_b200_mg_restrict", "odil_b200_adam_step", "odil_b200_gd_step",
-    "odil_b200_axpby",
+    "odil_b200_axpby", "odil_b200_multi_dot", "odil_b200_multi_axpy",
 ]
 
 
@@ -101,6 +101,8 @@ def load(build_if_missing=False):
                                         dbl, dbl, vp]
     lib.odil_b200_gd_step.argtypes = [ctypes.c_int, P(vp), P(vp), P(i64), ctypes.c_int, dbl, vp]
     lib.odil_b200_axpby.argtypes = [i64, ctypes.c_int, dbl, vp, dbl, vp, vp]
+    lib.odil_b200_multi_dot.argtypes = [vp, i64, ctypes.c_int, vp, i64, ctypes.c_int, vp, vp]
+    lib.odil_b200_multi_axpy.argtypes = [vp, i64, ctypes.c_int, vp, dbl, vp, vp, i64, ctypes.c_int, vp]
     for name in EXPORTS:
         if name not in ("odil_b200_last_error", "odil_b200_launch_count", "odil_b200_version"):
             getattr(lib, name).restype = ctypes.c_int
@@ -288,3 +290,17 @@ def gd_step(x, g, lr):
 def axpby(a, x, b, y):
     load()
     _check(_lib.odil_b200_axpby(x.numel(), dtype_code(x.dtype), float(a), _ptr(x), float(b), _ptr(y), _stream()))
+
+
+def multi_dot(V, k, g, out):
+    """out[r] = <V[r], g> for the first k rows of the row-major matrix V (device doubles)."""
+    load()
+    _check(_lib.odil_b200_multi_dot(_ptr(V), V.stride(0), int(k), _ptr(g), g.numel(), dtype_code(g.dtype), _ptr(out),
+                                    _stream()))
+
+
+def multi_axpy(V, k, coef, a0, g, d):
+    """d = a0*g + sum_r coef[r]*V[r]  (coef: device float64 tensor with k entries)."""
+    load()
+    _check(_lib.odil_b200_multi_axpy(_ptr(V), V.stride(0), int(k), _ptr(coef), float(a0), _ptr(g), _ptr(d), d.numel(),
+                                     dtype_code(d.dtype), _stream()))

@@ -5,8 +5,9 @@ an object with `.run(x0, loss_grad, epochs, callback, epoch_start, lr, **kw) -> 
   adam / adamn   device-resident Adam: one multi-tensor CUDA launch per epoch
                  (odil_b200_adam_step; reference AdamNativeOptimizer, optimizer.py:280-341)
   gd             device-resident gradient descent (odil_b200_gd_step; optimizer.py:256-277)
-  lbfgsb / lbfgs SciPy L-BFGS-B driving the device loss/gradient, exactly the reference's arrangement
-                 (optimizer.py:29-117): the flat fp64 unknown vector lives on the host.
+  lbfgsb / lbfgs device-resident L-BFGS (odil_b200/lbfgs.py: compact-form two-pass update + More-Thuente line
+                 search following L-BFGS-B 3.0's control flow); `lbfgsb_scipy` (or ODIL_LBFGS=scipy) is the
+                 reference's own arrangement, SciPy fmin_l_bfgs_b on a host fp64 vector (optimizer.py:29-117).
   adam_tf, tfp lbfgs: TensorFlow-only wrappers of the reference, not provided.
 """
 from argparse import Namespace
@@ -143,8 +144,61 @@ class LbfgsbOptimizer(Optimizer):
         return to_arrays(x), optinfo
 
 
+class LbfgsDeviceOptimizer(Optimizer):
+    """
+    `lbfgsb` with the vector algebra in HBM (odil_b200/lbfgs.py): same arguments and stopping rules as
+    LbfgsbOptimizer / scipy.optimize.fmin_l_bfgs_b for unconstrained problems, but the fp64 unknown
+    vector and the 2m history vectors never leave the device.
+    """
+
+    def __init__(self, pgtol=1e-16, m=50, maxls=50, factr=0, dtype=None, mod=None, **kwargs):
+        super().__init__(name="lbfgsb", displayname="L-BFGS-B (device)", dtype=dtype)
+        self.mod = mod
+        self.pgtol, self.m, self.maxls, self.factr = pgtol, m, maxls, factr
+
+    def run(self, x0, loss_grad, epochs=None, callback=None, epoch_start=0, **kwargs):
+        from . import lbfgs
+
+        self.epoch = epoch_start
+        tdtype, device = x0[0].dtype, x0[0].device
+        shapes = [tuple(a.shape) for a in x0]
+        sizes = [int(np.prod(s)) for s in shapes]
+        bounds = np.cumsum([0] + sizes)
+
+        def to_arrays(flat):
+            return [flat[bounds[i]:bounds[i + 1]].reshape(shapes[i]).to(tdtype).contiguous()
+                    for i in range(len(sizes))]
+
+        def func(flat):
+            self.evals += 1
+            loss, grads, pinfo = loss_grad(to_arrays(flat))
+            self.pinfo = pinfo
+            g = torch.cat([a.reshape(-1).to(torch.float64) for a in grads])
+            return float(loss), g
+
+        def on_iteration(flat):
+            self.epoch += 1
+            if callback:
+                callback(to_arrays(flat), self.epoch, self.pinfo)
+
+        flat0 = torch.cat([a.reshape(-1).to(torch.float64) for a in x0]).to(device)
+        x, f, info = lbfgs.minimize(func, flat0, m=self.m, maxiter=epochs, maxls=self.maxls, pgtol=self.pgtol,
+                                    factr=self.factr, callback=on_iteration)
+        optinfo = Namespace(warnflag=info["warnflag"], task=info["task"], evals=info["funcalls"], epochs=info["nit"])
+        if optinfo.warnflag not in [0, 1] or optinfo.epochs < epochs:
+            raise EarlyStopError(", ".join("{:}={:}".format(k, info.get(k, ""))
+                                           for k in ["warnflag", "task", "funcalls", "nit"]), optinfo)
+        return to_arrays(x), optinfo
+
+
 def make_optimizer(name, dtype=None, mod=None, **kwargs):
     if name in ("lbfgsb", "lbfgs"):
+        import os
+
+        if os.environ.get("ODIL_LBFGS", "device") == "scipy":
+            return LbfgsbOptimizer(dtype=dtype, mod=mod, **kwargs)
+        return LbfgsDeviceOptimizer(dtype=dtype, mod=mod, **kwargs)
+    if name == "lbfgsb_scipy":
         return LbfgsbOptimizer(dtype=dtype, mod=mod, **kwargs)
     if name in ("adam", "adamn"):
         return AdamNativeOptimizer(dtype=dtype, mod=mod, **kwargs)

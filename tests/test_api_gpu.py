@@ -194,8 +194,8 @@ def test_mg_interp_linear(method, ndim, loc4, dtype):
     func = lambda xx: sum(np.asarray(x) * np.sqrt(i + 1) for i, x in enumerate(xx))
     xx = domain.points(loc=loc)
     xxh = domainh.points(loc=loc)
-    if ndim == 1:
-        xx, xxh = [xx], [xxh]
+    if not isinstance(xx, tuple):
+        xx, xxh = (xx,), (xxh,)
     u, uh = func(xx), func(xxh)
     ui = odil.core.interp_to_finer(uh.astype(dtype), loc=loc, mod=domain.mod, method=method)
     assert np.max(np.abs(np.asarray(ui) - u)) <= np.finfo(dtype).eps * 100
@@ -221,8 +221,8 @@ def test_mg_restrict_linear_with_jumps(ndim, loc4, dtype):
 
     xx = domain.points(loc=loc)
     xxh = domainh.points(loc=loc)
-    if ndim == 1:
-        xx, xxh = [xx], [xxh]
+    if not isinstance(xx, tuple):
+        xx, xxh = (xx,), (xxh,)
     u, uh = func(xx).astype(dtype), func(xxh)
     uhr = odil.restrict_to_coarser(u, loc=loc, mod=domain.mod, method="conv")
     assert np.max(np.abs(np.asarray(uhr) - uh)) <= np.finfo(dtype).eps * 100 * 30

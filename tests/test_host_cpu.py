@@ -234,3 +234,37 @@ def test_engine_refuses_cpu():
     problem, state = ops.make_poisson((8, 8))
     with pytest.raises(odil.native.NativeError):
         problem.eval_loss_grad(state)
+
+
+def test_lbfgs_control_flow_matches_scipy(monkeypatch):
+    """The device L-BFGS driver (compact-form direction + dcsrch transcription) makes the same step-length
+    decisions as scipy.optimize.fmin_l_bfgs_b.  The four vector kernels are replaced by torch-CPU stand-ins
+    here; the kernels themselves are checked on the GPU (tests/test_kernels_gpu.py)."""
+    from scipy import optimize
+
+    from odil_b200 import lbfgs, native
+
+    monkeypatch.setattr(native, "multi_dot", lambda V, k, g, out: out.__setitem__(slice(0, k), V[:k] @ g))
+    monkeypatch.setattr(native, "multi_axpy", lambda V, k, coef, a0, g, d: d.copy_(a0 * g + coef[:k] @ V[:k]))
+    monkeypatch.setattr(native, "dot", lambda a, b, out: out.__setitem__(0, torch.dot(a, b)))
+    monkeypatch.setattr(native, "axpby", lambda a, x, b, y: y.copy_(a * x + (b * y if b != 0 else 0)))
+    rng = np.random.default_rng(0)
+    n = 40
+    A = rng.standard_normal((n, n))
+    A = A @ A.T + np.eye(n) * 0.1
+    b = rng.standard_normal(n)
+
+    def fnp(x):
+        r = A @ x - b
+        return 0.5 * r @ r + 0.1 * np.sum(x ** 4), A.T @ r + 0.4 * x ** 3
+
+    for m, iters in [(7, 60), (50, 40)]:
+        ref = []
+        _, _, info = optimize.fmin_l_bfgs_b(fnp, np.zeros(n), maxiter=iters, pgtol=1e-16, m=m, maxls=50, factr=0,
+                                            callback=lambda x: ref.append(fnp(x)[0]))
+        mine = []
+        x, f, inf = lbfgs.minimize(lambda x: (float(fnp(x.numpy())[0]), torch.from_numpy(fnp(x.numpy())[1])),
+                                   torch.zeros(n, dtype=torch.float64), m=m, maxiter=iters, maxls=50, pgtol=1e-16,
+                                   factr=0, callback=lambda x: mine.append(fnp(x.numpy())[0]))
+        assert inf["nit"] == info["nit"] and inf["funcalls"] == info["funcalls"]
+        assert np.max(np.abs(np.array(mine) / np.array(ref) - 1)) < 1e-7
