@@ -569,19 +569,33 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
     if (Ccol) cc = ldg4<T>(Ccol + zoff(kf0));
     const T w0 = p.w[0], w1 = p.w[1], w2 = p.w[2], w3 = p.w[3], w4 = p.w[4], w5 = p.w[5], w6 = p.w[6];
     int czm = zvar ? zcls(kf0 - 2) : 0, cz0 = zvar ? zcls(kf0 - 1) : 0, czp = zvar ? zcls(kf0) : 0;
+    // Running (wrapped) plane counters for the prefetches: k1 = plane kf+1, k2 = plane kf+2, zg1 = global kf+1.
+    const int wrapn = p.halo == 0 ? n0i : 0x7fffffff;
+    int k1 = kf0 + 1, k2 = kf0 + 2, zg1 = z0i + kf0 + 1;
+    if (p.halo == 0) {
+        while (k1 < 0) k1 += n0i;
+        while (k1 >= n0i) k1 -= n0i;
+        while (k2 < 0) k2 += n0i;
+        while (k2 >= n0i) k2 -= n0i;
+    }
+    while (zg1 < 0) zg1 += N0gi;
+    while (zg1 >= N0gi) zg1 -= N0gi;
 
     double acc2 = 0.0;
+    int pboff = 0;
     for (int kf = kf0; kf <= ze; ++kf) {
-        const int pb = (kf - kf0) & 1;
-        T* Ub = Us + pb * (FH * PITCH);
-        T* Fb = Fs + pb * (FH * PITCH);
+        T* Ub = Us + pboff;
+        T* Fb = Fs + pboff;
+        pboff = FH * PITCH - pboff;  // toggle between the two buffers
         // (a) prefetch the next plane's inputs
         if (kf < ze) {
-            const int64_t o1 = zoff(kf + 1);
-            un = ldg4<T>(Ucol + (has_z ? zoff(kf + 2) : o1));
+            const int64_t o1 = (int64_t)k1 * plane;
+            un = ldg4<T>(Ucol + (has_z ? (int64_t)k2 * plane : o1));
             if (edge) exn = ldg4<T>(Uecol + o1);
             if (Ccol) cn = ldg4<T>(Ccol + o1);
         }
+        k1 = k1 + 1 == wrapn ? 0 : k1 + 1;
+        k2 = k2 + 1 == wrapn ? 0 : k2 + 1;
         // (b) publish own U[kf] and F[kf-1]
         *reinterpret_cast<Vec4<T>*>(Ub + soff) = uc;
         *reinterpret_cast<Vec4<T>*>(Fb + soff) = fc;
@@ -676,7 +690,8 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
         if (zvar) {
             czm = cz0;
             cz0 = czp;
-            czp = zcls(kf + 1);
+            czp = cls1(zg1, N0gi, p.R0);
+            zg1 = zg1 + 1 == N0gi ? 0 : zg1 + 1;
         }
     }
     const double sum = block_sum(acc2, red);
