@@ -16,6 +16,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace odil {
@@ -88,6 +90,8 @@ struct odil_b200_plan {
     int rmax0;     // max |off| along axis 0
     void* star_table;  // device, typed [ncls][7] (c, zm, zp, ym, yp, xm, xp) when kind == 1
     int star_has_z;    // some class row couples axis 0 (even if the interior row does not)
+    int wrap_free;     // no coefficient multiplies a neighbour across a periodic boundary (TMA zero fill is exact)
+    int use_tma;       // 1: TMA-fed kernel when eligible
     int use_v3;        // 1: column-group kernel (default when N2 % 4 == 0), 0: v2 tile kernel + shell
 };
 
@@ -480,36 +484,108 @@ __device__ __forceinline__ Vec4<double> ldg4<double>(const double* p) {
     return Vec4<double>{a.x, a.y, b.x, b.y};
 }
 
-template <typename T, int TY, int TX>
-__global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Params<T> p) {
+// Interior rows: F for four consecutive cells of one row, and the adjoint gather of g.
+template <typename T>
+__device__ __forceinline__ Vec4<T> star_fwd(const Vec4<T>& cc, const Vec4<T>& uc, const Vec4<T>& um, const Vec4<T>& up,
+                                            const Vec4<T>& uym, const Vec4<T>& uyp, T ul, T ur, const T* w) {
+    Vec4<T> f;
+    f.x = cc.x + w[0] * uc.x + w[1] * um.x + w[2] * up.x + w[3] * uym.x + w[4] * uyp.x + w[5] * ul + w[6] * uc.y;
+    f.y = cc.y + w[0] * uc.y + w[1] * um.y + w[2] * up.y + w[3] * uym.y + w[4] * uyp.y + w[5] * uc.x + w[6] * uc.z;
+    f.z = cc.z + w[0] * uc.z + w[1] * um.z + w[2] * up.z + w[3] * uym.z + w[4] * uyp.z + w[5] * uc.y + w[6] * uc.w;
+    f.w = cc.w + w[0] * uc.w + w[1] * um.w + w[2] * up.w + w[3] * uym.w + w[4] * uyp.w + w[5] * uc.z + w[6] * ur;
+    return f;
+}
+
+template <typename T>
+__device__ __forceinline__ Vec4<T> star_adj(const Vec4<T>& fc, const Vec4<T>& fp, const Vec4<T>& fm, const Vec4<T>& fym,
+                                            const Vec4<T>& fyp, T fl, T fr, const T* w) {
+    Vec4<T> g;
+    g.x = w[0] * fc.x + w[1] * fp.x + w[2] * fm.x + w[3] * fyp.x + w[4] * fym.x + w[5] * fc.y + w[6] * fl;
+    g.y = w[0] * fc.y + w[1] * fp.y + w[2] * fm.y + w[3] * fyp.y + w[4] * fym.y + w[5] * fc.z + w[6] * fc.x;
+    g.z = w[0] * fc.z + w[1] * fp.z + w[2] * fm.z + w[3] * fyp.z + w[4] * fym.z + w[5] * fc.w + w[6] * fc.y;
+    g.w = w[0] * fc.w + w[1] * fp.w + w[2] * fm.w + w[3] * fyp.w + w[4] * fym.w + w[5] * fr + w[6] * fc.z;
+    return g;
+}
+
+// Boundary rows (rare): recompute the flagged cells with their own coefficient row.  `cxp` packs the
+// x-classes of cells x0-1 .. x0+4 (5 bits each).  Kept out of line so that the hot loop stays lean.
+template <typename T>
+__device__ __noinline__ void star_patch_fwd(Vec4<T>& f, unsigned mask, const T* __restrict__ tab, int rbase,
+                                            unsigned cxp, Vec4<T> cc, Vec4<T> uc, Vec4<T> um, Vec4<T> up,
+                                            Vec4<T> uym, Vec4<T> uyp, T ul, T ur) {
+    const T ucv[6] = {ul, uc.x, uc.y, uc.z, uc.w, ur};
+    const T umv[4] = {um.x, um.y, um.z, um.w}, upv[4] = {up.x, up.y, up.z, up.w};
+    const T uymv[4] = {uym.x, uym.y, uym.z, uym.w}, uypv[4] = {uyp.x, uyp.y, uyp.z, uyp.w};
+    const T ccv[4] = {cc.x, cc.y, cc.z, cc.w};
+    T fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (mask >> i & 1) {
+            const T* row = tab + (rbase + (int)((cxp >> (5 * (i + 1))) & 31u)) * 7;
+            fv[i] = ccv[i] + row[0] * ucv[i + 1] + row[1] * umv[i] + row[2] * upv[i] + row[3] * uymv[i] +
+                    row[4] * uypv[i] + row[5] * ucv[i] + row[6] * ucv[i + 2];
+        }
+    }
+    f = Vec4<T>{fv[0], fv[1], fv[2], fv[3]};
+}
+
+template <typename T>
+__device__ __noinline__ void star_patch_adj(Vec4<T>& g, unsigned mask, const T* __restrict__ tab, int C1, int C2,
+                                            int czm, int cz0, int czp, int cym, int cy, int cyp, unsigned cxp,
+                                            bool has_z, Vec4<T> fc, Vec4<T> fp, Vec4<T> fm, Vec4<T> fym, Vec4<T> fyp,
+                                            T fl, T fr) {
+    const T fcv[6] = {fl, fc.x, fc.y, fc.z, fc.w, fr};
+    const T fmv[4] = {fm.x, fm.y, fm.z, fm.w}, fpv[4] = {fp.x, fp.y, fp.z, fp.w};
+    const T fymv[4] = {fym.x, fym.y, fym.z, fym.w}, fypv[4] = {fyp.x, fyp.y, fyp.z, fyp.w};
+    T gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (mask >> i & 1) {
+            const int cxm = (cxp >> (5 * i)) & 31u, cx = (cxp >> (5 * (i + 1))) & 31u, cxq = (cxp >> (5 * (i + 2))) & 31u;
+            T gi = tab[((cz0 * C1 + cy) * C2 + cx) * 7 + 0] * fcv[i + 1];
+            if (has_z)
+                gi += tab[((czp * C1 + cy) * C2 + cx) * 7 + 1] * fpv[i] + tab[((czm * C1 + cy) * C2 + cx) * 7 + 2] * fmv[i];
+            gi += tab[((cz0 * C1 + cyp) * C2 + cx) * 7 + 3] * fypv[i] + tab[((cz0 * C1 + cym) * C2 + cx) * 7 + 4] * fymv[i];
+            gi += tab[((cz0 * C1 + cy) * C2 + cxq) * 7 + 5] * fcv[i + 2] + tab[((cz0 * C1 + cy) * C2 + cxm) * 7 + 6] * fcv[i];
+            gv[i] = gi;
+        }
+    }
+    g = Vec4<T>{gv[0], gv[1], gv[2], gv[3]};
+}
+
+// Threads: (TX/4 + 2) column groups x (TY + 4) rows.  Row ry holds y = ty0 - 2 + ry.
+//   rows 0 and TY+3      : loaders (only publish their U plane row: the y-neighbours of the F ring)
+//   rows 1 .. TY+2       : compute F for their column group (tile + 1-cell ring)
+//   rows 2 .. TY+1       : additionally compute g and the loss partial (the tile itself)
+// Each thread keeps U[k-1], U[k], U[k+1] (+ prefetched U[k+2]) and F[k-2], F[k-1], F[k] of its column
+// group in registers; in-plane neighbours go through double-buffered shared-memory planes.
+template <typename T, int TY, int TX, bool HASZ>
+__global__ void __launch_bounds__((TX / 4 + 2) * (TY + 4)) k_star_v3(StarV3Params<T> p) {
     constexpr int GXN = TX / 4 + 2;
-    constexpr int FH = TY + 2;
+    constexpr int NR = TY + 4;
     constexpr int PITCH = GXN * 4 + 8;
+    constexpr int PLN = NR * PITCH;
     constexpr int kTabSmem = 512;  // table entries kept in shared memory (27 classes x 7 = 189 for r = 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* Us = reinterpret_cast<T*>(smem_raw);  // [2][FH][PITCH]
-    T* Fs = Us + 2 * FH * PITCH;             // [2][FH][PITCH]
-    T* tab_s = Fs + 2 * FH * PITCH;          // [kTabSmem]
+    T* Us = reinterpret_cast<T*>(smem_raw);  // [2][NR][PITCH]
+    T* Fs = Us + 2 * PLN;                    // [2][NR][PITCH]
+    T* tab_s = Fs + 2 * PLN;                 // [kTabSmem]
     __shared__ double red[32];
 
     const int tid = threadIdx.x;
-    const int fy = tid / GXN, gx = tid - fy * GXN;
+    const int ry = tid / GXN, gx = tid - ry * GXN;
     const int tx0 = blockIdx.x * TX, ty0 = blockIdx.y * TY;
-    const int y = ty0 - 1 + fy, x0 = tx0 - 4 + 4 * gx;
+    const int y = ty0 - 2 + ry, x0 = tx0 - 4 + 4 * gx;
     const int yw = wrapi(y, p.N1), x0w = wrapi(x0, p.N2);
     const int n0i = (int)p.n0, N0gi = (int)p.N0g, z0i = (int)p.z0;
     const int zs = blockIdx.z * p.zchunk;
     const int ze = min(zs + p.zchunk, n0i);
     const int64_t plane = (int64_t)p.N1 * p.N2;
     const int col = yw * p.N2 + x0w;
-    const bool interior = fy >= 1 && fy <= TY && gx >= 1 && gx <= GXN - 2 && y < p.N1 && x0 < p.N2;
-    // in-plane neighbour row needed from global memory by the two edge rows of the F region
-    const bool edge_lo = fy == 0, edge_hi = fy == FH - 1;
-    const bool edge = edge_lo || edge_hi;
-    const int ecol = (edge_lo ? wrapi(y - 1, p.N1) : wrapi(y + 1, p.N1)) * p.N2 + x0w;
-    const int soff = fy * PITCH + 4 + 4 * gx;
+    const int soff = ry * PITCH + 4 + 4 * gx;
+    const bool frow = ry >= 1 && ry <= TY + 2;
+    const bool grow = ry >= 2 && ry <= TY + 1 && gx >= 1 && gx <= GXN - 2 && y < p.N1 && x0 < p.N2;
 
-    // Region classes of this thread's row and of the cells x0-1 .. x0+4 (computed once; columns are fixed).
     const int C1 = 2 * p.R1 + 1, C2 = 2 * p.R2 + 1;
     auto cls1 = [](int i, int n, int r) -> int {
         if (i < r) return i;
@@ -521,28 +597,32 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
     if (tab_in_smem)
         for (int i = tid; i < ncls * 7; i += blockDim.x) tab_s[i] = p.table[i];
     const T* __restrict__ tab = tab_in_smem ? tab_s : p.table;
+
+    // classes of the row and of the cells x0-1 .. x0+4 (packed 5 bits each); masks of non-interior cells
     const int cy = cls1(yw, p.N1, p.R1);
     const int cym = cls1(wrapi(yw - 1, p.N1), p.N1, p.R1), cyp = cls1(wrapi(yw + 1, p.N1), p.N1, p.R1);
-    int cxs[6];
+    unsigned cxp = 0, fmask = 0, amask = 0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) cxs[i] = cls1(wrapi(x0w + i - 1, p.N2), p.N2, p.R2);
-    unsigned fmask = 0, amask = 0;  // cells whose F row / g row is not the interior row because of y or x
+    for (int i = 0; i < 6; ++i) cxp |= (unsigned)cls1(wrapi(x0w + i - 1, p.N2), p.N2, p.R2) << (5 * i);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        if (cy != p.R1 || cxs[i + 1] != p.R2) fmask |= 1u << i;
-        if (cy != p.R1 || cym != p.R1 || cyp != p.R1 || cxs[i] != p.R2 || cxs[i + 1] != p.R2 || cxs[i + 2] != p.R2)
-            amask |= 1u << i;
+        const int a = (cxp >> (5 * i)) & 31u, b = (cxp >> (5 * (i + 1))) & 31u, c = (cxp >> (5 * (i + 2))) & 31u;
+        if (b != p.R2) fmask |= 1u << i;
+        if (a != p.R2 || b != p.R2 || c != p.R2) amask |= 1u << i;
     }
+    if (cy != p.R1) fmask = 0xFu;
+    if (cy != p.R1 || cym != p.R1 || cyp != p.R1) amask = 0xFu;
+    if (!frow) fmask = 0;
+    if (!grow) amask = 0;
 
-    // plane indices stay within a few planes of [0, n0): wrap by comparison (64-bit % is ~100 instructions)
-    auto zoff = [&](int k) -> int64_t {
+    auto zwrap = [&](int k) -> int {
         if (p.halo == 0) {
             while (k < 0) k += n0i;
             while (k >= n0i) k -= n0i;
         }
-        return (int64_t)k * plane;
+        return k;
     };
-    auto zcls = [&](int k) -> int {  // class of local plane k (global index wraps periodically)
+    auto zcls = [&](int k) -> int {
         int zg = z0i + k;
         while (zg < 0) zg += N0gi;
         while (zg >= N0gi) zg -= N0gi;
@@ -550,142 +630,91 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
     };
 
     const Vec4<T> zero4{T(0), T(0), T(0), T(0)};
-    Vec4<T> um = zero4, uc = zero4, up = zero4, un = zero4;  // U[kf-1], U[kf], U[kf+1], prefetch U[kf+2]
-    Vec4<T> ex = zero4, exn = zero4;                         // edge rows: U[kf] / U[kf+1] at the row outside
-    Vec4<T> cc = zero4, cn = zero4;                          // c[kf], c[kf+1]
-    Vec4<T> fm = zero4, fc = zero4;                          // F[kf-2], F[kf-1]
-    const bool has_z = p.has_z != 0;
-    const bool zvar = has_z || p.R0 > 0;
-    const int kf0 = has_z ? zs - 1 : zs;
+    Vec4<T> um = zero4, uc, up = zero4, un = zero4, cc = zero4, cn = zero4, fm = zero4, fc = zero4, fp = zero4;
+    const bool zvar = HASZ || p.R0 > 0;
+    const int kf0 = HASZ ? zs - 1 : zs;
     const T* __restrict__ Ucol = p.U + col;
-    const T* __restrict__ Uecol = p.U + ecol;
-    const T* __restrict__ Ccol = p.c ? p.c + col : nullptr;
-    if (has_z) {
-        um = ldg4<T>(Ucol + zoff(kf0 - 1));
-        up = ldg4<T>(Ucol + zoff(kf0 + 1));
+    const T* __restrict__ Ccol = (p.c && frow) ? p.c + col : nullptr;
+    if (HASZ) {
+        um = ldg4<T>(Ucol + (int64_t)zwrap(kf0 - 1) * plane);
+        up = ldg4<T>(Ucol + (int64_t)zwrap(kf0 + 1) * plane);
     }
-    uc = ldg4<T>(Ucol + zoff(kf0));
-    if (edge) ex = ldg4<T>(Uecol + zoff(kf0));
-    if (Ccol) cc = ldg4<T>(Ccol + zoff(kf0));
-    const T w0 = p.w[0], w1 = p.w[1], w2 = p.w[2], w3 = p.w[3], w4 = p.w[4], w5 = p.w[5], w6 = p.w[6];
+    uc = ldg4<T>(Ucol + (int64_t)zwrap(kf0) * plane);
+    if (Ccol) cc = ldg4<T>(Ccol + (int64_t)zwrap(kf0) * plane);
+    T w[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) w[i] = p.w[i];
     int czm = zvar ? zcls(kf0 - 2) : 0, cz0 = zvar ? zcls(kf0 - 1) : 0, czp = zvar ? zcls(kf0) : 0;
-    // Running (wrapped) plane counters for the prefetches: k1 = plane kf+1, k2 = plane kf+2, zg1 = global kf+1.
+    // running (wrapped) plane counters for the prefetches: k1 = plane kf+1, k2 = plane kf+2, zg1 = global kf+1
     const int wrapn = p.halo == 0 ? n0i : 0x7fffffff;
-    int k1 = kf0 + 1, k2 = kf0 + 2, zg1 = z0i + kf0 + 1;
-    if (p.halo == 0) {
-        while (k1 < 0) k1 += n0i;
-        while (k1 >= n0i) k1 -= n0i;
-        while (k2 < 0) k2 += n0i;
-        while (k2 >= n0i) k2 -= n0i;
-    }
+    int k1 = zwrap(kf0 + 1), k2 = zwrap(kf0 + 2), zg1 = z0i + kf0 + 1;
     while (zg1 < 0) zg1 += N0gi;
     while (zg1 >= N0gi) zg1 -= N0gi;
+    T* Gcol = p.G + col;
+    T* Fcol = p.Fout ? p.Fout + col : nullptr;
 
+    T accf = T(0);
     double acc2 = 0.0;
     int pboff = 0;
+#pragma unroll 2
     for (int kf = kf0; kf <= ze; ++kf) {
-        T* Ub = Us + pboff;
-        T* Fb = Fs + pboff;
-        pboff = FH * PITCH - pboff;  // toggle between the two buffers
-        // (a) prefetch the next plane's inputs
+        T* Ub = Us + pboff + soff;
+        T* Fb = Fs + pboff + soff;
+        pboff = PLN - pboff;
+        // (a) prefetch the next plane's inputs (consumed one iteration later)
         if (kf < ze) {
-            const int64_t o1 = (int64_t)k1 * plane;
-            un = ldg4<T>(Ucol + (has_z ? (int64_t)k2 * plane : o1));
-            if (edge) exn = ldg4<T>(Uecol + o1);
-            if (Ccol) cn = ldg4<T>(Ccol + o1);
+            un = ldg4<T>(Ucol + (int64_t)(HASZ ? k2 : k1) * plane);
+            if (Ccol) cn = ldg4<T>(Ccol + (int64_t)k1 * plane);
         }
         k1 = k1 + 1 == wrapn ? 0 : k1 + 1;
         k2 = k2 + 1 == wrapn ? 0 : k2 + 1;
         // (b) publish own U[kf] and F[kf-1]
-        *reinterpret_cast<Vec4<T>*>(Ub + soff) = uc;
-        *reinterpret_cast<Vec4<T>*>(Fb + soff) = fc;
+        *reinterpret_cast<Vec4<T>*>(Ub) = uc;
+        *reinterpret_cast<Vec4<T>*>(Fb) = fc;
         __syncthreads();
-        // (d) F[kf] for the own column group: interior row for all four cells, then patch boundary cells
-        Vec4<T> fp = zero4;
-        if (has_z || kf < ze) {
-            const Vec4<T> uym = edge_lo ? ex : *reinterpret_cast<const Vec4<T>*>(Ub + soff - PITCH);
-            const Vec4<T> uyp = edge_hi ? ex : *reinterpret_cast<const Vec4<T>*>(Ub + soff + PITCH);
-            const T ul = Ub[soff - 1], ur = Ub[soff + 4];
-            fp.x = cc.x + w0 * uc.x + w1 * um.x + w2 * up.x + w3 * uym.x + w4 * uyp.x + w5 * ul + w6 * uc.y;
-            fp.y = cc.y + w0 * uc.y + w1 * um.y + w2 * up.y + w3 * uym.y + w4 * uyp.y + w5 * uc.x + w6 * uc.z;
-            fp.z = cc.z + w0 * uc.z + w1 * um.z + w2 * up.z + w3 * uym.z + w4 * uyp.z + w5 * uc.y + w6 * uc.w;
-            fp.w = cc.w + w0 * uc.w + w1 * um.w + w2 * up.w + w3 * uym.w + w4 * uyp.w + w5 * uc.z + w6 * ur;
+        // (d) F[kf]
+        fp = zero4;
+        if (frow && (HASZ || kf < ze)) {
+            const Vec4<T> uym = *reinterpret_cast<const Vec4<T>*>(Ub - PITCH);
+            const Vec4<T> uyp = *reinterpret_cast<const Vec4<T>*>(Ub + PITCH);
+            const T ul = Ub[-1], ur = Ub[4];
+            fp = star_fwd<T>(cc, uc, um, up, uym, uyp, ul, ur, w);
             const unsigned fmk = (czp != p.R0) ? 0xFu : fmask;  // czp == class of plane kf here
-            if (fmk) {
-                const T ucv[6] = {ul, uc.x, uc.y, uc.z, uc.w, ur};
-                const T umv[4] = {um.x, um.y, um.z, um.w}, upv[4] = {up.x, up.y, up.z, up.w};
-                const T uymv[4] = {uym.x, uym.y, uym.z, uym.w}, uypv[4] = {uyp.x, uyp.y, uyp.z, uyp.w};
-                const T ccv[4] = {cc.x, cc.y, cc.z, cc.w};
-                T fv[4] = {fp.x, fp.y, fp.z, fp.w};
-                const int rbase = (czp * C1 + cy) * C2;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (fmk >> i & 1) {
-                        const T* row = tab + (rbase + cxs[i + 1]) * 7;
-                        fv[i] = ccv[i] + row[0] * ucv[i + 1] + row[1] * umv[i] + row[2] * upv[i] + row[3] * uymv[i] +
-                                row[4] * uypv[i] + row[5] * ucv[i] + row[6] * ucv[i + 2];
-                    }
-                }
-                fp = Vec4<T>{fv[0], fv[1], fv[2], fv[3]};
-            }
-            if (interior && kf >= zs && kf < ze) {
-                acc2 += (double)(fp.x * fp.x + fp.y * fp.y + fp.z * fp.z + fp.w * fp.w);
-                if (p.Fout) *reinterpret_cast<Vec4<T>*>(p.Fout + (int64_t)kf * plane + col) = fp;
+            if (fmk) star_patch_fwd<T>(fp, fmk, tab, (czp * C1 + cy) * C2, cxp, cc, uc, um, up, uym, uyp, ul, ur);
+            if (grow && kf >= zs && kf < ze) {
+                accf += fp.x * fp.x + fp.y * fp.y + fp.z * fp.z + fp.w * fp.w;
+                if (Fcol) *reinterpret_cast<Vec4<T>*>(Fcol + (int64_t)kf * plane) = fp;
             }
         }
         // (e) g[kf-1] from F[kf-2], F[kf-1], F[kf] (own column) and the in-plane neighbours of F[kf-1]
         const int kg = kf - 1;
-        if (interior && kg >= zs && kg < ze) {
-            const Vec4<T> fym = *reinterpret_cast<const Vec4<T>*>(Fb + soff - PITCH);
-            const Vec4<T> fyp = *reinterpret_cast<const Vec4<T>*>(Fb + soff + PITCH);
-            const T fl = Fb[soff - 1], fr = Fb[soff + 4];
-            Vec4<T> g;
-            g.x = w0 * fc.x + w1 * fp.x + w2 * fm.x + w3 * fyp.x + w4 * fym.x + w5 * fc.y + w6 * fl;
-            g.y = w0 * fc.y + w1 * fp.y + w2 * fm.y + w3 * fyp.y + w4 * fym.y + w5 * fc.z + w6 * fc.x;
-            g.z = w0 * fc.z + w1 * fp.z + w2 * fm.z + w3 * fyp.z + w4 * fym.z + w5 * fc.w + w6 * fc.y;
-            g.w = w0 * fc.w + w1 * fp.w + w2 * fm.w + w3 * fyp.w + w4 * fym.w + w5 * fr + w6 * fc.z;
+        if (grow && kg >= zs && kg < ze) {
+            const Vec4<T> fym = *reinterpret_cast<const Vec4<T>*>(Fb - PITCH);
+            const Vec4<T> fyp = *reinterpret_cast<const Vec4<T>*>(Fb + PITCH);
+            const T fl = Fb[-1], fr = Fb[4];
+            Vec4<T> g = star_adj<T>(fc, fp, fm, fym, fyp, fl, fr, w);
             // plane classes here: czm = class(kg-1), cz0 = class(kg), czp = class(kg+1)
-            const bool zslow = cz0 != p.R0 || (has_z && (czm != p.R0 || czp != p.R0));
+            const bool zslow = cz0 != p.R0 || (HASZ && (czm != p.R0 || czp != p.R0));
             const unsigned amk = zslow ? 0xFu : amask;
-            if (amk) {
-                const T fcv[6] = {fl, fc.x, fc.y, fc.z, fc.w, fr};
-                const T fmv[4] = {fm.x, fm.y, fm.z, fm.w}, fpv[4] = {fp.x, fp.y, fp.z, fp.w};
-                const T fymv[4] = {fym.x, fym.y, fym.z, fym.w}, fypv[4] = {fyp.x, fyp.y, fyp.z, fyp.w};
-                T gv[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (amk >> i & 1) {
-                        const int cx = cxs[i + 1], cxm = cxs[i], cxp = cxs[i + 2];
-                        T gi = tab[((cz0 * C1 + cy) * C2 + cx) * 7 + 0] * fcv[i + 1];
-                        if (has_z)
-                            gi += tab[((czp * C1 + cy) * C2 + cx) * 7 + 1] * fpv[i] +
-                                  tab[((czm * C1 + cy) * C2 + cx) * 7 + 2] * fmv[i];
-                        gi += tab[((cz0 * C1 + cyp) * C2 + cx) * 7 + 3] * fypv[i] +
-                              tab[((cz0 * C1 + cym) * C2 + cx) * 7 + 4] * fymv[i];
-                        gi += tab[((cz0 * C1 + cy) * C2 + cxp) * 7 + 5] * fcv[i + 2] +
-                              tab[((cz0 * C1 + cy) * C2 + cxm) * 7 + 6] * fcv[i];
-                        gv[i] = gi;
-                    }
-                }
-                g = Vec4<T>{gv[0], gv[1], gv[2], gv[3]};
-            }
+            if (amk)
+                star_patch_adj<T>(g, amk, tab, C1, C2, czm, cz0, czp, cym, cy, cyp, cxp, HASZ, fc, fp, fm, fym, fyp, fl,
+                                  fr);
             g.x *= p.scale;
             g.y *= p.scale;
             g.z *= p.scale;
             g.w *= p.scale;
-            *reinterpret_cast<Vec4<T>*>(p.G + (int64_t)kg * plane + col) = g;
+            *reinterpret_cast<Vec4<T>*>(Gcol + (int64_t)kg * plane) = g;
         }
         // (f) rotate
         fm = fc;
         fc = fp;
-        if (has_z) {
+        if (HASZ) {
             um = uc;
             uc = up;
             up = un;
         } else {
             uc = un;
         }
-        ex = exn;
         cc = cn;
         if (zvar) {
             czm = cz0;
@@ -693,7 +722,253 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2)) k_star_v3(StarV3Param
             czp = cls1(zg1, N0gi, p.R0);
             zg1 = zg1 + 1 == N0gi ? 0 : zg1 + 1;
         }
+        if (((kf - kf0) & 7) == 7) {  // fold the partial into the fp64 accumulator every 8 planes
+            acc2 += (double)accf;
+            accf = T(0);
+        }
     }
+    acc2 += (double)accf;
+    const double sum = block_sum(acc2, red);
+    if (tid == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sum;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Star kernel, TMA-fed (k_star_tma).  Same sweep as k_star_v3 but the U and c planes (tile + halo) are
+// brought into shared-memory rings by the Tensor Memory Accelerator (cp.async.bulk.tensor.3d, zero fill
+// outside the array) two planes ahead, signalled through mbarriers; F lives in a third ring.  Threads do
+// no global loads and keep no planes in registers: per plane they read their column group and its
+// neighbours from shared memory, write F, and (one plane later) gather g and store it with one STG.128.
+// Requires a "wrap-free" plan: no coefficient multiplies a neighbour across a periodic boundary (true
+// for every Dirichlet/Neumann-by-extrapolation operator; periodic problems use k_star_v3).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
+template <typename T>
+struct StarTmaParams {
+    T* G;
+    T* Fout;
+    double* partials;
+    const T* table;
+    int n0, N0g, z0, halo;
+    int N1, N2;
+    int R0, R1, R2;
+    T w[7];
+    T scale;
+    int zchunk;
+    int has_c;
+};
+
+template <typename T, int TY, int TX>
+__global__ void __launch_bounds__((TX / 4 + 2) * (TY + 4))
+    k_star_tma(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmC, StarTmaParams<T> p) {
+    constexpr int GXN = TX / 4 + 2;
+    constexpr int NR = TY + 4;
+    constexpr int BX = GXN * 4;        // dense row of the TMA box
+    constexpr int PLN = NR * BX;       // elements per plane slot
+    constexpr int NSU = 4, NSC = 2, NSF = 4;
+    constexpr int kTabSmem = 512;
+    constexpr uint32_t kBytes = PLN * sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [128 B pad][U ring][C ring][F ring][table][pad]
+    T* Us = reinterpret_cast<T*>(smem_raw + 128);
+    T* Cs = Us + NSU * PLN;
+    T* Fs = Cs + NSC * PLN;
+    T* tab_s = Fs + NSF * PLN;
+    __shared__ __align__(8) uint64_t bar_u[NSU];
+    __shared__ __align__(8) uint64_t bar_c[NSC];
+    __shared__ double red[32];
+
+    const int tid = threadIdx.x;
+    const int ry = tid / GXN, gx = tid - ry * GXN;
+    const int tx0 = blockIdx.x * TX, ty0 = blockIdx.y * TY;
+    const int y = ty0 - 2 + ry, x0 = tx0 - 4 + 4 * gx;
+    const int zs = blockIdx.z * p.zchunk;
+    const int ze = min(zs + p.zchunk, p.n0);
+    const int64_t plane = (int64_t)p.N1 * p.N2;
+    const int soff = ry * BX + 4 * gx;
+    const bool frow = ry >= 1 && ry <= TY + 2;
+    const bool in_dom = y >= 0 && y < p.N1 && x0 >= 0 && x0 < p.N2;
+    const bool grow = ry >= 2 && ry <= TY + 1 && gx >= 1 && gx <= GXN - 2 && in_dom;
+    const int col = y * p.N2 + x0;  // only used when grow
+
+    const int C1 = 2 * p.R1 + 1, C2 = 2 * p.R2 + 1;
+    auto cls1 = [](int i, int n, int r) -> int {
+        if (i < r) return i;
+        const int d = n - 1 - i;
+        return d < r ? 2 * r - d : r;
+    };
+    const int ncls = (2 * p.R0 + 1) * C1 * C2;
+    const bool tab_in_smem = ncls * 7 <= kTabSmem;
+    if (tab_in_smem)
+        for (int i = tid; i < ncls * 7; i += blockDim.x) tab_s[i] = p.table[i];
+    const T* __restrict__ tab = tab_in_smem ? tab_s : p.table;
+    const int yw = wrapi(y, p.N1), x0w = wrapi(x0, p.N2);
+    const int cy = cls1(yw, p.N1, p.R1);
+    const int cym = cls1(wrapi(yw - 1, p.N1), p.N1, p.R1), cyp = cls1(wrapi(yw + 1, p.N1), p.N1, p.R1);
+    unsigned cxp = 0, fmask = 0, amask = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) cxp |= (unsigned)cls1(wrapi(x0w + i - 1, p.N2), p.N2, p.R2) << (5 * i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int a = (cxp >> (5 * i)) & 31u, b = (cxp >> (5 * (i + 1))) & 31u, c = (cxp >> (5 * (i + 2))) & 31u;
+        if (b != p.R2) fmask |= 1u << i;
+        if (a != p.R2 || b != p.R2 || c != p.R2) amask |= 1u << i;
+    }
+    if (cy != p.R1) fmask = 0xFu;
+    if (cy != p.R1 || cym != p.R1 || cyp != p.R1) amask = 0xFu;
+    if (!frow) fmask = 0;
+    if (!grow) amask = 0;
+    auto zcls = [&](int k) -> int {
+        int zg = p.z0 + k;
+        while (zg < 0) zg += p.N0g;
+        while (zg >= p.N0g) zg -= p.N0g;
+        return cls1(zg, p.N0g, p.R0);
+    };
+
+    const int kf0 = zs - 1;
+    const int niter = ze - kf0 + 1;  // planes kf0 .. ze
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NSU; ++i) mbar_init(&bar_u[i], 1);
+#pragma unroll
+        for (int i = 0; i < NSC; ++i) mbar_init(&bar_c[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // plane q (relative: q = plane - (kf0 - 1)) lives in U slot q & 3; c plane qc = plane - kf0 in slot qc & 1
+    auto issue_u = [&](int q) {
+        mbar_expect_tx(&bar_u[q & 3], kBytes);
+        tma_load_3d(Us + (q & 3) * PLN, &tmU, &bar_u[q & 3], tx0 - 4, ty0 - 2, kf0 - 1 + q + p.halo);
+    };
+    auto issue_c = [&](int qc) {
+        mbar_expect_tx(&bar_c[qc & 1], kBytes);
+        tma_load_3d(Cs + (qc & 1) * PLN, &tmC, &bar_c[qc & 1], tx0 - 4, ty0 - 2, kf0 + qc + p.halo);
+    };
+    if (tid == 0) {
+        issue_u(0);
+        issue_u(1);
+        issue_u(2);
+        if (niter > 1) issue_u(3);
+        if (p.has_c) {
+            issue_c(0);
+            if (niter > 1) issue_c(1);
+        }
+    }
+    T w[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) w[i] = p.w[i];
+    const bool zvar = true;
+    int czm = zcls(kf0 - 2), cz0 = zcls(kf0 - 1), czp = zcls(kf0);
+    int zg1 = p.z0 + kf0 + 1;
+    while (zg1 < 0) zg1 += p.N0g;
+    while (zg1 >= p.N0g) zg1 -= p.N0g;
+    T* Gcol = p.G + col;
+    T* Fcol = p.Fout ? p.Fout + col : nullptr;
+    const Vec4<T> zero4{T(0), T(0), T(0), T(0)};
+
+    T accf = T(0);
+    double acc2 = 0.0;
+#pragma unroll 4
+    for (int it = 0; it < niter; ++it) {
+        const int kf = kf0 + it;
+        // planes kf-1, kf, kf+1 are q = it, it+1, it+2
+        const T* Um = Us + ((it)&3) * PLN + soff;
+        const T* Uc = Us + ((it + 1) & 3) * PLN + soff;
+        const T* Up = Us + ((it + 2) & 3) * PLN + soff;
+        T* Fw = Fs + (it & 3) * PLN + soff;
+        Vec4<T> fp = zero4;
+        if (frow) {
+            // plane kf+1 (q = it+2) is the last one to land; its k-th use of the slot has parity (q >> 2) & 1
+            mbar_wait(&bar_u[(it + 2) & 3], ((it + 2) >> 2) & 1);
+            if (it == 0) {
+                mbar_wait(&bar_u[0], 0);
+                mbar_wait(&bar_u[1], 0);
+            }
+            Vec4<T> cc = zero4;
+            if (p.has_c) {
+                mbar_wait(&bar_c[it & 1], (it >> 1) & 1);
+                cc = *reinterpret_cast<const Vec4<T>*>(Cs + (it & 1) * PLN + soff);
+            }
+            const Vec4<T> uc = *reinterpret_cast<const Vec4<T>*>(Uc);
+            const Vec4<T> um = *reinterpret_cast<const Vec4<T>*>(Um);
+            const Vec4<T> up = *reinterpret_cast<const Vec4<T>*>(Up);
+            const Vec4<T> uym = *reinterpret_cast<const Vec4<T>*>(Uc - BX);
+            const Vec4<T> uyp = *reinterpret_cast<const Vec4<T>*>(Uc + BX);
+            const T ul = Uc[-1], ur = Uc[4];
+            fp = star_fwd<T>(cc, uc, um, up, uym, uyp, ul, ur, w);
+            const unsigned fmk = (czp != p.R0) ? 0xFu : fmask;  // czp == class of plane kf here
+            if (fmk) star_patch_fwd<T>(fp, fmk, tab, (czp * C1 + cy) * C2, cxp, cc, uc, um, up, uym, uyp, ul, ur);
+            *reinterpret_cast<Vec4<T>*>(Fw) = fp;
+            if (grow && kf >= zs && kf < ze) {
+                accf += fp.x * fp.x + fp.y * fp.y + fp.z * fp.z + fp.w * fp.w;
+                if (Fcol) *reinterpret_cast<Vec4<T>*>(Fcol + (int64_t)kf * plane) = fp;
+            }
+        }
+        __syncthreads();
+        // refill the slots that every thread has finished reading: U plane kf-1's slot gets plane kf+3,
+        // c plane kf's slot gets plane kf+2
+        if (tid == 0) {
+            if (it + 4 <= niter) issue_u(it + 4);
+            if (p.has_c && it + 2 < niter) issue_c(it + 2);
+        }
+        // g[kf-1] from F[kf-2], F[kf-1], F[kf]
+        const int kg = kf - 1;
+        if (grow && kg >= zs && kg < ze) {
+            const T* Fc = Fs + ((it + 3) & 3) * PLN + soff;  // plane kf-1
+            const T* Fm = Fs + ((it + 2) & 3) * PLN + soff;  // plane kf-2
+            const Vec4<T> fc = *reinterpret_cast<const Vec4<T>*>(Fc);
+            const Vec4<T> fm = *reinterpret_cast<const Vec4<T>*>(Fm);
+            const Vec4<T> fym = *reinterpret_cast<const Vec4<T>*>(Fc - BX);
+            const Vec4<T> fyp = *reinterpret_cast<const Vec4<T>*>(Fc + BX);
+            const T fl = Fc[-1], fr = Fc[4];
+            Vec4<T> g = star_adj<T>(fc, fp, fm, fym, fyp, fl, fr, w);
+            const bool zslow = cz0 != p.R0 || czm != p.R0 || czp != p.R0;
+            const unsigned amk = zslow ? 0xFu : amask;
+            if (amk)
+                star_patch_adj<T>(g, amk, tab, C1, C2, czm, cz0, czp, cym, cy, cyp, cxp, true, fc, fp, fm, fym, fyp, fl,
+                                  fr);
+            g.x *= p.scale;
+            g.y *= p.scale;
+            g.z *= p.scale;
+            g.w *= p.scale;
+            *reinterpret_cast<Vec4<T>*>(Gcol + (int64_t)kg * plane) = g;
+        }
+        if (zvar) {
+            czm = cz0;
+            cz0 = czp;
+            czp = cls1(zg1, p.N0g, p.R0);
+            zg1 = zg1 + 1 == p.N0g ? 0 : zg1 + 1;
+        }
+        if ((it & 7) == 7) {
+            acc2 += (double)accf;
+            accf = T(0);
+        }
+    }
+    acc2 += (double)accf;
     const double sum = block_sum(acc2, red);
     if (tid == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sum;
 }
@@ -855,25 +1130,82 @@ static int launch_star_cfg(const StarParams<T>& sp, dim3 grid, bool vec, cudaStr
 
 template <typename T, int TY, int TX>
 static int launch_star_v3(const StarV3Params<T>& sp, dim3 grid, cudaStream_t st) {
-    constexpr int NT = (TX / 4 + 2) * (TY + 2);
-    const size_t smem = ((size_t)4 * (TY + 2) * ((TX / 4 + 2) * 4 + 8) + 512) * sizeof(T);
+    constexpr int NT = (TX / 4 + 2) * (TY + 4);
+    const size_t smem = ((size_t)4 * (TY + 4) * ((TX / 4 + 2) * 4 + 8) + 512) * sizeof(T);
     static bool attr_set = false;
     if (!attr_set) {
-        ODIL_CUDA(cudaFuncSetAttribute(k_star_v3<T, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ODIL_CUDA(cudaFuncSetAttribute(k_star_v3<T, TY, TX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        ODIL_CUDA(cudaFuncSetAttribute(k_star_v3<T, TY, TX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
         attr_set = true;
     }
-    k_star_v3<T, TY, TX><<<grid, NT, smem, st>>>(sp);
+    if (sp.has_z)
+        k_star_v3<T, TY, TX, true><<<grid, NT, smem, st>>>(sp);
+    else
+        k_star_v3<T, TY, TX, false><<<grid, NT, smem, st>>>(sp);
     ODIL_LAUNCHED();
     return 0;
 }
 
 static void star_v3_tile(int variant, int& TY, int& TX) {
     switch (variant) {
-        case 1: TY = 8; TX = 128; break;
-        case 2: TY = 14; TX = 128; break;
-        case 3: TY = 8; TX = 64; break;
-        default: TY = 16; TX = 128; break;
+        case 1: TY = 8; TX = 128; break;    // 408 threads
+        case 2: TY = 12; TX = 128; break;   // 544 threads
+        case 3: TY = 26; TX = 128; break;   // 1020 threads
+        default: TY = 16; TX = 128; break;  // 680 threads
     }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)ptr;
+    }
+    return fn;
+}
+
+// 3-D tensor map over a C-order (nplanes, N1, N2) array with a (1, BY, BX) box; zero fill outside.
+template <typename T>
+static int make_plane_map(CUtensorMap* map, const T* base, int64_t nplanes, int N1, int N2, int BY, int BX) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    ODIL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t gdim[3] = {(cuuint64_t)N2, (cuuint64_t)N1, (cuuint64_t)nplanes};
+    const cuuint64_t gstr[2] = {(cuuint64_t)N2 * sizeof(T), (cuuint64_t)N1 * N2 * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)BX, (cuuint32_t)BY, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    const CUresult r = enc(map, dt, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ODIL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return 0;
+}
+
+template <typename T, int TY, int TX>
+static int launch_star_tma(const CUtensorMap& tmU, const CUtensorMap& tmC, const StarTmaParams<T>& sp, dim3 grid,
+                           cudaStream_t st) {
+    constexpr int NT = (TX / 4 + 2) * (TY + 4);
+    constexpr int PLN = (TY + 4) * (TX + 8);
+    const size_t smem = 128 + (size_t)(4 + 2 + 4) * PLN * sizeof(T) + 512 * sizeof(T) + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ODIL_CUDA(cudaFuncSetAttribute(k_star_tma<T, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_star_tma<T, TY, TX><<<grid, NT, smem, st>>>(tmU, tmC, sp);
+    ODIL_LAUNCHED();
+    return 0;
 }
 
 static void star_tile(int variant, int& TY, int& TX) {
@@ -903,7 +1235,75 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     const int64_t n2 = plan->shape[plan->ndim - 1];
     const bool v3 = tiled && plan->use_v3 && (n2 % 4 == 0) && ((uintptr_t)U % 16 == 0) && ((uintptr_t)G % 16 == 0) &&
                     ((uintptr_t)c % 16 == 0) && ((uintptr_t)Fout % 16 == 0);
-    if (v3) {
+    const bool tma = v3 && plan->use_tma && plan->wrap_free && get_encode_tiled() != nullptr;
+    if (tma) {
+        StarTmaParams<T> sp;
+        sp.G = io.out;
+        sp.Fout = io.Fout;
+        sp.partials = plan->partials;
+        sp.table = (const T*)plan->star_table;
+        if (plan->ndim == 3) {
+            sp.n0 = (int)slab->n0;
+            sp.N0g = (int)plan->shape[0];
+            sp.z0 = (int)slab->z0;
+            sp.halo = slab->halo;
+            sp.N1 = (int)plan->shape[1];
+            sp.N2 = (int)plan->shape[2];
+            sp.R0 = plan->R[0];
+            sp.R1 = plan->R[1];
+            sp.R2 = plan->R[2];
+        } else {
+            sp.n0 = 1;
+            sp.N0g = 1;
+            sp.z0 = 0;
+            sp.halo = 0;
+            sp.N1 = (int)plan->shape[0];
+            sp.N2 = (int)plan->shape[1];
+            sp.R0 = 0;
+            sp.R1 = plan->R[0];
+            sp.R2 = plan->R[1];
+        }
+        for (int i = 0; i < 7; ++i) sp.w[i] = (T)plan->w[i];
+        sp.scale = (T)scale;
+        sp.has_c = io.c != nullptr;
+        int TY = 16;
+        const int TX = 128;
+        switch (plan->variant) {
+            case 1: TY = 8; break;
+            case 2: TY = 12; break;
+            case 3: TY = 26; break;
+            default: TY = 16; break;
+        }
+        const int gx = (sp.N2 + TX - 1) / TX, gy = (sp.N1 + TY - 1) / TY;
+        int zchunk = plan->zchunk;
+        if (zchunk <= 0) {
+            zchunk = 128;
+            while (zchunk > 16 && (int64_t)gx * gy * ((sp.n0 + zchunk - 1) / zchunk) < 148 * 2 * 4) zchunk /= 2;
+        }
+        if (zchunk > sp.n0) zchunk = sp.n0;
+        if (zchunk < 1) zchunk = 1;
+        sp.zchunk = zchunk;
+        const int gz = (sp.n0 + zchunk - 1) / zchunk;
+        ODIL_REQUIRE((int64_t)gx * gy * gz <= kPartialCapacity, "star grid exceeds the partials workspace");
+        dim3 grid(gx, gy, gz);
+        const int64_t planes_total = (int64_t)sp.n0 + 2 * sp.halo;
+        const int64_t plane_elems = (int64_t)sp.N1 * sp.N2;
+        CUtensorMap tmU, tmC;
+        if (int rc = make_plane_map<T>(&tmU, io.U - sp.halo * plane_elems, planes_total, sp.N1, sp.N2, TY + 4, TX + 8))
+            return rc;
+        if (int rc = make_plane_map<T>(&tmC, (io.c ? io.c : io.U) - sp.halo * plane_elems, planes_total, sp.N1, sp.N2,
+                                       TY + 4, TX + 8))
+            return rc;
+        int rc = 0;
+        switch (plan->variant) {
+            case 1: rc = launch_star_tma<T, 8, 128>(tmU, tmC, sp, grid, st); break;
+            case 2: rc = launch_star_tma<T, 12, 128>(tmU, tmC, sp, grid, st); break;
+            case 3: rc = launch_star_tma<T, 26, 128>(tmU, tmC, sp, grid, st); break;
+            default: rc = launch_star_tma<T, 16, 128>(tmU, tmC, sp, grid, st); break;
+        }
+        if (rc) return rc;
+        nparts = gx * gy * gz;
+    } else if (v3) {
         StarV3Params<T> sp;
         sp.U = io.U;
         sp.c = io.c;
@@ -953,8 +1353,8 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         int rc = 0;
         switch (plan->variant) {
             case 1: rc = launch_star_v3<T, 8, 128>(sp, grid, st); break;
-            case 2: rc = launch_star_v3<T, 14, 128>(sp, grid, st); break;
-            case 3: rc = launch_star_v3<T, 8, 64>(sp, grid, st); break;
+            case 2: rc = launch_star_v3<T, 12, 128>(sp, grid, st); break;
+            case 3: rc = launch_star_v3<T, 26, 128>(sp, grid, st); break;
             default: rc = launch_star_v3<T, 16, 128>(sp, grid, st); break;
         }
         if (rc) return rc;
@@ -1098,11 +1498,45 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
             if (a == 0) p->rmax0 = std::max(p->rmax0, std::abs(p->off[o][a]));
         }
     p->table.assign(table, table + (size_t)p->ncls * noff);
+    // wrap_free: every (class, offset) whose neighbour would cross the periodic boundary has a zero coefficient.
+    {
+        bool wf = true;
+        std::vector<int> cstr(ndim);
+        int cs2 = 1;
+        for (int a = ndim - 1; a >= 0; --a) {
+            cstr[a] = cs2;
+            cs2 *= 2 * p->R[a] + 1;
+        }
+        for (int cl = 0; cl < p->ncls && wf; ++cl)
+            for (int o = 0; o < noff && wf; ++o) {
+                if (p->table[(size_t)cl * noff + o] == 0.0) continue;
+                for (int a = 0; a < ndim; ++a) {
+                    const int d = p->off[o][a];
+                    if (d == 0) continue;
+                    const int r = p->R[a];
+                    const int c = (cl / cstr[a]) % (2 * r + 1);
+                    bool crosses;
+                    if (c < r)
+                        crosses = c + d < 0;            // low row i = c
+                    else if (c > r)
+                        crosses = (2 * r - c) < d;      // high row i = N-1-(2r-c)
+                    else
+                        crosses = std::abs(d) > r;      // interior rows next to the boundary rows
+                    if (crosses) {
+                        wf = false;
+                        break;
+                    }
+                }
+            }
+        p->wrap_free = wf ? 1 : 0;
+    }
     // Tiled eligibility: 2-D / 3-D, every offset a unit star arm, grid not degenerate.
     p->kind = 0;
     p->star_table = nullptr;
     p->star_has_z = 0;
     p->use_v3 = 1;
+    p->use_tma = 1;
+    p->wrap_free = 0;
     std::vector<double> star;
     for (int i = 0; i < 7; ++i) p->w[i] = 0.0;
     if ((ndim == 3 || ndim == 2) && total >= 512) {
@@ -1195,9 +1629,12 @@ int odil_b200_stencil_plan_kind(const odil_b200_plan* plan) { return plan ? plan
 
 int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant) {
     ODIL_REQUIRE(plan != nullptr, "null plan");
-    ODIL_REQUIRE((variant >= 0 && variant <= 3) || (variant >= 10 && variant <= 13), "variant=%d unknown", variant);
+    ODIL_REQUIRE((variant >= 0 && variant <= 3) || (variant >= 10 && variant <= 13) || (variant >= 20 && variant <= 23),
+                 "variant=%d unknown", variant);
     plan->zchunk = zchunk;
-    plan->use_v3 = variant < 10;  // 0..3: column-group kernel tiles; 10..13: v2 tile kernel + shell pass
+    // 0..3: TMA-fed kernel tiles (default); 10..13: v2 tile kernel + shell pass; 20..23: LDG column-group kernel
+    plan->use_tma = variant < 10;
+    plan->use_v3 = variant < 10 || variant >= 20;
     plan->variant = variant % 10;
     return 0;
 }

@@ -175,13 +175,20 @@ def test_star_plans_use_tiled_kernel():
     assert kinds == [0, 0, 0, 1, 1, 1, 1, 1, 0]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 10, 11, 12, 13])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 10, 11, 12, 13, 20, 21, 22, 23])
 @pytest.mark.parametrize("zchunk", [0, 1, 5, 64])
-def test_star_variants(variant, zchunk):
+@pytest.mark.parametrize("kind", ["random", "dirichlet"])
+def test_star_variants(variant, zchunk, kind):
+    """Tile variants of the three fused kernels: 0-3 TMA-fed (needs a wrap-free table, e.g. the Dirichlet
+    Poisson rows; random tables fall back to the LDG kernel), 10-13 tile + shell, 20-23 LDG column groups."""
     shape, rr = (20, 18, 36), (1, 1, 1)
     offsets = star_offsets(3)
     rng = np.random.default_rng(7)
-    table = rng.standard_normal((27, 7))
+    if kind == "random":
+        table = rng.standard_normal((27, 7))
+    else:
+        offsets, table, rr = orc.poisson_plan(3, [0.3, 0.2, 0.1])
+        table = table.reshape(27, 7) * (1 + 0.1 * rng.standard_normal((27, 7)))  # keeps the zero pattern
     U = rng.standard_normal(shape)
     c = rng.standard_normal(shape)
     plan = native.StencilPlan(shape, torch.float64, offsets, rr, table)
