@@ -132,151 +132,117 @@ struct Mg3 {
     int64_t fs0, fs1;      // fine strides
 };
 
-template <typename T>
-struct alignas(sizeof(T) * 2) Pair {
-    T a, b;
-};
-
-// Loads the 3x3 in-plane neighbourhood of coarse cell (J,K) on coarse plane `ii` (clamped), with the
-// single-face linear extrapolation in y and x already applied.
-template <typename T>
-__device__ __forceinline__ void load_plane9(const T* __restrict__ pz, const Mg3& m, int J, int K, T* v /*[3][3]*/) {
-    const int km = max(K - 1, 0), kp = min(K + 1, m.n2 - 1);
-    const int jj[3] = {max(J - 1, 0), J, min(J + 1, m.n1 - 1)};
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-        const T* py = pz + (int64_t)jj[dy] * m.cs1;
-        v[dy * 3 + 0] = __ldg(py + km);
-        v[dy * 3 + 1] = __ldg(py + K);
-        v[dy * 3 + 2] = __ldg(py + kp);
-    }
-    if (K == 0) {
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) v[dy * 3 + 0] = T(2) * v[dy * 3 + 1] - v[dy * 3 + 2];
-    }
-    if (K == m.n2 - 1) {
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) v[dy * 3 + 2] = T(2) * v[dy * 3 + 1] - v[dy * 3 + 0];
-    }
-    if (J == 0) {
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) v[0 * 3 + dx] = T(2) * v[1 * 3 + dx] - v[2 * 3 + dx];
-    }
-    if (J == m.n1 - 1) {
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) v[2 * 3 + dx] = T(2) * v[1 * 3 + dx] - v[0 * 3 + dx];
-    }
-}
-
-// In-plane (y, x) interpolation of one 3x3 neighbourhood to the 2x2 fine cells, integer weights (sum 16).
-template <typename T>
-__device__ __forceinline__ void plane_2x2(const T* v, T* r /*[2][2]*/) {
-    T ax[3][2];
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-        ax[dy][0] = v[dy * 3 + 0] + T(3) * v[dy * 3 + 1];
-        ax[dy][1] = T(3) * v[dy * 3 + 1] + v[dy * 3 + 2];
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        r[0 * 2 + c] = ax[0][c] + T(3) * ax[1][c];
-        r[1 * 2 + c] = T(3) * ax[1][c] + ax[2][c];
-    }
-}
-
-// One thread per coarse COLUMN (J, K), marching over the coarse planes of its z-chunk with the in-plane
-// interpolants of planes I-1, I, I+1 in registers: every coarse value is loaded once per column-neighbour,
-// fine rows are read/written as aligned pairs.
 template <typename T, bool CZ>
 __global__ void __launch_bounds__(128) k_interp_add3(MgGeom g, Mg3 m, const T* __restrict__ coarse, T cfac,
                                                      const T* __restrict__ term, T ffac, T* __restrict__ out,
-                                                     int cz_begin, int ncz, int out_z0, int coarse_z0, int zchunk) {
+                                                     int cz_begin, int ncz, int out_z0, int coarse_z0) {
     const int K = blockIdx.x * blockDim.x + threadIdx.x;
     const int J = blockIdx.y * blockDim.y + threadIdx.y;
+    const int I = cz_begin + blockIdx.z;
     if (K >= m.n2 || J >= m.n1) return;
-    const int Ib = cz_begin + blockIdx.z * zchunk;
-    const int Ie = min(Ib + zchunk, cz_begin + ncz);
+    const bool bz = CZ && (I == 0 || I == m.n0 - 1);
     const bool by = (J == 0 || J == m.n1 - 1);
     const bool bx = (K == 0 || K == m.n2 - 1);
-    const int nbyx = (int)by + (int)bx;
-    auto store = [&](int I, int a, int b, T r0, T r1) {
-        const int64_t fz = CZ ? 2 * (int64_t)I + a : (int64_t)I;
-        const int64_t lin = (fz - out_z0) * m.fs0 + (int64_t)(2 * J + b) * m.fs1 + 2 * K;
-        r0 *= cfac;
-        r1 *= cfac;
-        if (term) {
-            const Pair<T> t = *reinterpret_cast<const Pair<T>*>(term + lin);
-            r0 += ffac * t.a;
-            r1 += ffac * t.b;
-        }
-        *reinterpret_cast<Pair<T>*>(out + lin) = Pair<T>{r0, r1};
-    };
-    auto generic_cell = [&](int I) {
-        constexpr int NZ = CZ ? 2 : 1;
+    constexpr int NZ = CZ ? 2 : 1;
+    T res[NZ][2][2];
+    if ((int)bz + (int)by + (int)bx >= 2) {
         for (int a = 0; a < NZ; ++a)
-            for (int b = 0; b < 2; ++b) {
-                T r[2];
+            for (int b = 0; b < 2; ++b)
                 for (int c = 0; c < 2; ++c) {
                     const int64_t f3[ODIL_B200_MAX_NDIM] = {CZ ? 2 * (int64_t)I + a : (int64_t)I, 2 * (int64_t)J + b,
                                                             2 * (int64_t)K + c, 0};
                     const int64_t f2[ODIL_B200_MAX_NDIM] = {2 * (int64_t)J + b, 2 * (int64_t)K + c, 0, 0};
-                    r[c] = interp_cell_generic<T>(g, coarse, coarse_z0, g.ndim == 3 ? f3 : f2);
+                    res[a][b][c] = interp_cell_generic<T>(g, coarse, coarse_z0, g.ndim == 3 ? f3 : f2);
                 }
-                store(I, a, b, r[0], r[1]);
-            }
-    };
-    if (!CZ) {
-        for (int I = Ib; I < Ie; ++I) {
-            if (nbyx >= 2) {
-                generic_cell(I);
-                continue;
-            }
-            T v[9], r[4];
-            load_plane9<T>(coarse + (int64_t)(I - coarse_z0) * m.cs0, m, J, K, v);
-            plane_2x2<T>(v, r);
-            store(I, 0, 0, r[0] * T(1.0 / 16.0), r[1] * T(1.0 / 16.0));
-            store(I, 0, 1, r[2] * T(1.0 / 16.0), r[3] * T(1.0 / 16.0));
-        }
-        return;
-    }
-    // CZ: q[0..2] = in-plane interpolants (x16) of coarse planes I-1, I, I+1 (clamped to the array)
-    T q0[4], q1[4], q2[4];
-    auto load_q = [&](int ii, T* q) {
-        const int ic = min(max(ii, 0), m.n0 - 1);
-        T v[9];
-        load_plane9<T>(coarse + (int64_t)(ic - coarse_z0) * m.cs0, m, J, K, v);
-        plane_2x2<T>(v, q);
-    };
-    if (nbyx < 2) {
-        load_q(Ib - 1, q0);
-        load_q(Ib, q1);
-    }
-    for (int I = Ib; I < Ie; ++I) {
-        const bool bz = (I == 0 || I == m.n0 - 1);
-        if (nbyx < 2) load_q(I + 1, q2);
-        if (nbyx + (int)bz >= 2) {
-            generic_cell(I);
-        } else {
-            T lo[4], hi[4];
+    } else {
+        constexpr int DZ = CZ ? 3 : 1;
+        T v[DZ][3][3];
+        const int km = max(K - 1, 0), kp = min(K + 1, m.n2 - 1);
+        const int jm = max(J - 1, 0), jp = min(J + 1, m.n1 - 1);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                // single-face extrapolation along z (in-plane interpolation commutes with it)
-                const T zm = I == 0 ? T(2) * q1[i] - q2[i] : q0[i];
-                const T zp = I == m.n0 - 1 ? T(2) * q1[i] - q0[i] : q2[i];
-                lo[i] = (zm + T(3) * q1[i]) * T(1.0 / 64.0);
-                hi[i] = (T(3) * q1[i] + zp) * T(1.0 / 64.0);
-            }
-            store(I, 0, 0, lo[0], lo[1]);
-            store(I, 0, 1, lo[2], lo[3]);
-            store(I, 1, 0, hi[0], hi[1]);
-            store(I, 1, 1, hi[2], hi[3]);
-        }
+        for (int dz = 0; dz < DZ; ++dz) {
+            int ii = CZ ? min(max(I - 1 + dz, 0), m.n0 - 1) : I;
+            const T* pz = coarse + (int64_t)(ii - coarse_z0) * m.cs0;
+            const int jj[3] = {jm, J, jp};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            q0[i] = q1[i];
-            q1[i] = q2[i];
+            for (int dy = 0; dy < 3; ++dy) {
+                const T* py = pz + (int64_t)jj[dy] * m.cs1;
+                v[dz][dy][0] = __ldg(py + km);
+                v[dz][dy][1] = __ldg(py + K);
+                v[dz][dy][2] = __ldg(py + kp);
+            }
         }
+        // single-face linear extrapolation of the out-of-range neighbour (2*u[clamp] - u[reflect])
+        if (bx) {
+#pragma unroll
+            for (int dz = 0; dz < DZ; ++dz)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    if (K == 0) v[dz][dy][0] = T(2) * v[dz][dy][1] - v[dz][dy][2];
+                    if (K == m.n2 - 1) v[dz][dy][2] = T(2) * v[dz][dy][1] - v[dz][dy][0];
+                }
+        }
+        if (by) {
+#pragma unroll
+            for (int dz = 0; dz < DZ; ++dz)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    if (J == 0) v[dz][0][dx] = T(2) * v[dz][1][dx] - v[dz][2][dx];
+                    if (J == m.n1 - 1) v[dz][2][dx] = T(2) * v[dz][1][dx] - v[dz][0][dx];
+                }
+        }
+        if (CZ && bz) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    if (I == 0) v[0][dy][dx] = T(2) * v[DZ > 1 ? 1 : 0][dy][dx] - v[DZ - 1][dy][dx];
+                    if (I == m.n0 - 1) v[DZ - 1][dy][dx] = T(2) * v[DZ > 1 ? 1 : 0][dy][dx] - v[0][dy][dx];
+                }
+        }
+        // separable accumulation with integer weights
+        T ax[DZ][3][2];
+#pragma unroll
+        for (int dz = 0; dz < DZ; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                ax[dz][dy][0] = v[dz][dy][0] + T(3) * v[dz][dy][1];
+                ax[dz][dy][1] = T(3) * v[dz][dy][1] + v[dz][dy][2];
+            }
+        T ay[DZ][2][2];
+#pragma unroll
+        for (int dz = 0; dz < DZ; ++dz)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                ay[dz][0][c] = ax[dz][0][c] + T(3) * ax[dz][1][c];
+                ay[dz][1][c] = T(3) * ax[dz][1][c] + ax[dz][2][c];
+            }
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (CZ) {
+                    res[0][b][c] = (ay[0][b][c] + T(3) * ay[DZ > 1 ? 1 : 0][b][c]) * T(1.0 / 64.0);
+                    res[NZ - 1][b][c] = (T(3) * ay[DZ > 1 ? 1 : 0][b][c] + ay[DZ - 1][b][c]) * T(1.0 / 64.0);
+                } else {
+                    res[0][b][c] = ay[0][b][c] * T(1.0 / 16.0);
+                }
+            }
     }
+#pragma unroll
+    for (int a = 0; a < NZ; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int64_t fz = CZ ? 2 * (int64_t)I + a : (int64_t)I;
+            const int64_t lin = (fz - out_z0) * m.fs0 + (int64_t)(2 * J + b) * m.fs1 + 2 * K;
+            T r0 = cfac * res[a][b][0], r1 = cfac * res[a][b][1];
+            if (term) {
+                r0 += ffac * __ldg(term + lin);
+                r1 += ffac * __ldg(term + lin + 1);
+            }
+            out[lin] = r0;
+            out[lin + 1] = r1;
+        }
 }
 
 // Gather of fine gradient onto the PADDED coarse index q (separable 4-tap / 3-tap rule, clipped to
@@ -425,96 +391,60 @@ __device__ __forceinline__ void adjoint_weights(int J, int n, T* w) {
     if (J == n - 2) w[5] -= T(0.25);
 }
 
-// Fast transposed interpolation, cell-centred.  One thread per coarse COLUMN (J, K) marching over the coarse
-// planes of its z-chunk: the in-plane (y, x) reductions p(fz) of the fine planes 2I-2 .. 2I+3 live in a
-// register window that advances by two planes per coarse plane, so every fine plane is reduced once per
-// column; rows are read as aligned pairs.
-template <typename T>
-__device__ __forceinline__ T adjoint_plane(const T* __restrict__ pz, const Mg3& m, int J, int K, const T* wx,
-                                           const T* wy) {
-    const int nf1 = 2 * m.n1, nf2 = 2 * m.n2;
-    const int x0 = 2 * K - 2;
-    T acc = T(0);
-#pragma unroll
-    for (int ty = 0; ty < 6; ++ty) {
-        const int fy = 2 * J - 2 + ty;
-        if (wy[ty] == T(0) || fy < 0 || fy >= nf1) continue;
-        const T* py = pz + (int64_t)fy * m.fs1;
-        T accx = T(0);
-#pragma unroll
-        for (int pp = 0; pp < 3; ++pp) {
-            const int fx = x0 + 2 * pp;
-            if (fx >= 0 && fx + 1 < nf2 && (wx[2 * pp] != T(0) || wx[2 * pp + 1] != T(0))) {
-                const Pair<T> v = *reinterpret_cast<const Pair<T>*>(py + fx);
-                accx += wx[2 * pp] * v.a + wx[2 * pp + 1] * v.b;
-            }
-        }
-        acc += wy[ty] * accx;
-    }
-    return acc;
-}
-
+// Fast transposed interpolation, cell-centred, one thread per coarse cell, 6x6(x6) window read as
+// aligned pairs along x.
 template <typename T, bool CZ>
 __global__ void __launch_bounds__(128) k_interp_adjoint3(MgGeom g, Mg3 m, const T* __restrict__ gf, T scale,
-                                                         T* __restrict__ gc, int cz_begin, int ncz, int out_z0,
-                                                         int fine_z0, int zchunk) {
+                                                         T* __restrict__ gc, int cz_begin, int out_z0, int fine_z0) {
     const int K = blockIdx.x * blockDim.x + threadIdx.x;
     const int J = blockIdx.y * blockDim.y + threadIdx.y;
+    const int I = cz_begin + blockIdx.z;
     if (K >= m.n2 || J >= m.n1) return;
-    const int Ib = cz_begin + blockIdx.z * zchunk;
-    const int Ie = min(Ib + zchunk, cz_begin + ncz);
+    const bool bz = CZ && (I <= 1 || I >= m.n0 - 2);
     const bool by = (J <= 1 || J >= m.n1 - 2);
     const bool bx = (K <= 1 || K >= m.n2 - 2);
-    const int nbyx = (int)by + (int)bx;
-    T wx[6], wy[6];
-    adjoint_weights<T>(K, m.n2, wx);
-    adjoint_weights<T>(J, m.n1, wy);
-    auto generic_cell = [&](int I) -> T {
+    T acc;
+    if ((int)bz + (int)by + (int)bx >= 2) {
         const int64_t J3[ODIL_B200_MAX_NDIM] = {I, J, K, 0};
         const int64_t J2[ODIL_B200_MAX_NDIM] = {J, K, 0, 0};
-        return adjoint_cell_generic<T>(g, gf, fine_z0, g.ndim == 3 ? J3 : J2);
-    };
-    if (!CZ) {
-        for (int I = Ib; I < Ie; ++I) {
-            const T acc = nbyx >= 2 ? generic_cell(I) : adjoint_plane<T>(gf + (int64_t)(I - fine_z0) * m.fs0, m, J, K, wx, wy);
-            gc[(int64_t)(I - out_z0) * m.cs0 + (int64_t)J * m.cs1 + K] = scale * acc;
-        }
-        return;
-    }
-    const int nf0 = 2 * m.n0;
-    auto plane = [&](int fz) -> T {
-        if (fz < 0 || fz >= nf0 || nbyx >= 2) return T(0);
-        return adjoint_plane<T>(gf + (int64_t)(fz - fine_z0) * m.fs0, m, J, K, wx, wy);
-    };
-    // window pw[t] = p(2I - 2 + t).  Interior planes only need t = 1..4; t = 0 and 5 carry the pad
-    // corrections of coarse planes 1 and n0-2 (fine planes 0 and 2 n0 - 1).
-    T pw[6];
-    pw[0] = (Ib == 1) ? plane(0) : T(0);
+        acc = adjoint_cell_generic<T>(g, gf, fine_z0, g.ndim == 3 ? J3 : J2);
+    } else {
+        T wx[6], wy[6], wz[6];
+        adjoint_weights<T>(K, m.n2, wx);
+        adjoint_weights<T>(J, m.n1, wy);
+        if (CZ) adjoint_weights<T>(I, m.n0, wz);
+        const int nf1 = 2 * m.n1, nf2 = 2 * m.n2;
+        const int nf0 = CZ ? 2 * m.n0 : m.n0;
+        // clamp the x window into the array (weights of clipped cells are zero)
+        const int x0 = 2 * K - 2;
+        acc = T(0);
+        constexpr int TZ = CZ ? 6 : 1;
 #pragma unroll
-    for (int t = 1; t < 4; ++t) pw[t] = plane(2 * Ib - 2 + t);
-    for (int I = Ib; I < Ie; ++I) {
-        pw[4] = plane(2 * I + 2);
-        pw[5] = (I == m.n0 - 2) ? plane(2 * I + 3) : T(0);
-        const bool bz = (I <= 1 || I >= m.n0 - 2);
-        T acc;
-        if (nbyx + (int)bz >= 2) {
-            acc = generic_cell(I);
-        } else {
-            T wz[6];
-            adjoint_weights<T>(I, m.n0, wz);
-            acc = T(0);
+        for (int tz = 0; tz < TZ; ++tz) {
+            const int fz = CZ ? 2 * I - 2 + tz : I;
+            if (CZ && (wz[tz] == T(0) || fz < 0 || fz >= nf0)) continue;
+            const T* pz = gf + (int64_t)(fz - fine_z0) * m.fs0;
+            T accy = T(0);
 #pragma unroll
-            for (int t = 0; t < 6; ++t) acc += wz[t] * pw[t];
+            for (int ty = 0; ty < 6; ++ty) {
+                const int fy = 2 * J - 2 + ty;
+                if (wy[ty] == T(0) || fy < 0 || fy >= nf1) continue;
+                const T* py = pz + (int64_t)fy * m.fs1;
+                T accx = T(0);
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const int fx = x0 + 2 * p;
+                    if (fx >= 0 && fx + 1 < nf2) {
+                        accx += wx[2 * p] * __ldg(py + fx) + wx[2 * p + 1] * __ldg(py + fx + 1);
+                    }
+                }
+                accy += wy[ty] * accx;
+            }
+            acc += CZ ? wz[tz] * accy : accy;
         }
-        gc[(int64_t)(I - out_z0) * m.cs0 + (int64_t)J * m.cs1 + K] = scale * acc;
-        // advance the window by two fine planes: new pw[0] must be p(2I) only when the next plane is
-        // coarse 1 (its -1/4 correction reads fine plane 0), otherwise its weight is zero
-        const T p2 = pw[2], p3 = pw[3], p4 = pw[4];
-        pw[0] = (I + 1 == 1) ? p2 : T(0);
-        pw[1] = p3;
-        pw[2] = p4;
-        pw[3] = plane(2 * I + 3);
     }
+    const int64_t lin = (int64_t)(I - out_z0) * m.cs0 + (int64_t)J * m.cs1 + K;
+    gc[lin] = scale * acc;
 }
 
 // One thread per coarse cell; joint pad on the fine array (only 'n' axes ever leave the range).
@@ -664,36 +594,33 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
         if (fast3_geometry(g, m, cz) && (!cz || pairs)) {
             const int zb = (int)(ndim == 3 ? (cz ? r.fz_begin / 2 : r.fz_begin) : 0);
             const int nz = (int)(ndim == 3 ? (cz ? (r.fz_end - r.fz_begin) / 2 : r.fz_end - r.fz_begin) : 1);
-            dim3 block(32, 4, 1);
-            const int gx = (m.n2 + 31) / 32, gy = (m.n1 + 3) / 4;
-            // enough z-chunks to fill the GPU several times over, each long enough to amortise the 2-plane start-up
-            int zchunk = 16;
-            while (zchunk > 4 && (int64_t)gx * gy * ((nz + zchunk - 1) / zchunk) < 148 * 16) zchunk /= 2;
-            if (!cz) zchunk = 1;
-            dim3 grid(gx, gy, (nz + zchunk - 1) / zchunk);
-            const int oz0 = (int)(ndim == 3 ? r.out_z0 : 0), cz0 = (int)(ndim == 3 ? r.coarse_z0 : 0);
-            if (grid.y <= 65535 && grid.z <= 65535) {
-                if (dtype == ODIL_B200_F32) {
-                    if (cz)
-                        k_interp_add3<float, true><<<grid, block, 0, st>>>(g, m, (const float*)coarse, (float)cfac,
-                                                                         (const float*)fine_term, (float)ffac,
-                                                                         (float*)out, zb, nz, oz0, cz0, zchunk);
-                    else
-                        k_interp_add3<float, false><<<grid, block, 0, st>>>(g, m, (const float*)coarse, (float)cfac,
-                                                                          (const float*)fine_term, (float)ffac,
-                                                                          (float*)out, zb, nz, oz0, cz0, zchunk);
-                } else {
-                    if (cz)
-                        k_interp_add3<double, true><<<grid, block, 0, st>>>(g, m, (const double*)coarse, cfac,
-                                                                          (const double*)fine_term, ffac, (double*)out,
-                                                                          zb, nz, oz0, cz0, zchunk);
-                    else
-                        k_interp_add3<double, false><<<grid, block, 0, st>>>(g, m, (const double*)coarse, cfac,
-                                                                           (const double*)fine_term, ffac,
-                                                                           (double*)out, zb, nz, oz0, cz0, zchunk);
+            if (nz <= 65535) {
+                dim3 block(64, 2, 1);
+                dim3 grid((m.n2 + 63) / 64, (m.n1 + 1) / 2, nz);
+                const int oz0 = (int)(ndim == 3 ? r.out_z0 : 0), cz0 = (int)(ndim == 3 ? r.coarse_z0 : 0);
+                if (grid.y <= 65535) {
+                    if (dtype == ODIL_B200_F32) {
+                        if (cz)
+                            k_interp_add3<float, true><<<grid, block, 0, st>>>(g, m, (const float*)coarse, (float)cfac,
+                                                                             (const float*)fine_term, (float)ffac,
+                                                                             (float*)out, zb, nz, oz0, cz0);
+                        else
+                            k_interp_add3<float, false><<<grid, block, 0, st>>>(g, m, (const float*)coarse, (float)cfac,
+                                                                              (const float*)fine_term, (float)ffac,
+                                                                              (float*)out, zb, nz, oz0, cz0);
+                    } else {
+                        if (cz)
+                            k_interp_add3<double, true><<<grid, block, 0, st>>>(g, m, (const double*)coarse, cfac,
+                                                                              (const double*)fine_term, ffac,
+                                                                              (double*)out, zb, nz, oz0, cz0);
+                        else
+                            k_interp_add3<double, false><<<grid, block, 0, st>>>(g, m, (const double*)coarse, cfac,
+                                                                               (const double*)fine_term, ffac,
+                                                                               (double*)out, zb, nz, oz0, cz0);
+                    }
+                    ODIL_LAUNCHED();
+                    return 0;
                 }
-                ODIL_LAUNCHED();
-                return 0;
             }
         }
     }
@@ -732,30 +659,25 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
         if (fast3_geometry(g, m, cz)) {
             const int zb = (int)(ndim == 3 ? r.cz_begin : 0);
             const int nz = (int)(ndim == 3 ? r.cz_end - r.cz_begin : 1);
-            dim3 block(32, 4, 1);
-            const int gx = (m.n2 + 31) / 32, gy = (m.n1 + 3) / 4;
-            int zchunk = 16;
-            while (zchunk > 4 && (int64_t)gx * gy * ((nz + zchunk - 1) / zchunk) < 148 * 16) zchunk /= 2;
-            if (!cz) zchunk = 1;
-            dim3 grid(gx, gy, (nz + zchunk - 1) / zchunk);
+            dim3 block(64, 2, 1);
+            dim3 grid((m.n2 + 63) / 64, (m.n1 + 1) / 2, nz);
             const int oz0 = (int)(ndim == 3 ? r.out_z0 : 0), fz0 = (int)(ndim == 3 ? r.fine_z0 : 0);
-            if (grid.z <= 65535 && grid.y <= 65535) {
+            if (nz <= 65535 && grid.y <= 65535) {
                 if (dtype == ODIL_B200_F32) {
                     if (cz)
                         k_interp_adjoint3<float, true><<<grid, block, 0, st>>>(g, m, (const float*)g_fine, (float)scale,
-                                                                             (float*)g_coarse, zb, nz, oz0, fz0, zchunk);
+                                                                             (float*)g_coarse, zb, oz0, fz0);
                     else
-                        k_interp_adjoint3<float, false><<<grid, block, 0, st>>>(
-                            g, m, (const float*)g_fine, (float)scale, (float*)g_coarse, zb, nz, oz0, fz0, zchunk);
+                        k_interp_adjoint3<float, false><<<grid, block, 0, st>>>(g, m, (const float*)g_fine,
+                                                                              (float)scale, (float*)g_coarse, zb, oz0,
+                                                                              fz0);
                 } else {
                     if (cz)
                         k_interp_adjoint3<double, true><<<grid, block, 0, st>>>(g, m, (const double*)g_fine, scale,
-                                                                              (double*)g_coarse, zb, nz, oz0, fz0,
-                                                                              zchunk);
+                                                                              (double*)g_coarse, zb, oz0, fz0);
                     else
                         k_interp_adjoint3<double, false><<<grid, block, 0, st>>>(g, m, (const double*)g_fine, scale,
-                                                                               (double*)g_coarse, zb, nz, oz0, fz0,
-                                                                               zchunk);
+                                                                               (double*)g_coarse, zb, oz0, fz0);
                 }
                 ODIL_LAUNCHED();
                 return 0;
