@@ -591,7 +591,7 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
         Mg3 m;
         bool cz = false;
         const bool pairs = (r.fz_begin % 2 == 0) && (r.fz_end % 2 == 0);
-        if (fast3_geometry(g, m, cz) && (!cz || pairs)) {
+        if (fast3_geometry(g, m, cz) && (!cz || pairs) && !(ndim == 2 && range != nullptr)) {
             const int zb = (int)(ndim == 3 ? (cz ? r.fz_begin / 2 : r.fz_begin) : 0);
             const int nz = (int)(ndim == 3 ? (cz ? (r.fz_end - r.fz_begin) / 2 : r.fz_end - r.fz_begin) : 1);
             if (nz <= 65535) {
@@ -656,7 +656,7 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
     {
         Mg3 m;
         bool cz = false;
-        if (fast3_geometry(g, m, cz)) {
+        if (fast3_geometry(g, m, cz) && !(ndim == 2 && range != nullptr)) {
             const int zb = (int)(ndim == 3 ? r.cz_begin : 0);
             const int nz = (int)(ndim == 3 ? r.cz_end - r.cz_begin : 1);
             dim3 block(64, 2, 1);

@@ -71,9 +71,11 @@ class SlabInfo:
 
     def gather(self, local):
         """Global tensor assembled from the owned planes of every rank (collective)."""
+        own = self.owned(local).contiguous()
+        if self.world == 1:
+            return own.clone()
         import torch.distributed as dist
 
-        own = self.owned(local).contiguous()
         parts = [torch.empty_like(own) for _ in range(self.world)]
         dist.all_gather(parts, own, group=self.group)
         return torch.cat(parts, dim=0)
