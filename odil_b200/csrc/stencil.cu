@@ -751,12 +751,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+    uint32_t spins = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();  // a lost TMA must fail loudly, never hang the device
     } while (!ok);
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
@@ -783,10 +785,10 @@ struct StarTmaParams {
 };
 
 template <typename T, int TY, int TX>
-__global__ void __launch_bounds__((TX / 4 + 2) * (TY + 4))
+__global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2), ((TX / 4 + 2) * (TY + 2) <= 352 ? 2 : 1))
     k_star_tma(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmC, StarTmaParams<T> p) {
     constexpr int GXN = TX / 4 + 2;
-    constexpr int NR = TY + 4;
+    constexpr int NR = TY + 4;         // rows of a staged plane: tile + 2-cell halo (U of the F ring's neighbours)
     constexpr int BX = GXN * 4;        // dense row of the TMA box
     constexpr int PLN = NR * BX;       // elements per plane slot
     constexpr int NSU = 4, NSC = 2, NSF = 4;
@@ -802,18 +804,21 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 4))
     __shared__ __align__(8) uint64_t bar_c[NSC];
     __shared__ double red[32];
 
+    // One thread per float4 column group of the F region: rows ry = 1 .. TY+2 of the staged plane.
     const int tid = threadIdx.x;
-    const int ry = tid / GXN, gx = tid - ry * GXN;
+    const int ry = tid / GXN + 1, gx = tid - (ry - 1) * GXN;
+    const int lane = tid & 31;
     const int tx0 = blockIdx.x * TX, ty0 = blockIdx.y * TY;
     const int y = ty0 - 2 + ry, x0 = tx0 - 4 + 4 * gx;
     const int zs = blockIdx.z * p.zchunk;
     const int ze = min(zs + p.zchunk, p.n0);
     const int64_t plane = (int64_t)p.N1 * p.N2;
     const int soff = ry * BX + 4 * gx;
-    const bool frow = ry >= 1 && ry <= TY + 2;
     const bool in_dom = y >= 0 && y < p.N1 && x0 >= 0 && x0 < p.N2;
     const bool grow = ry >= 2 && ry <= TY + 1 && gx >= 1 && gx <= GXN - 2 && in_dom;
     const int col = y * p.N2 + x0;  // only used when grow
+    // x-neighbours come from the adjacent lanes' registers; lanes at a warp or row edge read shared memory
+    const bool shl_ok = lane > 0 && gx > 0, shr_ok = lane < 31 && gx < GXN - 1;
 
     const int C1 = 2 * p.R1 + 1, C2 = 2 * p.R2 + 1;
     auto cls1 = [](int i, int n, int r) -> int {
@@ -840,7 +845,6 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 4))
     }
     if (cy != p.R1) fmask = 0xFu;
     if (cy != p.R1 || cym != p.R1 || cyp != p.R1) amask = 0xFu;
-    if (!frow) fmask = 0;
     if (!grow) amask = 0;
     auto zcls = [&](int k) -> int {
         int zg = p.z0 + k;
@@ -881,7 +885,6 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 4))
     T w[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) w[i] = p.w[i];
-    const bool zvar = true;
     int czm = zcls(kf0 - 2), cz0 = zcls(kf0 - 1), czp = zcls(kf0);
     int zg1 = p.z0 + kf0 + 1;
     while (zg1 < 0) zg1 += p.N0g;
@@ -890,61 +893,60 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 4))
     T* Fcol = p.Fout ? p.Fout + col : nullptr;
     const Vec4<T> zero4{T(0), T(0), T(0), T(0)};
 
+    // own column in registers: U[kf-1], U[kf] (U[kf+1] is read when its plane lands), F[kf-2], F[kf-1]
+    mbar_wait(&bar_u[0], 0);
+    mbar_wait(&bar_u[1], 0);
+    Vec4<T> um = *reinterpret_cast<const Vec4<T>*>(Us + 0 * PLN + soff);
+    Vec4<T> uc = *reinterpret_cast<const Vec4<T>*>(Us + 1 * PLN + soff);
+    Vec4<T> fm = zero4, fc = zero4;
+
     T accf = T(0);
     double acc2 = 0.0;
 #pragma unroll 4
     for (int it = 0; it < niter; ++it) {
         const int kf = kf0 + it;
-        // planes kf-1, kf, kf+1 are q = it, it+1, it+2
-        const T* Um = Us + ((it)&3) * PLN + soff;
+        // plane kf lives in U slot (it+1)&3, plane kf+1 in slot (it+2)&3
         const T* Uc = Us + ((it + 1) & 3) * PLN + soff;
-        const T* Up = Us + ((it + 2) & 3) * PLN + soff;
         T* Fw = Fs + (it & 3) * PLN + soff;
-        Vec4<T> fp = zero4;
-        if (frow) {
-            // plane kf+1 (q = it+2) is the last one to land; its k-th use of the slot has parity (q >> 2) & 1
-            mbar_wait(&bar_u[(it + 2) & 3], ((it + 2) >> 2) & 1);
-            if (it == 0) {
-                mbar_wait(&bar_u[0], 0);
-                mbar_wait(&bar_u[1], 0);
-            }
-            Vec4<T> cc = zero4;
-            if (p.has_c) {
-                mbar_wait(&bar_c[it & 1], (it >> 1) & 1);
-                cc = *reinterpret_cast<const Vec4<T>*>(Cs + (it & 1) * PLN + soff);
-            }
-            const Vec4<T> uc = *reinterpret_cast<const Vec4<T>*>(Uc);
-            const Vec4<T> um = *reinterpret_cast<const Vec4<T>*>(Um);
-            const Vec4<T> up = *reinterpret_cast<const Vec4<T>*>(Up);
-            const Vec4<T> uym = *reinterpret_cast<const Vec4<T>*>(Uc - BX);
-            const Vec4<T> uyp = *reinterpret_cast<const Vec4<T>*>(Uc + BX);
-            const T ul = Uc[-1], ur = Uc[4];
-            fp = star_fwd<T>(cc, uc, um, up, uym, uyp, ul, ur, w);
-            const unsigned fmk = (czp != p.R0) ? 0xFu : fmask;  // czp == class of plane kf here
-            if (fmk) star_patch_fwd<T>(fp, fmk, tab, (czp * C1 + cy) * C2, cxp, cc, uc, um, up, uym, uyp, ul, ur);
-            *reinterpret_cast<Vec4<T>*>(Fw) = fp;
-            if (grow && kf >= zs && kf < ze) {
-                accf += fp.x * fp.x + fp.y * fp.y + fp.z * fp.z + fp.w * fp.w;
-                if (Fcol) *reinterpret_cast<Vec4<T>*>(Fcol + (int64_t)kf * plane) = fp;
-            }
+        // plane kf+1 (q = it+2): its use count of the slot is q >> 2
+        mbar_wait(&bar_u[(it + 2) & 3], ((it + 2) >> 2) & 1);
+        const Vec4<T> up = *reinterpret_cast<const Vec4<T>*>(Us + ((it + 2) & 3) * PLN + soff);
+        Vec4<T> cc = zero4;
+        if (p.has_c) {
+            mbar_wait(&bar_c[it & 1], (it >> 1) & 1);
+            cc = *reinterpret_cast<const Vec4<T>*>(Cs + (it & 1) * PLN + soff);
         }
+        const Vec4<T> uym = *reinterpret_cast<const Vec4<T>*>(Uc - BX);
+        const Vec4<T> uyp = *reinterpret_cast<const Vec4<T>*>(Uc + BX);
+        T ul = __shfl_up_sync(0xffffffffu, uc.w, 1), ur = __shfl_down_sync(0xffffffffu, uc.x, 1);
+        if (!shl_ok) ul = Uc[-1];
+        if (!shr_ok) ur = Uc[4];
+        Vec4<T> fp = star_fwd<T>(cc, uc, um, up, uym, uyp, ul, ur, w);
+        const unsigned fmk = (czp != p.R0) ? 0xFu : fmask;  // czp == class of plane kf here
+        if (fmk) star_patch_fwd<T>(fp, fmk, tab, (czp * C1 + cy) * C2, cxp, cc, uc, um, up, uym, uyp, ul, ur);
+        *reinterpret_cast<Vec4<T>*>(Fw) = fp;
+        if (grow && kf >= zs && kf < ze) {
+            accf += fp.x * fp.x + fp.y * fp.y + fp.z * fp.z + fp.w * fp.w;
+            if (Fcol) *reinterpret_cast<Vec4<T>*>(Fcol + (int64_t)kf * plane) = fp;
+        }
+        // x-neighbours of F[kf-1] (own registers of the adjacent lanes), before any divergence
+        T fl = __shfl_up_sync(0xffffffffu, fc.w, 1), fr = __shfl_down_sync(0xffffffffu, fc.x, 1);
         __syncthreads();
-        // refill the slots that every thread has finished reading: U plane kf-1's slot gets plane kf+3,
-        // c plane kf's slot gets plane kf+2
+        // refill the slots every thread has finished reading: U plane kf's... (kf-1 is only in registers now,
+        // its slot was released one iteration ago; plane kf is still needed next iteration as y-neighbour? no:
+        // next iteration reads planes kf+1 (neighbours) and kf+2 (own) -> slot of plane kf is free)
         if (tid == 0) {
-            if (it + 4 <= niter) issue_u(it + 4);
+            if (it + 4 <= niter + 1) issue_u(it + 4);  // into slot it & 3 (plane kf-1: released)
             if (p.has_c && it + 2 < niter) issue_c(it + 2);
         }
-        // g[kf-1] from F[kf-2], F[kf-1], F[kf]
+        // g[kf-1] from F[kf-2], F[kf-1], F[kf] (registers) and the in-plane neighbours of F[kf-1]
         const int kg = kf - 1;
         if (grow && kg >= zs && kg < ze) {
             const T* Fc = Fs + ((it + 3) & 3) * PLN + soff;  // plane kf-1
-            const T* Fm = Fs + ((it + 2) & 3) * PLN + soff;  // plane kf-2
-            const Vec4<T> fc = *reinterpret_cast<const Vec4<T>*>(Fc);
-            const Vec4<T> fm = *reinterpret_cast<const Vec4<T>*>(Fm);
             const Vec4<T> fym = *reinterpret_cast<const Vec4<T>*>(Fc - BX);
             const Vec4<T> fyp = *reinterpret_cast<const Vec4<T>*>(Fc + BX);
-            const T fl = Fc[-1], fr = Fc[4];
+            if (!shl_ok) fl = Fc[-1];
+            if (!shr_ok) fr = Fc[4];
             Vec4<T> g = star_adj<T>(fc, fp, fm, fym, fyp, fl, fr, w);
             const bool zslow = cz0 != p.R0 || czm != p.R0 || czp != p.R0;
             const unsigned amk = zslow ? 0xFu : amask;
@@ -957,12 +959,14 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 4))
             g.w *= p.scale;
             *reinterpret_cast<Vec4<T>*>(Gcol + (int64_t)kg * plane) = g;
         }
-        if (zvar) {
-            czm = cz0;
-            cz0 = czp;
-            czp = cls1(zg1, p.N0g, p.R0);
-            zg1 = zg1 + 1 == p.N0g ? 0 : zg1 + 1;
-        }
+        um = uc;
+        uc = up;
+        fm = fc;
+        fc = fp;
+        czm = cz0;
+        cz0 = czp;
+        czp = cls1(zg1, p.N0g, p.R0);
+        zg1 = zg1 + 1 == p.N0g ? 0 : zg1 + 1;
         if ((it & 7) == 7) {
             acc2 += (double)accf;
             accf = T(0);
@@ -1195,7 +1199,7 @@ static int make_plane_map(CUtensorMap* map, const T* base, int64_t nplanes, int 
 template <typename T, int TY, int TX>
 static int launch_star_tma(const CUtensorMap& tmU, const CUtensorMap& tmC, const StarTmaParams<T>& sp, dim3 grid,
                            cudaStream_t st) {
-    constexpr int NT = (TX / 4 + 2) * (TY + 4);
+    constexpr int NT = (TX / 4 + 2) * (TY + 2);
     constexpr int PLN = (TY + 4) * (TX + 8);
     const size_t smem = 128 + (size_t)(4 + 2 + 4) * PLN * sizeof(T) + 512 * sizeof(T) + 128;
     static bool attr_set = false;
@@ -1235,7 +1239,12 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     const int64_t n2 = plan->shape[plan->ndim - 1];
     const bool v3 = tiled && plan->use_v3 && (n2 % 4 == 0) && ((uintptr_t)U % 16 == 0) && ((uintptr_t)G % 16 == 0) &&
                     ((uintptr_t)c % 16 == 0) && ((uintptr_t)Fout % 16 == 0);
-    const bool tma = v3 && plan->use_tma && plan->wrap_free && get_encode_tiled() != nullptr;
+    bool tma = v3 && plan->use_tma && plan->wrap_free && get_encode_tiled() != nullptr;
+    if (tma) {  // the three plane rings must fit the 227 KB of shared memory of one SM
+        static const int tys[4] = {16, 8, 12, 26};
+        const size_t need = 128 + (size_t)10 * (tys[plan->variant & 3] + 4) * (128 + 8) * sizeof(T) + 512 * sizeof(T) + 128;
+        if (need > 227 * 1024) tma = false;
+    }
     if (tma) {
         StarTmaParams<T> sp;
         sp.G = io.out;
@@ -1472,7 +1481,7 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
     p->noff = noff;
     p->ncls = 1;
     p->zchunk = 0;
-    p->variant = 0;
+    p->variant = 1;  // TY = 8 tiles: best measured at 512^3 fp32 on B200 (bench_kernels.py)
     p->table_dev = nullptr;
     p->partials = nullptr;
     int64_t total = 1;
@@ -1536,7 +1545,6 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
     p->star_has_z = 0;
     p->use_v3 = 1;
     p->use_tma = 1;
-    p->wrap_free = 0;
     std::vector<double> star;
     for (int i = 0; i < 7; ++i) p->w[i] = 0.0;
     if ((ndim == 3 || ndim == 2) && total >= 512) {
