@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--steps", type=int, default=30)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     p.add_argument("--size", type=int, default=512, help="cells per axis (per GPU along axis 0)")
@@ -108,20 +108,22 @@ def cpu_epoch_rate(size, levels, steps, warmup, dtype):
 
     ncpu = os.cpu_count()
     tdt = torch.float32 if dtype == "f32" else torch.float64
-    ep = port.PoissonAdamEpoch((size,) * 3, levels, dtype=tdt)
     # Use the thread count that serves the reference best on this host (oversubscribing a many-core box
-    # with tiny elementwise ops is much slower than a moderate count): one probe epoch per candidate.
+    # with small elementwise ops is much slower than a moderate count): quick probe on a 96^3 grid.
+    probe = port.PoissonAdamEpoch((96,) * 3, min(levels, 4), dtype=tdt)
     best, cores = None, ncpu
-    for nthr in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+    for nthr in sorted({min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
         torch.set_num_threads(nthr)
-        ep.step()
+        probe.step()
         t0 = time.perf_counter()
-        ep.step()
+        probe.step()
         dt1 = time.perf_counter() - t0
         if best is None or dt1 < best:
             best, cores = dt1, nthr
+    del probe
     torch.set_num_threads(cores)
-    for _ in range(max(0, warmup - 1)):
+    ep = port.PoissonAdamEpoch((size,) * 3, levels, dtype=tdt)
+    for _ in range(max(1, warmup)):
         ep.step()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -252,15 +254,23 @@ def run_b200(args):
         return t_.item()
 
     native.set_timer_hook(timed)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~0.2 s to start: sample from the warm-up on, all of it under load
     t = 0
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         t += 1
         epoch(t)
     sync_all()
-    timers.clear()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        # keep the device busy until the sampler has produced its first lines (not timed)
+        t_wait = time.time()
+        while len(sampler.lines) < 2 and time.time() - t_wait < 3.0:
+            t += 1
+            epoch(t)
+            torch.cuda.synchronize()
+    sync_all()
+    timers.clear()
     launches0 = native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -285,10 +295,19 @@ def run_b200(args):
             gbs = alg_bytes[name] / (per_step * 1e-3) / 1e9
             kern[name].update({"achieved_GBs": gbs, "frac": gbs / peak})
     fused = kern.get("stencil_fused", {})
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_fused_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("cells") == ncells_local and tj.get("dtype") == args.dtype:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
-        "bound": "hbm", "kernel": "odil_b200_stencil_fused (k_star_v3: residual + loss + adjoint in one sweep)",
+        "bound": "hbm",
+        "kernel": "odil_b200_stencil_fused (k_star_tma: TMA-fed residual + loss + adjoint in one sweep, + reduce)",
         "achieved": fused.get("achieved_GBs"), "peak": peak, "unit": "GB/s", "frac": fused.get("frac"),
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes["stencil_fused"], "ms_per_launch": fused.get("ms_per_step"),
         "note": "3*s bytes per cell (read U, read c, write g); time = CUDA events around the C-ABI call on the "
                 "launch stream, averaged over the timed steps (rank 0)",

@@ -132,6 +132,11 @@ struct Mg3 {
     int64_t fs0, fs1;      // fine strides
 };
 
+template <typename T>
+struct alignas(sizeof(T) * 2) Pair {
+    T a, b;
+};
+
 template <typename T, bool CZ>
 __global__ void __launch_bounds__(128) k_interp_add3(MgGeom g, Mg3 m, const T* __restrict__ coarse, T cfac,
                                                      const T* __restrict__ term, T ffac, T* __restrict__ out,
@@ -237,11 +242,11 @@ __global__ void __launch_bounds__(128) k_interp_add3(MgGeom g, Mg3 m, const T* _
             const int64_t lin = (fz - out_z0) * m.fs0 + (int64_t)(2 * J + b) * m.fs1 + 2 * K;
             T r0 = cfac * res[a][b][0], r1 = cfac * res[a][b][1];
             if (term) {
-                r0 += ffac * __ldg(term + lin);
-                r1 += ffac * __ldg(term + lin + 1);
+                const Pair<T> t = *reinterpret_cast<const Pair<T>*>(term + lin);  // 2K is even: aligned pair
+                r0 += ffac * t.a;
+                r1 += ffac * t.b;
             }
-            out[lin] = r0;
-            out[lin + 1] = r1;
+            *reinterpret_cast<Pair<T>*>(out + lin) = Pair<T>{r0, r1};
         }
 }
 
@@ -435,7 +440,8 @@ __global__ void __launch_bounds__(128) k_interp_adjoint3(MgGeom g, Mg3 m, const 
                 for (int p = 0; p < 3; ++p) {
                     const int fx = x0 + 2 * p;
                     if (fx >= 0 && fx + 1 < nf2) {
-                        accx += wx[2 * p] * __ldg(py + fx) + wx[2 * p + 1] * __ldg(py + fx + 1);
+                        const Pair<T> v = *reinterpret_cast<const Pair<T>*>(py + fx);  // fx is even: aligned pair
+                        accx += wx[2 * p] * v.a + wx[2 * p + 1] * v.b;
                     }
                 }
                 accy += wy[ty] * accx;

@@ -790,10 +790,10 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2), ((TX / 4 + 2) * (TY +
     constexpr int GXN = TX / 4 + 2;
     constexpr int NR = TY + 4;         // rows of a staged plane: tile + 2-cell halo (U of the F ring's neighbours)
     constexpr int BX = GXN * 4;        // dense row of the TMA box
-    constexpr int PLN = NR * BX;       // elements per plane slot
+    constexpr int PLN = ((NR * BX + 31) / 32) * 32;  // elements per plane slot, 128-byte multiple (TMA destination)
     constexpr int NSU = 4, NSC = 2, NSF = 4;
     constexpr int kTabSmem = 512;
-    constexpr uint32_t kBytes = PLN * sizeof(T);
+    constexpr uint32_t kBytes = NR * BX * sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // [128 B pad][U ring][C ring][F ring][table][pad]
     T* Us = reinterpret_cast<T*>(smem_raw + 128);
@@ -1200,7 +1200,7 @@ template <typename T, int TY, int TX>
 static int launch_star_tma(const CUtensorMap& tmU, const CUtensorMap& tmC, const StarTmaParams<T>& sp, dim3 grid,
                            cudaStream_t st) {
     constexpr int NT = (TX / 4 + 2) * (TY + 2);
-    constexpr int PLN = (TY + 4) * (TX + 8);
+    constexpr int PLN = (((TY + 4) * (TX + 8) + 31) / 32) * 32;
     const size_t smem = 128 + (size_t)(4 + 2 + 4) * PLN * sizeof(T) + 512 * sizeof(T) + 128;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1242,7 +1242,7 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     bool tma = v3 && plan->use_tma && plan->wrap_free && get_encode_tiled() != nullptr;
     if (tma) {  // the three plane rings must fit the 227 KB of shared memory of one SM
         static const int tys[4] = {16, 8, 12, 26};
-        const size_t need = 128 + (size_t)10 * (tys[plan->variant & 3] + 4) * (128 + 8) * sizeof(T) + 512 * sizeof(T) + 128;
+        const size_t need = 128 + (size_t)10 * (((tys[(plan->variant < 0 ? 1 : plan->variant) & 3] + 4) * (128 + 8) + 31) / 32 * 32) * sizeof(T) + 512 * sizeof(T) + 128;
         if (need > 227 * 1024) tma = false;
     }
     if (tma) {
@@ -1277,7 +1277,8 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         sp.has_c = io.c != nullptr;
         int TY = 16;
         const int TX = 128;
-        switch (plan->variant) {
+        const int tvar = plan->variant < 0 ? 1 : plan->variant;  // auto: TY = 8
+        switch (tvar) {
             case 1: TY = 8; break;
             case 2: TY = 12; break;
             case 3: TY = 26; break;
@@ -1304,7 +1305,7 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
                                        TY + 4, TX + 8))
             return rc;
         int rc = 0;
-        switch (plan->variant) {
+        switch (tvar) {
             case 1: rc = launch_star_tma<T, 8, 128>(tmU, tmC, sp, grid, st); break;
             case 2: rc = launch_star_tma<T, 12, 128>(tmU, tmC, sp, grid, st); break;
             case 3: rc = launch_star_tma<T, 26, 128>(tmU, tmC, sp, grid, st); break;
@@ -1346,7 +1347,8 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         for (int i = 0; i < 7; ++i) sp.w[i] = (T)plan->w[i];
         sp.scale = (T)scale;
         int TY, TX;
-        star_v3_tile(plan->variant, TY, TX);
+        const int vvar = plan->variant < 0 ? 0 : plan->variant;  // auto: TY = 16
+        star_v3_tile(vvar, TY, TX);
         const int gx = (sp.N2 + TX - 1) / TX, gy = (sp.N1 + TY - 1) / TY;
         int zchunk = plan->zchunk;
         if (zchunk <= 0) {
@@ -1360,7 +1362,7 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         ODIL_REQUIRE((int64_t)gx * gy * gz <= kPartialCapacity, "star grid exceeds the partials workspace");
         dim3 grid(gx, gy, gz);
         int rc = 0;
-        switch (plan->variant) {
+        switch (vvar) {
             case 1: rc = launch_star_v3<T, 8, 128>(sp, grid, st); break;
             case 2: rc = launch_star_v3<T, 12, 128>(sp, grid, st); break;
             case 3: rc = launch_star_v3<T, 26, 128>(sp, grid, st); break;
@@ -1407,7 +1409,8 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         sp.wxp = (T)plan->w[6];
         sp.scale = (T)scale;
         int TY, TX;
-        star_tile(plan->variant, TY, TX);
+        const int wvar = plan->variant < 0 ? 2 : plan->variant;  // auto: 16 x 128 tiles
+        star_tile(wvar, TY, TX);
         const int gx = (sp.N2 + TX - 1) / TX, gy = (sp.N1 + TY - 1) / TY;
         int zchunk = plan->zchunk;
         if (zchunk <= 0) {
@@ -1423,7 +1426,7 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         dim3 grid(gx, gy, gz);
         const bool vec = (sp.N2 % 4 == 0) && ((uintptr_t)G % 16 == 0);
         int rc = 0;
-        switch (plan->variant) {
+        switch (wvar) {
             case 1: rc = launch_star_cfg<T, 16, 64, 256>(sp, grid, vec, st); break;
             case 2: rc = launch_star_cfg<T, 16, 128, 512>(sp, grid, vec, st); break;
             case 3: rc = launch_star_cfg<T, 4, 128, 128>(sp, grid, vec, st); break;
@@ -1481,7 +1484,7 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
     p->noff = noff;
     p->ncls = 1;
     p->zchunk = 0;
-    p->variant = 1;  // TY = 8 tiles: best measured at 512^3 fp32 on B200 (bench_kernels.py)
+    p->variant = -1;  // auto: best measured tile per kernel at 512^3 fp32 on B200 (tools/bench_kernels.py)
     p->table_dev = nullptr;
     p->partials = nullptr;
     int64_t total = 1;
