@@ -93,6 +93,9 @@ struct odil_b200_plan {
     int wrap_free;     // no coefficient multiplies a neighbour across a periodic boundary (TMA zero fill is exact)
     int use_tma;       // 1: TMA-fed kernel when eligible
     int use_v3;        // 1: column-group kernel (default when N2 % 4 == 0), 0: v2 tile kernel + shell
+    int use_star7;     // 1: k_star7 (default when eligible)
+    int no_xu;         // tuning: force the general coefficient registers
+    int star_xu;       // z-/y-arm coefficients of the interior y/z classes do not depend on the x class
 };
 
 namespace odil {
@@ -977,6 +980,10 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2), ((TX / 4 + 2) * (TY +
     if (tid == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sum;
 }
 
+}  // namespace odil
+#include "star7.cuh"
+namespace odil {
+
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
@@ -1212,6 +1219,77 @@ static int launch_star_tma(const CUtensorMap& tmU, const CUtensorMap& tmC, const
     return 0;
 }
 
+template <typename T, int VW, int TY, bool XU>
+static int launch_star7(const odil_b200_plan* plan, const odil_b200_slab* slab, const T* U, const T* c, T scale, T* G,
+                        T* Fout, int* nparts, cudaStream_t st) {
+    using Cfg = Star7Cfg<T, VW, TY>;
+    Star7Params<T> sp;
+    sp.G = G;
+    sp.Fout = Fout;
+    sp.partials = plan->partials;
+    sp.table = (const T*)plan->star_table;
+    if (plan->ndim == 3) {
+        sp.n0 = (int)slab->n0;
+        sp.N0g = (int)plan->shape[0];
+        sp.z0 = (int)slab->z0;
+        sp.halo = slab->halo;
+        sp.N1 = (int)plan->shape[1];
+        sp.N2 = (int)plan->shape[2];
+        sp.R0 = plan->R[0];
+        sp.R1 = plan->R[1];
+        sp.R2 = plan->R[2];
+    } else {
+        sp.n0 = 1;
+        sp.N0g = 1;
+        sp.z0 = 0;
+        sp.halo = 0;
+        sp.N1 = (int)plan->shape[0];
+        sp.N2 = (int)plan->shape[1];
+        sp.R0 = 0;
+        sp.R1 = plan->R[0];
+        sp.R2 = plan->R[1];
+    }
+    sp.scale = scale;
+    sp.has_c = c != nullptr;
+    const int gx = (sp.N2 + Cfg::TX - 1) / Cfg::TX, gy = (sp.N1 + TY - 1) / TY;
+    int zchunk = plan->zchunk;
+    if (zchunk <= 0) {
+        // fill the 148 x MINB CTA slots in whole waves while keeping the 2-plane lead-in of a chunk small:
+        // cost(gz) ~ waves(gz) * (planes per chunk + lead-in)
+        const int64_t slots = 148 * (XU ? Cfg::MINB_XU : Cfg::MINB), layer = (int64_t)gx * gy;
+        int64_t best = -1;
+        for (int gz = 1; gz <= std::max(1, sp.n0 / 8); ++gz) {
+            const int zc = (sp.n0 + gz - 1) / gz;
+            const int gzr = (sp.n0 + zc - 1) / zc;
+            const int64_t cost = ((layer * gzr + slots - 1) / slots) * (zc + 5);
+            if (best < 0 || cost < best) {
+                best = cost;
+                zchunk = zc;
+            }
+        }
+    }
+    if (zchunk > sp.n0) zchunk = sp.n0;
+    if (zchunk < 1) zchunk = 1;
+    sp.zchunk = zchunk;
+    const int gz = (sp.n0 + zchunk - 1) / zchunk;
+    ODIL_REQUIRE((int64_t)gx * gy * gz <= kPartialCapacity, "star grid exceeds the partials workspace");
+    const int64_t planes_total = (int64_t)sp.n0 + 2 * sp.halo;
+    const int64_t plane_elems = (int64_t)sp.N1 * sp.N2;
+    CUtensorMap tmU, tmC;
+    if (int rc = make_plane_map<T>(&tmU, U - sp.halo * plane_elems, planes_total, sp.N1, sp.N2, Cfg::RU, Cfg::BX)) return rc;
+    if (int rc = make_plane_map<T>(&tmC, (c ? c : U) - sp.halo * plane_elems, planes_total, sp.N1, sp.N2, Cfg::RC, Cfg::BX))
+        return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ODIL_CUDA(cudaFuncSetAttribute(k_star7<T, VW, TY, XU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    k_star7<T, VW, TY, XU><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM, st>>>(tmU, tmC, sp);
+    ODIL_LAUNCHED();
+    *nparts = gx * gy * gz;
+    return 0;
+}
+
 static void star_tile(int variant, int& TY, int& TX) {
     switch (variant) {
         case 1: TY = 16; TX = 64; break;
@@ -1245,7 +1323,22 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         const size_t need = 128 + (size_t)10 * (((tys[(plan->variant < 0 ? 1 : plan->variant) & 3] + 4) * (128 + 8) + 31) / 32 * 32) * sizeof(T) + 512 * sizeof(T) + 128;
         if (need > 227 * 1024) tma = false;
     }
-    if (tma) {
+    constexpr int VW7 = 16 / (int)sizeof(T);
+    const bool star7 = tiled && plan->use_star7 && plan->wrap_free && get_encode_tiled() != nullptr && (n2 % VW7 == 0) &&
+                       ((uintptr_t)U % 16 == 0) && ((uintptr_t)G % 16 == 0) && ((uintptr_t)c % 16 == 0) &&
+                       ((uintptr_t)Fout % 16 == 0);
+    if (star7) {
+        int rc;
+#define ODIL_S7(TY_, XU_) launch_star7<T, VW7, TY_, XU_>(plan, slab, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)
+        const bool xu = plan->star_xu && !plan->no_xu;
+        switch (plan->variant) {
+            case 1: rc = xu ? ODIL_S7(16, true) : ODIL_S7(16, false); break;
+            case 2: rc = xu ? ODIL_S7(8, true) : ODIL_S7(8, false); break;
+            default: rc = xu ? ODIL_S7(12, true) : ODIL_S7(12, false); break;
+        }
+#undef ODIL_S7
+        if (rc) return rc;
+    } else if (tma) {
         StarTmaParams<T> sp;
         sp.G = io.out;
         sp.Fout = io.Fout;
@@ -1548,6 +1641,9 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
     p->star_has_z = 0;
     p->use_v3 = 1;
     p->use_tma = 1;
+    p->use_star7 = 1;
+    p->star_xu = 0;
+    p->no_xu = 0;
     std::vector<double> star;
     for (int i = 0; i < 7; ++i) p->w[i] = 0.0;
     if ((ndim == 3 || ndim == 2) && total >= 512) {
@@ -1588,6 +1684,17 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
                     star[(size_t)cl * 7 + slot] += p->table[(size_t)cl * noff + o];
                     if ((slot == 1 || slot == 2) && p->table[(size_t)cl * noff + o] != 0.0) p->star_has_z = 1;
                 }
+            }
+            // x-uniform arms: for the interior classes along every axis but the last, the four z/y arm
+            // coefficients are the same for every class along the last axis
+            {
+                const int C2 = 2 * p->R[ndim - 1] + 1;
+                const int rowbase = (cint / C2) * C2;  // interior classes of the leading axes, x class 0
+                bool xu = true;
+                for (int cx = 0; cx < C2 && xu; ++cx)
+                    for (int sl = 1; sl <= 4; ++sl)
+                        if (star[(size_t)(rowbase + cx) * 7 + sl] != star[(size_t)cint * 7 + sl]) xu = false;
+                p->star_xu = xu ? 1 : 0;
             }
         }
     }
@@ -1640,10 +1747,17 @@ int odil_b200_stencil_plan_kind(const odil_b200_plan* plan) { return plan ? plan
 
 int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant) {
     ODIL_REQUIRE(plan != nullptr, "null plan");
-    ODIL_REQUIRE((variant >= 0 && variant <= 3) || (variant >= 10 && variant <= 13) || (variant >= 20 && variant <= 23),
+    ODIL_REQUIRE((variant >= 0 && variant <= 3) || (variant >= 10 && variant <= 13) ||
+                     (variant >= 20 && variant <= 23) || (variant >= 30 && variant <= 32) ||
+                     (variant >= 40 && variant <= 42) || variant == -1,
                  "variant=%d unknown", variant);
     plan->zchunk = zchunk;
-    // 0..3: TMA-fed kernel tiles (default); 10..13: v2 tile kernel + shell pass; 20..23: LDG column-group kernel
+    // -1 / 30..32: k_star7 (default; tiles of 12 / 16 / 8 rows); 40..42: same with per-cell z/y-arm coefficients
+    // even when the plan allows the x-uniform form; 0..3: previous TMA-fed kernel;
+    // 10..13: v2 tile kernel + shell pass; 20..23: LDG column-group kernel
+    if (variant < 0) variant = 30;
+    plan->use_star7 = variant >= 30;
+    plan->no_xu = variant >= 40;
     plan->use_tma = variant < 10;
     plan->use_v3 = variant < 10 || variant >= 20;
     plan->variant = variant % 10;
