@@ -35,7 +35,7 @@ inline int fail(const char* fmt, ...) {
 #define ODIL_LAUNCHED()                                                                                  \
     do {                                                                                                 \
         ::odil::launch_counter()++;                                                                      \
-        cudaError_t e_ = cudaPeekAtLastError();                                                          \
+        cudaError_t e_ = cudaGetLastError(); /* clears a refused launch so that it does not stick */   \
         if (e_ != cudaSuccess)                                                                           \
             return ::odil::fail("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
     } while (0)

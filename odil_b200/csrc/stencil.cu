@@ -95,6 +95,10 @@ struct odil_b200_plan {
     int use_v3;        // 1: column-group kernel (default when N2 % 4 == 0), 0: v2 tile kernel + shell
     int use_star7;     // 1: k_star7 (default when eligible)
     int no_xu;         // tuning: force the general coefficient registers
+    int use_star8;     // 1: k_star8 (default when eligible): one row per warp, host-built work list
+    // work list of k_star8 (device copy + the key it was built for)
+    mutable void* work_dev;
+    mutable int work_cap, work_n, work_key[6];
     int star_xu;       // z-/y-arm coefficients of the interior y/z classes do not depend on the x class
 };
 
@@ -982,6 +986,7 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2), ((TX / 4 + 2) * (TY +
 
 }  // namespace odil
 #include "star7.cuh"
+#include "star8.cuh"
 namespace odil {
 
 // ------------------------------------------------------------------------------------------------
@@ -1290,6 +1295,120 @@ static int launch_star7(const odil_b200_plan* plan, const odil_b200_slab* slab, 
     return 0;
 }
 
+// Work list of k_star8: tiles of up to NR rows x TX columns times z-chunks, chosen so that the CTAs fill the
+// SMs in whole waves with equal work.  cost ~ waves * (planes per chunk + lead-in) * (rows per CTA + ring rows).
+static void build_work8(int NR, int TX, int slots, int n0, int N1, int N2, int zchunk, std::vector<S8Work>& out) {
+    const int gx = (N2 + TX - 1) / TX;
+    int64_t best = -1;
+    int best_rmax = NR, best_zc = n0;
+    for (int rmax = 1; rmax <= NR; ++rmax) {
+        const int nblk = (N1 + rmax - 1) / rmax;
+        const int gz_lo = zchunk > 0 ? std::max(1, (n0 + zchunk - 1) / zchunk) : 1;
+        const int gz_hi = zchunk > 0 ? gz_lo : std::max(1, n0 / 8);
+        for (int gz = gz_lo; gz <= gz_hi; ++gz) {
+            const int zc = (n0 + gz - 1) / gz;
+            const int gzr = (n0 + zc - 1) / zc;
+            const int64_t ncta = (int64_t)gx * nblk * gzr;
+            if (ncta > kPartialCapacity) continue;
+            const int64_t cost = ((ncta + slots - 1) / slots) * (zc + 6) * (rmax + 3);
+            if (best < 0 || cost < best) {
+                best = cost;
+                best_rmax = rmax;
+                best_zc = zc;
+            }
+        }
+    }
+    const int nblk = (N1 + best_rmax - 1) / best_rmax;
+    out.clear();
+    for (int zs = 0; zs < n0; zs += best_zc)
+        for (int b = 0; b < nblk; ++b) {
+            const int y0 = (int)((int64_t)b * N1 / nblk), y1 = (int)((int64_t)(b + 1) * N1 / nblk);
+            if (y1 <= y0) continue;
+            for (int bx = 0; bx < gx; ++bx) out.push_back(S8Work{bx * TX, y0, y1 - y0, zs, std::min(n0, zs + best_zc), 0, 0, 0});
+        }
+}
+
+template <typename T, int VW, int NR, bool XU>
+static int launch_star8(const odil_b200_plan* plan, const odil_b200_slab* slab, const T* U, const T* c, T scale, T* G,
+                        T* Fout, int* nparts, cudaStream_t st) {
+    using Cfg = Star8Cfg<T, VW, NR>;
+    Star8Params<T> sp;
+    sp.G = G;
+    sp.Fout = Fout;
+    sp.partials = plan->partials;
+    sp.table = (const T*)plan->star_table;
+    if (plan->ndim == 3) {
+        sp.n0 = (int)slab->n0;
+        sp.N0g = (int)plan->shape[0];
+        sp.z0 = (int)slab->z0;
+        sp.halo = slab->halo;
+        sp.N1 = (int)plan->shape[1];
+        sp.N2 = (int)plan->shape[2];
+        sp.R0 = plan->R[0];
+        sp.R1 = plan->R[1];
+        sp.R2 = plan->R[2];
+    } else {
+        sp.n0 = 1;
+        sp.N0g = 1;
+        sp.z0 = 0;
+        sp.halo = 0;
+        sp.N1 = (int)plan->shape[0];
+        sp.N2 = (int)plan->shape[1];
+        sp.R0 = 0;
+        sp.R1 = plan->R[0];
+        sp.R2 = plan->R[1];
+    }
+    sp.scale = scale;
+    sp.has_c = c != nullptr;
+    const int key[6] = {sp.n0, sp.N1, sp.N2, NR, plan->zchunk, Cfg::TX};
+    if (memcmp(key, plan->work_key, sizeof(key)) != 0) {
+        std::vector<S8Work> work;
+        build_work8(NR, Cfg::TX, 148 * Cfg::CTAS_PER_SM, sp.n0, sp.N1, sp.N2, plan->zchunk, work);
+        ODIL_REQUIRE(!work.empty() && (int64_t)work.size() <= kPartialCapacity, "star work list has %lld entries",
+                     (long long)work.size());
+        if ((int)work.size() > plan->work_cap) {
+            if (plan->work_dev) cudaFree(plan->work_dev);
+            plan->work_dev = nullptr;
+            plan->work_cap = 0;
+            ODIL_CUDA(cudaMalloc(&plan->work_dev, sizeof(S8Work) * work.size()));
+            plan->work_cap = (int)work.size();
+        }
+        // pageable source: the copy is staged before the call returns, so `work` may go out of scope
+        ODIL_CUDA(cudaMemcpyAsync(plan->work_dev, work.data(), sizeof(S8Work) * work.size(), cudaMemcpyHostToDevice, st));
+        plan->work_n = (int)work.size();
+        memcpy(plan->work_key, key, sizeof(key));
+    }
+    sp.work = (const S8Work*)plan->work_dev;
+    const int64_t planes_total = (int64_t)sp.n0 + 2 * sp.halo;
+    const int64_t plane_elems = (int64_t)sp.N1 * sp.N2;
+    CUtensorMap tmU, tmC;
+    if (int rc = make_plane_map<T>(&tmU, U - sp.halo * plane_elems, planes_total, sp.N1, sp.N2, Cfg::RU, Cfg::BX)) return rc;
+    if (int rc = make_plane_map<T>(&tmC, (c ? c : U) - sp.halo * plane_elems, planes_total, sp.N1, sp.N2, Cfg::RC, Cfg::BX))
+        return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ODIL_CUDA(cudaFuncSetAttribute(k_star8<T, VW, NR, XU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    k_star8<T, VW, NR, XU><<<plan->work_n, Cfg::NT, Cfg::SMEM, st>>>(tmU, tmC, sp);
+    {
+        launch_counter()++;
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cudaFuncAttributes fa;
+            memset(&fa, 0, sizeof(fa));
+            cudaFuncGetAttributes(&fa, k_star8<T, VW, NR, XU>);
+            cudaGetLastError();
+            return fail("k_star8<NR=%d> launch (%d CTAs x %d threads, %zu B dynamic smem) -> %s [numRegs=%d maxThreadsPerBlock=%d "
+                        "static smem=%zu maxDynamic=%d local=%zu]",
+                        NR, plan->work_n, Cfg::NT, (size_t)Cfg::SMEM, cudaGetErrorString(e), fa.numRegs, fa.maxThreadsPerBlock,
+                        fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes);
+        }
+    }
+    *nparts = plan->work_n;
+    return 0;
+}
+
 static void star_tile(int variant, int& TY, int& TX) {
     switch (variant) {
         case 1: TY = 16; TX = 64; break;
@@ -1327,7 +1446,18 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     const bool star7 = tiled && plan->use_star7 && plan->wrap_free && get_encode_tiled() != nullptr && (n2 % VW7 == 0) &&
                        ((uintptr_t)U % 16 == 0) && ((uintptr_t)G % 16 == 0) && ((uintptr_t)c % 16 == 0) &&
                        ((uintptr_t)Fout % 16 == 0);
-    if (star7) {
+    if (star7 && plan->use_star8) {
+        int rc;
+#define ODIL_S8(NR_, XU_) launch_star8<T, VW7, NR_, XU_>(plan, slab, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)
+        const bool xu = plan->star_xu && !plan->no_xu;
+        switch (plan->variant) {
+            case 1: rc = xu ? ODIL_S8(12, true) : ODIL_S8(12, false); break;
+            case 2: rc = xu ? ODIL_S8(8, true) : ODIL_S8(8, false); break;
+            default: rc = xu ? ODIL_S8(14, true) : ODIL_S8(14, false); break;
+        }
+#undef ODIL_S8
+        if (rc) return rc;
+    } else if (star7) {
         int rc;
 #define ODIL_S7(TY_, XU_) launch_star7<T, VW7, TY_, XU_>(plan, slab, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)
         const bool xu = plan->star_xu && !plan->no_xu;
@@ -1644,6 +1774,11 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
     p->use_star7 = 1;
     p->star_xu = 0;
     p->no_xu = 0;
+    p->use_star8 = 1;
+    p->work_dev = nullptr;
+    p->work_cap = 0;
+    p->work_n = 0;
+    for (int i = 0; i < 6; ++i) p->work_key[i] = -1;
     std::vector<double> star;
     for (int i = 0; i < 7; ++i) p->w[i] = 0.0;
     if ((ndim == 3 || ndim == 2) && total >= 512) {
@@ -1689,11 +1824,15 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
             // coefficients are the same for every class along the last axis
             {
                 const int C2 = 2 * p->R[ndim - 1] + 1;
-                const int rowbase = (cint / C2) * C2;  // interior classes of the leading axes, x class 0
+                const int C1 = ndim >= 2 ? 2 * p->R[ndim - 2] + 1 : 1;
+                const int cz_int = ndim == 3 ? p->R[0] : 0;  // interior class of axis 0 (3-D only)
                 bool xu = true;
-                for (int cx = 0; cx < C2 && xu; ++cx)
-                    for (int sl = 1; sl <= 4; ++sl)
-                        if (star[(size_t)(rowbase + cx) * 7 + sl] != star[(size_t)cint * 7 + sl]) xu = false;
+                for (int cy = 0; cy < C1 && xu; ++cy) {
+                    const int rowbase = (cz_int * C1 + cy) * C2;
+                    for (int cx = 1; cx < C2 && xu; ++cx)
+                        for (int sl = 1; sl <= 4; ++sl)
+                            if (star[(size_t)(rowbase + cx) * 7 + sl] != star[(size_t)rowbase * 7 + sl]) xu = false;
+                }
                 p->star_xu = xu ? 1 : 0;
             }
         }
@@ -1739,6 +1878,7 @@ int odil_b200_stencil_plan_destroy(odil_b200_plan* plan) {
     if (plan->table_dev) cudaFree(plan->table_dev);
     if (plan->partials) cudaFree(plan->partials);
     if (plan->star_table) cudaFree(plan->star_table);
+    if (plan->work_dev) cudaFree(plan->work_dev);
     delete plan;
     return 0;
 }
@@ -1749,18 +1889,22 @@ int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant) {
     ODIL_REQUIRE(plan != nullptr, "null plan");
     ODIL_REQUIRE((variant >= 0 && variant <= 3) || (variant >= 10 && variant <= 13) ||
                      (variant >= 20 && variant <= 23) || (variant >= 30 && variant <= 32) ||
-                     (variant >= 40 && variant <= 42) || variant == -1,
+                     (variant >= 40 && variant <= 42) || (variant >= 50 && variant <= 52) ||
+                     (variant >= 60 && variant <= 62) || variant == -1,
                  "variant=%d unknown", variant);
     plan->zchunk = zchunk;
-    // -1 / 30..32: k_star7 (default; tiles of 12 / 16 / 8 rows); 40..42: same with per-cell z/y-arm coefficients
-    // even when the plan allows the x-uniform form; 0..3: previous TMA-fed kernel;
-    // 10..13: v2 tile kernel + shell pass; 20..23: LDG column-group kernel
-    if (variant < 0) variant = 30;
+    // -1 / 50..52: k_star8 (default; up to 14 / 12 / 8 rows per CTA); 60..62: same with per-cell z/y-arm
+    // coefficients even when the plan allows the x-uniform form; 30..32 / 40..42: k_star7 (tiles of 12 / 16 / 8
+    // rows, x-uniform / per-cell arms); 0..3: previous TMA-fed kernel; 10..13: v2 tile kernel + shell pass;
+    // 20..23: LDG column-group kernel
+    if (variant < 0) variant = 50;
+    plan->use_star8 = variant >= 50;
     plan->use_star7 = variant >= 30;
-    plan->no_xu = variant >= 40;
+    plan->no_xu = (variant >= 40 && variant < 50) || variant >= 60;
     plan->use_tma = variant < 10;
     plan->use_v3 = variant < 10 || variant >= 20;
     plan->variant = variant % 10;
+    for (int i = 0; i < 6; ++i) plan->work_key[i] = -1;
     return 0;
 }
 
