@@ -4,6 +4,9 @@
 // (restrict_to_coarser).  The boundary rule is the JOINT pad  P = 2*symmetric(u) - reflect(u)
 // (core.py:640-643): for an out-of-range tap q the value is 2*u[clamp(q)] - u[reflect(q)] with
 // clamp/reflect applied to all axes at once, so corners are not the tensor product of 1-D rules.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace odil {
@@ -572,6 +575,25 @@ static bool fast3_geometry(const MgGeom& g, Mg3& m, bool& cz) {
 }
 
 }  // namespace odil
+#include "mg_march.cuh"
+namespace odil {
+
+// z-chunk of the marching transfer kernels: enough CTAs (128 threads) to fill 148 SMs ~12 times over, chunks of
+// at least 8 coarse planes so that the 2-plane lead-in stays small
+static int march_chunk(const Mg3& m, int ncz) {
+    const int64_t layer = (int64_t)((m.n2 / 2 + 31) / 32) * ((m.n1 + 3) / 4);
+    int gz = (int)std::max<int64_t>(1, (148 * 12 + layer - 1) / layer);
+    int zc = (ncz + gz - 1) / gz;
+    if (zc < 8) zc = 8;
+    if (zc > ncz) zc = ncz;
+    return zc;
+}
+static bool march_ok(const Mg3& m, bool cz, int ndim, const void* a, const void* b, const void* c) {
+    return cz && ndim == 3 && m.n2 % 2 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) &&
+           ((uintptr_t)c % 16 == 0) && getenv("ODIL_B200_MG_OLD") == nullptr;
+}
+
+}  // namespace odil
 
 using namespace odil;
 
@@ -597,6 +619,36 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
         Mg3 m;
         bool cz = false;
         const bool pairs = (r.fz_begin % 2 == 0) && (r.fz_end % 2 == 0);
+        if (fast3_geometry(g, m, cz) && march_ok(m, cz, ndim, coarse, fine_term, out) && r.fz_end > r.fz_begin &&
+            out != fine_term) {
+            const int ib = (int)(r.fz_begin >> 1), ie = (int)(((r.fz_end - 1) >> 1) + 1);
+            const int zc = march_chunk(m, ie - ib);
+            dim3 block(32, 4, 1);
+            dim3 grid((m.n2 / 2 + 31) / 32, (m.n1 + 3) / 4, (ie - ib + zc - 1) / zc);
+            const int nfix = 4 * (int)(r.fz_end - r.fz_begin) + 8 * (m.n1 + m.n2);
+            if (grid.y <= 65535 && grid.z <= 65535) {
+                if (dtype == ODIL_B200_F32) {
+                    k_interp_add3m<float><<<grid, block, 0, st>>>(m, (const float*)coarse, (float)cfac,
+                                                                  (const float*)fine_term, (float)ffac, (float*)out,
+                                                                  (int)r.fz_begin, (int)r.fz_end, (int)r.out_z0,
+                                                                  (int)r.coarse_z0, zc);
+                    k_interp_fix_edges<float><<<(nfix + 127) / 128, 128, 0, st>>>(
+                        g, m, (const float*)coarse, (float)cfac, (const float*)fine_term, (float)ffac, (float*)out,
+                        (int)r.fz_begin, (int)r.fz_end, (int)r.out_z0, (int)r.coarse_z0);
+                } else {
+                    k_interp_add3m<double><<<grid, block, 0, st>>>(m, (const double*)coarse, cfac,
+                                                                   (const double*)fine_term, ffac, (double*)out,
+                                                                   (int)r.fz_begin, (int)r.fz_end, (int)r.out_z0,
+                                                                   (int)r.coarse_z0, zc);
+                    k_interp_fix_edges<double><<<(nfix + 127) / 128, 128, 0, st>>>(
+                        g, m, (const double*)coarse, cfac, (const double*)fine_term, ffac, (double*)out, (int)r.fz_begin,
+                        (int)r.fz_end, (int)r.out_z0, (int)r.coarse_z0);
+                }
+                launch_counter()++;
+                ODIL_LAUNCHED();
+                return 0;
+            }
+        }
         if (fast3_geometry(g, m, cz) && (!cz || pairs) && !(ndim == 2 && range != nullptr)) {
             const int zb = (int)(ndim == 3 ? (cz ? r.fz_begin / 2 : r.fz_begin) : 0);
             const int nz = (int)(ndim == 3 ? (cz ? (r.fz_end - r.fz_begin) / 2 : r.fz_end - r.fz_begin) : 1);
@@ -662,6 +714,32 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
     {
         Mg3 m;
         bool cz = false;
+        if (fast3_geometry(g, m, cz) && march_ok(m, cz, ndim, g_fine, g_coarse, nullptr)) {
+            const int zc = march_chunk(m, (int)(r.cz_end - r.cz_begin));
+            dim3 block(32, 4, 1);
+            dim3 grid((m.n2 / 2 + 31) / 32, (m.n1 + 3) / 4, (unsigned)((r.cz_end - r.cz_begin + zc - 1) / zc));
+            const int nfix = 16 * (int)(r.cz_end - r.cz_begin) + 16 * (m.n1 + m.n2);
+            if (grid.y <= 65535 && grid.z <= 65535) {
+                if (dtype == ODIL_B200_F32) {
+                    k_interp_adjoint3m<float><<<grid, block, 0, st>>>(m, (const float*)g_fine, (float)scale,
+                                                                      (float*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
+                                                                      (int)r.out_z0, (int)r.fine_z0, zc);
+                    k_adjoint_fix_edges<float><<<(nfix + 127) / 128, 128, 0, st>>>(
+                        g, m, (const float*)g_fine, (float)scale, (float*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
+                        (int)r.out_z0, (int)r.fine_z0);
+                } else {
+                    k_interp_adjoint3m<double><<<grid, block, 0, st>>>(m, (const double*)g_fine, scale,
+                                                                       (double*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
+                                                                       (int)r.out_z0, (int)r.fine_z0, zc);
+                    k_adjoint_fix_edges<double><<<(nfix + 127) / 128, 128, 0, st>>>(
+                        g, m, (const double*)g_fine, scale, (double*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
+                        (int)r.out_z0, (int)r.fine_z0);
+                }
+                launch_counter()++;
+                ODIL_LAUNCHED();
+                return 0;
+            }
+        }
         if (fast3_geometry(g, m, cz) && !(ndim == 2 && range != nullptr)) {
             const int zb = (int)(ndim == 3 ? r.cz_begin : 0);
             const int nz = (int)(ndim == 3 ? r.cz_end - r.cz_begin : 1);
