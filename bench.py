@@ -305,7 +305,7 @@ def run_b200(args):
         pass
     roofline = {
         "bound": "hbm",
-        "kernel": "odil_b200_stencil_fused (k_star_tma: TMA-fed residual + loss + adjoint in one sweep, + reduce)",
+        "kernel": "odil_b200_stencil_fused (k_star8: TMA-fed residual + loss + adjoint gradient in one sweep, + reduce)",
         "achieved": fused.get("achieved_GBs"), "peak": peak, "unit": "GB/s", "frac": fused.get("frac"),
         "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes["stencil_fused"], "ms_per_launch": fused.get("ms_per_step"),

@@ -322,7 +322,7 @@ struct MgAdjThread {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_interp_adjoint3m(Mg3 m, const T* __restrict__ gf, T scale,
+__global__ void __launch_bounds__(128, 4) k_interp_adjoint3m(Mg3 m, const T* __restrict__ gf, T scale,
                                                           T* __restrict__ gc, int cz_begin, int cz_end, int out_z0,
                                                           int fine_z0, int zc) {
     const int lane = threadIdx.x;
@@ -386,35 +386,87 @@ __global__ void __launch_bounds__(128) k_interp_adjoint3m(Mg3 m, const T* __rest
 }
 
 // Coarse cells with two or more axes within 2 of a face: the joint pad is not separable there; recompute them
-// with the generic transpose.  One thread per cell: 16 per coarse plane (z-edges) + the y- and x-edges of the
-// four boundary planes.
+// with the generic transpose  (I^T g)[J] = sum_{q: clamp(q)=J} 2 G(q) - sum_{q: reflect(q)=J} G(q),  G(q) = the
+// 4x4x4-tap gather of the fine gradient onto the padded coarse index q.  ONE WARP PER CELL: the (candidate q,
+// tap) pairs are dealt to the lanes and summed in a fixed order (a single thread walking the up to 27 x 64
+// taps took ~60 us, which was the whole cost of the coarse levels).  16 cells per coarse plane (z-edges) + the
+// y- and x-edges of the four boundary planes.
 template <typename T>
-__global__ void __launch_bounds__(128) k_adjoint_fix_edges(MgGeom g, Mg3 m, const T* __restrict__ gf, T scale,
+__global__ void __launch_bounds__(128) k_adjoint_fix_edges(Mg3 m, const T* __restrict__ gf, T scale,
                                                            T* __restrict__ gc, int cz_begin, int cz_end, int out_z0,
                                                            int fine_z0) {
     const int nz = cz_end - cz_begin;
+    const int lane = threadIdx.x & 31;
     auto bnd = [](int i, int n) { return i < 2 ? i : n - 4 + i; };  // 0, 1, n-2, n-1
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int I, J, K;
+    int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;          // cell index = warp index
+    int c[3];
     if (t < 16 * nz) {
-        I = cz_begin + (t >> 4);
-        J = bnd(t & 3, m.n1);
-        K = bnd((t >> 2) & 3, m.n2);
+        c[0] = cz_begin + (t >> 4);
+        c[1] = bnd(t & 3, m.n1);
+        c[2] = bnd((t >> 2) & 3, m.n2);
     } else if ((t -= 16 * nz) < 16 * m.n1) {
-        I = bnd(t & 3, m.n0);
-        K = bnd((t >> 2) & 3, m.n2);
-        J = t >> 4;
+        c[0] = bnd(t & 3, m.n0);
+        c[2] = bnd((t >> 2) & 3, m.n2);
+        c[1] = t >> 4;
     } else if ((t -= 16 * m.n1) < 16 * m.n2) {
-        I = bnd(t & 3, m.n0);
-        J = bnd((t >> 2) & 3, m.n1);
-        K = t >> 4;
+        c[0] = bnd(t & 3, m.n0);
+        c[1] = bnd((t >> 2) & 3, m.n1);
+        c[2] = t >> 4;
     } else {
         return;
     }
-    if (I < cz_begin || I >= cz_end) return;
-    const int64_t J3[ODIL_B200_MAX_NDIM] = {I, J, K, 0};
-    const int64_t lin = (int64_t)(I - out_z0) * m.cs0 + (int64_t)J * m.cs1 + K;
-    gc[lin] = scale * adjoint_cell_generic<T>(g, gf, fine_z0, J3);
+    if (c[0] < cz_begin || c[0] >= cz_end) return;  // warp-uniform
+    const int n[3] = {m.n0, m.n1, m.n2};
+    const int64_t fs[3] = {m.fs0, m.fs1, 1};
+    // candidate padded indices per axis: the cell itself, -1 if it is one of the two lowest, n if one of the two highest
+    int cand[3][3], nc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        int kk = 0;
+        cand[a][kk++] = c[a];
+        if (c[a] <= 1) cand[a][kk++] = -1;
+        if (c[a] >= n[a] - 2) cand[a][kk++] = n[a];
+        nc[a] = kk;
+    }
+    const int ncombo = nc[0] * nc[1] * nc[2];
+    T acc = T(0);
+    for (int item = lane; item < ncombo * 64; item += 32) {
+        const int combo = item >> 6, tap = item & 63;
+        int q[3];
+        int r = combo;
+        q[2] = cand[2][r % nc[2]];
+        r /= nc[2];
+        q[1] = cand[1][r % nc[1]];
+        r /= nc[1];
+        q[0] = cand[0][r];
+        bool mc = true, mr = true, outside = false;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int qc = q[a] < 0 ? 0 : (q[a] > n[a] - 1 ? n[a] - 1 : q[a]);
+            const int qr = q[a] < 0 ? 1 : (q[a] > n[a] - 1 ? n[a] - 2 : q[a]);
+            mc = mc && qc == c[a];
+            mr = mr && qr == c[a];
+            outside = outside || q[a] < 0 || q[a] > n[a] - 1;
+        }
+        // an in-range q is the plain value u[q]: coefficient 1 when q == J
+        const T coef = outside ? T((mc ? 2 : 0) - (mr ? 1 : 0)) : T(1);
+        if (coef == T(0)) continue;
+        const int tt[3] = {tap >> 4, (tap >> 2) & 3, tap & 3};
+        T w = coef;
+        int64_t lin = 0;
+        bool ok = true;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int fi = 2 * q[a] - 1 + tt[a];  // fine cells 2q-1 .. 2q+2, weights 1/4 3/4 3/4 1/4
+            ok = ok && fi >= 0 && fi < 2 * n[a];
+            w *= (tt[a] == 0 || tt[a] == 3) ? T(0.25) : T(0.75);
+            lin += (int64_t)(a == 0 ? fi - fine_z0 : fi) * fs[a];
+        }
+        if (ok) acc = fma(w, __ldg(gf + lin), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) gc[(int64_t)(c[0] - out_z0) * m.cs0 + (int64_t)c[1] * m.cs1 + c[2]] = scale * acc;
 }
 
 }  // namespace odil

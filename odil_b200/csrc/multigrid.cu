@@ -724,15 +724,15 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
                     k_interp_adjoint3m<float><<<grid, block, 0, st>>>(m, (const float*)g_fine, (float)scale,
                                                                       (float*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                                                                       (int)r.out_z0, (int)r.fine_z0, zc);
-                    k_adjoint_fix_edges<float><<<(nfix + 127) / 128, 128, 0, st>>>(
-                        g, m, (const float*)g_fine, (float)scale, (float*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
+                    k_adjoint_fix_edges<float><<<(nfix + 3) / 4, 128, 0, st>>>(
+                        m, (const float*)g_fine, (float)scale, (float*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                         (int)r.out_z0, (int)r.fine_z0);
                 } else {
                     k_interp_adjoint3m<double><<<grid, block, 0, st>>>(m, (const double*)g_fine, scale,
                                                                        (double*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                                                                        (int)r.out_z0, (int)r.fine_z0, zc);
-                    k_adjoint_fix_edges<double><<<(nfix + 127) / 128, 128, 0, st>>>(
-                        g, m, (const double*)g_fine, scale, (double*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
+                    k_adjoint_fix_edges<double><<<(nfix + 3) / 4, 128, 0, st>>>(
+                        m, (const double*)g_fine, scale, (double*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                         (int)r.out_z0, (int)r.fine_z0);
                 }
                 launch_counter()++;
