@@ -150,6 +150,17 @@ int odil_b200_gd_step(int ntensors, void* const* x, const void* const* g, const 
 /* y = a*x + b*y  (L-BFGS building block; also used for scaling). */
 int odil_b200_axpby(int64_t count, int dtype, double a, const void* x, double b, void* y, void* stream);
 
+/* Conjugate-gradient vector updates with the step scalars read from DEVICE memory (num[0] / den[0]; a zero
+ * denominator gives a zero step), so an iteration never waits for the host:
+ *   cg_update_xr:  alpha = num/den;  x += alpha p;  r -= alpha q
+ *   cg_update_p:   beta  = num/den;  p = r + beta p
+ * Together with odil_b200_dot and the stencil forward / adjoint products they replace the sparse solves the
+ * reference calls for Newton on the normal equations M^T M x = M^T rhs (linsolver.py:18-26, util.py:152-187). */
+int odil_b200_cg_update_xr(int64_t count, int dtype, const double* num, const double* den, const void* p, const void* q,
+                           void* x, void* r, void* stream);
+int odil_b200_cg_update_p(int64_t count, int dtype, const double* num, const double* den, const void* r, void* p,
+                          void* stream);
+
 /* L-BFGS building blocks (compact form). V: row-major [k][ld] matrix holding the history vectors
  * (k <= 256 rows of `count` elements).  Replaces the host vector algebra inside SciPy's
  * fmin_l_bfgs_b that the reference calls (optimizer.py:95-105).

@@ -658,7 +658,19 @@ class Problem:
         return engine.operator_values(self.domain.arrays_from_state(state)), engine.names
 
     def _eval_operator_grad_b200(self, state):
-        raise NotImplementedError("eval_operator_grad / linearize: next row (SURVEY.md 8f-1)")
+        """(values, [ {(key, shift, loc): coefficient array} per output ], names) like `_eval_operator_grad_tf`
+        (core.py:1313-1361); affine operators only: the derivatives are the region-typed tables on the grid."""
+        from .newton import StencilJacobian
+
+        engine = self._engine(state)
+        values = engine.operator_values(self.domain.arrays_from_state(state))
+        jac = StencilJacobian(engine)
+        grads = []
+        for d in jac.diagonals():
+            loc = "c" * self.domain.ndim
+            grads.append({(key, shift, loc): Known(torch.as_tensor(coef, dtype=engine.tdtype, device=engine.device))
+                          for (key, shift), coef in d.items()})
+        return values, grads, engine.names
 
     def eval_loss_grad(self, state):
         """
@@ -682,7 +694,18 @@ class Problem:
         return self._eval_operator_grad(state)
 
     def linearize(self, state, modsp=None):
-        raise NotImplementedError("linearize (Newton): next row (SURVEY.md 8f-1)")
+        """
+        Returns (vector, matrix) with operator(packed + d) = vector + matrix.dot(d) (core.py:1113-1217).
+        `vector` is a flat device tensor; `matrix` is a matrix-free `newton.StencilJacobian` (products on the
+        device; `.tocsr()` gives the SciPy matrix the reference assembles).  Affine operators, multigrid off.
+        """
+        if not state.initialized:
+            raise RuntimeError("Uninitialized state, use `state = domain.init_state(state)`")
+        from .newton import StencilJacobian, residual_vector
+
+        engine = self._engine(state)
+        vector = residual_vector(engine, self.domain.arrays_from_state(state))
+        return vector, StencilJacobian(engine)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -233,98 +233,118 @@ struct MgQ {
     T a, b;
 };
 
-template <typename T>
-struct MgAdjThread {
-    const T* __restrict__ gf;
-    int64_t fs0, fs1;
-    int fine_z0, nf0, nf1;
-    int J, k4, ex;
-    bool valid, edge, lane0, lane31;
-    MgW6<T> wx0, wx1, wy;
-
-    // x-gather of the y-gathered row sums: s = fine cells 4k .. 4k+3, e = the pair outside the warp's span
-    __device__ __forceinline__ MgQ<T> xgather(const T (&s)[4], const T (&e)[2]) const {
-        T lz = __shfl_up_sync(0xffffffffu, s[2], 1), lw = __shfl_up_sync(0xffffffffu, s[3], 1);
-        T rx = __shfl_down_sync(0xffffffffu, s[0], 1), ry = __shfl_down_sync(0xffffffffu, s[1], 1);
-        lz = lane0 ? e[0] : lz;
-        lw = lane0 ? e[1] : lw;
-        rx = lane31 ? e[0] : rx;
-        ry = lane31 ? e[1] : ry;
-        const T f[8] = {lz, lw, s[0], s[1], s[2], s[3], rx, ry};  // fine cells 4k-2 .. 4k+5
-        MgQ<T> q{T(0), T(0)};
+// One warp-uniform variant per row class: BY = the coarse row is within 2 of a y face (6 fine rows with pad
+// corrections, clipped rows carry zero weight) or interior (4 fine rows 2J-1 .. 2J+2, no clipping).
+template <typename T, bool BY>
+__device__ __forceinline__ void mg_adj_march(const Mg3& m, const T* __restrict__ gf, T scale, T* __restrict__ gc,
+                                             int Ibeg, int Iend, int out_z0, int fine_z0, int J, int k, int lane) {
+    constexpr int NROW = BY ? 6 : 4, R0 = BY ? 0 : 1;
+    const int nf0 = 2 * m.n0, nf1 = 2 * m.n1, nf2 = 2 * m.n2;
+    const bool valid = 2 * k < m.n2;
+    const bool lane0 = lane == 0, lane31 = lane == 31;
+    // neighbours outside the warp's span: lane 0 reads (4k-2, 4k-1), lane 31 reads (4k+4, 4k+5)
+    const int ex = lane0 ? 4 * k - 2 : 4 * k + 4;
+    const bool edge = valid && (lane0 || lane31) && ex >= 0 && ex + 1 < nf2;
+    const MgW6<T> wx0 = mg_adjw<T>(valid ? 2 * k : 2, m.n2), wx1 = mg_adjw<T>(valid ? 2 * k + 1 : 3, m.n2);
+    const MgW6<T> wy = mg_adjw<T>(J, m.n1);
+    int roff[NROW];  // element offsets of the own vector in the rows 2J-2+R0 .. (clipped rows: zero weight)
 #pragma unroll
-        for (int t = 0; t < 6; ++t) {
-            q.a = fma(wx0.w[t], f[t], q.a);
-            q.b = fma(wx1.w[t], f[t + 2], q.b);
+    for (int i = 0; i < NROW; ++i) roff[i] = min(max(2 * J - 2 + R0 + i, 0), nf1 - 1) * (int)m.fs1;
+    const int vcol = valid ? 4 * k : 0, ecol = edge ? ex : 0;
+    // fine planes this chunk may touch (the outermost taps carry weight only next to the domain faces: fine plane 0
+    // for I == 1, the last fine plane for I == n0-2; elsewhere they belong to the neighbouring chunk / slab)
+    const int fz_lo = Ibeg == 1 ? 0 : max(2 * Ibeg - 1, 0);
+    const int fz_hi = Iend - 1 == m.n0 - 2 ? nf0 - 1 : min(2 * Iend, nf0 - 1);
+
+    MgQ<T> Q0{T(0), T(0)}, Q1 = Q0, Q2 = Q0, Q3 = Q0;
+    for (int I = Ibeg - 2; I < Iend; ++I) {
+        // in-plane gather of the fine planes 2I+2, 2I+3: ALL loads first (2 * NROW vectors in flight per thread)
+        const int fa = 2 * I + 2, fb = 2 * I + 3;
+        const bool va = fa >= fz_lo && fa <= fz_hi, vb = fb >= fz_lo && fb <= fz_hi;
+        const T* pa = gf + (int64_t)(min(max(fa, fz_lo), fz_hi) - fine_z0) * m.fs0;
+        const T* pb = gf + (int64_t)(min(max(fb, fz_lo), fz_hi) - fine_z0) * m.fs0;
+        MgVec4<T> v[2][NROW];
+        Pair<T> ev[2][NROW];
+#pragma unroll
+        for (int i = 0; i < NROW; ++i) {
+            v[0][i] = mg_ld4<T>(pa + roff[i] + vcol);
+            v[1][i] = mg_ld4<T>(pb + roff[i] + vcol);
         }
-        return q;
-    }
-
-    // In-plane gather of NP consecutive fine planes fz, fz+1 (all inside the array and needed): fine rows
-    // 2J-2+R0 .. +NROW-1.  ALL loads are issued before the first use, so a thread has NP*NROW vectors in flight.
-    template <int NP, int NROW, int R0>
-    __device__ __forceinline__ void planes(int fz, MgQ<T> (&q)[NP]) const {
-        MgVec4<T> v[NP][NROW];
-        Pair<T> ev[NP][NROW];
-        const T* pz = gf + (int64_t)(fz - fine_z0) * fs0;
-#pragma unroll
-        for (int p = 0; p < NP; ++p)
+        if (lane0 || lane31) {
 #pragma unroll
             for (int i = 0; i < NROW; ++i) {
-                const int fy = min(max(2 * J - 2 + R0 + i, 0), nf1 - 1);  // clipped rows carry zero weight
-                const T* py = pz + (int64_t)p * fs0 + (int64_t)fy * fs1;
-                v[p][i] = valid ? mg_ld4<T>(py + k4) : MgVec4<T>{T(0), T(0), T(0), T(0)};
-                ev[p][i] = edge ? mg_ld2<T>(py + ex) : Pair<T>{T(0), T(0)};
+                ev[0][i] = mg_ld2<T>(pa + roff[i] + ecol);
+                ev[1][i] = mg_ld2<T>(pb + roff[i] + ecol);
             }
+        }
+        MgQ<T> Qn[2];
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            T s[4] = {T(0), T(0), T(0), T(0)}, e[2] = {T(0), T(0)};
+        for (int p = 0; p < 2; ++p) {
+            T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0), e0 = T(0), e1 = T(0);
 #pragma unroll
             for (int i = 0; i < NROW; ++i) {
                 const T w = wy.w[R0 + i];
-                s[0] = fma(w, v[p][i].x, s[0]);
-                s[1] = fma(w, v[p][i].y, s[1]);
-                s[2] = fma(w, v[p][i].z, s[2]);
-                s[3] = fma(w, v[p][i].w, s[3]);
-                e[0] = fma(w, ev[p][i].a, e[0]);
-                e[1] = fma(w, ev[p][i].b, e[1]);
+                s0 = fma(w, v[p][i].x, s0);
+                s1 = fma(w, v[p][i].y, s1);
+                s2 = fma(w, v[p][i].z, s2);
+                s3 = fma(w, v[p][i].w, s3);
             }
-            q[p] = xgather(s, e);
+            if (lane0 || lane31) {
+#pragma unroll
+                for (int i = 0; i < NROW; ++i) {
+                    const T w = wy.w[R0 + i];
+                    e0 = fma(w, ev[p][i].a, e0);
+                    e1 = fma(w, ev[p][i].b, e1);
+                }
+            }
+            if (!valid) s0 = s1 = s2 = s3 = T(0);
+            if (!edge) e0 = e1 = T(0);
+            T lz = __shfl_up_sync(0xffffffffu, s2, 1), lw = __shfl_up_sync(0xffffffffu, s3, 1);
+            T rx = __shfl_down_sync(0xffffffffu, s0, 1), ry = __shfl_down_sync(0xffffffffu, s1, 1);
+            lz = lane0 ? e0 : lz;
+            lw = lane0 ? e1 : lw;
+            rx = lane31 ? e0 : rx;
+            ry = lane31 ? e1 : ry;
+            const T f[8] = {lz, lw, s0, s1, s2, s3, rx, ry};  // fine cells 4k-2 .. 4k+5
+            T qa = T(0), qb = T(0);
+#pragma unroll
+            for (int t = 0; t < 6; ++t) {
+                qa = fma(wx0.w[t], f[t], qa);
+                qb = fma(wx1.w[t], f[t + 2], qb);
+            }
+            const bool vp = p == 0 ? va : vb;
+            Qn[p] = MgQ<T>{vp ? qa : T(0), vp ? qb : T(0)};
         }
-    }
-
-    // one plane, possibly outside the array / not needed (CTA-uniform conditions)
-    __device__ __forceinline__ MgQ<T> inplane(int fz, bool needed, bool by) const {
-        MgQ<T> q[1] = {MgQ<T>{T(0), T(0)}};
-        if (needed && fz >= 0 && fz < nf0) {
-            if (by)
-                planes<1, 6, 0>(fz, q);
-            else
-                planes<1, 4, 1>(fz, q);
+        if (I >= Ibeg) {
+            const MgW6<T> wz = mg_adjw<T>(I, m.n0);
+            T a0 = wz.w[0] * Q0.a, a1 = wz.w[0] * Q0.b;
+            a0 = fma(wz.w[1], Q1.a, a0);
+            a1 = fma(wz.w[1], Q1.b, a1);
+            a0 = fma(wz.w[2], Q2.a, a0);
+            a1 = fma(wz.w[2], Q2.b, a1);
+            a0 = fma(wz.w[3], Q3.a, a0);
+            a1 = fma(wz.w[3], Q3.b, a1);
+            a0 = fma(wz.w[4], Qn[0].a, a0);
+            a1 = fma(wz.w[4], Qn[0].b, a1);
+            a0 = fma(wz.w[5], Qn[1].a, a0);
+            a1 = fma(wz.w[5], Qn[1].b, a1);
+            // (cells with two or more axes within 2 of a face are rewritten by k_adjoint_fix_edges)
+            if (valid) {
+                const int64_t lin = (int64_t)(I - out_z0) * m.cs0 + (int64_t)J * m.cs1 + 2 * k;
+                *reinterpret_cast<Pair<T>*>(gc + lin) = Pair<T>{scale * a0, scale * a1};
+            }
         }
-        return q[0];
+        Q0 = Q2;
+        Q1 = Q3;
+        Q2 = Qn[0];
+        Q3 = Qn[1];
     }
-    // the two planes 2I+2, 2I+3 of a marching step
-    __device__ __forceinline__ void inplane2(int fz, bool needed1, bool by, MgQ<T>& qa, MgQ<T>& qb) const {
-        if (needed1 && fz >= 0 && fz + 1 < nf0) {
-            MgQ<T> q[2];
-            if (by)
-                planes<2, 6, 0>(fz, q);
-            else
-                planes<2, 4, 1>(fz, q);
-            qa = q[0];
-            qb = q[1];
-        } else {
-            qa = inplane(fz, true, by);
-            qb = inplane(fz + 1, needed1, by);
-        }
-    }
-};
+}
 
 template <typename T>
 __global__ void __launch_bounds__(128, 4) k_interp_adjoint3m(Mg3 m, const T* __restrict__ gf, T scale,
-                                                          T* __restrict__ gc, int cz_begin, int cz_end, int out_z0,
-                                                          int fine_z0, int zc) {
+                                                             T* __restrict__ gc, int cz_begin, int cz_end, int out_z0,
+                                                             int fine_z0, int zc) {
     const int lane = threadIdx.x;
     const int k = blockIdx.x * 32 + lane;
     const int J = blockIdx.y * 4 + threadIdx.y;
@@ -332,57 +352,10 @@ __global__ void __launch_bounds__(128, 4) k_interp_adjoint3m(Mg3 m, const T* __r
     const int Ibeg = cz_begin + blockIdx.z * zc;
     const int Iend = min(Ibeg + zc, cz_end);
     if (Ibeg >= Iend) return;
-    MgAdjThread<T> th;
-    th.gf = gf;
-    th.fs0 = m.fs0;
-    th.fs1 = m.fs1;
-    th.fine_z0 = fine_z0;
-    th.nf0 = 2 * m.n0;
-    th.nf1 = 2 * m.n1;
-    th.J = J;
-    th.k4 = 4 * k;
-    th.valid = 2 * k < m.n2;
-    th.lane0 = lane == 0;
-    th.lane31 = lane == 31;
-    // neighbours outside the warp's span: lane 0 reads (4k-2, 4k-1), lane 31 reads (4k+4, 4k+5)
-    th.ex = lane == 0 ? 4 * k - 2 : 4 * k + 4;
-    th.edge = th.valid && (lane == 0 || lane == 31) && th.ex >= 0 && th.ex + 1 < 2 * m.n2;
-    th.wx0 = mg_adjw<T>(th.valid ? 2 * k : 2, m.n2);
-    th.wx1 = mg_adjw<T>(th.valid ? 2 * k + 1 : 3, m.n2);
-    th.wy = mg_adjw<T>(J, m.n1);
-    const bool by = J <= 1 || J >= m.n1 - 2;
-
-    // window of Q over the fine planes 2I-2 .. 2I+3
-    // (the outermost taps carry weight only next to the domain faces: fine plane 0 for I == 1, the last fine
-    //  plane for I == n0-2; elsewhere those planes belong to the neighbouring chunk / slab and are not touched)
-    MgQ<T> Q0 = th.inplane(2 * Ibeg - 2, Ibeg == 1, by), Q1 = th.inplane(2 * Ibeg - 1, true, by);
-    MgQ<T> Q2, Q3;
-    th.inplane2(2 * Ibeg, true, by, Q2, Q3);
-    for (int I = Ibeg; I < Iend; ++I) {
-        MgQ<T> Q4, Q5;
-        th.inplane2(2 * I + 2, I + 1 < Iend || I == m.n0 - 2, by, Q4, Q5);
-        const MgW6<T> wz = mg_adjw<T>(I, m.n0);
-        T a0 = wz.w[0] * Q0.a, a1 = wz.w[0] * Q0.b;
-        a0 = fma(wz.w[1], Q1.a, a0);
-        a1 = fma(wz.w[1], Q1.b, a1);
-        a0 = fma(wz.w[2], Q2.a, a0);
-        a1 = fma(wz.w[2], Q2.b, a1);
-        a0 = fma(wz.w[3], Q3.a, a0);
-        a1 = fma(wz.w[3], Q3.b, a1);
-        a0 = fma(wz.w[4], Q4.a, a0);
-        a1 = fma(wz.w[4], Q4.b, a1);
-        a0 = fma(wz.w[5], Q5.a, a0);
-        a1 = fma(wz.w[5], Q5.b, a1);
-        if (th.valid) {
-            // (cells with two or more axes within 2 of a face are rewritten by k_adjoint_fix_edges)
-            const int64_t lin = (int64_t)(I - out_z0) * m.cs0 + (int64_t)J * m.cs1 + 2 * k;
-            *reinterpret_cast<Pair<T>*>(gc + lin) = Pair<T>{scale * a0, scale * a1};
-        }
-        Q0 = Q2;
-        Q1 = Q3;
-        Q2 = Q4;
-        Q3 = Q5;
-    }
+    if (J <= 1 || J >= m.n1 - 2)
+        mg_adj_march<T, true>(m, gf, scale, gc, Ibeg, Iend, out_z0, fine_z0, J, k, lane);
+    else
+        mg_adj_march<T, false>(m, gf, scale, gc, Ibeg, Iend, out_z0, fine_z0, J, k, lane);
 }
 
 // Coarse cells with two or more axes within 2 of a face: the joint pad is not separable there; recompute them

@@ -87,6 +87,30 @@ __global__ void __launch_bounds__(256) k_axpby(int64_t n, T a, const T* __restri
     }
 }
 
+// Conjugate-gradient vector updates; the step scalars are read from device memory (num[0] / den[0]), so an
+// iteration never waits for the host.
+template <typename T>
+__global__ void __launch_bounds__(256) k_cg_update_xr(int64_t n, const double* __restrict__ num,
+                                                      const double* __restrict__ den, const T* __restrict__ p,
+                                                      const T* __restrict__ q, T* __restrict__ x, T* __restrict__ r) {
+    const double d = den[0];
+    const T alpha = d != 0.0 ? (T)(num[0] / d) : T(0);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        x[i] += alpha * p[i];
+        r[i] -= alpha * q[i];
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_cg_update_p(int64_t n, const double* __restrict__ num,
+                                                     const double* __restrict__ den, const T* __restrict__ r,
+                                                     T* __restrict__ p) {
+    const double d = den[0];
+    const T beta = d != 0.0 ? (T)(num[0] / d) : T(0);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = r[i] + beta * p[i];
+}
+
 template <typename T, bool DOT>
 __global__ void __launch_bounds__(256) k_dot_partial(const T* __restrict__ x, const T* __restrict__ y, int64_t n,
                                                      double* __restrict__ partials) {
@@ -270,6 +294,38 @@ int odil_b200_axpby(int64_t count, int dtype, double a, const void* x, double b,
         k_axpby<float><<<blocks_for(count, 4), 256, 0, st>>>(count, (float)a, (const float*)x, (float)b, (float*)y);
     else if (dtype == ODIL_B200_F64)
         k_axpby<double><<<blocks_for(count, 4), 256, 0, st>>>(count, a, (const double*)x, b, (double*)y);
+    else
+        return fail("dtype=%d unsupported", dtype);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+int odil_b200_cg_update_xr(int64_t count, int dtype, const double* num, const double* den, const void* p, const void* q,
+                           void* x, void* r, void* stream) {
+    ODIL_REQUIRE(num && den && p && q && x && r && count >= 0, "cg_update_xr: bad arguments");
+    if (count == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ODIL_B200_F32)
+        k_cg_update_xr<float><<<blocks_for(count, 4), 256, 0, st>>>(count, num, den, (const float*)p, (const float*)q,
+                                                                    (float*)x, (float*)r);
+    else if (dtype == ODIL_B200_F64)
+        k_cg_update_xr<double><<<blocks_for(count, 4), 256, 0, st>>>(count, num, den, (const double*)p, (const double*)q,
+                                                                     (double*)x, (double*)r);
+    else
+        return fail("dtype=%d unsupported", dtype);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+int odil_b200_cg_update_p(int64_t count, int dtype, const double* num, const double* den, const void* r, void* p,
+                          void* stream) {
+    ODIL_REQUIRE(num && den && r && p && count >= 0, "cg_update_p: bad arguments");
+    if (count == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ODIL_B200_F32)
+        k_cg_update_p<float><<<blocks_for(count, 4), 256, 0, st>>>(count, num, den, (const float*)r, (float*)p);
+    else if (dtype == ODIL_B200_F64)
+        k_cg_update_p<double><<<blocks_for(count, 4), 256, 0, st>>>(count, num, den, (const double*)r, (double*)p);
     else
         return fail("dtype=%d unsupported", dtype);
     ODIL_LAUNCHED();

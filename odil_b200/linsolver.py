@@ -1,8 +1,9 @@
 """
 Command-line flags owned by the reference's linsolver module (src/odil/linsolver.py:90-131; note it
 also defines --lr and --nlvl) and the host sparse solvers used by Newton.  The Newton path
-(linearize + solve) is a "next" row; `solve` keeps the SciPy normal-equation path
-for callers that assemble a matrix themselves.
+(SURVEY.md 8f-1): `solve` takes either a SciPy matrix (the reference's normal-equation path) or the
+matrix-free `newton.StencilJacobian` that `Problem.linearize` returns (`--linsolver cg_b200`: CG on the
+device; any other name: the SciPy solver on `matrix.tocsr()`).
 """
 import numpy as np
 
@@ -13,6 +14,19 @@ def solve(matr, rhs, args, status=None, linsolver="direct"):
     import scipy.sparse.linalg
 
     status = status if status is not None else dict()
+    from .newton import StencilJacobian, cg_normal
+
+    if isinstance(matr, StencilJacobian):
+        import torch
+
+        if linsolver in ("cg_b200", "cg"):
+            # matrix-free CG on the device; everything stays in HBM
+            return cg_normal(matr, rhs, tol=getattr(args, "linsolver_tol", 1e-6),
+                             maxiter=getattr(args, "linsolver_maxiter", None),
+                             damp=getattr(args, "linsolver_damp", 0) or 0.0, status=status)
+        # the reference's SciPy solvers on the assembled matrix (small grids)
+        sol = solve(matr.tocsr(), rhs.detach().cpu().numpy().astype(np.float64), args, status, linsolver)
+        return torch.as_tensor(np.asarray(sol), dtype=matr.dtype, device=matr.device)
     if getattr(args, "linsolver_maxiter", None) is None:
         args.linsolver_maxiter = 1000 if linsolver == "lsqr" else 50
     normal = matr.T.dot(matr).tocsr()
@@ -43,7 +57,7 @@ def solve(matr, rhs, args, status=None, linsolver="direct"):
 def add_arguments(parser):
     parser.add_argument("--linsolver", type=str, default="direct",
                         choices=["multigrid", "direct", "directsq", "direct_cu", "sparseqr", "lsqr", "lsqr_cu",
-                                 "bicgstab"], help="Linear solver to use")
+                                 "bicgstab", "cg_b200"], help="Linear solver to use (cg_b200: matrix-free CG on the GPU)")
     parser.add_argument("--linsolver_maxiter", type=int, default=None,
                         help="Maximum number of iterations of linear solver")
     parser.add_argument("--linsolver_tol", type=float, default=1e-6, help="Tolerance for linear solver")

@@ -23,7 +23,8 @@ EXPORTS = [
     "odil_b200_stencil_adjoint", "odil_b200_stencil_fused", "odil_b200_stencil_plan_kind",
     "odil_b200_stencil_plan_tune", "odil_b200_sum_squares", "odil_b200_dot", "odil_b200_mg_interp_add",
     "odil_b200_mg_interp_adjoint", "odil_b200_mg_restrict", "odil_b200_adam_step", "odil_b200_gd_step",
-    "odil_b200_axpby", "odil_b200_multi_dot", "odil_b200_multi_axpy",
+    "odil_b200_axpby", "odil_b200_multi_dot", "odil_b200_multi_axpy", "odil_b200_cg_update_xr",
+    "odil_b200_cg_update_p",
 ]
 
 
@@ -103,6 +104,8 @@ def load(build_if_missing=False):
     lib.odil_b200_axpby.argtypes = [i64, ctypes.c_int, dbl, vp, dbl, vp, vp]
     lib.odil_b200_multi_dot.argtypes = [vp, i64, ctypes.c_int, vp, i64, ctypes.c_int, vp, vp]
     lib.odil_b200_multi_axpy.argtypes = [vp, i64, ctypes.c_int, vp, dbl, vp, vp, i64, ctypes.c_int, vp]
+    lib.odil_b200_cg_update_xr.argtypes = [i64, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.odil_b200_cg_update_p.argtypes = [i64, ctypes.c_int, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("odil_b200_last_error", "odil_b200_launch_count", "odil_b200_version"):
             getattr(lib, name).restype = ctypes.c_int
@@ -290,6 +293,19 @@ def gd_step(x, g, lr):
 def axpby(a, x, b, y):
     load()
     _check(_lib.odil_b200_axpby(x.numel(), dtype_code(x.dtype), float(a), _ptr(x), float(b), _ptr(y), _stream()))
+
+
+def cg_update_xr(num, den, p, q, x, r):
+    """alpha = num/den (device doubles); x += alpha p; r -= alpha q."""
+    load()
+    _check(_lib.odil_b200_cg_update_xr(x.numel(), dtype_code(x.dtype), _ptr(num), _ptr(den), _ptr(p), _ptr(q), _ptr(x),
+                                       _ptr(r), _stream()))
+
+
+def cg_update_p(num, den, r, p):
+    """beta = num/den (device doubles); p = r + beta p."""
+    load()
+    _check(_lib.odil_b200_cg_update_p(p.numel(), dtype_code(p.dtype), _ptr(num), _ptr(den), _ptr(r), _ptr(p), _stream()))
 
 
 def multi_dot(V, k, g, out):
