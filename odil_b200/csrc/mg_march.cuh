@@ -8,9 +8,9 @@
 // (= four fine cells, one vector) of one coarse row and marches along axis 0, carrying the in-plane partial
 // results of the neighbouring planes in registers, so every coarse value / fine vector is loaded once per
 // thread instead of 27 / 48 scalar loads per coarse cell.
-// Boundary rule: the joint pad P = 2*symmetric(u) - reflect(u) (core.py:640-643).  With one axis out of range
-// it is the linear extrapolation along that axis (done in registers); with two or more it is not separable and
-// those few edge / corner values go through the generic per-value routines of multigrid.cu.
+// Boundary rule: the joint pad P = 2*symmetric(u) - reflect(u) (core.py:640-643), exact in both kernels: the
+// interpolation loads u[clamp(q)] and, predicated, u[reflect(q)]; its transpose uses the separable 6-tap weights
+// (exact with one axis out of range) plus a closed-form correction for the cells near an edge or a corner.
 #pragma once
 
 namespace odil {
@@ -77,26 +77,64 @@ __device__ __forceinline__ MgP<T> mg_reduce(const MgNb<T>& n) {
     return P;
 }
 
-// plane inside the array; out-of-range y / x neighbours by linear extrapolation along their axis (exact unless
-// two axes leave the range at once -- those fine cells are rewritten by k_interp_fix_edges)
+// In-plane result of the padded coarse plane zp in [-1, n0] with the joint pad applied literally: a neighbour q with
+// any coordinate out of range is 2*u[clamp(q)] - u[reflect(q)] (clamp / reflect on ALL axes at once, core.py:640-643).
+// Exact for every thread and plane; used where two or more axes can leave the range at once.
 template <typename T>
-__device__ __forceinline__ MgP<T> mg_plane_inrange(const T* __restrict__ coarse, int coarse_z0, int64_t cs0, int64_t cs1,
-                                                   int n1, int n2, int zp, int J, int k) {
+__device__ __noinline__ MgP<T> mg_plane_joint(Mg3 m, const T* __restrict__ coarse, int coarse_z0, int zp, int J, int k) {
+    const int zc = min(max(zp, 0), m.n0 - 1), zr = zp < 0 ? 1 : (zp > m.n0 - 1 ? m.n0 - 2 : zp);
+    const bool oz = zp != zc;
+    const T* pzc = coarse + (int64_t)(zc - coarse_z0) * m.cs0;
+    const T* pzr = coarse + (int64_t)(zr - coarse_z0) * m.cs0;
+    const int xl = 2 * k - 1, xr = 2 * k + 2;
+    const int xlc = max(xl, 0), xlr = xl < 0 ? 1 : xl;
+    const int xrc = min(xr, m.n2 - 1), xrr = xr > m.n2 - 1 ? m.n2 - 2 : xr;
+    const bool oxl = xl < 0, oxr = xr > m.n2 - 1;
     MgNb<T> n;
-    const T* pz = coarse + (int64_t)(zp - coarse_z0) * cs0;
-    const int xl = max(2 * k - 1, 0), xr = min(2 * k + 2, n2 - 1);
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
-        const int jj = min(max(J - 1 + dy, 0), n1 - 1);
-        const T* py = pz + (int64_t)jj * cs1;
+        const int yq = J - 1 + dy;
+        const int yc = min(max(yq, 0), m.n1 - 1), yr = yq < 0 ? 1 : (yq > m.n1 - 1 ? m.n1 - 2 : yq);
+        const bool ozy = oz || yq != yc;
+        const T* pa = pzc + (int64_t)yc * m.cs1;
+        const T* pb = pzr + (int64_t)yr * m.cs1;
+        const Pair<T> mid = mg_ld2<T>(pa + 2 * k);
+        T v0 = __ldg(pa + xlc), v3 = __ldg(pa + xrc);
+        T v1 = mid.a, v2 = mid.b;
+        if (ozy) {  // the whole row of neighbours is out of range along z and / or y
+            const Pair<T> midb = mg_ld2<T>(pb + 2 * k);
+            v1 = T(2) * v1 - midb.a;
+            v2 = T(2) * v2 - midb.b;
+        }
+        if (ozy || oxl) v0 = T(2) * v0 - __ldg(pb + xlr);
+        if (ozy || oxr) v3 = T(2) * v3 - __ldg(pb + xrr);
+        n.v[dy][0] = v0;
+        n.v[dy][1] = v1;
+        n.v[dy][2] = v2;
+        n.v[dy][3] = v3;
+    }
+    return mg_reduce<T>(n);
+}
+
+// Plane inside the array with at most ONE axis of each neighbour out of range: the joint pad is then the linear
+// extrapolation along that axis, done with selects on values that are loaded anyway (no second load, no branch).
+template <typename T>
+__device__ __forceinline__ MgP<T> mg_plane_inrange(const Mg3& m, const T* __restrict__ coarse, int coarse_z0, int zp, int J,
+                                                   int k) {
+    MgNb<T> n;
+    const T* pz = coarse + (int64_t)(zp - coarse_z0) * m.cs0;
+    const int xl = max(2 * k - 1, 0), xr = min(2 * k + 2, m.n2 - 1);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        const int jj = min(max(J - 1 + dy, 0), m.n1 - 1);
+        const T* py = pz + (int64_t)jj * m.cs1;
         const Pair<T> mid = mg_ld2<T>(py + 2 * k);
         n.v[dy][0] = __ldg(py + xl);
         n.v[dy][1] = mid.a;
         n.v[dy][2] = mid.b;
         n.v[dy][3] = __ldg(py + xr);
     }
-    // single-axis linear extrapolation of the out-of-range neighbours (2 u[clamp] - u[reflect])
-    const bool x_lo = k == 0, x_hi = 2 * k + 2 > n2 - 1, y_lo = J == 0, y_hi = J == n1 - 1;
+    const bool x_lo = k == 0, x_hi = 2 * k + 2 > m.n2 - 1, y_lo = J == 0, y_hi = J == m.n1 - 1;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
         n.v[dy][0] = x_lo ? T(2) * n.v[dy][1] - n.v[dy][2] : n.v[dy][0];
@@ -110,52 +148,22 @@ __device__ __forceinline__ MgP<T> mg_plane_inrange(const T* __restrict__ coarse,
     return mg_reduce<T>(n);
 }
 
+// Dispatcher: the out-of-line joint loader only where two or more axes can leave the range at once (the four corner
+// columns of every plane, the boundary rows / columns of the two padded planes -1 and n0).
 template <typename T>
 __device__ __forceinline__ MgP<T> mg_plane(const Mg3& m, const T* __restrict__ coarse, int coarse_z0, int zp, int J, int k) {
-    if (zp >= 0 && zp <= m.n0 - 1) return mg_plane_inrange<T>(coarse, coarse_z0, m.cs0, m.cs1, m.n1, m.n2, zp, J, k);
-    // padded plane -1 / n0: linear extrapolation along axis 0 of the in-plane results
-    const MgP<T> Pa = mg_plane_inrange<T>(coarse, coarse_z0, m.cs0, m.cs1, m.n1, m.n2, zp < 0 ? 0 : m.n0 - 1, J, k);
-    const MgP<T> Pb = mg_plane_inrange<T>(coarse, coarse_z0, m.cs0, m.cs1, m.n1, m.n2, zp < 0 ? 1 : m.n0 - 2, J, k);
+    const bool bx = k == 0 || 2 * k + 2 > m.n2 - 1, by = J == 0 || J == m.n1 - 1;
+    const bool zout = zp < 0 || zp > m.n0 - 1;
+    if (zout ? (bx || by) : (bx && by)) return mg_plane_joint<T>(m, coarse, coarse_z0, zp, J, k);
+    if (!zout) return mg_plane_inrange<T>(m, coarse, coarse_z0, zp, J, k);
+    const MgP<T> Pa = mg_plane_inrange<T>(m, coarse, coarse_z0, zp < 0 ? 0 : m.n0 - 1, J, k);
+    const MgP<T> Pb = mg_plane_inrange<T>(m, coarse, coarse_z0, zp < 0 ? 1 : m.n0 - 2, J, k);
     MgP<T> P;
 #pragma unroll
     for (int b = 0; b < 2; ++b)
 #pragma unroll
         for (int c = 0; c < 4; ++c) P.v[b][c] = T(2) * Pa.v[b][c] - Pb.v[b][c];
     return P;
-}
-
-// Fine cells on the EDGES of the fine box (two or more axes at index 0 / last): the joint pad is not the product
-// of the per-axis extrapolations there; recompute them with the generic per-cell routine.  One thread per cell:
-// 4 per fine plane (z-edges) + the y- and x-edges of the first / last fine plane.
-template <typename T>
-__global__ void __launch_bounds__(128) k_interp_fix_edges(MgGeom g, Mg3 m, const T* __restrict__ coarse, T cfac,
-                                                          const T* __restrict__ term, T ffac, T* __restrict__ out,
-                                                          int fz_begin, int fz_end, int out_z0, int coarse_z0) {
-    const int nf0 = 2 * m.n0, nf1 = 2 * m.n1, nf2 = 2 * m.n2;
-    const int nz = fz_end - fz_begin;
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int fz, fy, fx;
-    if (t < 4 * nz) {
-        fz = fz_begin + (t >> 2);
-        fy = (t & 1) ? nf1 - 1 : 0;
-        fx = (t & 2) ? nf2 - 1 : 0;
-    } else if ((t -= 4 * nz) < 4 * nf1) {
-        fz = (t & 1) ? nf0 - 1 : 0;
-        fx = (t & 2) ? nf2 - 1 : 0;
-        fy = t >> 2;
-    } else if ((t -= 4 * nf1) < 4 * nf2) {
-        fz = (t & 1) ? nf0 - 1 : 0;
-        fy = (t & 2) ? nf1 - 1 : 0;
-        fx = t >> 2;
-    } else {
-        return;
-    }
-    if (fz < fz_begin || fz >= fz_end) return;
-    const int64_t f3[ODIL_B200_MAX_NDIM] = {fz, fy, fx, 0};
-    const int64_t lin = (int64_t)(fz - out_z0) * m.fs0 + (int64_t)fy * m.fs1 + fx;
-    T r = cfac * interp_cell_generic<T>(g, coarse, coarse_z0, f3);
-    if (term) r += ffac * __ldg(term + lin);
-    out[lin] = r;
 }
 
 // grid (ceil(n2 / 64), ceil(n1 / 4), z-chunks), block (32, 4): thread = coarse cells 2k, 2k+1 of coarse row J
@@ -232,6 +240,74 @@ template <typename T>
 struct MgQ {
     T a, b;
 };
+
+// Joint-pad correction of the transposed interpolation.  The separable 6-tap weights treat the pad as successive
+// per-axis linear extrapolations, prod_a (2 C_a - R_a) (C = clamp, R = reflect); the reference pads jointly,
+// 2 prod_a C_a - prod_a R_a (core.py:640-643).  They agree when one axis leaves the range; for a padded index q
+// with the out-of-range axis set S, |S| >= 2, the difference transposes to
+//     gc[J] += coef(pattern of J) * G(q),   G(q) = gather of the fine gradient onto q,
+// with coef = -2, +2, +2, -2 for the patterns CC, CR, RC, RR (|S| = 2) and -6 (CCC), +4 (one R), -2 (two R), 0 (RRR)
+// (|S| = 3).  Along an out-of-range axis the gather has the single tap 1/4 on the first / last fine cell, along the
+// others the 4 taps (1,3,3,1)/4 on the fine cells 2q-1 .. 2q+2.  Only coarse cells with two or more coordinates
+// within 2 of a face are affected; the cost is at most 13 loads for such a cell.
+template <typename T>
+__device__ __forceinline__ T mg_adj_joint_correction(const Mg3& m, const T* __restrict__ gf, int fine_z0, int I, int J, int K) {
+    const int c[3] = {I, J, K};
+    const int n[3] = {m.n0, m.n1, m.n2};
+    const int64_t fs[3] = {m.fs0, m.fs1, 1};
+    int side[3], pat[3];  // side: -1 low, +1 high, 0 not near a face; pat: 0 = clamp target, 1 = reflect target
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        side[a] = c[a] <= 1 ? -1 : (c[a] >= n[a] - 2 ? 1 : 0);
+        pat[a] = (c[a] == 0 || c[a] == n[a] - 1) ? 0 : 1;
+    }
+    T acc = T(0);
+    // subsets S of the axes near a face, |S| >= 2: masks 3, 5, 6, 7
+#pragma unroll
+    for (int mask = 3; mask <= 7; ++mask) {
+        if (mask == 4) continue;
+        bool ok = true;
+        int nr = 0, ns = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (mask >> a & 1) {
+                ok = ok && side[a] != 0;
+                nr += pat[a];
+                ++ns;
+            }
+        if (!ok) continue;
+        const T coef = ns == 2 ? (nr == 1 ? T(2) : T(-2)) : (nr == 0 ? T(-6) : (nr == 1 ? T(4) : (nr == 2 ? T(-2) : T(0))));
+        if (coef == T(0)) continue;
+        // G(q): q_a = -1 / n for a in S (single tap), q_a = c_a otherwise (4 taps)
+        int64_t base = 0;
+        T w0 = coef;
+        int free_axis = -1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (mask >> a & 1) {
+                const int fi = side[a] < 0 ? 0 : 2 * n[a] - 1;
+                base += (int64_t)(a == 0 ? fi - fine_z0 : fi) * fs[a];
+                w0 *= T(0.25);
+            } else {
+                free_axis = a;
+            }
+        }
+        if (free_axis < 0) {
+            acc = fma(w0, __ldg(gf + base), acc);
+        } else {
+            const int a = free_axis;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int fi = 2 * c[a] - 1 + t;
+                if (fi >= 0 && fi < 2 * n[a]) {
+                    const T w = (t == 0 || t == 3) ? T(0.25) : T(0.75);
+                    acc = fma(w0 * w, __ldg(gf + base + (int64_t)(a == 0 ? fi - fine_z0 : fi) * fs[a]), acc);
+                }
+            }
+        }
+    }
+    return acc;
+}
 
 // One warp-uniform variant per row class: BY = the coarse row is within 2 of a y face (6 fine rows with pad
 // corrections, clipped rows carry zero weight) or interior (4 fine rows 2J-1 .. 2J+2, no clipping).
@@ -328,7 +404,8 @@ __device__ __forceinline__ void mg_adj_march(const Mg3& m, const T* __restrict__
             a1 = fma(wz.w[4], Qn[0].b, a1);
             a0 = fma(wz.w[5], Qn[1].a, a0);
             a1 = fma(wz.w[5], Qn[1].b, a1);
-            // (cells with two or more axes within 2 of a face are rewritten by k_adjoint_fix_edges)
+            // (cells with two or more coordinates within 2 of a face get the joint-pad correction from
+            //  k_adjoint_joint_fix, launched right after this kernel)
             if (valid) {
                 const int64_t lin = (int64_t)(I - out_z0) * m.cs0 + (int64_t)J * m.cs1 + 2 * k;
                 *reinterpret_cast<Pair<T>*>(gc + lin) = Pair<T>{scale * a0, scale * a1};
@@ -358,88 +435,37 @@ __global__ void __launch_bounds__(128, 4) k_interp_adjoint3m(Mg3 m, const T* __r
         mg_adj_march<T, false>(m, gf, scale, gc, Ibeg, Iend, out_z0, fine_z0, J, k, lane);
 }
 
-// Coarse cells with two or more axes within 2 of a face: the joint pad is not separable there; recompute them
-// with the generic transpose  (I^T g)[J] = sum_{q: clamp(q)=J} 2 G(q) - sum_{q: reflect(q)=J} G(q),  G(q) = the
-// 4x4x4-tap gather of the fine gradient onto the padded coarse index q.  ONE WARP PER CELL: the (candidate q,
-// tap) pairs are dealt to the lanes and summed in a fixed order (a single thread walking the up to 27 x 64
-// taps took ~60 us, which was the whole cost of the coarse levels).  16 cells per coarse plane (z-edges) + the
-// y- and x-edges of the four boundary planes.
+// gc += scale * (joint-pad correction) on the coarse cells with two or more coordinates within 2 of a face: 16 per
+// coarse plane (z-edges) + the y- and x-edges of the four boundary planes; at most 13 loads per cell.  Cells that
+// belong to two families (the corners) are handled by the first family only.
 template <typename T>
-__global__ void __launch_bounds__(128) k_adjoint_fix_edges(Mg3 m, const T* __restrict__ gf, T scale,
-                                                           T* __restrict__ gc, int cz_begin, int cz_end, int out_z0,
-                                                           int fine_z0) {
+__global__ void __launch_bounds__(128) k_adjoint_joint_fix(Mg3 m, const T* __restrict__ gf, T scale, T* __restrict__ gc,
+                                                           int cz_begin, int cz_end, int out_z0, int fine_z0) {
     const int nz = cz_end - cz_begin;
-    const int lane = threadIdx.x & 31;
     auto bnd = [](int i, int n) { return i < 2 ? i : n - 4 + i; };  // 0, 1, n-2, n-1
-    int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;          // cell index = warp index
-    int c[3];
-    if (t < 16 * nz) {
-        c[0] = cz_begin + (t >> 4);
-        c[1] = bnd(t & 3, m.n1);
-        c[2] = bnd((t >> 2) & 3, m.n2);
-    } else if ((t -= 16 * nz) < 16 * m.n1) {
-        c[0] = bnd(t & 3, m.n0);
-        c[2] = bnd((t >> 2) & 3, m.n2);
-        c[1] = t >> 4;
-    } else if ((t -= 16 * m.n1) < 16 * m.n2) {
-        c[0] = bnd(t & 3, m.n0);
-        c[1] = bnd((t >> 2) & 3, m.n1);
-        c[2] = t >> 4;
+    auto near = [](int i, int n) { return i <= 1 || i >= n - 2; };
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int I, J, K;
+    if (t < 16 * nz) {  // y and x near a face, every plane
+        I = cz_begin + (t >> 4);
+        J = bnd(t & 3, m.n1);
+        K = bnd((t >> 2) & 3, m.n2);
+    } else if ((t -= 16 * nz) < 16 * m.n1) {  // z and x near a face, rows not near a y face
+        I = bnd(t & 3, m.n0);
+        K = bnd((t >> 2) & 3, m.n2);
+        J = t >> 4;
+        if (near(J, m.n1)) return;
+    } else if ((t -= 16 * m.n1) < 16 * m.n2) {  // z and y near a face, columns not near an x face
+        I = bnd(t & 3, m.n0);
+        J = bnd((t >> 2) & 3, m.n1);
+        K = t >> 4;
+        if (near(K, m.n2)) return;
     } else {
         return;
     }
-    if (c[0] < cz_begin || c[0] >= cz_end) return;  // warp-uniform
-    const int n[3] = {m.n0, m.n1, m.n2};
-    const int64_t fs[3] = {m.fs0, m.fs1, 1};
-    // candidate padded indices per axis: the cell itself, -1 if it is one of the two lowest, n if one of the two highest
-    int cand[3][3], nc[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        int kk = 0;
-        cand[a][kk++] = c[a];
-        if (c[a] <= 1) cand[a][kk++] = -1;
-        if (c[a] >= n[a] - 2) cand[a][kk++] = n[a];
-        nc[a] = kk;
-    }
-    const int ncombo = nc[0] * nc[1] * nc[2];
-    T acc = T(0);
-    for (int item = lane; item < ncombo * 64; item += 32) {
-        const int combo = item >> 6, tap = item & 63;
-        int q[3];
-        int r = combo;
-        q[2] = cand[2][r % nc[2]];
-        r /= nc[2];
-        q[1] = cand[1][r % nc[1]];
-        r /= nc[1];
-        q[0] = cand[0][r];
-        bool mc = true, mr = true, outside = false;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const int qc = q[a] < 0 ? 0 : (q[a] > n[a] - 1 ? n[a] - 1 : q[a]);
-            const int qr = q[a] < 0 ? 1 : (q[a] > n[a] - 1 ? n[a] - 2 : q[a]);
-            mc = mc && qc == c[a];
-            mr = mr && qr == c[a];
-            outside = outside || q[a] < 0 || q[a] > n[a] - 1;
-        }
-        // an in-range q is the plain value u[q]: coefficient 1 when q == J
-        const T coef = outside ? T((mc ? 2 : 0) - (mr ? 1 : 0)) : T(1);
-        if (coef == T(0)) continue;
-        const int tt[3] = {tap >> 4, (tap >> 2) & 3, tap & 3};
-        T w = coef;
-        int64_t lin = 0;
-        bool ok = true;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const int fi = 2 * q[a] - 1 + tt[a];  // fine cells 2q-1 .. 2q+2, weights 1/4 3/4 3/4 1/4
-            ok = ok && fi >= 0 && fi < 2 * n[a];
-            w *= (tt[a] == 0 || tt[a] == 3) ? T(0.25) : T(0.75);
-            lin += (int64_t)(a == 0 ? fi - fine_z0 : fi) * fs[a];
-        }
-        if (ok) acc = fma(w, __ldg(gf + lin), acc);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) gc[(int64_t)(c[0] - out_z0) * m.cs0 + (int64_t)c[1] * m.cs1 + c[2]] = scale * acc;
+    if (I < cz_begin || I >= cz_end) return;
+    const int64_t lin = (int64_t)(I - out_z0) * m.cs0 + (int64_t)J * m.cs1 + K;
+    gc[lin] += scale * mg_adj_joint_correction<T>(m, gf, fine_z0, I, J, K);
 }
 
 }  // namespace odil

@@ -619,32 +619,23 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
         Mg3 m;
         bool cz = false;
         const bool pairs = (r.fz_begin % 2 == 0) && (r.fz_end % 2 == 0);
-        if (fast3_geometry(g, m, cz) && march_ok(m, cz, ndim, coarse, fine_term, out) && r.fz_end > r.fz_begin &&
-            out != fine_term) {
+        if (fast3_geometry(g, m, cz) && march_ok(m, cz, ndim, coarse, fine_term, out) && r.fz_end > r.fz_begin) {
             const int ib = (int)(r.fz_begin >> 1), ie = (int)(((r.fz_end - 1) >> 1) + 1);
             const int zc = march_chunk(m, ie - ib);
             dim3 block(32, 4, 1);
             dim3 grid((m.n2 / 2 + 31) / 32, (m.n1 + 3) / 4, (ie - ib + zc - 1) / zc);
-            const int nfix = 4 * (int)(r.fz_end - r.fz_begin) + 8 * (m.n1 + m.n2);
             if (grid.y <= 65535 && grid.z <= 65535) {
                 if (dtype == ODIL_B200_F32) {
                     k_interp_add3m<float><<<grid, block, 0, st>>>(m, (const float*)coarse, (float)cfac,
                                                                   (const float*)fine_term, (float)ffac, (float*)out,
                                                                   (int)r.fz_begin, (int)r.fz_end, (int)r.out_z0,
                                                                   (int)r.coarse_z0, zc);
-                    k_interp_fix_edges<float><<<(nfix + 127) / 128, 128, 0, st>>>(
-                        g, m, (const float*)coarse, (float)cfac, (const float*)fine_term, (float)ffac, (float*)out,
-                        (int)r.fz_begin, (int)r.fz_end, (int)r.out_z0, (int)r.coarse_z0);
                 } else {
                     k_interp_add3m<double><<<grid, block, 0, st>>>(m, (const double*)coarse, cfac,
                                                                    (const double*)fine_term, ffac, (double*)out,
                                                                    (int)r.fz_begin, (int)r.fz_end, (int)r.out_z0,
                                                                    (int)r.coarse_z0, zc);
-                    k_interp_fix_edges<double><<<(nfix + 127) / 128, 128, 0, st>>>(
-                        g, m, (const double*)coarse, cfac, (const double*)fine_term, ffac, (double*)out, (int)r.fz_begin,
-                        (int)r.fz_end, (int)r.out_z0, (int)r.coarse_z0);
                 }
-                launch_counter()++;
                 ODIL_LAUNCHED();
                 return 0;
             }
@@ -724,18 +715,18 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
                     k_interp_adjoint3m<float><<<grid, block, 0, st>>>(m, (const float*)g_fine, (float)scale,
                                                                       (float*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                                                                       (int)r.out_z0, (int)r.fine_z0, zc);
-                    k_adjoint_fix_edges<float><<<(nfix + 3) / 4, 128, 0, st>>>(
+                    k_adjoint_joint_fix<float><<<(nfix + 127) / 128, 128, 0, st>>>(
                         m, (const float*)g_fine, (float)scale, (float*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                         (int)r.out_z0, (int)r.fine_z0);
                 } else {
                     k_interp_adjoint3m<double><<<grid, block, 0, st>>>(m, (const double*)g_fine, scale,
                                                                        (double*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                                                                        (int)r.out_z0, (int)r.fine_z0, zc);
-                    k_adjoint_fix_edges<double><<<(nfix + 3) / 4, 128, 0, st>>>(
+                    k_adjoint_joint_fix<double><<<(nfix + 127) / 128, 128, 0, st>>>(
                         m, (const double*)g_fine, scale, (double*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                         (int)r.out_z0, (int)r.fine_z0);
                 }
-                launch_counter()++;
+                launch_counter()++;  // two launches
                 ODIL_LAUNCHED();
                 return 0;
             }
