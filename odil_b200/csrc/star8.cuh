@@ -47,7 +47,12 @@ struct Star8Cfg {
     static constexpr int SLOT_U = ((RU * BXB + 127) / 128) * 128;
     static constexpr int SLOT_C = ((RC * BXB + 127) / 128) * 128;
     static constexpr int SLOT_F = RC * BXB;
-    static constexpr int NSU = 4, NSC = 3, NSF = 3;
+    // TMA stages in flight (one U plane + one c plane each): the U ring holds one slot more (the plane whose halo
+    // rows are still being read); ncu showed warps waiting ~12 % of the time on the stage barrier with 3 stages
+    static constexpr int NST = 6;
+    // F ring: 4 slots, so that a warp may store F[k] as soon as its readers have published plane k-2 (they are
+    // then done with F[k-4]) and needs plane k-1 of its neighbours only when it gathers g[k-1]
+    static constexpr int NSU = NST + 1, NSC = NST, NSF = 4;
     static constexpr int TAB = 1024;
     static constexpr int OFF_U = 128, OFF_C = OFF_U + NSU * SLOT_U, OFF_F = OFF_C + NSC * SLOT_C;
     static constexpr int OFF_TAB = OFF_F + NSF * SLOT_F;
@@ -96,6 +101,34 @@ __device__ __forceinline__ uint32_t s8_mbar_test(uint32_t bar, uint32_t parity) 
     return ok;
 }
 
+// Running ring positions of one warp (warp-uniform): U slot of plane kf / kf+1, c slot and stage barrier of plane kf.
+template <int SLOT_U, int SLOT_C, int NSU, int NST>
+struct S8Ring {
+    uint32_t ucur, unxt, c, bar, par;
+    __device__ __forceinline__ void init() {
+        ucur = SLOT_U;       // plane kf0 (q = 1)
+        unxt = 2 * SLOT_U;   // plane kf0 + 1 (q = 2)
+        c = 0;
+        bar = 0;
+        par = 0;
+    }
+    __device__ __forceinline__ void advance() {
+        ucur = unxt;
+        unxt += SLOT_U;
+        if (unxt == NSU * SLOT_U) unxt = 0;
+        c += SLOT_C;
+        bar += 8;
+        if (bar == 8 * NST) {
+            bar = 0;
+            c = 0;
+            par ^= 1u;
+        }
+    }
+    // barrier offset / parity of the NEXT plane's stage
+    __device__ __forceinline__ uint32_t next_bar() const { return bar + 8 == 8 * NST ? 0u : bar + 8; }
+    __device__ __forceinline__ uint32_t next_par() const { return bar + 8 == 8 * NST ? par ^ 1u : par; }
+};
+
 // g of VW consecutive cells; the y-arm coefficients come from the rows above / below (ayp: yp coefficient of
 // the cell at y-1, aym: ym coefficient of the cell at y+1), everything else from the own row.
 template <typename T, int VW, bool XU>
@@ -127,7 +160,9 @@ struct S8Row {
     using Cfg = Star8Cfg<T, VW, NR>;
     using PackT = Pack<T, VW>;
     static constexpr int BXB = Cfg::BXB, SLOT_U = Cfg::SLOT_U, SLOT_C = Cfg::SLOT_C, SLOT_F = Cfg::SLOT_F;
+    using Ring = S8Ring<Cfg::SLOT_U, Cfg::SLOT_C, Cfg::NSU, Cfg::NST>;
 
+    Ring ring;
     PackT U[3], F[3];
     S7W<T, VW, XU> wf;  // forward row of the own cells (own y class, interior z class)
     S7W<T, VW, XU> wa;  // only arms 2, 3 are used: ym coefficient of the cell at y+1, yp coefficient of the cell at y-1
@@ -155,13 +190,14 @@ struct S8Row {
             r = lane0 ? r : e;
         }
     }
-    // the three warps whose F[kf-1] this row reads have published plane `it - 1` (which also means they are
-    // done reading this row's F[kf-3], whose ring slot F[kf] is about to take)
-    __device__ __forceinline__ void wait_neighbours(int it) const {
+    // the three warps this row exchanges F with (row above, row below, x-ring) have published plane `need`:
+    // need = it - 2 before storing F[kf] (they are done reading F[kf-4], whose ring slot it takes),
+    // need = it - 1 before gathering g[kf-1] (their F[kf-1] is in the ring)
+    __device__ __forceinline__ void wait_neighbours(int need) const {
         uint32_t spins = 0;
         while (true) {
             const int a = s8_peek(pub_up), b = s8_peek(pub_dn), c = s8_peek(pub_x);
-            if (min(a, min(b, c)) >= it - 1) break;
+            if (min(a, min(b, c)) >= need) break;
             if (++spins > (1u << 24)) __trap();
         }
     }
@@ -171,28 +207,30 @@ struct S8Row {
 
     // steady state: planes kf-2 .. kf interior and owned, c present, F not stored
     template <int PH>
-    __device__ __forceinline__ void lean(const int it, const uint32_t par, uint32_t& ready, T*& gptr, const int64_t plane) {
+    __device__ __forceinline__ void lean(const int it, uint32_t& ready, T*& gptr, const int64_t plane) {
         constexpr int IM = PH, IC = (PH + 1) % 3, IP = (PH + 2) % 3;  // U planes kf-1, kf, kf+1
         constexpr int JP = PH, JC = (PH + 2) % 3, JM = (PH + 1) % 3;  // F planes kf, kf-1, kf-2
-        const uint32_t ucur = su + ((it + 1) & 3) * SLOT_U;
-        const uint32_t unxt = su + ((it + 2) & 3) * SLOT_U;
-        wait_stage(sbar + 8 * PH, par, ready);
+        const uint32_t ucur = su + ring.ucur;
+        const uint32_t unxt = su + ring.unxt;
+        wait_stage(sbar + ring.bar, ring.par, ready);
         U[IP] = lds(unxt);
         const PackT uyt = lds(ucur - BXB);
         const PackT uyb = lds(ucur + BXB);
-        const PackT cc = lds(sc + PH * SLOT_C);
+        const PackT cc = lds(sc + ring.c);
         T ul, ur;
         xnb(U[IC], ucur, ul, ur);
         F[JP] = s7_fwd<T, VW, XU>(wf, cc, U[IC], U[IM], U[IP], uyt, uyb, ul, ur);
-        wait_neighbours(it);
-        s7_sts(sf + PH * SLOT_F, F[JP]);
+        wait_neighbours(it - 2);
+        s7_sts(sf + (it & 3) * SLOT_F, F[JP]);
         __syncwarp();
         if (lane0) s8_publish(pub_me, it);
         // test the next stage now: the answer is there by the time the next plane starts
-        ready = s8_mbar_test(sbar + 8 * ((PH + 1) % 3), PH == 2 ? par ^ 1u : par);
+        ready = s8_mbar_test(sbar + ring.next_bar(), ring.next_par());
+        ring.advance();
 #pragma unroll
         for (int j = 0; j < VW; ++j) accf = fma(F[JP].v[j], F[JP].v[j], accf);
-        const uint32_t fprev = sf + JC * SLOT_F;
+        wait_neighbours(it - 1);
+        const uint32_t fprev = sf + ((it + 3) & 3) * SLOT_F;
         const PackT fyt = lds(fprev - BXB);
         const PackT fyb = lds(fprev + BXB);
         T fl, fr;
@@ -217,19 +255,20 @@ struct S8Row {
 
     // general plane: z flags for everything, planes of a boundary z class through the table
     template <int PH>
-    __device__ __forceinline__ void step(const int it, const uint32_t par, const Flags& fl) {
+    __device__ __forceinline__ void step(const int it, const Flags& fl) {
         constexpr int IM = PH, IC = (PH + 1) % 3, IP = (PH + 2) % 3;
         constexpr int JP = PH, JC = (PH + 2) % 3, JM = (PH + 1) % 3;
         const int kf = fl.kf0 + it;
         const int zg = fl.z0 + kf;
-        const uint32_t ucur = su + ((it + 1) & 3) * SLOT_U;
-        const uint32_t unxt = su + ((it + 2) & 3) * SLOT_U;
-        s7_mbar_wait(sbar + 8 * PH, par);
+        const uint32_t ucur = su + ring.ucur;
+        const uint32_t unxt = su + ring.unxt;
+        s7_mbar_wait(sbar + ring.bar, ring.par);
         U[IP] = lds(unxt);
         const PackT uyt = lds(ucur - BXB);
         const PackT uyb = lds(ucur + BXB);
         PackT cc = zero();
-        if (fl.has_c) cc = lds(sc + PH * SLOT_C);
+        if (fl.has_c) cc = lds(sc + ring.c);
+        ring.advance();
         T ul, ur;
         xnb(U[IC], ucur, ul, ur);
         const bool zin = zg >= 0 && zg < fl.gm.N0g;
@@ -240,8 +279,8 @@ struct S8Row {
             F[JP] = s7_slow_fwd<T, VW>(fl.tab, fl.gm, zg, fl.y, fl.x0, cc, U[IC], U[IM], U[IP], uyt, uyb, ul, ur);
         else
             F[JP] = s7_fwd<T, VW, XU>(wf, cc, U[IC], U[IM], U[IP], uyt, uyb, ul, ur);
-        wait_neighbours(it);
-        s7_sts(sf + PH * SLOT_F, F[JP]);
+        wait_neighbours(it - 2);
+        s7_sts(sf + (it & 3) * SLOT_F, F[JP]);
         __syncwarp();
         if (lane0) s8_publish(pub_me, it);
         if (kf >= fl.zs && kf < fl.ze) {
@@ -249,7 +288,8 @@ struct S8Row {
             for (int j = 0; j < VW; ++j) accf = fma(F[JP].v[j], F[JP].v[j], accf);
             if (fl.Fcol && xin) *reinterpret_cast<PackT*>(fl.Fcol + (int64_t)kf * fl.plane) = F[JP];
         }
-        const uint32_t fprev = sf + JC * SLOT_F;
+        wait_neighbours(it - 1);
+        const uint32_t fprev = sf + ((it + 3) & 3) * SLOT_F;
         const PackT fyt = lds(fprev - BXB);
         const PackT fyb = lds(fprev + BXB);
         T fll, frr;
@@ -276,7 +316,7 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
     constexpr int TX = Cfg::TX, BX = Cfg::BX, NT = Cfg::NT, BXB = Cfg::BXB;
     constexpr int SLOT_U = Cfg::SLOT_U, SLOT_C = Cfg::SLOT_C, SLOT_F = Cfg::SLOT_F, SZ = (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar_stage[3];
+    __shared__ __align__(8) uint64_t bar_stage[Cfg::NST];
     __shared__ __align__(8) uint64_t bar_pro;
     __shared__ int pub[32];  // published plane per working warp: rows 0..NR-1, y-ring NR, x-ring NR+1
     __shared__ double red[32];
@@ -303,7 +343,7 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
     if (tid == 0) {
         mbar_init(&bar_pro, 1);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) mbar_init(&bar_stage[i], 1);
+        for (int i = 0; i < Cfg::NST; ++i) mbar_init(&bar_stage[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -375,17 +415,18 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
 #pragma unroll
             for (int q = 0; q < 3; ++q) m.F[q] = m.zero();
             m.accf = T(0);
-            uint32_t par = 0, ready = 0;
-            for (int it = 0; it < niter; it += 3, par ^= 1u) {
+            uint32_t ready = 0;
+            m.ring.init();
+            for (int it = 0; it < niter; it += 3) {
                 if (it >= it_lo && it + 2 <= it_hi) {
                     T* gptr = fl.Gcol + (int64_t)(kf0 + it - 1) * fl.plane;
-                    m.template lean<0>(it, par, ready, gptr, fl.plane);
-                    m.template lean<1>(it + 1, par, ready, gptr, fl.plane);
-                    m.template lean<2>(it + 2, par, ready, gptr, fl.plane);
+                    m.template lean<0>(it, ready, gptr, fl.plane);
+                    m.template lean<1>(it + 1, ready, gptr, fl.plane);
+                    m.template lean<2>(it + 2, ready, gptr, fl.plane);
                 } else {
-                    m.template step<0>(it, par, fl);
-                    if (it + 1 < niter) m.template step<1>(it + 1, par, fl);
-                    if (it + 2 < niter) m.template step<2>(it + 2, par, fl);
+                    m.template step<0>(it, fl);
+                    if (it + 1 < niter) m.template step<1>(it + 1, fl);
+                    if (it + 2 < niter) m.template step<2>(it + 2, fl);
                     ready = 0;
                 }
                 acc2 += (double)m.accf;
@@ -413,18 +454,20 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
         s7_mbar_wait(sbarp, 0);
         PackT umT = lds(suT), umD = lds(suD), ucT = lds(suT + SLOT_U), ucD = lds(suD + SLOT_U);
         int ph = 0;
-        uint32_t par = 0;
+        S8Ring<SLOT_U, SLOT_C, Cfg::NSU, Cfg::NST> ring;
+        ring.init();
         for (int it = 0; it < niter; ++it) {
             const int zg = p.z0 + kf0 + it;
-            const uint32_t ocur = ((it + 1) & 3) * SLOT_U, onxt = ((it + 2) & 3) * SLOT_U;
-            s7_mbar_wait(sbar + 8 * ph, par);
+            const uint32_t ocur = ring.ucur, onxt = ring.unxt, oc = ring.c;
+            s7_mbar_wait(sbar + ring.bar, ring.par);
+            ring.advance();
             const PackT upT = lds(suT + onxt), upD = lds(suD + onxt);
             const bool zin = zg >= 0 && zg < p.N0g;
             const bool zslow = zin && s7_cls(zg, p.N0g, p.R0) != p.R0;
             PackT fT = zero, fD = zero;
             if (zin && domT) {
                 const PackT uym = lds(suT + ocur - BXB), uyp = lds(suT + ocur + BXB);
-                const PackT cc = p.has_c ? lds(scT + ph * SLOT_C) : zero;
+                const PackT cc = p.has_c ? lds(scT + oc) : zero;
                 T ul = __shfl_up_sync(0xffffffffu, ucT.v[VW - 1], 1), ur = __shfl_down_sync(0xffffffffu, ucT.v[0], 1);
                 const T e = s7_lds1_if(suT + ocur + eoffB, edge, (T*)nullptr);
                 if (edge) {
@@ -438,7 +481,7 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
             }
             if (zin && domD) {
                 const PackT uym = lds(suD + ocur - BXB), uyp = lds(suD + ocur + BXB);
-                const PackT cc = p.has_c ? lds(scD + ph * SLOT_C) : zero;
+                const PackT cc = p.has_c ? lds(scD + oc) : zero;
                 T ul = __shfl_up_sync(0xffffffffu, ucD.v[VW - 1], 1), ur = __shfl_down_sync(0xffffffffu, ucD.v[0], 1);
                 const T e = s7_lds1_if(suD + ocur + eoffB, edge, (T*)nullptr);
                 if (edge) {
@@ -452,29 +495,27 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
             }
             {  // rows 0 and nrows-1 are done reading the ring slots this plane overwrites
                 uint32_t spins = 0;
-                while (min(s8_peek(pub_a), s8_peek(pub_b)) < it - 1)
+                while (min(s8_peek(pub_a), s8_peek(pub_b)) < it - 2)
                     if (++spins > (1u << 24)) __trap();
             }
-            s7_sts(sfT + ph * SLOT_F, fT);
-            s7_sts(sfD + ph * SLOT_F, fD);
+            s7_sts(sfT + (it & 3) * SLOT_F, fT);
+            s7_sts(sfD + (it & 3) * SLOT_F, fD);
             __syncwarp();
             if (lane0) s8_publish(pub_me, it);
             umT = ucT;
             ucT = upT;
             umD = ucD;
             ucD = upD;
-            if (++ph == 3) {
-                ph = 0;
-                par ^= 1u;
-            }
+            if (++ph == 3) ph = 0;
         }
     } else {
         // ------------------------------------------------------------------ x-ring warp (+ TMA producer)
-        // stage j = { U plane kf0 + 1 + j -> U slot (j + 2) & 3,  c plane kf0 + j -> c slot j % 3 }, barrier j % 3
+        // stage j = { U plane kf0 + 1 + j -> U slot (j + 2) % NSU,  c plane kf0 + j -> c slot j % NST }, barrier j % NST
+        constexpr int NST = Cfg::NST, NSU = Cfg::NSU;
         auto issue_stage = [&](int j) {
-            const int b = j % 3;
+            const int b = j % NST;
             mbar_expect_tx(&bar_stage[b], Cfg::BYTES_U + (p.has_c ? Cfg::BYTES_C : 0u));
-            tma_load_3d(smem_raw + Cfg::OFF_U + ((j + 2) & 3) * SLOT_U, &tmU, &bar_stage[b], tx0 - VW, ty0 - 2,
+            tma_load_3d(smem_raw + Cfg::OFF_U + ((j + 2) % NSU) * SLOT_U, &tmU, &bar_stage[b], tx0 - VW, ty0 - 2,
                         kf0 + 1 + j + p.halo);
             if (p.has_c)
                 tma_load_3d(smem_raw + Cfg::OFF_C + b * SLOT_C, &tmC, &bar_stage[b], tx0 - VW, ty0 - 1, kf0 + j + p.halo);
@@ -483,8 +524,7 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
             mbar_expect_tx(&bar_pro, 2 * Cfg::BYTES_U);
             tma_load_3d(smem_raw + Cfg::OFF_U, &tmU, &bar_pro, tx0 - VW, ty0 - 2, kf0 - 1 + p.halo);
             tma_load_3d(smem_raw + Cfg::OFF_U + SLOT_U, &tmU, &bar_pro, tx0 - VW, ty0 - 2, kf0 + p.halo);
-            issue_stage(0);
-            if (niter > 1) issue_stage(1);
+            for (int j = 0; j < NST - 1 && j < niter; ++j) issue_stage(j);
         }
         const bool active = lane < 2 * nrows;
         const int side = lane & 1, f = active ? (lane >> 1) + 1 : 1;  // F rows 1 .. nrows
@@ -504,15 +544,17 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
         s7_mbar_wait(sbarp, 0);
         T um = s7_lds1(uo, (T*)nullptr), uc = s7_lds1(uo + SLOT_U, (T*)nullptr);
         int ph = 0;
-        uint32_t par = 0;
+        S8Ring<SLOT_U, SLOT_C, Cfg::NSU, Cfg::NST> ring;
+        ring.init();
         for (int it = 0; it < niter; ++it) {
             const int zg = p.z0 + kf0 + it;
-            const uint32_t ucur = uo + ((it + 1) & 3) * SLOT_U, unxt = uo + ((it + 2) & 3) * SLOT_U;
-            s7_mbar_wait(sbar + 8 * ph, par);
+            const uint32_t ucur = uo + ring.ucur, unxt = uo + ring.unxt, oc = ring.c;
+            s7_mbar_wait(sbar + ring.bar, ring.par);
+            ring.advance();
             const T up = s7_lds1(unxt, (T*)nullptr);
             T fv = T(0);
             if (dom && zg >= 0 && zg < p.N0g) {
-                const T cc = p.has_c ? s7_lds1(co + ph * SLOT_C, (T*)nullptr) : T(0);
+                const T cc = p.has_c ? s7_lds1(co + oc, (T*)nullptr) : T(0);
                 const T uym = s7_lds1(ucur - BXB, (T*)nullptr), uyp = s7_lds1(ucur + BXB, (T*)nullptr);
                 const T ul = s7_lds1(ucur - SZ, (T*)nullptr), ur = s7_lds1(ucur + SZ, (T*)nullptr);
                 const int cz = s7_cls(zg, p.N0g, p.R0);
@@ -525,28 +567,25 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
             }
             {  // the row warps are done reading the ring slot this plane overwrites
                 uint32_t spins = 0;
-                while (!__all_sync(0xffffffffu, s8_peek(pub_row) >= it - 1))
+                while (!__all_sync(0xffffffffu, s8_peek(pub_row) >= it - 2))
                     if (++spins > (1u << 24)) __trap();
             }
-            if (active) s7_sts1(fo + ph * SLOT_F, fv);
+            if (active) s7_sts1(fo + (it & 3) * SLOT_F, fv);
             __syncwarp();
             if (lane == 0) s8_publish(pub_me, it);
             um = uc;
             uc = up;
-            if ((it == 0 && 2 < niter) || it + 3 < niter) {
+            if ((it == 0 && NST - 1 < niter) || it + NST < niter) {
                 // every other warp has published plane `it`: the U plane kf and the c plane kf are consumed
                 uint32_t spins = 0;
                 while (!__all_sync(0xffffffffu, s8_peek(pub_w) >= it))
                     if (++spins > (1u << 26)) __trap();
                 if (lane == 0) {
-                    if (it == 0 && 2 < niter) issue_stage(2);
-                    if (it + 3 < niter) issue_stage(it + 3);
+                    if (it == 0 && NST - 1 < niter) issue_stage(NST - 1);
+                    if (it + NST < niter) issue_stage(it + NST);
                 }
             }
-            if (++ph == 3) {
-                ph = 0;
-                par ^= 1u;
-            }
+            if (++ph == 3) ph = 0;
         }
     }
     const double sum = block_sum(acc2, red);
