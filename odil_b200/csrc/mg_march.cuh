@@ -168,7 +168,7 @@ __device__ __forceinline__ MgP<T> mg_plane(const Mg3& m, const T* __restrict__ c
 
 // grid (ceil(n2 / 64), ceil(n1 / 4), z-chunks), block (32, 4): thread = coarse cells 2k, 2k+1 of coarse row J
 template <typename T>
-__global__ void __launch_bounds__(128) k_interp_add3m(Mg3 m, const T* __restrict__ coarse, T cfac,
+__global__ void __launch_bounds__(128, 5) k_interp_add3m(Mg3 m, const T* __restrict__ coarse, T cfac,
                                                       const T* __restrict__ term, T ffac, T* __restrict__ out,
                                                       int fz_begin, int fz_end, int out_z0, int coarse_z0, int zc) {
     const int k = blockIdx.x * 32 + threadIdx.x;

@@ -578,15 +578,28 @@ static bool fast3_geometry(const MgGeom& g, Mg3& m, bool& cz) {
 #include "mg_march.cuh"
 namespace odil {
 
-// z-chunk of the marching transfer kernels: enough CTAs (128 threads) to fill 148 SMs ~12 times over, chunks of
-// at least 8 coarse planes so that the 2-plane lead-in stays small
-static int march_chunk(const Mg3& m, int ncz) {
+// z-chunk of the marching transfer kernels (CTAs of 128 threads, `ctas_per_sm` resident per SM by their
+// __launch_bounds__): the number of chunks is chosen so that the CTAs fill the 148 SMs in (nearly) whole waves --
+// the first version used 1792 CTAs on 888 slots = 2.02 waves, i.e. a third wave for 2 % of the work -- with
+// chunks of at least 8 coarse planes so that the 2-plane lead-in stays small.
+static int march_chunk(const Mg3& m, int ncz, int ctas_per_sm) {
     const int64_t layer = (int64_t)((m.n2 / 2 + 31) / 32) * ((m.n1 + 3) / 4);
-    int gz = (int)std::max<int64_t>(1, (148 * 12 + layer - 1) / layer);
-    int zc = (ncz + gz - 1) / gz;
-    if (zc < 8) zc = 8;
-    if (zc > ncz) zc = ncz;
-    return zc;
+    const int64_t slots = 148 * (int64_t)ctas_per_sm;
+    int best_zc = ncz;
+    double best = -1.0;
+    for (int gz = 1; gz <= std::max(1, ncz / 8); ++gz) {
+        const int zc = (ncz + gz - 1) / gz;
+        const int gzr = (ncz + zc - 1) / zc;
+        const int64_t ctas = layer * gzr;
+        const int64_t waves = (ctas + slots - 1) / slots;
+        // time ~ waves * (planes per chunk + lead-in); fewer, longer chunks win ties
+        const double cost = (double)waves * (zc + 2);
+        if (best < 0 || cost < best * 0.999) {
+            best = cost;
+            best_zc = zc;
+        }
+    }
+    return best_zc;
 }
 static bool march_ok(const Mg3& m, bool cz, int ndim, const void* a, const void* b, const void* c) {
     return cz && ndim == 3 && m.n2 % 2 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) &&
@@ -621,7 +634,7 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
         const bool pairs = (r.fz_begin % 2 == 0) && (r.fz_end % 2 == 0);
         if (fast3_geometry(g, m, cz) && march_ok(m, cz, ndim, coarse, fine_term, out) && r.fz_end > r.fz_begin) {
             const int ib = (int)(r.fz_begin >> 1), ie = (int)(((r.fz_end - 1) >> 1) + 1);
-            const int zc = march_chunk(m, ie - ib);
+            const int zc = march_chunk(m, ie - ib, 5);
             dim3 block(32, 4, 1);
             dim3 grid((m.n2 / 2 + 31) / 32, (m.n1 + 3) / 4, (ie - ib + zc - 1) / zc);
             if (grid.y <= 65535 && grid.z <= 65535) {
@@ -706,7 +719,7 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
         Mg3 m;
         bool cz = false;
         if (fast3_geometry(g, m, cz) && march_ok(m, cz, ndim, g_fine, g_coarse, nullptr)) {
-            const int zc = march_chunk(m, (int)(r.cz_end - r.cz_begin));
+            const int zc = march_chunk(m, (int)(r.cz_end - r.cz_begin), 4);
             dim3 block(32, 4, 1);
             dim3 grid((m.n2 / 2 + 31) / 32, (m.n1 + 3) / 4, (unsigned)((r.cz_end - r.cz_begin + zc - 1) / zc));
             const int nfix = 16 * (int)(r.cz_end - r.cz_begin) + 16 * (m.n1 + m.n2);
