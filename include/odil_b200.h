@@ -119,7 +119,8 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
 /* g_coarse = scale * I^T g_fine  (exact transpose of interp incl. the joint 2*symmetric-reflect
  * pad; this is what AD of core.py:606-700 produces, NOT restrict_to_coarser).
  * Slabs: computes coarse planes [cz_begin, cz_end) (global); g_fine points at global fine plane
- * fine_z0 and must hold planes 2*cz_begin-1 .. 2*cz_end (clipped to the domain). */
+ * fine_z0 and must hold planes 2*cz_begin-2 .. 2*cz_end+1 (clipped to the domain; the outermost two
+ * are only read for the pad corrections of the coarse planes 1 and n-2). */
 typedef struct {
     int64_t cz_begin, cz_end;
     int64_t out_z0;  /* global coarse plane at the g_coarse pointer */

@@ -412,3 +412,92 @@ def test_fullsize_mg_transpose(cshape):
     linf = sum((i + 1.0) * x.reshape([-1 if a == i else 1 for a in range(ndim)]) / (2 * cshape[i])
                for i, x in enumerate(xf))
     assert (Iu - linf).abs().max().item() < 1e-12
+
+
+# --------------------------------------------------------------------------------------------------
+# k_star8 / k_star7 (the hot kernels) on awkward shapes, every tile variant, x-uniform and per-cell arms
+# --------------------------------------------------------------------------------------------------
+STAR8_SHAPES = [(20, 18, 36), (7, 33, 260), (5, 15, 8), (45, 132), (64, 16, 128)]
+
+
+@pytest.mark.parametrize("variant", [-1, 50, 51, 52, 60, 61, 62, 30, 31, 32, 40, 42])
+@pytest.mark.parametrize("zchunk", [0, 1, 5])
+@pytest.mark.parametrize("shape", STAR8_SHAPES)
+def test_star8_variants(variant, zchunk, shape):
+    """Default dispatch (-1) and every tile variant of k_star8 (50-52 x-uniform arms, 60-62 per-cell arms) and k_star7
+    (30-32, 40-42): g, sum F^2 and F against the oracle, with and without the constant term."""
+    nd = len(shape)
+    rng = np.random.default_rng(11)
+    offsets, table, rr = orc.poisson_plan(nd, [0.3, 0.2, 0.1][:nd])
+    ncls = 3 ** nd
+    table = np.asarray(table).reshape(ncls, 2 * nd + 1)
+    if variant >= 60 or (40 <= variant < 50):
+        table = table * (1 + 0.1 * rng.standard_normal(table.shape))  # keeps the zero pattern; arms now depend on x
+    tshape = (3,) * nd + (2 * nd + 1,)
+    for prec in ("f64", "f32"):
+        npd, td = DT[prec]
+        U = rng.standard_normal(shape).astype(npd)
+        c = rng.standard_normal(shape).astype(npd)
+        plan = native.StencilPlan(shape, td, offsets, rr, table)
+        assert plan.kind == 1
+        if variant >= 0:
+            plan.tune(zchunk=zchunk, variant=variant)
+        elif zchunk:
+            plan.tune(zchunk=zchunk, variant=-1)
+        F_ref = orc.stencil_forward(U.astype(np.float64), offsets, table.reshape(tshape), rr, c.astype(np.float64))
+        g_ref = orc.stencil_adjoint(F_ref, offsets, table.reshape(tshape), rr, 0.5)
+        tol = TOL[prec] * 10
+        G = torch.full(shape, float("nan"), dtype=td, device="cuda")
+        F = torch.full(shape, float("nan"), dtype=td, device="cuda")
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dev(U), dev(c), 0.5, G, ss)
+        assert relerr(G.cpu().numpy(), g_ref) < tol
+        assert abs(ss.item() - np.sum(F_ref ** 2)) < tol * np.sum(F_ref ** 2)
+        G.fill_(float("nan"))
+        plan.fused(dev(U), dev(c), 0.5, G, ss, F_out=F)
+        assert relerr(F.cpu().numpy(), F_ref) < tol
+        assert relerr(G.cpu().numpy(), g_ref) < tol
+        F0 = orc.stencil_forward(U.astype(np.float64), offsets, table.reshape(tshape), rr, None)
+        plan.fused(dev(U), None, 0.5, G, ss)
+        assert abs(ss.item() - np.sum(F0 ** 2)) < tol * np.sum(F0 ** 2)
+        assert relerr(G.cpu().numpy(), orc.stencil_adjoint(F0, offsets, table.reshape(tshape), rr, 0.5)) < tol
+
+
+# --------------------------------------------------------------------------------------------------
+# marching multigrid transfers: odd shapes, plane ranges (what a slab passes), against the oracle
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cshape", [(4, 4, 4), (5, 7, 6), (9, 4, 34), (33, 17, 64), (6, 66, 130)])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_marching_transfers(cshape, prec):
+    npd, td = DT[prec]
+    rng = np.random.default_rng(3)
+    fshape = tuple(2 * s for s in cshape)
+    coarse = rng.standard_normal(cshape).astype(npd)
+    term = rng.standard_normal(fshape).astype(npd)
+    ref = 1.3 * term.astype(np.float64) + 0.7 * orc.interp_to_finer(coarse.astype(np.float64), "ccc")
+    tol = 100 * np.finfo(npd).eps
+    out = torch.full(fshape, float("nan"), dtype=td, device="cuda")
+    native.mg_interp_add(cshape, "ccc", dev(coarse), 0.7, dev(term), 1.3, out)
+    assert relerr(out.cpu().numpy(), ref) < tol
+    native.mg_interp_add(cshape, "ccc", dev(coarse), 0.7, None, 0.0, out)
+    assert relerr(out.cpu().numpy(), 0.7 * orc.interp_to_finer(coarse.astype(np.float64), "ccc")) < tol
+    g_ref = 0.9 * orc.interp_adjoint(term.astype(np.float64), "ccc", cshape)
+    gc = torch.full(cshape, float("nan"), dtype=td, device="cuda")
+    native.mg_interp_adjoint(cshape, "ccc", dev(term), 0.9, gc)
+    assert relerr(gc.cpu().numpy(), g_ref) < tol
+    # plane ranges with shifted array origins, as the slab decomposition passes them
+    n0 = cshape[0]
+    if n0 >= 5:
+        for (cb, ce) in [(0, 2), (1, n0 - 1), (n0 - 2, n0), (2, 3)]:
+            fb, fe = 2 * cb, 2 * ce
+            # interp: fine planes [fb, fe) from coarse planes cb-1 .. ce (clipped), arrays start at those planes
+            c_lo, c_hi = max(cb - 1, 0), min(ce + 1, n0)
+            o = torch.full((fe - fb,) + fshape[1:], float("nan"), dtype=td, device="cuda")
+            native.mg_interp_add(cshape, "ccc", dev(coarse[c_lo:c_hi]), 0.7, dev(term[fb:fe]), 1.3, o, rng=(fb, fe, fb, c_lo))
+            assert relerr(o.cpu().numpy(), ref[fb:fe]) < tol
+            # transpose: coarse planes [cb, ce) from fine planes 2cb-2 .. 2ce+1 (clipped; the outermost two carry the
+            # pad corrections of the coarse planes 1 and n0-2)
+            f_lo, f_hi = max(2 * cb - 2, 0), min(2 * ce + 2, fshape[0])
+            gg = torch.full((ce - cb,) + tuple(cshape[1:]), float("nan"), dtype=td, device="cuda")
+            native.mg_interp_adjoint(cshape, "ccc", dev(term[f_lo:f_hi]), 0.9, gg, rng=(cb, ce, cb, f_lo))
+            assert relerr(gg.cpu().numpy(), g_ref[cb:ce]) < tol
