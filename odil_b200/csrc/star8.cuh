@@ -47,18 +47,24 @@ struct Star8Cfg {
     static constexpr int SLOT_U = ((RU * BXB + 127) / 128) * 128;
     static constexpr int SLOT_C = ((RC * BXB + 127) / 128) * 128;
     static constexpr int SLOT_F = RC * BXB;
-    // TMA stages in flight (one U plane + one c plane each): the U ring holds one slot more (the plane whose halo
-    // rows are still being read); ncu showed warps waiting ~12 % of the time on the stage barrier with 3 stages
-    static constexpr int NST = 6;
+    // Rings of 6 slots (U planes, c planes, stage barriers) with 5 TMA stages in flight (one U plane + one c plane
+    // each): the period 6 = 2 x 3 lines up with the 3-way unrolled plane loop, so a row warp derives every ring
+    // position from the trip parity.
+    static constexpr int NST = 6, NFL = 5;
     // F ring: 4 slots, so that a warp may store F[k] as soon as its readers have published plane k-2 (they are
     // then done with F[k-4]) and needs plane k-1 of its neighbours only when it gathers g[k-1]
-    static constexpr int NSU = NST + 1, NSC = NST, NSF = 4;
+    static constexpr int NSU = 6, NSC = 6, NSF = 4;
     static constexpr int TAB = 1024;
     static constexpr int OFF_U = 128, OFF_C = OFF_U + NSU * SLOT_U, OFF_F = OFF_C + NSC * SLOT_C;
     static constexpr int OFF_TAB = OFF_F + NSF * SLOT_F;
     static constexpr uint32_t BYTES_U = RU * BXB;
     static constexpr uint32_t BYTES_C = RC * BXB;
-    static constexpr size_t SMEM = OFF_TAB + sizeof(T) * TAB + 64;
+    // stage barriers, prologue barrier and the published-plane words live in the dynamic block too: their shared
+    // addresses are then `base + constant` (taking the address of a static __shared__ variable made ptxas
+    // re-derive it with S2R SR_CgaCtaId three times per plane)
+    static constexpr int OFF_BAR = ((OFF_TAB + (int)sizeof(T) * TAB + 15) / 16) * 16;
+    static constexpr int OFF_PUB = OFF_BAR + 8 * (NST + 1);
+    static constexpr size_t SMEM = OFF_PUB + 4 * 32 + 64;
     static constexpr int CTAS_PER_SM = (NT <= 320 && 2 * SMEM <= 225 * 1024) ? 2 : 1;
     // register budget: the register file is 4 x 16384 (one bank per scheduler) and warps are dealt round-robin, so
     // a CTA of W warps needs ceil(W / 4) warps' worth of registers in one bank (measured: 544 threads x 120
@@ -160,9 +166,30 @@ struct S8Row {
     using Cfg = Star8Cfg<T, VW, NR>;
     using PackT = Pack<T, VW>;
     static constexpr int BXB = Cfg::BXB, SLOT_U = Cfg::SLOT_U, SLOT_C = Cfg::SLOT_C, SLOT_F = Cfg::SLOT_F;
-    using Ring = S8Ring<Cfg::SLOT_U, Cfg::SLOT_C, Cfg::NSU, Cfg::NST>;
-
-    Ring ring;
+    // ring positions of the current trip (3 planes): stage j = it sits in slot j % 6 = 3 h + PH (h = trip parity);
+    // uA / uB = byte offset of U slot 3 h / 3 (1 - h), cb = 3 h, par = (it / 6) & 1
+    uint32_t uA, uB, cb, par;
+    __device__ __forceinline__ void ring_init() {
+        uA = 0;
+        uB = 3 * SLOT_U;
+        cb = 0;
+        par = 0;
+    }
+    __device__ __forceinline__ void ring_next_trip() {
+        const uint32_t t = uA;
+        uA = uB;
+        uB = t;
+        cb ^= 3u;
+        par ^= (cb == 0u);
+    }
+    template <int PH>
+    __device__ __forceinline__ uint32_t u_cur() const {  // U plane kf: slot (it + 1) % 6
+        return PH == 0 ? uA + SLOT_U : (PH == 1 ? uA + 2 * SLOT_U : uB);
+    }
+    template <int PH>
+    __device__ __forceinline__ uint32_t u_nxt() const {  // U plane kf + 1: slot (it + 2) % 6
+        return PH == 0 ? uA + 2 * SLOT_U : (PH == 1 ? uB : uB + SLOT_U);
+    }
     PackT U[3], F[3];
     S7W<T, VW, XU> wf;  // forward row of the own cells (own y class, interior z class)
     S7W<T, VW, XU> wa;  // only arms 2, 3 are used: ym coefficient of the cell at y+1, yp coefficient of the cell at y-1
@@ -171,6 +198,7 @@ struct S8Row {
     uint32_t su, sc, sf;  // shared byte addresses of the own cells in U slot 0 / c slot 0 / F slot 0
     uint32_t sbar;        // bar_stage[0]
     uint32_t pub_me, pub_up, pub_dn, pub_x;  // published-plane words: own, row above, row below, x-ring
+    int seen;                                // smallest plane seen published by those three
     int eoffB;
     bool edge, lane0, xin;
 
@@ -193,11 +221,13 @@ struct S8Row {
     // the three warps this row exchanges F with (row above, row below, x-ring) have published plane `need`:
     // need = it - 2 before storing F[kf] (they are done reading F[kf-4], whose ring slot it takes),
     // need = it - 1 before gathering g[kf-1] (their F[kf-1] is in the ring)
-    __device__ __forceinline__ void wait_neighbours(int need) const {
+    // `seen` caches the smallest published plane of the three: the poll before the store usually already shows
+    // plane it-1, and the wait before the gather then costs nothing
+    __device__ __forceinline__ void wait_neighbours(int need, int& seen) const {
         uint32_t spins = 0;
-        while (true) {
+        while (seen < need) {
             const int a = s8_peek(pub_up), b = s8_peek(pub_dn), c = s8_peek(pub_x);
-            if (min(a, min(b, c)) >= need) break;
+            seen = min(a, min(b, c));
             if (++spins > (1u << 24)) __trap();
         }
     }
@@ -210,26 +240,26 @@ struct S8Row {
     __device__ __forceinline__ void lean(const int it, uint32_t& ready, T*& gptr, const int64_t plane) {
         constexpr int IM = PH, IC = (PH + 1) % 3, IP = (PH + 2) % 3;  // U planes kf-1, kf, kf+1
         constexpr int JP = PH, JC = (PH + 2) % 3, JM = (PH + 1) % 3;  // F planes kf, kf-1, kf-2
-        const uint32_t ucur = su + ring.ucur;
-        const uint32_t unxt = su + ring.unxt;
-        wait_stage(sbar + ring.bar, ring.par, ready);
+        const uint32_t ucur = su + u_cur<PH>();
+        const uint32_t unxt = su + u_nxt<PH>();
+        wait_stage(sbar + 8 * (cb + PH), par, ready);
         U[IP] = lds(unxt);
         const PackT uyt = lds(ucur - BXB);
         const PackT uyb = lds(ucur + BXB);
-        const PackT cc = lds(sc + ring.c);
+        const PackT cc = lds(sc + (cb + PH) * SLOT_C);
         T ul, ur;
         xnb(U[IC], ucur, ul, ur);
         F[JP] = s7_fwd<T, VW, XU>(wf, cc, U[IC], U[IM], U[IP], uyt, uyb, ul, ur);
-        wait_neighbours(it - 2);
+        wait_neighbours(it - 2, seen);
         s7_sts(sf + (it & 3) * SLOT_F, F[JP]);
         __syncwarp();
         if (lane0) s8_publish(pub_me, it);
         // test the next stage now: the answer is there by the time the next plane starts
-        ready = s8_mbar_test(sbar + ring.next_bar(), ring.next_par());
-        ring.advance();
+        ready = PH < 2 ? s8_mbar_test(sbar + 8 * (cb + PH + 1), par)
+                       : s8_mbar_test(sbar + 8 * (cb ^ 3u), par ^ (cb == 3u));
 #pragma unroll
         for (int j = 0; j < VW; ++j) accf = fma(F[JP].v[j], F[JP].v[j], accf);
-        wait_neighbours(it - 1);
+        wait_neighbours(it - 1, seen);
         const uint32_t fprev = sf + ((it + 3) & 3) * SLOT_F;
         const PackT fyt = lds(fprev - BXB);
         const PackT fyb = lds(fprev + BXB);
@@ -260,15 +290,14 @@ struct S8Row {
         constexpr int JP = PH, JC = (PH + 2) % 3, JM = (PH + 1) % 3;
         const int kf = fl.kf0 + it;
         const int zg = fl.z0 + kf;
-        const uint32_t ucur = su + ring.ucur;
-        const uint32_t unxt = su + ring.unxt;
-        s7_mbar_wait(sbar + ring.bar, ring.par);
+        const uint32_t ucur = su + u_cur<PH>();
+        const uint32_t unxt = su + u_nxt<PH>();
+        s7_mbar_wait(sbar + 8 * (cb + PH), par);
         U[IP] = lds(unxt);
         const PackT uyt = lds(ucur - BXB);
         const PackT uyb = lds(ucur + BXB);
         PackT cc = zero();
-        if (fl.has_c) cc = lds(sc + ring.c);
-        ring.advance();
+        if (fl.has_c) cc = lds(sc + (cb + PH) * SLOT_C);
         T ul, ur;
         xnb(U[IC], ucur, ul, ur);
         const bool zin = zg >= 0 && zg < fl.gm.N0g;
@@ -279,7 +308,7 @@ struct S8Row {
             F[JP] = s7_slow_fwd<T, VW>(fl.tab, fl.gm, zg, fl.y, fl.x0, cc, U[IC], U[IM], U[IP], uyt, uyb, ul, ur);
         else
             F[JP] = s7_fwd<T, VW, XU>(wf, cc, U[IC], U[IM], U[IP], uyt, uyb, ul, ur);
-        wait_neighbours(it - 2);
+        wait_neighbours(it - 2, seen);
         s7_sts(sf + (it & 3) * SLOT_F, F[JP]);
         __syncwarp();
         if (lane0) s8_publish(pub_me, it);
@@ -288,7 +317,7 @@ struct S8Row {
             for (int j = 0; j < VW; ++j) accf = fma(F[JP].v[j], F[JP].v[j], accf);
             if (fl.Fcol && xin) *reinterpret_cast<PackT*>(fl.Fcol + (int64_t)kf * fl.plane) = F[JP];
         }
-        wait_neighbours(it - 1);
+        wait_neighbours(it - 1, seen);
         const uint32_t fprev = sf + ((it + 3) & 3) * SLOT_F;
         const PackT fyt = lds(fprev - BXB);
         const PackT fyb = lds(fprev + BXB);
@@ -316,11 +345,14 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
     constexpr int TX = Cfg::TX, BX = Cfg::BX, NT = Cfg::NT, BXB = Cfg::BXB;
     constexpr int SLOT_U = Cfg::SLOT_U, SLOT_C = Cfg::SLOT_C, SLOT_F = Cfg::SLOT_F, SZ = (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar_stage[Cfg::NST];
-    __shared__ __align__(8) uint64_t bar_pro;
-    __shared__ int pub[32];  // published plane per working warp: rows 0..NR-1, y-ring NR, x-ring NR+1
+    uint64_t* bar_stage = reinterpret_cast<uint64_t*>(smem_raw + Cfg::OFF_BAR);
+    uint64_t* bar_pro_p = bar_stage + Cfg::NST;
+    int* pub = reinterpret_cast<int*>(smem_raw + Cfg::OFF_PUB);  // published plane per working warp: rows 0..NR-1,
+                                                                 // y-ring NR, x-ring NR+1
     __shared__ double red[32];
-    const uint32_t sm0 = smem_u32(smem_raw);
+    uint32_t sm0 = smem_u32(smem_raw);
+    // opaque to ptxas: otherwise it re-derives the shared window base (S2R SR_CgaCtaId + LEA) at every use
+    asm volatile("" : "+r"(sm0));
     const uint32_t sU = sm0 + Cfg::OFF_U, sC = sm0 + Cfg::OFF_C, sF = sm0 + Cfg::OFF_F;
     T* tab_s = reinterpret_cast<T*>(smem_raw + Cfg::OFF_TAB);
 
@@ -337,11 +369,11 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
         for (int i = tid; i < ncls * 7; i += NT) tab_s[i] = p.table[i];
     const T* __restrict__ tab = tab_in_smem ? tab_s : p.table;
     const S7Geom gm{p.N0g, p.N1, p.N2, p.R0, p.R1, p.R2};
-    const uint32_t sbar = smem_u32(&bar_stage[0]), sbarp = smem_u32(&bar_pro), spub = smem_u32(&pub[0]);
+    const uint32_t sbar = sm0 + Cfg::OFF_BAR, sbarp = sbar + 8 * Cfg::NST, spub = sm0 + Cfg::OFF_PUB;
     if (tid < 32) pub[tid] = -1;
 
     if (tid == 0) {
-        mbar_init(&bar_pro, 1);
+        mbar_init(bar_pro_p, 1);
 #pragma unroll
         for (int i = 0; i < Cfg::NST; ++i) mbar_init(&bar_stage[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -416,7 +448,8 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
             for (int q = 0; q < 3; ++q) m.F[q] = m.zero();
             m.accf = T(0);
             uint32_t ready = 0;
-            m.ring.init();
+            m.ring_init();
+            m.seen = -1;
             for (int it = 0; it < niter; it += 3) {
                 if (it >= it_lo && it + 2 <= it_hi) {
                     T* gptr = fl.Gcol + (int64_t)(kf0 + it - 1) * fl.plane;
@@ -429,6 +462,7 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
                     if (it + 2 < niter) m.template step<2>(it + 2, fl);
                     ready = 0;
                 }
+                m.ring_next_trip();
                 acc2 += (double)m.accf;
                 m.accf = T(0);
             }
@@ -511,7 +545,7 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
     } else {
         // ------------------------------------------------------------------ x-ring warp (+ TMA producer)
         // stage j = { U plane kf0 + 1 + j -> U slot (j + 2) % NSU,  c plane kf0 + j -> c slot j % NST }, barrier j % NST
-        constexpr int NST = Cfg::NST, NSU = Cfg::NSU;
+        constexpr int NST = Cfg::NST, NSU = Cfg::NSU, NFL = Cfg::NFL;
         auto issue_stage = [&](int j) {
             const int b = j % NST;
             mbar_expect_tx(&bar_stage[b], Cfg::BYTES_U + (p.has_c ? Cfg::BYTES_C : 0u));
@@ -521,10 +555,10 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
                 tma_load_3d(smem_raw + Cfg::OFF_C + b * SLOT_C, &tmC, &bar_stage[b], tx0 - VW, ty0 - 1, kf0 + j + p.halo);
         };
         if (lane == 0) {
-            mbar_expect_tx(&bar_pro, 2 * Cfg::BYTES_U);
-            tma_load_3d(smem_raw + Cfg::OFF_U, &tmU, &bar_pro, tx0 - VW, ty0 - 2, kf0 - 1 + p.halo);
-            tma_load_3d(smem_raw + Cfg::OFF_U + SLOT_U, &tmU, &bar_pro, tx0 - VW, ty0 - 2, kf0 + p.halo);
-            for (int j = 0; j < NST - 1 && j < niter; ++j) issue_stage(j);
+            mbar_expect_tx(bar_pro_p, 2 * Cfg::BYTES_U);
+            tma_load_3d(smem_raw + Cfg::OFF_U, &tmU, bar_pro_p, tx0 - VW, ty0 - 2, kf0 - 1 + p.halo);
+            tma_load_3d(smem_raw + Cfg::OFF_U + SLOT_U, &tmU, bar_pro_p, tx0 - VW, ty0 - 2, kf0 + p.halo);
+            for (int j = 0; j < NFL - 1 && j < niter; ++j) issue_stage(j);
         }
         const bool active = lane < 2 * nrows;
         const int side = lane & 1, f = active ? (lane >> 1) + 1 : 1;  // F rows 1 .. nrows
@@ -575,14 +609,14 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
             if (lane == 0) s8_publish(pub_me, it);
             um = uc;
             uc = up;
-            if ((it == 0 && NST - 1 < niter) || it + NST < niter) {
+            if ((it == 0 && NFL - 1 < niter) || it + NFL < niter) {
                 // every other warp has published plane `it`: the U plane kf and the c plane kf are consumed
                 uint32_t spins = 0;
                 while (!__all_sync(0xffffffffu, s8_peek(pub_w) >= it))
                     if (++spins > (1u << 26)) __trap();
                 if (lane == 0) {
-                    if (it == 0 && NST - 1 < niter) issue_stage(NST - 1);
-                    if (it + NST < niter) issue_stage(it + NST);
+                    if (it == 0 && NFL - 1 < niter) issue_stage(NFL - 1);
+                    if (it + NFL < niter) issue_stage(it + NFL);
                 }
             }
             if (++ph == 3) ph = 0;
