@@ -337,20 +337,22 @@ __device__ __forceinline__ void mg_adj_march(const Mg3& m, const T* __restrict__
         // in-plane gather of the fine planes 2I+2, 2I+3: ALL loads first (2 * NROW vectors in flight per thread)
         const int fa = 2 * I + 2, fb = 2 * I + 3;
         const bool va = fa >= fz_lo && fa <= fz_hi, vb = fb >= fz_lo && fb <= fz_hi;
-        const T* pa = gf + (int64_t)(min(max(fa, fz_lo), fz_hi) - fine_z0) * m.fs0;
-        const T* pb = gf + (int64_t)(min(max(fb, fz_lo), fz_hi) - fine_z0) * m.fs0;
+        // 32-bit element offsets (the host routes arrays of 2^31 or more elements to the older kernels): one
+        // IMAD.WIDE per load instead of a 64-bit multiply-add chain
+        const unsigned oa = (unsigned)(min(max(fa, fz_lo), fz_hi) - fine_z0) * (unsigned)m.fs0;
+        const unsigned ob = (unsigned)(min(max(fb, fz_lo), fz_hi) - fine_z0) * (unsigned)m.fs0;
         MgVec4<T> v[2][NROW];
         Pair<T> ev[2][NROW];
 #pragma unroll
         for (int i = 0; i < NROW; ++i) {
-            v[0][i] = mg_ld4<T>(pa + roff[i] + vcol);
-            v[1][i] = mg_ld4<T>(pb + roff[i] + vcol);
+            v[0][i] = mg_ld4<T>(gf + (oa + (unsigned)(roff[i] + vcol)));
+            v[1][i] = mg_ld4<T>(gf + (ob + (unsigned)(roff[i] + vcol)));
         }
         if (lane0 || lane31) {
 #pragma unroll
             for (int i = 0; i < NROW; ++i) {
-                ev[0][i] = mg_ld2<T>(pa + roff[i] + ecol);
-                ev[1][i] = mg_ld2<T>(pb + roff[i] + ecol);
+                ev[0][i] = mg_ld2<T>(gf + (oa + (unsigned)(roff[i] + ecol)));
+                ev[1][i] = mg_ld2<T>(gf + (ob + (unsigned)(roff[i] + ecol)));
             }
         }
         MgQ<T> Qn[2];
@@ -359,7 +361,8 @@ __device__ __forceinline__ void mg_adj_march(const Mg3& m, const T* __restrict__
             T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0), e0 = T(0), e1 = T(0);
 #pragma unroll
             for (int i = 0; i < NROW; ++i) {
-                const T w = wy.w[R0 + i];
+                // interior rows: the four taps are the literal constants 1/4 3/4 3/4 1/4 (immediate-operand FFMA)
+                const T w = BY ? wy.w[R0 + i] : ((i == 0 || i == 3) ? T(0.25) : T(0.75));
                 s0 = fma(w, v[p][i].x, s0);
                 s1 = fma(w, v[p][i].y, s1);
                 s2 = fma(w, v[p][i].z, s2);
@@ -368,7 +371,7 @@ __device__ __forceinline__ void mg_adj_march(const Mg3& m, const T* __restrict__
             if (lane0 || lane31) {
 #pragma unroll
                 for (int i = 0; i < NROW; ++i) {
-                    const T w = wy.w[R0 + i];
+                    const T w = BY ? wy.w[R0 + i] : ((i == 0 || i == 3) ? T(0.25) : T(0.75));
                     e0 = fma(w, ev[p][i].a, e0);
                     e1 = fma(w, ev[p][i].b, e1);
                 }
@@ -392,18 +395,25 @@ __device__ __forceinline__ void mg_adj_march(const Mg3& m, const T* __restrict__
             Qn[p] = MgQ<T>{vp ? qa : T(0), vp ? qb : T(0)};
         }
         if (I >= Ibeg) {
-            const MgW6<T> wz = mg_adjw<T>(I, m.n0);
-            T a0 = wz.w[0] * Q0.a, a1 = wz.w[0] * Q0.b;
-            a0 = fma(wz.w[1], Q1.a, a0);
-            a1 = fma(wz.w[1], Q1.b, a1);
-            a0 = fma(wz.w[2], Q2.a, a0);
-            a1 = fma(wz.w[2], Q2.b, a1);
-            a0 = fma(wz.w[3], Q3.a, a0);
-            a1 = fma(wz.w[3], Q3.b, a1);
-            a0 = fma(wz.w[4], Qn[0].a, a0);
-            a1 = fma(wz.w[4], Qn[0].b, a1);
-            a0 = fma(wz.w[5], Qn[1].a, a0);
-            a1 = fma(wz.w[5], Qn[1].b, a1);
+            T a0, a1;
+            if (I >= 2 && I <= m.n0 - 3) {  // interior coarse plane: taps 1/4 3/4 3/4 1/4 on the planes 2I-1 .. 2I+2
+                a0 = T(0.25) * (Q1.a + Qn[0].a) + T(0.75) * (Q2.a + Q3.a);
+                a1 = T(0.25) * (Q1.b + Qn[0].b) + T(0.75) * (Q2.b + Q3.b);
+            } else {
+                const MgW6<T> wz = mg_adjw<T>(I, m.n0);
+                a0 = wz.w[0] * Q0.a;
+                a1 = wz.w[0] * Q0.b;
+                a0 = fma(wz.w[1], Q1.a, a0);
+                a1 = fma(wz.w[1], Q1.b, a1);
+                a0 = fma(wz.w[2], Q2.a, a0);
+                a1 = fma(wz.w[2], Q2.b, a1);
+                a0 = fma(wz.w[3], Q3.a, a0);
+                a1 = fma(wz.w[3], Q3.b, a1);
+                a0 = fma(wz.w[4], Qn[0].a, a0);
+                a1 = fma(wz.w[4], Qn[0].b, a1);
+                a0 = fma(wz.w[5], Qn[1].a, a0);
+                a1 = fma(wz.w[5], Qn[1].b, a1);
+            }
             // (cells with two or more coordinates within 2 of a face get the joint-pad correction from
             //  k_adjoint_joint_fix, launched right after this kernel)
             if (valid) {

@@ -602,6 +602,7 @@ static int march_chunk(const Mg3& m, int ncz, int ctas_per_sm) {
     return best_zc;
 }
 static bool march_ok(const Mg3& m, bool cz, int ndim, const void* a, const void* b, const void* c) {
+    if (8 * (int64_t)m.n0 * m.n1 * m.n2 >= (1ll << 31)) return false;  // 32-bit element offsets inside
     return cz && ndim == 3 && m.n2 % 2 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) &&
            ((uintptr_t)c % 16 == 0) && getenv("ODIL_B200_MG_OLD") == nullptr;
 }
