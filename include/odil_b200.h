@@ -85,6 +85,13 @@ int odil_b200_stencil_adjoint(const odil_b200_plan* plan, const odil_b200_slab* 
 int odil_b200_stencil_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* U, const void* c,
                             double scale, void* G_out, void* F_out, double* sumsq_out, void* stream);
 
+/* Inspection of the launch plan of the fused star sweep (host only, no device work): the CTAs the work-list kernel
+ * is launched with for a slab of n0 planes of an (N0, N1, N2) grid -- per CTA {x origin, y origin, rows, first plane,
+ * end plane} (5 int32).  Fills up to `cap` entries and returns the number of CTAs (<0 on error).  `variant` and
+ * `zchunk` as in odil_b200_stencil_plan_tune (-1 / 0 = defaults).  The list tiles the slab exactly once and is sized
+ * to fill the 148 SMs in whole waves with equal work per CTA. */
+int odil_b200_star_worklist(int dtype, int variant, int64_t n0, int64_t N1, int64_t N2, int zchunk, int32_t* out, int cap);
+
 /* Which kernel the plan dispatches the fused sweep to: 0 = generic per-cell, 1 = tiled 3-D star. */
 int odil_b200_stencil_plan_kind(const odil_b200_plan* plan);
 /* Tuning knobs of the tiled kernel (0 keeps the default): planes per z-chunk. */

@@ -1685,6 +1685,21 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     return 0;
 }
 
+template <typename T, int VW, int NR>
+static int worklist_for(int n0, int N1, int N2, int zchunk, int32_t* out, int cap) {
+    using Cfg = Star8Cfg<T, VW, NR>;
+    std::vector<S8Work> work;
+    build_work8(NR, Cfg::TX, 148 * Cfg::CTAS_PER_SM, n0, N1, N2, zchunk, work);
+    for (size_t i = 0; i < work.size() && (int)i < cap; ++i) {
+        out[5 * i + 0] = work[i].tx0;
+        out[5 * i + 1] = work[i].ty0;
+        out[5 * i + 2] = work[i].nrows;
+        out[5 * i + 3] = work[i].zs;
+        out[5 * i + 4] = work[i].ze;
+    }
+    return (int)work.size();
+}
+
 }  // namespace odil
 
 extern "C" {
@@ -1884,6 +1899,22 @@ int odil_b200_stencil_plan_destroy(odil_b200_plan* plan) {
 }
 
 int odil_b200_stencil_plan_kind(const odil_b200_plan* plan) { return plan ? plan->kind : -1; }
+
+int odil_b200_star_worklist(int dtype, int variant, int64_t n0, int64_t N1, int64_t N2, int zchunk, int32_t* out, int cap) {
+    ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    ODIL_REQUIRE(n0 >= 1 && N1 >= 1 && N2 >= 1 && n0 < (1 << 30) && N1 < (1 << 30) && N2 < (1 << 30), "bad shape");
+    ODIL_REQUIRE(cap >= 0 && (out != nullptr || cap == 0), "bad output buffer");
+    const int v = variant < 0 ? 0 : variant % 10;
+    const int a = (int)n0, b = (int)N1, c = (int)N2;
+    if (dtype == ODIL_B200_F32) {
+        if (v == 1) return worklist_for<float, 4, 12>(a, b, c, zchunk, out, cap);
+        if (v == 2) return worklist_for<float, 4, 8>(a, b, c, zchunk, out, cap);
+        return worklist_for<float, 4, 14>(a, b, c, zchunk, out, cap);
+    }
+    if (v == 1) return worklist_for<double, 2, 12>(a, b, c, zchunk, out, cap);
+    if (v == 2) return worklist_for<double, 2, 8>(a, b, c, zchunk, out, cap);
+    return worklist_for<double, 2, 14>(a, b, c, zchunk, out, cap);
+}
 
 int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant) {
     ODIL_REQUIRE(plan != nullptr, "null plan");

@@ -24,7 +24,7 @@ EXPORTS = [
     "odil_b200_stencil_plan_tune", "odil_b200_sum_squares", "odil_b200_dot", "odil_b200_mg_interp_add",
     "odil_b200_mg_interp_adjoint", "odil_b200_mg_restrict", "odil_b200_adam_step", "odil_b200_gd_step",
     "odil_b200_axpby", "odil_b200_multi_dot", "odil_b200_multi_axpy", "odil_b200_cg_update_xr",
-    "odil_b200_cg_update_p",
+    "odil_b200_cg_update_p", "odil_b200_star_worklist",
 ]
 
 
@@ -106,6 +106,7 @@ def load(build_if_missing=False):
     lib.odil_b200_multi_axpy.argtypes = [vp, i64, ctypes.c_int, vp, dbl, vp, vp, i64, ctypes.c_int, vp]
     lib.odil_b200_cg_update_xr.argtypes = [i64, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.odil_b200_cg_update_p.argtypes = [i64, ctypes.c_int, vp, vp, vp, vp, vp]
+    lib.odil_b200_star_worklist.argtypes = [ctypes.c_int, ctypes.c_int, i64, i64, i64, ctypes.c_int, P(i32), ctypes.c_int]
     for name in EXPORTS:
         if name not in ("odil_b200_last_error", "odil_b200_launch_count", "odil_b200_version"):
             getattr(lib, name).restype = ctypes.c_int
@@ -293,6 +294,22 @@ def gd_step(x, g, lr):
 def axpby(a, x, b, y):
     load()
     _check(_lib.odil_b200_axpby(x.numel(), dtype_code(x.dtype), float(a), _ptr(x), float(b), _ptr(y), _stream()))
+
+
+def star_worklist(dtype, n0, N1, N2, variant=-1, zchunk=0):
+    """CTAs of the fused star sweep for a slab of n0 planes: int32 array [ncta, 5] = x0, y0, rows, z begin, z end
+    (host-side inspection, needs no GPU)."""
+    load()
+    import numpy as np
+
+    code = dtype_code(dtype)
+    n = _lib.odil_b200_star_worklist(code, int(variant), int(n0), int(N1), int(N2), int(zchunk), None, 0)
+    if n < 0:
+        raise NativeError(_lib.odil_b200_last_error().decode())
+    out = np.zeros((n, 5), dtype=np.int32)
+    _check(min(0, _lib.odil_b200_star_worklist(code, int(variant), int(n0), int(N1), int(N2), int(zchunk),
+                                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n)))
+    return out
 
 
 def cg_update_xr(num, den, p, q, x, r):

@@ -293,3 +293,32 @@ def test_newton_jacobian_assembly_matches_oracle(cshape):
     diag = jac.diagonals()[0]
     assert all(tuple(v.shape) == tuple(cshape) for v in diag.values())
     assert {k[1] for k in diag} == {tuple(int(x) for x in o) for o in spec["offsets"]}
+
+
+@pytest.mark.parametrize("dtype,shape,variant,zchunk", [
+    (np.float32, (512, 512, 512), -1, 0), (np.float32, (64, 40, 136), -1, 0), (np.float32, (1, 1024, 1024), -1, 0),
+    (np.float64, (256, 256, 512), -1, 0), (np.float32, (100, 45, 132), 51, 7), (np.float32, (512, 512, 512), 52, 64),
+])
+def test_star_worklist_tiles_the_slab_once(dtype, shape, variant, zchunk):
+    """Launch plan of the fused star sweep (host logic of k_star8): the CTAs tile the slab exactly once, respect the
+    rows-per-CTA limit, and the headline grid fills the 148 SMs in one balanced wave."""
+    from odil_b200 import native
+
+    n0, N1, N2 = shape
+    work = native.star_worklist(dtype, n0, N1, N2, variant=variant, zchunk=zchunk)
+    vw = 4 if dtype == np.float32 else 2
+    tx = 32 * vw
+    nr_max = {-1: 14, 51: 12, 52: 8}[variant]
+    cover = np.zeros((n0, N1, (N2 + tx - 1) // tx), dtype=np.int32)
+    for x0, y0, rows, zs, ze in work:
+        assert x0 % tx == 0 and 0 <= x0 < N2
+        assert 1 <= rows <= nr_max and 0 <= y0 and y0 + rows <= N1
+        assert 0 <= zs < ze <= n0
+        cover[zs:ze, y0:y0 + rows, x0 // tx] += 1
+    assert cover.min() == 1 and cover.max() == 1
+    if shape == (512, 512, 512) and variant == -1:
+        assert len(work) == 148                       # one CTA per SM, one wave
+        assert set(work[:, 2]) <= {13, 14}            # 512 rows x 4 column blocks over 148 CTAs
+        assert np.all(work[:, 3] == 0) and np.all(work[:, 4] == 512)
+    if zchunk:
+        assert np.max(work[:, 4] - work[:, 3]) <= zchunk
