@@ -153,6 +153,13 @@ int odil_b200_mg_restrict(int ndim, const int64_t* fshape, const char* loc, int 
 int odil_b200_adam_step(int ntensors, void* const* x, void* const* m, void* const* v, const void* const* g,
                         const int64_t* counts, int dtype, double alpha, double one_minus_beta1,
                         double one_minus_beta2, double epsilon, void* stream);
+/* Same update with the step size read from DEVICE memory (alpha_dev[0], a double holding a value exactly
+ * representable in the array dtype): the launch arguments no longer change from epoch to epoch, so a whole epoch
+ * (residual + gradient + transfers + this update) can be captured once into a CUDA graph and replayed
+ * (optimizer.py:307-326: alpha is the only per-epoch scalar). */
+int odil_b200_adam_step_dev(int ntensors, void* const* x, void* const* m, void* const* v, const void* const* g,
+                            const int64_t* counts, int dtype, const double* alpha_dev, double one_minus_beta1,
+                            double one_minus_beta2, double epsilon, void* stream);
 int odil_b200_gd_step(int ntensors, void* const* x, const void* const* g, const int64_t* counts, int dtype,
                       double lr, void* stream);
 /* y = a*x + b*y  (L-BFGS building block; also used for scaling). */

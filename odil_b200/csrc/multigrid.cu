@@ -576,7 +576,20 @@ static bool fast3_geometry(const MgGeom& g, Mg3& m, bool& cz) {
 
 }  // namespace odil
 #include "mg_march.cuh"
+#include "mg_tile2d.cuh"
 namespace odil {
+
+// 2-D cell-centred whole-array transfers through the shared-memory tile kernels (mg_tile2d.cuh).
+static bool tile2_ok(const MgGeom& g, bool whole, const void* a, const void* b, const void* c) {
+    static const bool enabled = [] {
+        const char* e = getenv("ODIL_B200_MG2D");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled || !whole || g.ndim != 2 || g.loc[0] != LOC_C || g.loc[1] != LOC_C) return false;
+    if (g.cn[0] < 2 || g.cn[1] < 2 || g.cn[1] % 2 != 0) return false;
+    if (4 * g.cn[0] * g.cn[1] >= (1ll << 31) || (g.cn[0] + kM2Y - 1) / kM2Y > 65535) return false;
+    return ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)c % 16 == 0);
+}
 
 // z-chunk of the marching transfer kernels (CTAs of 128 threads, `ctas_per_sm` resident per SM by their
 // __launch_bounds__): the number of chunks is chosen so that the CTAs fill the 148 SMs in (nearly) whole waves --
@@ -629,6 +642,19 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
     ODIL_REQUIRE(nb < (1ll << 31), "grid too large");
     cudaStream_t st = (cudaStream_t)stream;
     ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    if (tile2_ok(g, r.fz_begin == 0 && r.fz_end == g.fn[0] && r.out_z0 == 0 && r.coarse_z0 == 0, coarse, fine_term,
+                 out)) {
+        const int n0 = (int)g.cn[0], n1 = (int)g.cn[1];
+        dim3 grid((n1 + kM2X - 1) / kM2X, (n0 + kM2Y - 1) / kM2Y);
+        if (dtype == ODIL_B200_F32)
+            k_interp_add2t<float><<<grid, kM2Threads, 0, st>>>((const float*)coarse, (float)cfac,
+                                                               (const float*)fine_term, (float)ffac, (float*)out, n0, n1);
+        else
+            k_interp_add2t<double><<<grid, kM2Threads, 0, st>>>((const double*)coarse, cfac, (const double*)fine_term,
+                                                                ffac, (double*)out, n0, n1);
+        ODIL_LAUNCHED();
+        return 0;
+    }
     {
         Mg3 m;
         bool cz = false;
@@ -716,6 +742,26 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
     ODIL_REQUIRE(nb < (1ll << 31), "grid too large");
     cudaStream_t st = (cudaStream_t)stream;
     ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    if (tile2_ok(g, r.cz_begin == 0 && r.cz_end == g.cn[0] && r.out_z0 == 0 && r.fine_z0 == 0, g_fine, g_coarse,
+                 nullptr)) {
+        const int n0 = (int)g.cn[0], n1 = (int)g.cn[1];
+        dim3 grid((n1 + kM2X - 1) / kM2X, (n0 + kM2Y - 1) / kM2Y);
+        if (dtype == ODIL_B200_F32) {
+            k_interp_adjoint2t<float><<<grid, kM2Threads, m2_adjoint_smem<float>(), st>>>(
+                (const float*)g_fine, (float)scale, (float*)g_coarse, n0, n1);
+        } else {
+            static bool attr_set = false;
+            if (!attr_set) {
+                ODIL_CUDA(cudaFuncSetAttribute(k_interp_adjoint2t<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)m2_adjoint_smem<double>()));
+                attr_set = true;
+            }
+            k_interp_adjoint2t<double><<<grid, kM2Threads, m2_adjoint_smem<double>(), st>>>(
+                (const double*)g_fine, scale, (double*)g_coarse, n0, n1);
+        }
+        ODIL_LAUNCHED();
+        return 0;
+    }
     {
         Mg3 m;
         bool cz = false;

@@ -17,6 +17,7 @@ struct AdamBatch {
     int64_t n[kMaxTensors];
     int vec[kMaxTensors];  // 1 if all four pointers are 16-byte aligned
     T alpha, omb1, omb2, eps;
+    const double* alpha_dev;  // when set, the step size is read from device memory (graph-replayable epochs)
 };
 
 template <typename T>
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) k_adam(AdamBatch<T> b) {
     const T* __restrict__ g = b.g[t];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const T alpha = b.alpha_dev ? (T)__ldg(b.alpha_dev) : b.alpha;
     if (b.vec[t]) {
         const int64_t n4 = n / 4;
         for (int64_t i = tid; i < n4; i += stride) {
@@ -46,17 +48,17 @@ __global__ void __launch_bounds__(256) k_adam(AdamBatch<T> b) {
             Vec4<T> mm = reinterpret_cast<Vec4<T>*>(m)[i];
             Vec4<T> vv = reinterpret_cast<Vec4<T>*>(v)[i];
             const Vec4<T> gg = reinterpret_cast<const Vec4<T>*>(g)[i];
-            adam_one(xx.x, mm.x, vv.x, gg.x, b.alpha, b.omb1, b.omb2, b.eps);
-            adam_one(xx.y, mm.y, vv.y, gg.y, b.alpha, b.omb1, b.omb2, b.eps);
-            adam_one(xx.z, mm.z, vv.z, gg.z, b.alpha, b.omb1, b.omb2, b.eps);
-            adam_one(xx.w, mm.w, vv.w, gg.w, b.alpha, b.omb1, b.omb2, b.eps);
+            adam_one(xx.x, mm.x, vv.x, gg.x, alpha, b.omb1, b.omb2, b.eps);
+            adam_one(xx.y, mm.y, vv.y, gg.y, alpha, b.omb1, b.omb2, b.eps);
+            adam_one(xx.z, mm.z, vv.z, gg.z, alpha, b.omb1, b.omb2, b.eps);
+            adam_one(xx.w, mm.w, vv.w, gg.w, alpha, b.omb1, b.omb2, b.eps);
             reinterpret_cast<Vec4<T>*>(x)[i] = xx;
             reinterpret_cast<Vec4<T>*>(m)[i] = mm;
             reinterpret_cast<Vec4<T>*>(v)[i] = vv;
         }
-        for (int64_t i = n4 * 4 + tid; i < n; i += stride) adam_one(x[i], m[i], v[i], g[i], b.alpha, b.omb1, b.omb2, b.eps);
+        for (int64_t i = n4 * 4 + tid; i < n; i += stride) adam_one(x[i], m[i], v[i], g[i], alpha, b.omb1, b.omb2, b.eps);
     } else {
-        for (int64_t i = tid; i < n; i += stride) adam_one(x[i], m[i], v[i], g[i], b.alpha, b.omb1, b.omb2, b.eps);
+        for (int64_t i = tid; i < n; i += stride) adam_one(x[i], m[i], v[i], g[i], alpha, b.omb1, b.omb2, b.eps);
     }
 }
 
@@ -197,9 +199,11 @@ static unsigned blocks_for(int64_t n, int per_thread) {
 
 template <typename T>
 static int run_adam(int nt, void* const* x, void* const* m, void* const* v, const void* const* g,
-                    const int64_t* counts, double alpha, double omb1, double omb2, double eps, cudaStream_t st) {
+                    const int64_t* counts, double alpha, const double* alpha_dev, double omb1, double omb2, double eps,
+                    cudaStream_t st) {
     for (int base = 0; base < nt; base += kMaxTensors) {
         AdamBatch<T> b;
+        b.alpha_dev = alpha_dev;
         const int k = nt - base < kMaxTensors ? nt - base : kMaxTensors;
         int64_t nmax = 0;
         for (int i = 0; i < k; ++i) {
@@ -270,11 +274,25 @@ int odil_b200_adam_step(int ntensors, void* const* x, void* const* m, void* cons
                         double one_minus_beta2, double epsilon, void* stream) {
     ODIL_REQUIRE(ntensors >= 0 && (ntensors == 0 || (x && m && v && g && counts)), "adam: bad arguments");
     if (dtype == ODIL_B200_F32)
-        return run_adam<float>(ntensors, x, m, v, g, counts, alpha, one_minus_beta1, one_minus_beta2, epsilon,
+        return run_adam<float>(ntensors, x, m, v, g, counts, alpha, nullptr, one_minus_beta1, one_minus_beta2, epsilon,
                                (cudaStream_t)stream);
     if (dtype == ODIL_B200_F64)
-        return run_adam<double>(ntensors, x, m, v, g, counts, alpha, one_minus_beta1, one_minus_beta2, epsilon,
+        return run_adam<double>(ntensors, x, m, v, g, counts, alpha, nullptr, one_minus_beta1, one_minus_beta2, epsilon,
                                 (cudaStream_t)stream);
+    return fail("dtype=%d unsupported", dtype);
+}
+
+int odil_b200_adam_step_dev(int ntensors, void* const* x, void* const* m, void* const* v, const void* const* g,
+                            const int64_t* counts, int dtype, const double* alpha_dev, double one_minus_beta1,
+                            double one_minus_beta2, double epsilon, void* stream) {
+    ODIL_REQUIRE(alpha_dev && ntensors >= 0 && (ntensors == 0 || (x && m && v && g && counts)),
+                 "adam_dev: bad arguments");
+    if (dtype == ODIL_B200_F32)
+        return run_adam<float>(ntensors, x, m, v, g, counts, 0.0, alpha_dev, one_minus_beta1, one_minus_beta2, epsilon,
+                               (cudaStream_t)stream);
+    if (dtype == ODIL_B200_F64)
+        return run_adam<double>(ntensors, x, m, v, g, counts, 0.0, alpha_dev, one_minus_beta1, one_minus_beta2,
+                                epsilon, (cudaStream_t)stream);
     return fail("dtype=%d unsupported", dtype);
 }
 

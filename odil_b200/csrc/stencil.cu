@@ -99,6 +99,8 @@ struct odil_b200_plan {
     // work list of k_star8 (device copy + the key it was built for)
     mutable void* work_dev;
     mutable int work_cap, work_n, work_key[6];
+    int use_tile2d;    // 1: k_tile2d for 2-D grids (default; env ODIL_B200_TILE2D=0 or an explicit variant disables)
+    int h2[2];         // stencil radius per axis (2-D plans)
     int star_xu;       // z-/y-arm coefficients of the interior y/z classes do not depend on the x class
 };
 
@@ -987,6 +989,7 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2), ((TX / 4 + 2) * (TY +
 }  // namespace odil
 #include "star7.cuh"
 #include "star8.cuh"
+#include "tile2d.cuh"
 namespace odil {
 
 // ------------------------------------------------------------------------------------------------
@@ -1418,6 +1421,61 @@ static void star_tile(int variant, int& TY, int& TX) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 2-D tile kernel (tile2d.cuh)
+// ------------------------------------------------------------------------------------------------
+static bool tile2d_ok(const odil_b200_plan* plan, const odil_b200_slab* slab) {
+    if (!plan->use_tile2d || plan->ndim != 2) return false;
+    if (slab->halo > 0 || slab->n0 != plan->shape[0] || slab->z0 != 0) return false;
+    if (plan->h2[0] > kT2MaxRadius || plan->h2[1] > kT2MaxRadius || plan->ncls > 255) return false;
+    const int64_t N0 = plan->shape[0], N1 = plan->shape[1];
+    if (N0 * N1 >= (1ll << 31) || N0 < 1 || N1 < 1) return false;
+    const int64_t gx = (N1 + kT2X - 1) / kT2X, gy = (N0 + kT2Y - 1) / kT2Y;
+    if (gy > 65535 || gx * gy > kPartialCapacity) return false;
+    return (size_t)plan->ncls * plan->noff * 8 <= 64 * 1024;
+}
+
+template <typename T, int MODE>
+static int launch_tile2d(const odil_b200_plan* plan, const T* A, const T* c, T scale, T* out, T* Fout, int* nparts,
+                         cudaStream_t st) {
+    Tile2Params<T> p;
+    p.A = A;
+    p.c = c;
+    p.out = out;
+    p.Fout = Fout;
+    p.table = (const T*)plan->table_dev;
+    p.partials = plan->partials;
+    p.scale = scale;
+    p.N0 = (int)plan->shape[0];
+    p.N1 = (int)plan->shape[1];
+    p.R0 = plan->R[0];
+    p.R1 = plan->R[1];
+    p.H0 = plan->h2[0];
+    p.H1 = plan->h2[1];
+    p.noff = plan->noff;
+    p.ncls = plan->ncls;
+    int AH, AW, FH, FW;
+    t2_dims<MODE>(p.H0, p.H1, AH, AW, FH, FW);
+    p.magicA = (unsigned)((1ull << 32) / (unsigned)AW + 1);
+    p.magicF = (unsigned)((1ull << 32) / (unsigned)FW + 1);
+    for (int o = 0; o < ODIL_B200_MAX_OFFSETS; ++o) {
+        p.dy[o] = o < plan->noff ? (signed char)plan->off[o][0] : 0;
+        p.dx[o] = o < plan->noff ? (signed char)plan->off[o][1] : 0;
+    }
+    const size_t smem = t2_smem_bytes<T, MODE>(p.H0, p.H1, p.ncls, p.noff);
+    static size_t smem_set = 48 * 1024;  // per template instantiation
+    if (smem > smem_set) {
+        ODIL_CUDA(cudaFuncSetAttribute(k_tile2d<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    dim3 grid((p.N1 + kT2X - 1) / kT2X, (p.N0 + kT2Y - 1) / kT2Y);
+    k_tile2d<T, MODE><<<grid, kT2Threads, smem, st>>>(p);
+    ODIL_LAUNCHED();
+    if (nparts) *nparts = (int)(grid.x * grid.y);
+    return 0;
+}
+
 template <typename T>
 static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* U, const void* c,
                      double scale, void* G, void* Fout, double* sumsq, cudaStream_t st) {
@@ -1431,6 +1489,12 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     io.table = (const T*)plan->table_dev;
     io.scale = (T)scale;
     int nparts = 0;
+    if (tile2d_ok(plan, slab)) {
+        if (int rc = launch_tile2d<T, 2>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)) return rc;
+        k_reduce_partials<<<1, 1024, 0, st>>>(plan->partials, nparts, sumsq);
+        ODIL_LAUNCHED();
+        return 0;
+    }
     const bool slab_mode = slab->halo > 0 || slab->n0 != plan->shape[0] || slab->z0 != 0;
     bool tiled = plan->kind == 1 && !(plan->ndim == 2 && slab_mode);
     const int64_t n2 = plan->shape[plan->ndim - 1];
@@ -1790,6 +1854,14 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
     p->star_xu = 0;
     p->no_xu = 0;
     p->use_star8 = 1;
+    {
+        const char* e = getenv("ODIL_B200_TILE2D");
+        p->use_tile2d = !(e && e[0] == '0');
+        p->h2[0] = p->h2[1] = 0;
+        if (ndim == 2)
+            for (int o = 0; o < noff; ++o)
+                for (int a = 0; a < 2; ++a) p->h2[a] = std::max(p->h2[a], std::abs(p->off[o][a]));
+    }
     p->work_dev = nullptr;
     p->work_cap = 0;
     p->work_n = 0;
@@ -1921,9 +1993,13 @@ int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant) {
     ODIL_REQUIRE((variant >= 0 && variant <= 3) || (variant >= 10 && variant <= 13) ||
                      (variant >= 20 && variant <= 23) || (variant >= 30 && variant <= 32) ||
                      (variant >= 40 && variant <= 42) || (variant >= 50 && variant <= 52) ||
-                     (variant >= 60 && variant <= 62) || variant == -1,
+                     (variant >= 60 && variant <= 62) || variant == 70 || variant == 71 || variant == -1,
                  "variant=%d unknown", variant);
     plan->zchunk = zchunk;
+    // 70 / 71: 2-D tile kernel on / off with the default 3-D choice; any explicit star variant also turns it off
+    // (so the star kernels stay reachable on 2-D grids)
+    plan->use_tile2d = variant == 70 || variant == -1;
+    if (variant >= 70) variant = -1;
     // -1 / 50..52: k_star8 (default; up to 14 / 12 / 8 rows per CTA); 60..62: same with per-cell z/y-arm
     // coefficients even when the plan allows the x-uniform form; 30..32 / 40..42: k_star7 (tiles of 12 / 16 / 8
     // rows, x-uniform / per-cell arms); 0..3: previous TMA-fed kernel; 10..13: v2 tile kernel + shell pass;
@@ -1955,6 +2031,13 @@ int odil_b200_stencil_forward(const odil_b200_plan* plan, const odil_b200_slab* 
                               const void* F_in, void* F_out, void* stream) {
     if (int rc = check_slab(plan, slab, plan ? plan->rmax0 : 0)) return rc;
     ODIL_REQUIRE(U && F_out, "null array");
+    if (tile2d_ok(plan, slab)) {
+        if (plan->dtype == ODIL_B200_F32)
+            return launch_tile2d<float, 0>(plan, (const float*)U, (const float*)F_in, 1.f, (float*)F_out, nullptr,
+                                           nullptr, (cudaStream_t)stream);
+        return launch_tile2d<double, 0>(plan, (const double*)U, (const double*)F_in, 1.0, (double*)F_out, nullptr,
+                                        nullptr, (cudaStream_t)stream);
+    }
     GenParams gp;
     fill_gen_params(plan, slab, gp);
     BoxList all;
@@ -1973,6 +2056,13 @@ int odil_b200_stencil_adjoint(const odil_b200_plan* plan, const odil_b200_slab* 
                               const void* G_in, void* G_out, void* stream) {
     if (int rc = check_slab(plan, slab, plan ? plan->rmax0 : 0)) return rc;
     ODIL_REQUIRE(F && G_out, "null array");
+    if (tile2d_ok(plan, slab)) {
+        if (plan->dtype == ODIL_B200_F32)
+            return launch_tile2d<float, 1>(plan, (const float*)F, (const float*)G_in, (float)scale, (float*)G_out,
+                                           nullptr, nullptr, (cudaStream_t)stream);
+        return launch_tile2d<double, 1>(plan, (const double*)F, (const double*)G_in, scale, (double*)G_out, nullptr,
+                                        nullptr, (cudaStream_t)stream);
+    }
     GenParams gp;
     fill_gen_params(plan, slab, gp);
     BoxList all;

@@ -39,8 +39,11 @@ class _Fetch:
         if self._terms is None:
             host = self.sums.detach().cpu().numpy()
             self._terms = [self.dtype.type(s / n) for s, n in zip(host, self.counts)]
-            self.sums = None
         return self._terms
+
+    def rearm(self):
+        """Forget the host copy: the device sums were rewritten in place (CUDA-graph replay of the epoch)."""
+        self._terms = None
 
 
 class LazyScalar:

@@ -24,7 +24,7 @@ EXPORTS = [
     "odil_b200_stencil_plan_tune", "odil_b200_sum_squares", "odil_b200_dot", "odil_b200_mg_interp_add",
     "odil_b200_mg_interp_adjoint", "odil_b200_mg_restrict", "odil_b200_adam_step", "odil_b200_gd_step",
     "odil_b200_axpby", "odil_b200_multi_dot", "odil_b200_multi_axpy", "odil_b200_cg_update_xr",
-    "odil_b200_cg_update_p", "odil_b200_star_worklist",
+    "odil_b200_cg_update_p", "odil_b200_star_worklist", "odil_b200_adam_step_dev",
 ]
 
 
@@ -100,6 +100,8 @@ def load(build_if_missing=False):
     lib.odil_b200_mg_restrict.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, vp, vp]
     lib.odil_b200_adam_step.argtypes = [ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), ctypes.c_int, dbl, dbl,
                                         dbl, dbl, vp]
+    lib.odil_b200_adam_step_dev.argtypes = [ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), ctypes.c_int, vp, dbl,
+                                            dbl, dbl, vp]
     lib.odil_b200_gd_step.argtypes = [ctypes.c_int, P(vp), P(vp), P(i64), ctypes.c_int, dbl, vp]
     lib.odil_b200_axpby.argtypes = [i64, ctypes.c_int, dbl, vp, dbl, vp, vp]
     lib.odil_b200_multi_dot.argtypes = [vp, i64, ctypes.c_int, vp, i64, ctypes.c_int, vp, vp]
@@ -279,6 +281,21 @@ def adam_step(x, m, v, g, alpha, omb1, omb2, eps):
     _call("adam_step", lambda: _check(_lib.odil_b200_adam_step(
         n, _ptr_array(x, dt), _ptr_array(m, dt, cnt), _ptr_array(v, dt, cnt), _ptr_array(g, dt, cnt), counts,
         dtype_code(x[0].dtype), float(alpha), float(omb1), float(omb2), float(eps), _stream())))
+
+
+def adam_step_dev(x, m, v, g, alpha_dev, omb1, omb2, eps):
+    """adam_step with the step size in a 1-element float64 CUDA tensor (constant launch arguments: graph-capturable)."""
+    load()
+    if alpha_dev.dtype != torch.float64 or not alpha_dev.is_cuda or alpha_dev.numel() != 1:
+        raise NativeError("adam_step_dev: alpha_dev must be a 1-element float64 CUDA tensor")
+    n = len(x)
+    cnt = [t.numel() for t in x]
+    counts = (ctypes.c_int64 * n)(*cnt)
+    dt = x[0].dtype
+    _call("adam_step", lambda: _check(_lib.odil_b200_adam_step_dev(
+        n, _ptr_array(x, dt), _ptr_array(m, dt, cnt), _ptr_array(v, dt, cnt), _ptr_array(g, dt, cnt), counts,
+        dtype_code(x[0].dtype), ctypes.c_void_p(alpha_dev.data_ptr()), float(omb1), float(omb2), float(eps),
+        _stream())))
 
 
 def gd_step(x, g, lr):

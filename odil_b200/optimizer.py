@@ -10,6 +10,7 @@ an object with `.run(x0, loss_grad, epochs, callback, epoch_start, lr, **kw) -> 
                  reference's own arrangement, SciPy fmin_l_bfgs_b on a host fp64 vector (optimizer.py:29-117).
   adam_tf, tfp lbfgs: TensorFlow-only wrappers of the reference, not provided.
 """
+import os
 from argparse import Namespace
 
 import numpy as np
@@ -62,20 +63,65 @@ class AdamNativeOptimizer(Optimizer):
         self.mod = mod
 
     def run(self, x0, loss_grad, epochs=None, callback=None, lr=1e-3, epoch_start=0, beta_1=0.9, beta_2=0.999,
-            epsilon=1e-7, jit=True, **kwargs):
+            epsilon=1e-7, jit=True, graph=None, **kwargs):
+        """
+        graph: replay each epoch (loss_grad + Adam update) as ONE CUDA graph after two eager epochs.  The
+        reference's `jit` compiles the epoch into one XLA program (optimizer.py:321-326); this is the B200
+        counterpart for launch-bound (small-grid) problems: ~10 kernel launches and their ctypes calls become
+        one cudaGraphLaunch.  Default: env ODIL_B200_GRAPH (0).  Same kernels, same arithmetic, same results.
+        """
         dtype = np.dtype(self.dtype if self.dtype is not None else np.float32)
         x = _device_copy(x0)
         m = [torch.zeros_like(e) for e in x]
         v = [torch.zeros_like(e) for e in x]
         eps = float(dtype.type(epsilon))
-        for epoch in range(epoch_start + 1, epoch_start + epochs + 1):
+        if graph is None:
+            graph = os.environ.get("ODIL_B200_GRAPH", "0") not in ("", "0")
+        first, last = epoch_start + 1, epoch_start + epochs
+        eager_until = last if not graph else min(last, first + 1)
+        for epoch in range(first, eager_until + 1):
             self.evals += 1
             loss, grads, pinfo = loss_grad(x)
             alpha, omb1, omb2 = adam_scalars(lr, beta_1, beta_2, epoch - epoch_start, dtype)
             native.adam_step(x, m, v, grads, alpha, omb1, omb2, eps)
             if epoch > 0 and callback is not None:
                 callback(x, epoch, pinfo)
+        if eager_until < last:
+            self._run_graph(x, m, v, loss_grad, callback, lr, beta_1, beta_2, eps, dtype, epoch_start,
+                            eager_until + 1, last)
         return x, Namespace(epochs=epochs, evals=self.evals)
+
+    def _run_graph(self, x, m, v, loss_grad, callback, lr, beta_1, beta_2, eps, dtype, epoch_start, first, last):
+        """Epochs first..last as replays of one captured graph.  Only the step size changes between epochs: the
+        host tabulates it for every epoch (in `dtype`, like the eager path) and the head of the graph picks
+        entry `step` of the device copy and advances `step`, so a replay reads nothing from the host and the
+        host may run ahead of the device freely."""
+        dev = x[0].device
+        table = torch.tensor([adam_scalars(lr, beta_1, beta_2, e - epoch_start, dtype)[0]
+                              for e in range(first, last + 1)], dtype=torch.float64).to(dev)
+        step = torch.zeros(1, dtype=torch.int64, device=dev)
+        alpha_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+        _, omb1, omb2 = adam_scalars(lr, beta_1, beta_2, 1, dtype)
+        held = list(x)  # the tensors whose addresses the graph holds
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            torch.index_select(table, 0, step, out=alpha_dev)
+            step.add_(1)
+            loss, grads, pinfo = loss_grad(held)
+            native.adam_step_dev(held, m, v, grads, alpha_dev, omb1, omb2, eps)
+        fetch = getattr(loss, "_fetch", None)
+        self._graph = g  # owns the memory pool of grads / sums that pinfo still points into after run()
+        for epoch in range(first, last + 1):
+            self.evals += 1
+            for i in range(len(held)):
+                if x[i] is not held[i]:  # a callback replaced the array (callback_update_state)
+                    held[i].copy_(x[i])
+                    x[i] = held[i]
+            g.replay()
+            if fetch is not None:
+                fetch.rearm()
+            if epoch > 0 and callback is not None:
+                callback(x, epoch, pinfo)
 
 
 class GdOptimizer(Optimizer):

@@ -501,3 +501,132 @@ def test_marching_transfers(cshape, prec):
             gg = torch.full((ce - cb,) + tuple(cshape[1:]), float("nan"), dtype=td, device="cuda")
             native.mg_interp_adjoint(cshape, "ccc", dev(term[f_lo:f_hi]), 0.9, gg, rng=(cb, ce, cb, f_lo))
             assert relerr(gg.cpu().numpy(), g_ref[cb:ce]) < tol
+
+
+# --------------------------------------------------------------------------------------------------
+# k_tile2d: any offset set of small radius on 2-D grids (the wave example's footprint), all three modes
+# --------------------------------------------------------------------------------------------------
+TILE2D_CASES = [
+    # shape, offsets (None = star), rwidth
+    ((70, 150), [(0, 0), (-1, 0), (-2, 0), (-1, -1), (-1, 1)], (2, 1)),        # wave footprint, 3 x 3 tiles
+    ((32, 64), None, (1, 1)),                                                  # exactly one tile
+    ((33, 65), None, (1, 1)),                                                  # one cell over in both axes
+    ((3, 5), [(0, 0), (2, -2), (-1, 1)], (1, 2)),                              # grid smaller than the halo
+    ((40, 66), [(0, 0), (3, 0), (0, -4), (-2, 2)], (0, 0)),                    # radius 3 / 4, fully periodic
+    ((96, 200), [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)], (1, 1)),  # 9-point box
+    ((1, 300), [(0, 0), (0, -1), (0, 1)], (0, 1)),                             # single row
+    ((130, 7), [(0, 0), (1, 0), (-1, 0), (0, 1)], (3, 1)),                     # narrow, wide regions
+]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("case", range(len(TILE2D_CASES)))
+def test_tile2d_matches_oracle_and_generic(prec, case):
+    nd, td = DT[prec]
+    shape, offsets, rr = TILE2D_CASES[case]
+    offsets = offsets or star_offsets(2)
+    rng = np.random.default_rng(500 + case)
+    tshape = tuple(2 * r + 1 for r in rr) + (len(offsets),)
+    table = rng.standard_normal(tshape)
+    U = rng.standard_normal(shape).astype(nd)
+    c = rng.standard_normal(shape).astype(nd)
+    Gin = rng.standard_normal(shape).astype(nd)
+    scale = 2.0 / U.size
+    F_ref = orc.stencil_forward(U.astype(np.float64), offsets, table, rr, c.astype(np.float64))
+    g_ref = orc.stencil_adjoint(F_ref, offsets, table, rr, scale)
+    tol = TOL[prec] * 10
+    res = {}
+    for variant in (70, 71):  # 70: k_tile2d, 71: the per-cell generic kernel
+        plan = native.StencilPlan(shape, td, offsets, rr, table.reshape(-1, len(offsets)))
+        plan.tune(variant=variant)
+        dU, dc = dev(U), dev(c)
+        F = torch.full_like(dU, float("nan"))
+        plan.forward(dU, dc, F)
+        G = torch.full_like(dU, float("nan"))
+        plan.adjoint(dev(F_ref.astype(nd)), scale, dev(Gin), G)
+        G2 = torch.full_like(dU, float("nan"))
+        F2 = torch.full_like(dU, float("nan"))
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dU, dc, scale, G2, ss, F_out=F2)
+        G3 = torch.full_like(dU, float("nan"))
+        ss0 = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dU, None, scale, G3, ss0)
+        res[variant] = [t.cpu().numpy() for t in (F, G, G2, F2, ss, G3, ss0)]
+        F, G, G2, F2, ss, G3, ss0 = res[variant]
+        assert relerr(F, F_ref) < tol and relerr(F2, F_ref) < tol
+        assert relerr(G, g_ref + Gin.astype(np.float64)) < tol
+        assert relerr(G2, g_ref) < tol
+        assert abs(ss[0] - np.sum(F_ref ** 2)) < tol * np.sum(F_ref ** 2)
+        F0 = orc.stencil_forward(U.astype(np.float64), offsets, table, rr, None)
+        assert abs(ss0[0] - np.sum(F0 ** 2)) < tol * np.sum(F0 ** 2)
+        assert relerr(G3, orc.stencil_adjoint(F0, offsets, table, rr, scale)) < tol
+    # same summation order in both kernels: the arrays agree to rounding of the fused multiply-adds
+    eps = np.finfo(nd).eps
+    for a, b in zip(res[70][:4], res[71][:4]):
+        assert relerr(a, b) < 8 * eps
+
+
+def test_tile2d_large_wave_footprint_properties():
+    """2048 x 4096 fp32 (BASELINE configs[2] scale): linearity of the fused sweep in (U, c) and the adjoint
+    identity <A U, F> = <U, A^T F> through the forward / adjoint modes."""
+    shape, rr = (2048, 4096), (2, 1)
+    offsets = [(0, 0), (-1, 0), (-2, 0), (-1, -1), (-1, 1)]
+    rng = np.random.default_rng(9)
+    table = rng.standard_normal((15, 5))
+    plan = native.StencilPlan(shape, torch.float64, offsets, rr, table)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    U = torch.randn(shape, dtype=torch.float64, device="cuda", generator=gen)
+    V = torch.randn(shape, dtype=torch.float64, device="cuda", generator=gen)
+    AU, ATV = torch.empty_like(U), torch.empty_like(U)
+    plan.forward(U, None, AU)
+    plan.adjoint(V, 1.0, None, ATV)
+    lhs, rhs = (AU * V).sum().item(), (U * ATV).sum().item()
+    assert abs(lhs - rhs) < 1e-10 * max(abs(lhs), 1.0) + 1e-6
+    G, ss = torch.empty_like(U), torch.zeros(1, dtype=torch.float64, device="cuda")
+    plan.fused(U, None, 0.5, G, ss)
+    assert abs(ss.item() - (AU * AU).sum().item()) < 1e-10 * ss.item()
+    ATAU = torch.empty_like(U)
+    plan.adjoint(AU, 0.5, None, ATAU)
+    assert (G - ATAU).abs().max().item() < 1e-9 * ATAU.abs().max().item()
+
+
+# --------------------------------------------------------------------------------------------------
+# 2-D cell-centred transfers through shared-memory tiles (k_interp_add2t / k_interp_adjoint2t)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cshape", [(2, 2), (3, 4), (16, 64), (17, 66), (5, 130), (40, 2), (33, 128), (64, 200),
+                                    (3, 3)])  # the last one (odd width) stays on the per-cell kernels
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_tile2d_transfers(cshape, prec):
+    npd, td = DT[prec]
+    rng = np.random.default_rng(11)
+    fshape = tuple(2 * s for s in cshape)
+    coarse = rng.standard_normal(cshape).astype(npd)
+    term = rng.standard_normal(fshape).astype(npd)
+    I = orc.interp_to_finer(coarse.astype(np.float64), "cc")
+    tol = 100 * np.finfo(npd).eps
+    out = torch.full(fshape, float("nan"), dtype=td, device="cuda")
+    native.mg_interp_add(cshape, "cc", dev(coarse), 0.7, dev(term), 1.3, out)
+    assert relerr(out.cpu().numpy(), 1.3 * term.astype(np.float64) + 0.7 * I) < tol
+    native.mg_interp_add(cshape, "cc", dev(coarse), 1.0, None, 0.0, out)
+    assert relerr(out.cpu().numpy(), I) < tol
+    gc = torch.full(cshape, float("nan"), dtype=td, device="cuda")
+    native.mg_interp_adjoint(cshape, "cc", dev(term), 0.9, gc)
+    assert relerr(gc.cpu().numpy(), 0.9 * orc.interp_adjoint(term.astype(np.float64), "cc", cshape)) < tol
+
+
+def test_tile2d_transfers_transpose_identity_large():
+    """1024^2 -> 2048^2 (configs[1] scale and above): <I u, v> = <u, I^T v>, and I reproduces linear functions."""
+    cshape, fshape = (1024, 1024), (2048, 2048)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    u = torch.randn(cshape, dtype=torch.float64, device="cuda", generator=gen)
+    v = torch.randn(fshape, dtype=torch.float64, device="cuda", generator=gen)
+    Iu, ITv = torch.empty_like(v), torch.empty_like(u)
+    native.mg_interp_add(cshape, "cc", u, 1.0, None, 0.0, Iu)
+    native.mg_interp_adjoint(cshape, "cc", v, 1.0, ITv)
+    lhs, rhs = (Iu * v).sum().item(), (u * ITv).sum().item()
+    assert abs(lhs - rhs) < 1e-10 * max(abs(lhs), 1.0) + 1e-7
+    yc = (torch.arange(1024, dtype=torch.float64, device="cuda") + 0.5) / 1024
+    yf = (torch.arange(2048, dtype=torch.float64, device="cuda") + 0.5) / 2048
+    lin = (2 * yc[:, None] - 3 * yc[None, :] + 1).contiguous()
+    native.mg_interp_add(cshape, "cc", lin, 1.0, None, 0.0, Iu)
+    assert (Iu - (2 * yf[:, None] - 3 * yf[None, :] + 1)).abs().max().item() < 1e-12

@@ -28,15 +28,20 @@ def sync_time(fn, n):
     return (time.perf_counter() - t0) / n
 
 
-def config1():
-    problem, state = ops.make_poisson((1024, 1024), 3, np.float32)
-    args = run_args(epochs=50, lr=0.005)
-    odil.util.optimize_grad(args, "adam", problem, state, None)  # warm-up (trace, plans)
-    n = 500
-    args = run_args(epochs=n, lr=0.005)
-    dt = sync_time(lambda: odil.util.optimize_grad(args, "adam", problem, state, None), n)
-    print(f"configs[1] 2-D Poisson 1024^2, 3-level multigrid, Adam, f32: {dt*1e6:.1f} us/epoch, "
-          f"{1024*1024/dt/1e6:.0f} Mcells/s (launch-bound: L2-resident working set)", flush=True)
+def config1(shape=(1024, 1024), nlvl=3, n=500):
+    import os
+    cells = int(np.prod(shape))
+    for flag in ["0", "1"]:
+        os.environ["ODIL_B200_GRAPH"] = flag
+        problem, state = ops.make_poisson(shape, nlvl, np.float32)
+        args = run_args(epochs=50, lr=0.005)
+        odil.util.optimize_grad(args, "adam", problem, state, None)  # warm-up (trace, plans)
+        args = run_args(epochs=n, lr=0.005)
+        dt = sync_time(lambda: odil.util.optimize_grad(args, "adam", problem, state, None), n)
+        how = "one CUDA graph per epoch" if flag == "1" else "eager launches"
+        print(f"configs[1] Poisson {'x'.join(map(str, shape))}, {nlvl}-level multigrid, Adam, f32, {how}: "
+              f"{dt*1e6:.1f} us/epoch, {cells/dt/1e6:.0f} Mcells/s", flush=True)
+    os.environ["ODIL_B200_GRAPH"] = "0"
 
 
 def config2(nt=2048, nx=4096, iters=20):
@@ -87,6 +92,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["1", "2", "blocks", "4"]
     if "1" in which:
         config1()
+        config1((128, 128, 128), 3, 300)
     if "2" in which:
         config2()
     if "blocks" in which:
