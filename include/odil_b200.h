@@ -92,9 +92,14 @@ int odil_b200_stencil_fused(const odil_b200_plan* plan, const odil_b200_slab* sl
  * to fill the 148 SMs in whole waves with equal work per CTA. */
 int odil_b200_star_worklist(int dtype, int variant, int64_t n0, int64_t N1, int64_t N2, int zchunk, int32_t* out, int cap);
 
-/* Which kernel the plan dispatches the fused sweep to: 0 = generic per-cell, 1 = tiled 3-D star. */
+/* Classification of the plan's offsets: 1 = unit-arm star on a 2-D / 3-D grid (3-D: the TMA-fed marching sweep),
+ * 0 = anything else.  2-D plans of either kind run the shared-memory tile kernel (any offsets of radius <= 4) on a
+ * single GPU; 1-D, 4-D, non-star 3-D plans and 2-D slabs run the per-cell kernel. */
 int odil_b200_stencil_plan_kind(const odil_b200_plan* plan);
-/* Tuning knobs of the tiled kernel (0 keeps the default): planes per z-chunk. */
+/* Tuning knobs (0 / -1 keep the defaults): planes per z-chunk of the star kernels; `variant` selects a kernel
+ * generation / tile shape of the star sweep (50-52, 60-62 current; 30-42, 20-23, 10-13, 0-3 earlier ones, kept as
+ * measured history), 70 / 71 switch the 2-D tile kernel on / off (any explicit star variant also switches it off,
+ * so the star kernels stay reachable on 2-D grids). */
 int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant);
 
 /* sumsq_out[0] = sum x^2 (double accumulate).  Replaces mean(square(f)) of a materialised F
