@@ -10,11 +10,11 @@ import odil_b200 as _impl
 from odil_b200 import *  # noqa: F401,F403
 from odil_b200 import (  # noqa: F401
     Array, Context, Domain, EarlyStopError, Field, History, ModB200, MultigridField, NeuralNet, NonAffineError,
-    Problem, State, interp_to_finer, make_callback, optimize, printlog, restrict_to_coarser, set_log_file,
-    setup_outdir,
+    Problem, State, interp_to_finer, make_callback, optimize, parse_raw_xmf, printlog, read_raw, read_raw_with_xmf,
+    restrict_to_coarser, set_log_file, setup_outdir, write_raw_with_xmf, write_raw_xmf, write_vtk_poly,
 )
 
-for _name in ["backend", "core", "history", "linsolver", "native", "optimizer", "util", "engine"]:
+for _name in ["backend", "core", "history", "io", "plotutil", "linsolver", "native", "optimizer", "util", "engine"]:
     sys.modules[__name__ + "." + _name] = importlib.import_module("odil_b200." + _name)
     globals()[_name] = sys.modules[__name__ + "." + _name]
 
@@ -34,8 +34,8 @@ def __getattr__(name):
         mod = importlib.import_module("odil_b200.runtime")
         sys.modules[__name__ + ".runtime"] = mod
         return mod
-    if name in ("plot", "plotutil", "io"):
-        raise AttributeError(f"odil.{name} (plotting / file formats) is outside the B200 hot-path build")
+    if name == "plot":
+        raise AttributeError("odil.plot (plot_1d / plot_2d figure layouts) is outside the B200 hot-path build")
     raise AttributeError(name)
 
 

@@ -10,7 +10,7 @@ unchanged with ODIL_BACKEND=b200 (the default and only backend).
 # ruff: noqa: F401
 __version__ = "0.1.0"
 
-from . import backend, core, history, linsolver, native, optimizer, util
+from . import backend, core, history, io, linsolver, native, optimizer, plotutil, util
 from .backend import ModB200, NonAffineError
 from .core import (
     Array,
@@ -25,6 +25,7 @@ from .core import (
     restrict_to_coarser,
 )
 from .history import History
+from .io import parse_raw_xmf, read_raw, read_raw_with_xmf, write_raw_with_xmf, write_raw_xmf, write_vtk_poly
 from .optimizer import EarlyStopError
 from .util import make_callback, optimize, printlog, set_log_file, setup_outdir
 
