@@ -11,7 +11,7 @@ unchanged with ODIL_BACKEND=b200 (the default and only backend).
 __version__ = "0.1.0"
 
 from . import backend, core, history, io, linsolver, native, optimizer, plotutil, util
-from .backend import ModB200, NonAffineError
+from .backend import ModB200, ModBase, ModNumpy, ModTensorflow, NonAffineError
 from .core import (
     Array,
     Context,

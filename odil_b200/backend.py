@@ -389,7 +389,11 @@ def _unary_known(fn):
     return f
 
 
-class ModB200:
+class ModBase:
+    """Name of the reference's backend base class (backend.py:13-47), kept for `isinstance` checks in user code."""
+
+
+class ModB200(ModBase):
     """NumPy-like namespace handed to operators as `ctx.mod` / `domain.mod`."""
     jax = None
     tf = None
@@ -644,3 +648,20 @@ class ModB200:
 
     def norm(self, x):
         return self._reduce(torch.linalg.vector_norm, x)
+
+
+class _ForeignBackend(ModBase):
+    """The reference's other backends are not part of this package: the names exist so that scripts which branch on
+    `isinstance(mod, odil.backend.ModTensorflow)` (e.g. the reference's tests/test_mg_restrict.py:55) keep working
+    -- the check is simply False -- while constructing one fails loudly."""
+
+    def __init__(self, *args, **kwargs):
+        raise NonAffineError(f"{type(self).__name__} is not available: odil_b200 has one backend, ModB200")
+
+
+class ModNumpy(_ForeignBackend):
+    pass
+
+
+class ModTensorflow(_ForeignBackend):
+    pass

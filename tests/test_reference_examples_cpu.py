@@ -96,3 +96,42 @@ def test_reference_wave_operator_traces_to_the_oracle_plan(load_example):
     F_ref = orc.wave_residual(U, 1.0 / 16, 2.0 / 12, np.asarray(extra.left_u), np.asarray(extra.right_u),
                               np.asarray(extra.init_u), np.asarray(extra.init_ut), args.kimp)
     assert np.max(np.abs(F - F_ref)) < 1e-10 * np.max(np.abs(F_ref))
+
+
+def test_reference_basic_fields_script_traces(load_example):
+    """examples/basic/fields.py: cell, node and face fields as multigrid unknowns plus an unused NeuralNet in the
+    state; every output is `field - func(points)`, i.e. an identity plan with the constant -func."""
+    ns = load_example("examples/basic/fields.py", [])
+    args = ns["parse_args"]()
+    problem, state = ns["make_problem"](args)
+    domain = problem.domain
+    assert {k: type(v).__name__ for k, v in state.fields.items()} == {
+        "uc": "MultigridField", "un": "MultigridField", "ufx": "MultigridField", "ufy": "MultigridField",
+        "net": "NeuralNet"}
+    eng = ResidualEngine(problem, state, trace_only=True)
+    assert eng.names == ["uc", "un", "ufx", "ufy"] and all(o.fused for o in eng.outputs)
+    for out, loc in zip(eng.outputs, ["cc", "nn", "nc", "cn"]):
+        spec = out.blocks[0].spec
+        assert np.asarray(spec["table"]).tolist() == [[1.0]] and tuple(map(tuple, spec["offsets"])) == ((0, 0),)
+        x, y = (np.asarray(p) for p in domain.points(loc=loc))
+        assert tuple(out.shape) == tuple(domain.size(loc=loc))
+        assert np.allclose(out.const.cpu().numpy(), -(x * 0.25 + y * 0.5), rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("cmd", [["tests/test_domain.py"], ["-m", "pytest", "-q", "-p", "no:cacheprovider",
+                                                           "tests/test_io.py"]])
+def test_reference_host_side_tests_pass_unmodified(cmd, tmp_path):
+    """The reference's own host-side tests (state packing round trips, tests/test_domain.py; RAW + XMF round trip,
+    tests/test_io.py) run as they are with this repository's `odil` on the path.  (Its other tests evaluate
+    operators and therefore need the GPU.)"""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    argv = [sys.executable] + [os.path.join(REF, a) if a.endswith(".py") else a for a in cmd]
+    env = dict(os.environ, PYTHONPATH=root)
+    r = subprocess.run(argv, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-2000:]
+    assert "FAIL" not in out, out[-2000:]
+    if cmd[0].endswith("test_domain.py"):
+        assert out.count("PASS") == 4
