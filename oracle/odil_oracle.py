@@ -275,6 +275,32 @@ def wave_residual(U, dt, dx, left_u, right_u, init_u, init_ut, kimp):
     return np.where(it == 0, (U - u0[None, :]) * kimp, fu)
 
 
+def wave2_residual(U, dt, dx, dy, bnd, init_u, init_ut, kimp):
+    """The wave operator of examples/wave/wave.py:29-75 carried to two space dimensions, (t, x, y) layout
+    (BASELINE configs[2]: u_tt = u_xx + u_yy at level t-1).  `bnd` = dict of Dirichlet data on the four faces,
+    each of shape (nt, n_other): xlo, xhi (functions of t, y), ylo, yhi (functions of t, x); init_u, init_ut of
+    shape (nx, ny).  Same building blocks as the (t, x) operator: quadratic half-cell extrapolation at the faces
+    (core.py:1439-1445), `it == 1` uses init_ut, the `it == 0` row imposes the initial field."""
+    nt, nx, ny = U.shape
+    it = np.arange(nt)[:, None, None]
+    ix = np.arange(nx)[None, :, None]
+    iy = np.arange(ny)[None, None, :]
+    utm = np.roll(U, 1, 0)
+    utmm = np.roll(U, 2, 0)
+    uxm, uxp = np.roll(utm, 1, 1), np.roll(utm, -1, 1)
+    uym, uyp = np.roll(utm, 1, 2), np.roll(utm, -1, 2)
+    prev = lambda a: np.roll(a, 1, 0)  # boundary data at time level t-1
+    uxm = np.where(ix == 0, extrap_quadh(uxp, utm, prev(bnd["xlo"])[:, None, :]), uxm)
+    uxp = np.where(ix == nx - 1, extrap_quadh(uxm, utm, prev(bnd["xhi"])[:, None, :]), uxp)
+    uym = np.where(iy == 0, extrap_quadh(uyp, utm, prev(bnd["ylo"])[:, :, None]), uym)
+    uyp = np.where(iy == ny - 1, extrap_quadh(uym, utm, prev(bnd["yhi"])[:, :, None]), uyp)
+    v_new = (U - utm) / dt
+    v_old = np.where(it == 1, init_ut[None], (utm - utmm) / dt)
+    fu = (v_new - v_old) / dt - (uxm - 2 * utm + uxp) / dx ** 2 - (uym - 2 * utm + uyp) / dy ** 2
+    u0 = init_u + 0.5 * dt * init_ut
+    return np.where(it == 0, (U - u0[None]) * kimp, fu)
+
+
 def loss_terms(values):
     """core.py:1093-1095: terms = mean(square(F_k)); loss = sum; norms = sqrt(terms)."""
     terms = [np.mean(np.square(v)) for v in values]

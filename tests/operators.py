@@ -114,3 +114,63 @@ def make_wave(cshape, nlvl=0, dtype=np.float64):
     state.fields["u"] = np.zeros(domain.cshape)
     state = domain.init_state(state)
     return odil.Problem(wave_operator, domain, extra), state
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs[2]: the wave operator in two space dimensions, (t, x, y) grid
+# --------------------------------------------------------------------------------------------------
+def wave2_exact(t, x, y):
+    """Sum of plane waves travelling along x, y and the diagonal: an exact solution of u_tt = u_xx + u_yy."""
+    u, ut = 0, 0
+    for i, (kx, ky) in enumerate([(1, 0), (0, 1), (1, 1), (2, -1), (1, 2)], start=1):
+        w = np.pi * np.hypot(kx, ky)
+        ph = np.pi * (kx * x + ky * y) + 0.3 * i
+        u = u + np.cos(ph - w * t)
+        ut = ut + w * np.sin(ph - w * t)
+    return u / 10, ut / 10
+
+
+def wave2_operator(ctx):
+    """u_tt = u_xx + u_yy on a (t, x, y) grid, written with the calls of examples/wave/wave.py:29-75."""
+    mod, extra = ctx.mod, ctx.extra
+    dt, dx, dy = ctx.step()
+    it, ix, iy = ctx.indices()
+    nt, nx, ny = ctx.size()
+    u, utm, utmm = ctx.field("u"), ctx.field("u", -1, 0, 0), ctx.field("u", -2, 0, 0)
+    uxm, uxp = ctx.field("u", -1, -1, 0), ctx.field("u", -1, 1, 0)
+    uym, uyp = ctx.field("u", -1, 0, -1), ctx.field("u", -1, 0, 1)
+    ex = odil.core.extrap_quadh
+
+    def prev(a):  # boundary data at time level t-1
+        return mod.roll(a, 1, axis=0)
+
+    uxm = mod.where(ix == 0, ex(uxp, utm, prev(extra.xlo)[:, None, :]), uxm)
+    uxp = mod.where(ix == nx - 1, ex(uxm, utm, prev(extra.xhi)[:, None, :]), uxp)
+    uym = mod.where(iy == 0, ex(uyp, utm, prev(extra.ylo)[:, :, None]), uym)
+    uyp = mod.where(iy == ny - 1, ex(uym, utm, prev(extra.yhi)[:, :, None]), uyp)
+    v_new = (u - utm) / dt
+    v_old = mod.where(it == 1, extra.init_ut[None], (utm - utmm) / dt)
+    fu = (v_new - v_old) / dt - (uxm - 2 * utm + uxp) / dx ** 2 - (uym - 2 * utm + uyp) / dy ** 2
+    u0 = extra.init_u + 0.5 * dt * extra.init_ut
+    fu = mod.where(it == 0, (u - u0[None]) * extra.kimp, fu)
+    return [("fu", fu)]
+
+
+def make_wave2(cshape, dtype=np.float64):
+    domain = odil.Domain(cshape=tuple(cshape), dimnames=("t", "x", "y"), lower=(0, -1, -1), upper=(1, 1, 1),
+                         dtype=dtype, multigrid=False)
+    t1, x1, y1 = domain.points_1d()
+    T, X, Y = np.meshgrid(t1, x1, y1, indexing="ij")
+    lo, hi = domain.lower, domain.upper
+    extra = argparse.Namespace(kimp=1.0)
+    extra.xlo = wave2_exact(T[:, 0, :], lo[1], Y[:, 0, :])[0].astype(dtype)
+    extra.xhi = wave2_exact(T[:, 0, :], hi[1], Y[:, 0, :])[0].astype(dtype)
+    extra.ylo = wave2_exact(T[:, :, 0], X[:, :, 0], lo[2])[0].astype(dtype)
+    extra.yhi = wave2_exact(T[:, :, 0], X[:, :, 0], hi[2])[0].astype(dtype)
+    u0, ut0 = wave2_exact(lo[0], X[0], Y[0])
+    extra.init_u, extra.init_ut = u0.astype(dtype), ut0.astype(dtype)
+    extra.ref_u = wave2_exact(T, X, Y)[0]
+    state = odil.State()
+    state.fields["u"] = np.zeros(domain.cshape)
+    state = domain.init_state(state)
+    return odil.Problem(wave2_operator, domain, extra), state

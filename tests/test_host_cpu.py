@@ -54,6 +54,36 @@ def test_trace_poisson_rhs_matches_golden(golden):
     assert np.max(np.abs(np.asarray(problem.extra.rhs) - g["p2d_16_L3_f64_rhs"])) < 1e-11
 
 
+@pytest.mark.parametrize("cshape", [(10, 8, 6), (7, 12, 9)])
+def test_trace_wave2_matches_direct_operator(cshape):
+    """BASELINE configs[2] footprint: the wave operator in two space dimensions lowers to 7 offsets
+    (t, t-1, t-2 and the four space neighbours at t-1) x 45 classes (rows it == 0 and it == 1 distinct)."""
+    problem, state = ops.make_wave2(cshape)
+    eng = ResidualEngine(problem, state, trace_only=True)
+    out = eng.outputs[0]
+    assert eng.names == ["fu"] and out.fused
+    spec = out.blocks[0].spec
+    assert spec["rwidth"] == (2, 1, 1) and spec["table"].shape[0] == 45
+    assert sorted(map(tuple, spec["offsets"])) == sorted(
+        [(0, 0, 0), (-1, 0, 0), (-2, 0, 0), (-1, -1, 0), (-1, 1, 0), (-1, 0, -1), (-1, 0, 1)])
+    e = problem.extra
+    U = np.random.default_rng(2).standard_normal(cshape)
+    F = plan_apply(spec, U, out.const.cpu().numpy())
+    nt, nx, ny = cshape
+    F_ref = orc.wave2_residual(U, 1.0 / nt, 2.0 / nx, 2.0 / ny, dict(xlo=e.xlo, xhi=e.xhi, ylo=e.ylo, yhi=e.yhi),
+                               e.init_u, e.init_ut, 1.0)
+    assert np.max(np.abs(F - F_ref)) < 1e-10 * np.max(np.abs(F_ref))
+    # the discrete equations are consistent: the exact solution leaves a residual that shrinks with the grid
+    res = []
+    for n in (12, 24):
+        p2, _ = ops.make_wave2((n, n, n))
+        x = p2.extra
+        R = orc.wave2_residual(x.ref_u, 1.0 / n, 2.0 / n, 2.0 / n, dict(xlo=x.xlo, xhi=x.xhi, ylo=x.ylo, yhi=x.yhi),
+                               x.init_u, x.init_ut, 1.0)
+        res.append(np.sqrt(np.mean(R[2:] ** 2)))
+    assert res[1] < 0.5 * res[0]
+
+
 @pytest.mark.parametrize("cshape,nlvl", [((16, 12), 0), ((16, 8), 2)])
 def test_trace_wave_matches_direct_operator(golden, cshape, nlvl):
     problem, state = ops.make_wave(cshape, nlvl)

@@ -1,7 +1,8 @@
 """
 Secondary configurations of BASELINE.json measured through the public API (not bench lines; the headline is
 bench.py): configs[1] 2-D Poisson 1024^2 / 3 levels / Adam / fp32, configs[2]-like wave inverse with the device
-L-BFGS, configs[4]-like Newton + CG on a Poisson system, plus the raw L-BFGS building blocks.
+L-BFGS, configs[2] itself (wave in two space dimensions, `3` on the command line; not in the default set),
+configs[4]-like Newton + CG on a Poisson system, plus the raw L-BFGS building blocks.
 Usage: python tools/bench_configs.py
 """
 import argparse
@@ -64,6 +65,25 @@ def config2(nt=2048, nx=4096, iters=20):
           f"{dt*1e3:.2f} ms/iteration, {nt*nx/dt/1e6:.0f} Mcells/s", flush=True)
 
 
+def config3(shape=(256, 512, 512), iters=10):
+    """BASELINE configs[2] at full size: (t, x, y) = 256 x 512 x 512 fp32 (67 M unknowns), device L-BFGS m=50.
+    History: 2 x 50 x 67 M x 8 B = 54 GB of the 180 GB; the sweep runs in the per-cell kernel (not a star)."""
+    problem, state = ops.make_wave2(shape, np.float32)
+    args = run_args(epochs=2, bfgs_m=50)
+
+    def run(a):
+        try:
+            odil.util.optimize_grad(a, "lbfgsb", problem, state, None)
+        except odil.EarlyStopError:
+            pass
+
+    run(args)
+    dt = sync_time(lambda: run(run_args(epochs=iters, bfgs_m=50)), iters)
+    cells = int(np.prod(shape))
+    print(f"configs[2] wave (t,x,y) = {'x'.join(map(str, shape))} ({cells/1e6:.1f} M unknowns), device L-BFGS m=50, "
+          f"f32: {dt*1e3:.2f} ms/iteration, {cells/dt/1e6:.0f} Mcells/s", flush=True)
+
+
 def lbfgs_blocks(n=64 * 1024 * 1024, k=100):
     V = torch.randn(k, n, dtype=torch.float64, device="cuda")
     g = torch.randn(n, dtype=torch.float64, device="cuda")
@@ -95,6 +115,8 @@ if __name__ == "__main__":
         config1((128, 128, 128), 3, 300)
     if "2" in which:
         config2()
+    if "3" in which:
+        config3()
     if "blocks" in which:
         lbfgs_blocks()
     if "4" in which:
