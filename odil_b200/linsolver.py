@@ -54,23 +54,31 @@ def solve(matr, rhs, args, status=None, linsolver="direct"):
     raise ValueError("Unknown linsolver=" + linsolver)
 
 
+# (flag, type, default, help) -- names, types and defaults of linsolver.py:90-131; `cg_b200` is the one addition
+_FLAGS = [
+    ("linsolver", str, "direct", "solver of the Newton step; cg_b200 = matrix-free conjugate gradients on the GPU"),
+    ("linsolver_maxiter", int, None, "iteration limit of iterative solvers"),
+    ("linsolver_tol", float, 1e-6, "tolerance of iterative solvers"),
+    ("linsolver_damp", float, 0, "Tikhonov damping d: solves (J^T J + d^2 I) x = J^T r"),
+    ("linsolver_dampdiag", float, 0, "as linsolver_damp, scaled by the diagonal of J^T J"),
+    ("linsolver_verbose", int, 0, "print the solver's status every step"),
+    ("linsolver_history", int, 0, "record the solver's status in train.csv"),
+    ("lr", float, 1e-3, "learning rate of the gradient optimizers"),
+    ("nlvl", int, 100, "upper bound on multigrid levels"),
+    ("smooth_pre", int, 2, "algebraic multigrid: smoothing steps before coarsening"),
+    ("smooth_post", int, 2, "algebraic multigrid: smoothing steps after prolongation"),
+    ("omega", float, 0.6, "algebraic multigrid: relaxation factor of the Jacobi smoother"),
+    ("ndirect", int, 3, "algebraic multigrid: grids up to this size are solved directly"),
+    ("restriction", str, "full", "algebraic multigrid: restriction operator"),
+]
+_CHOICES = {
+    "linsolver": ["multigrid", "direct", "directsq", "direct_cu", "sparseqr", "lsqr", "lsqr_cu", "bicgstab",
+                  "cg_b200"],
+    "restriction": ("full", "half", "injection"),
+}
+
+
 def add_arguments(parser):
-    parser.add_argument("--linsolver", type=str, default="direct",
-                        choices=["multigrid", "direct", "directsq", "direct_cu", "sparseqr", "lsqr", "lsqr_cu",
-                                 "bicgstab", "cg_b200"], help="Linear solver to use (cg_b200: matrix-free CG on the GPU)")
-    parser.add_argument("--linsolver_maxiter", type=int, default=None,
-                        help="Maximum number of iterations of linear solver")
-    parser.add_argument("--linsolver_tol", type=float, default=1e-6, help="Tolerance for linear solver")
-    parser.add_argument("--linsolver_damp", type=float, default=0, help="Relaxation factor (0: no relaxation)")
-    parser.add_argument("--linsolver_dampdiag", type=float, default=0,
-                        help="Multiplier for diagonal (0: no relaxation)")
-    parser.add_argument("--linsolver_verbose", type=int, default=0, help="Verbosity level for linsolver messages")
-    parser.add_argument("--linsolver_history", type=int, default=0, help="Dump history from linsolver status")
-    parser.add_argument("--lr", type=float, default=1e-3, help="Learning rate")
-    parser.add_argument("--nlvl", type=int, default=100, help="Multigrid levels")
-    parser.add_argument("--smooth_pre", type=int, default=2, help="Pre-smoothing steps")
-    parser.add_argument("--smooth_post", type=int, default=2, help="Post-smoothing steps")
-    parser.add_argument("--omega", type=float, default=0.6, help="Jacobi smoother relaxation factor")
-    parser.add_argument("--ndirect", type=int, default=3, help="Systems on smaller grids are solved with direct solver")
-    parser.add_argument("--restriction", type=str, choices=("full", "half", "injection"), default="full",
-                        help="Multigrid restriction type")
+    for name, typ, default, text in _FLAGS:
+        parser.add_argument("--" + name, type=typ, default=default, help=text,
+                            **({"choices": _CHOICES[name]} if name in _CHOICES else {}))

@@ -10,7 +10,6 @@ The reference's house style sheet (`odil.mplstyle`) is a matter of looks and is 
 """
 import os
 
-_extlist = None
 _mpl = None
 
 
@@ -32,57 +31,59 @@ def _matplotlib():
     return _mpl
 
 
+class _Settings:
+    extensions = ["png"]
+
+
 def set_extlist(extlist=None):
-    """File extensions `savefig` writes; None re-reads ODIL_EXTLIST (comma-separated, default png)."""
-    global _extlist
-    _extlist = os.environ.get("ODIL_EXTLIST", "png").split(",") if extlist is None else extlist
+    """Chooses the file types `savefig` writes: a list of extensions, or None to take them from the environment
+    variable ODIL_EXTLIST (comma-separated, "png" when unset)."""
+    _Settings.extensions = list(extlist) if extlist is not None else os.environ.get("ODIL_EXTLIST", "png").split(",")
 
 
 set_extlist()
 
 
 def apply_clip_box(ax, artists, lower=(0, 0), upper=(1, 1.02)):
-    """Clips `artists` to the box [lower, upper] given in axes coordinates of `ax`."""
-    tr = _matplotlib().transforms
-    box = tr.TransformedBbox(tr.Bbox([lower, upper]), ax.transAxes)
-    for a in artists:
-        a.set_clip_box(box)
+    """Restricts drawing of `artists` to the rectangle lower..upper, given as fractions of the axes `ax`."""
+    transforms = _matplotlib().transforms
+    region = transforms.TransformedBbox(transforms.Bbox.from_extents(*lower, *upper), ax.transAxes)
+    for artist in artists:
+        artist.set_clip_box(region)
 
 
-# time stamps are blanked so that re-running a script reproduces the files bit for bit
-_NO_DATES = {"svg": {"Date": None}, "pdf": {"DateModified": None, "CreationDate": None}}
+def _without_timestamps(ext):
+    """Metadata that blanks the creation dates vector formats embed, so that reruns give identical files."""
+    return {"svg": {"Date": None}, "pdf": {"CreationDate": None, "DateModified": None}}.get(ext, {})
 
 
 def savefig(fig, path_without_ext, extlist=None, skip_existing=False, printf=None, **kwargs):
-    """Saves `fig` once per extension (`extlist`, default from `set_extlist`); `printf` receives each path."""
-    say = printf if printf is not None else (lambda _: None)
-    for ext in (_extlist if extlist is None else extlist):
-        path = path_without_ext + "." + ext
-        if skip_existing and os.path.isfile(path):
-            say("skip existing '{}'".format(path))
-            continue
-        say(path)
-        fig.savefig(path, metadata=_NO_DATES.get(ext, {}), **kwargs)
+    """Writes `fig` to `path_without_ext.<ext>` for every extension (default: `set_extlist`).  Existing files are
+    kept when `skip_existing`; `printf`, if given, is told each path (or that it was skipped)."""
+    for ext in (_Settings.extensions if extlist is None else extlist):
+        target = "{}.{}".format(path_without_ext, ext)
+        exists = skip_existing and os.path.isfile(target)
+        if printf is not None:
+            printf("skip existing '{}'".format(target) if exists else target)
+        if not exists:
+            fig.savefig(target, metadata=_without_timestamps(ext), **kwargs)
 
 
 def savelegend(fig, ax, path, **kwargs):
-    """Saves the legend of `ax` alone, cropped to its extent."""
+    """Writes the legend of `ax` as a figure of its own, cropped to the legend."""
     _matplotlib()
-    import matplotlib.pyplot as plt
+    from matplotlib import pyplot
 
-    figleg, axleg = plt.subplots()
-    handles, labels = ax.get_legend_handles_labels()
-    legend = axleg.legend(handles, labels, loc="center", frameon=False)
-    axleg.set_axis_off()
-    figleg.canvas.draw()
-    bbox = legend.get_window_extent().transformed(fig.dpi_scale_trans.inverted())
-    savefig(figleg, path, bbox_inches=bbox, **kwargs)
+    sheet, blank = pyplot.subplots()
+    blank.set_axis_off()
+    entries = blank.legend(*ax.get_legend_handles_labels(), loc="center", frameon=False)
+    sheet.canvas.draw()
+    extent = entries.get_window_extent().transformed(fig.dpi_scale_trans.inverted())
+    savefig(sheet, path, bbox_inches=extent, **kwargs)
 
 
 def set_log_ticks(axis):
-    """Unlabelled minor ticks at 2..9 x 10^k on a logarithmic axis."""
-    import numpy as np
-
+    """Minor ticks without labels at 2, 3, ..., 9 times every power of ten of a logarithmic axis."""
     ticker = _matplotlib().ticker
-    axis.set_minor_locator(ticker.LogLocator(base=10.0, subs=np.arange(0.1, 0.99, 0.1), numticks=12))
+    axis.set_minor_locator(ticker.LogLocator(base=10.0, subs=[k / 10 for k in range(1, 10)], numticks=12))
     axis.set_minor_formatter(ticker.NullFormatter())

@@ -1,11 +1,18 @@
 """
-Driver utilities: shared command-line flags, the optimize() entry points and the per-epoch callback
-that writes train.log / train.csv and reports throughput in Mcells/s (reference src/odil/util.py).
-The throughput definition is the headline metric of this repository:
-    Mcells/s = prod(domain.cshape) / (wall time per epoch, callback time excluded) / 1e6
-(util.py:383-386, :408-419).
+Driver layer around the engine: the command-line flags every ODIL problem script shares, `optimize()` and its two
+back ends (gradient optimizers, Newton), output-directory set-up, and the per-epoch callback that writes
+`train.log` / `train.csv`, plots, checkpoints and reports throughput.  Public names, flag names and defaults, log
+lines and file formats follow the reference (src/odil/util.py: flags :70-149, `optimize_newton` :152-187,
+`optimize_grad` :190-240, `setup_outdir` :281-334, `make_callback` :337-466) so that scripts and the tools that
+read their output keep working.
+
+The throughput line is the headline metric of this repository:
+    Mcells/s = prod(domain.cshape) / (wall time per epoch, callback time excluded) / 1e6      (util.py:408-419)
+The device runs ahead of the host here (nothing in an epoch synchronises), so the callback drains the device before
+it reads the clock whenever it is about to report, record, plot or checkpoint.
 """
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -17,219 +24,264 @@ import psutil
 from .history import History
 from .optimizer import Optimizer, make_optimizer
 
-g_log_file = sys.stderr
-g_log_echo = False
 
-
-def assert_equal(first, second, msg=""):
-    if not (first == second):
-        raise ValueError("Expected equal '{:}' and '{:}'{}".format(first, second, msg))
+# --------------------------------------------------------------------------------------------------
+# Logging and small helpers
+# --------------------------------------------------------------------------------------------------
+class _Log:
+    stream = sys.stderr
+    echo = False
 
 
 def set_log_file(f=None, echo=None):
-    global g_log_file, g_log_echo
+    """Redirects `printlog` to the open file `f`; `echo` also copies every line to stderr."""
     if f is not None:
-        g_log_file = f
+        _Log.stream = f
     if echo is not None:
-        g_log_echo = echo
+        _Log.echo = echo
 
 
 def printlog(*msg):
-    line = " ".join(map(str, msg)) + "\n"
-    if g_log_echo and g_log_file != sys.stderr:
-        sys.stderr.write(line)
-        sys.stderr.flush()
-    g_log_file.write(line)
-    g_log_file.flush()
+    text = " ".join(str(m) for m in msg) + "\n"
+    targets = [_Log.stream]
+    if _Log.echo and _Log.stream is not sys.stderr:
+        targets.insert(0, sys.stderr)
+    for t in targets:
+        t.write(text)
+        t.flush()
 
 
-class Timer:
-    """Stack of named wall-clock timers."""
-
-    def __init__(self):
-        self._starts = []
-        self.counters = dict()
-
-    def push(self, key=None):
-        self._starts.append((key, time.time()))
-
-    def pop(self, key=None):
-        k0, t0 = self._starts.pop()
-        assert k0 is None or key is None or k0 == key, \
-            "Inconsistent keys passed to push() and pop(): {:} and {:}".format(k0, key)
-        key = k0 if key is None else key
-        self.counters[key] = self.counters.get(key, 0.0) + time.time() - t0
-
-    def append(self, timer):
-        for k, v in timer.counters.items():
-            self.counters[k] = self.counters.get(k, 0.0) + v
+def assert_equal(first, second, msg=""):
+    if first != second:
+        raise ValueError("Expected equal '{:}' and '{:}'{}".format(first, second, msg))
 
 
 def get_error(u, v):
-    d = np.asarray(u) - np.asarray(v)
-    return np.mean(abs(d)), np.mean(d ** 2) ** 0.5, np.max(abs(d))
+    """(mean absolute, root mean square, maximum) difference of two arrays."""
+    d = np.abs(np.asarray(u) - np.asarray(v))
+    return np.mean(d), np.sqrt(np.mean(d * d)), np.max(d)
+
+
+class Timer:
+    """Named wall-clock totals.  `push(key)` / `pop(key)` bracket a section (sections nest); `section(key)` does
+    the same as a context manager; `append(other)` adds another timer's totals."""
+
+    def __init__(self):
+        self.counters = {}
+        self._open = []
+
+    def push(self, key=None):
+        self._open.append((key, time.time()))
+
+    def pop(self, key=None):
+        opened, t0 = self._open.pop()
+        if opened is not None and key is not None and opened != key:
+            raise AssertionError("Inconsistent keys passed to push() and pop(): {:} and {:}".format(opened, key))
+        name = opened if key is None else key
+        self.counters[name] = self.counters.get(name, 0.0) + (time.time() - t0)
+
+    @contextlib.contextmanager
+    def section(self, key):
+        self.push(key)
+        try:
+            yield self
+        finally:
+            self.pop(key)
+
+    def append(self, timer):
+        for name, total in timer.counters.items():
+            self.counters[name] = self.counters.get(name, 0.0) + total
+
+
+# --------------------------------------------------------------------------------------------------
+# Command line
+# --------------------------------------------------------------------------------------------------
+# (flag, type, default, help); a default of ... stands for "none given"
+_FLAGS = [
+    ("epochs", int, None, "number of epochs; default: frames * plot_every"),
+    ("every_factor", float, 1, "scales plot_every, report_every and history_every"),
+    ("plot_every", int, 5, "plot every this many epochs"),
+    ("report_every", int, 10, "print a report every this many epochs"),
+    ("history_every", int, 1, "add a row to train.csv every this many epochs"),
+    ("checkpoint_every", int, 0, "write checkpoint_*.pickle every this many epochs (0: never)"),
+    ("frames", int, 10, "number of plotted frames (0 also drops the frame of the initial state)"),
+    ("outdir", str, ".", "directory for args.json, train.log, train.csv, plots and checkpoints"),
+    ("optimizer", str, "adamn", "adam / adamn, gd, lbfgsb / lbfgs, newton"),
+    ("seed", int, 1000, "random seed (numpy and the backend)"),
+    ("plot_title", int, 0, "put a title on plots"),
+    ("plotext", str, "pdf", "file extension of plots"),
+    ("history_full", int, 0, "record every epoch in train.csv below this epoch"),
+    ("montage", int, 1, "assemble plots with montage"),
+    ("double", int, None, "1: float64, 0: float32; default: the runtime's dtype"),
+    ("echo", int, 0, "copy the log to stderr"),
+    ("epoch_start", int, 0, "epoch counter of the initial state"),
+    ("frame_start", int, 0, "frame counter of the initial state"),
+    ("checkpoint", str, ..., "start from this state_*.pickle / checkpoint_*.pickle"),
+    ("checkpoint_train", str, ..., "history pickle to continue train.csv from; default: derived from --checkpoint, "
+                                   "'' disables"),
+    ("callback_update_state", int, 0, "let the callback modify the state the optimizer continues from"),
+    ("bfgs_m", int, 50, "L-BFGS: number of correction pairs"),
+    ("bfgs_maxls", int, 50, "L-BFGS: line-search evaluations per iteration"),
+    ("bfgs_pgtol", float, None, "L-BFGS-B: projected-gradient tolerance"),
+    ("adam_epsilon", float, ..., "Adam: epsilon"),
+    ("adam_beta_1", float, ..., "Adam: beta_1"),
+    ("adam_beta_2", float, ..., "Adam: beta_2"),
+    ("multigrid", int, 0, "represent fields as multigrid hierarchies"),
+    ("mg_interp", str, "stack", "multigrid interpolation formulation (one CUDA kernel serves both)"),
+    ("dump_data", int, 1, "write data_*.pickle with every plot"),
+    ("jac_nsmp0", int, 50, "Jacobi optimizer: samples at initialisation"),
+    ("jac_nsmp1", int, 1, "Jacobi optimizer: samples per step"),
+    ("jac_factor", float, 1, "Jacobi optimizer: factor of the diagonal update"),
+    ("jac_epsilon", float, 1e-8, "Jacobi optimizer: epsilon"),
+    ("nn_initializer", str, "legacy", "initial weights of neural networks"),
+]
+_CHOICES = {"mg_interp": ["conv", "stack"], "nn_initializer": ["legacy", "glorot", "lecun", "he"]}
 
 
 def add_arguments(parser):
-    """Flags shared by all problem scripts (util.py:70-149); names, defaults and help kept."""
-    a = parser.add_argument
-    a("--epochs", type=int, default=None, help="Maximum epochs, defaults to product of plot_every and frames")
-    a("--every_factor", type=float, default=1, help="Multiplier for all *_every options")
-    a("--plot_every", type=int, default=5, help="Epochs between plots")
-    a("--report_every", type=int, default=10, help="Epochs between reports to stdout")
-    a("--history_every", type=int, default=1, help="Epochs between entries of training history")
-    a("--checkpoint_every", type=int, default=0, help="Epochs between checkpoints")
-    a("--frames", type=int, default=10, help="Frames to plot. Zero disables first frame.")
-    a("--outdir", type=str, default=".", help="Output directory")
-    a("--optimizer", type=str, default="adamn", help="Optimizer")
-    a("--seed", default=1000, type=int, help="Seed for numpy.random and the backend's random")
-    a("--plot_title", type=int, default=0, help="Enable title in plots")
-    a("--plotext", type=str, default="pdf", help="Extension of plots")
-    a("--history_full", type=int, default=0, help="Number of epochs to write history at every point")
-    a("--montage", type=int, default=1, help="Run montage after plotting")
-    a("--double", type=int, default=None, help="Double precision. Defaults to runtime.dtype")
-    a("--echo", type=int, default=0, help="Echo log to stderr")
-    a("--epoch_start", type=int, default=0, help="Initial value of epoch")
-    a("--frame_start", type=int, default=0, help="Initial value of frame")
-    a("--checkpoint", type=str, help="Continue from checkpoint in state_*.pickle")
-    a("--checkpoint_train", type=str,
-      help="Continue from history in state_*_train.pickle. By default, infers the name from --checkpoint. "
-           "Set to '' to disable default behavior")
-    a("--callback_update_state", type=int, default=0, help="Update state after callback")
-    a("--bfgs_m", type=int, default=50, help="History size for L-BFGS")
-    a("--bfgs_maxls", type=int, default=50, help="Max evaluations in line search")
-    a("--bfgs_pgtol", type=float, default=None, help="Convergence tolerance for L-BFGS-B")
-    a("--adam_epsilon", type=float, help="Parameter epsilon in Adam")
-    a("--adam_beta_1", type=float, help="Parameter beta_1 in Adam")
-    a("--adam_beta_2", type=float, help="Parameter beta_2 in Adam")
-    a("--multigrid", type=int, default=0, help="Use multigrid decomposition")
-    a("--mg_interp", type=str, default="stack", choices=["conv", "stack"],
-      help="Multigrid interpolation method (both map to the same CUDA kernel)")
-    a("--dump_data", type=int, default=1, help="Dump data_*.pickle with every plot")
-    a("--jac_nsmp0", type=int, default=50, help="Number of samples for initialization of Jacobi optimizer")
-    a("--jac_nsmp1", type=int, default=1, help="Number of samples for each step of Jacobi optimizer")
-    a("--jac_factor", type=float, default=1, help="Factor for the diagonal update of Jacobi optimizer")
-    a("--jac_epsilon", type=float, default=1e-8, help="Parameter epsilon in Jacobi optimizer")
-    a("--nn_initializer", type=str, default="legacy", choices=["legacy", "glorot", "lecun", "he"],
-      help="Initializer for weights of neural networks")
+    """Adds the flags shared by all problem scripts (same names, types and defaults as util.py:70-149)."""
+    for name, typ, default, text in _FLAGS:
+        kw = {"type": typ, "help": text}
+        if default is not ...:
+            kw["default"] = default
+        if name in _CHOICES:
+            kw["choices"] = _CHOICES[name]
+        parser.add_argument("--" + name, **kw)
+
+
+# --------------------------------------------------------------------------------------------------
+# Optimization entry points
+# --------------------------------------------------------------------------------------------------
+def _progress_info(problem, state):
+    loss, _, terms, names, norms = problem.eval_loss_grad(state)
+    return {"terms": terms, "names": names, "norms": norms, "loss": loss}
 
 
 def optimize_newton(args, problem, state, callback=None, **kwargs):
-    domain = problem.domain
-
-    def eval_pinfo(state):
-        loss, _, terms, names, norms = problem.eval_loss_grad(state)
-        return {"terms": terms, "names": names, "norms": norms, "loss": loss}
-
+    """Newton iterations  state += solve(J, -F)  with the linear solver named by `args.linsolver`; the callback
+    sees the initial state as epoch `epoch_start` and every iterate after it."""
     from .linsolver import solve
 
+    domain = problem.domain
     opt = Optimizer(name="newton", displayname="Newton")
     printlog("Running {} optimizer".format(opt.displayname))
-    pinfo = eval_pinfo(state)
     if callback:
-        callback(state, args.epoch_start, pinfo)
-    for epoch in range(args.epoch_start, args.epochs):
-        vector, matrix = problem.linearize(state)
+        callback(state, args.epoch_start, _progress_info(problem, state))
+    for epoch in range(args.epoch_start + 1, args.epochs + 1):
+        residual, jacobian = problem.linearize(state)
         opt.evals += 1
-        linstatus = dict()
-        delta = solve(matrix, -vector, args, linstatus, args.linsolver)
+        status = {}
+        step = solve(jacobian, -residual, args, status, args.linsolver)
         if args.linsolver_verbose:
-            printlog(linstatus)
-        packed = domain.pack_state(state)
-        domain.unpack_state(packed + delta, state)
+            printlog(status)
+        domain.unpack_state(domain.pack_state(state) + step, state)
         if callback:
-            pinfo = eval_pinfo(state)
-            pinfo["linsolver"] = linstatus
-            callback(state, epoch + 1, pinfo)
+            info = _progress_info(problem, state)
+            info["linsolver"] = status
+            callback(state, epoch, info)
     return domain.arrays_from_state(state), argparse.Namespace(epochs=args.epochs, evals=args.epochs)
 
 
+_OPTIMIZER_FLAGS = {"bfgs_m": "m", "bfgs_pgtol": "pgtol", "bfgs_maxls": "maxls", "adam_epsilon": "epsilon",
+                    "adam_beta_1": "beta_1", "adam_beta_2": "beta_2"}
+
+
 def optimize_grad(args, optname, problem, state, callback=None, **kwargs):
-    """Gradient-based optimization of `state` (util.py:190-240)."""
+    """Runs the gradient optimizer `optname` on `state` for epochs `epoch_start + 1 .. epochs`.  The callback first
+    sees the initial state (its loss is the first row of train.csv), then every epoch."""
     domain = problem.domain
-    mod = domain.mod
 
     def loss_grad(arrays):
         domain.arrays_to_state(arrays, state)
         loss, grads, terms, names, norms = problem.eval_loss_grad(state)
         return loss, grads, {"terms": terms, "names": names, "norms": norms, "loss": loss}
 
-    def callback_wrap(arrays, epoch, pinfo):
+    def on_epoch(arrays, epoch, pinfo):
         domain.arrays_to_state(arrays, state)
         callback(state, epoch, pinfo)
         if args.callback_update_state:
-            new = domain.arrays_from_state(state)
-            for i in range(len(new)):
-                arrays[i] = new[i]
+            arrays[:] = domain.arrays_from_state(state)
 
-    for flag, name in [("bfgs_m", "m"), ("bfgs_pgtol", "pgtol"), ("bfgs_maxls", "maxls"), ("adam_epsilon", "epsilon"),
-                       ("adam_beta_1", "beta_1"), ("adam_beta_2", "beta_2")]:
+    for flag, name in _OPTIMIZER_FLAGS.items():
         if getattr(args, flag, None) is not None:
             kwargs[name] = getattr(args, flag)
-
-    opt = make_optimizer(optname, dtype=domain.dtype, mod=mod, **kwargs)
+    opt = make_optimizer(optname, dtype=domain.dtype, mod=domain.mod, **kwargs)
     printlog("Running {} optimizer".format(opt.displayname))
-    # The row for epoch_start carries the loss of the initial state.
     arrays = domain.arrays_from_state(state)
-    _, _, pinfo = loss_grad(arrays)
     if callback:
-        callback(state, args.epoch_start, pinfo)
+        callback(state, args.epoch_start, loss_grad(arrays)[2])
+    else:
+        loss_grad(arrays)  # builds the engine before the optimizer's first timed epoch
     arrays, optinfo = opt.run(arrays, loss_grad=loss_grad, epochs=args.epochs - args.epoch_start,
-                              callback=callback_wrap if callback else None, epoch_start=args.epoch_start,
-                              lr=args.lr, **kwargs)
+                              callback=on_epoch if callback else None, epoch_start=args.epoch_start, lr=args.lr,
+                              **kwargs)
     domain.arrays_to_state(arrays, state)
     return arrays, optinfo
 
 
 def optimize(args, optname, problem, state, callback, **kwargs):
+    """`optname` "newton" runs Newton iterations, anything else is a gradient optimizer of `make_optimizer`."""
     if optname == "newton":
         return optimize_newton(args, problem, state, callback, **kwargs)
     return optimize_grad(args, optname, problem, state, callback, **kwargs)
 
 
+# --------------------------------------------------------------------------------------------------
+# Process / device bookkeeping
+# --------------------------------------------------------------------------------------------------
 def get_memory_usage_kb():
+    """Resident set size of this process in KiB."""
     return psutil.Process().memory_info().rss // 1024
 
 
-def get_gpu_memory_usage_kb():
-    """(bytes in use, bytes reserved by the allocator) on the current device, in KiB."""
+def _cuda():
     try:
         import torch
 
-        if torch.cuda.is_available():
-            return torch.cuda.memory_allocated() // 1024, torch.cuda.memory_reserved() // 1024
+        return torch.cuda if torch.cuda.is_available() else None
     except Exception:
-        pass
-    return 0, 0
+        return None
+
+
+def get_gpu_memory_usage_kb():
+    """(allocated, reserved by the caching allocator) on the current device, in KiB; zeros without a GPU."""
+    cuda = _cuda()
+    return (cuda.memory_allocated() // 1024, cuda.memory_reserved() // 1024) if cuda else (0, 0)
+
+
+_ENV_KEYS = ("OMP_NUM_THREADS", "CUDA_VISIBLE_DEVICES", "ODIL_WARN", "ODIL_BACKEND", "ODIL_JIT", "ODIL_MT",
+             "ODIL_DTYPE")
 
 
 def get_env_config():
-    keys = ["OMP_NUM_THREADS", "CUDA_VISIBLE_DEVICES", "ODIL_WARN", "ODIL_BACKEND", "ODIL_JIT", "ODIL_MT", "ODIL_DTYPE"]
-    return {k: os.environ.get(k, "") for k in keys}
+    return {k: os.environ.get(k, "") for k in _ENV_KEYS}
 
 
 def setup_outdir(args, relpath_args=None):
-    """Creates the output directory with args.json and train.log, enters it, fixes *_every and seeds."""
+    """
+    Prepares a run: creates `args.outdir`, records the configuration in `args.json` (flags, relevant environment,
+    runtime settings), makes it the working directory, opens `train.log`, rewrites the path-valued flags named in
+    `relpath_args` relative to it, applies `every_factor`, derives `epochs` when it was left open, and seeds NumPy
+    and the backend.
+    """
     from . import runtime
 
-    outdir = args.outdir
-    os.makedirs(outdir, exist_ok=True)
-    with open(os.path.join(outdir, "args.json"), "w") as f:
-        d = dict(vars(args), **get_env_config(), runtime_backend=runtime.backend_name,
-                 runtime_dtype=runtime.dtype_name, runtime_jit=runtime.enable_jit, runtime_gpu=runtime.enable_gpu)
-        json.dump(d, f, sort_keys=True, indent=4)
-    os.chdir(outdir)
+    os.makedirs(args.outdir, exist_ok=True)
+    config = dict(vars(args))
+    config.update(get_env_config())
+    config.update(runtime_backend=runtime.backend_name, runtime_dtype=runtime.dtype_name,
+                  runtime_jit=runtime.enable_jit, runtime_gpu=runtime.enable_gpu)
+    with open(os.path.join(args.outdir, "args.json"), "w") as f:
+        json.dump(config, f, sort_keys=True, indent=4)
+    os.chdir(args.outdir)
     set_log_file(open("train.log", "w"), echo=args.echo)
-    for k in relpath_args or []:
-        if getattr(args, k):
-            setattr(args, k, os.path.relpath(getattr(args, k), start=outdir))
-
-    def scaled(v):
-        return None if v is None else max(1, round(v * args.every_factor))
-
-    args.plot_every = scaled(args.plot_every)
-    args.history_every = scaled(args.history_every)
-    args.report_every = scaled(args.report_every)
+    for name in relpath_args or ():
+        if getattr(args, name):
+            setattr(args, name, os.path.relpath(getattr(args, name), start=args.outdir))
+    for name in ("plot_every", "history_every", "report_every"):
+        every = getattr(args, name)
+        if every is not None:
+            setattr(args, name, max(1, round(every * args.every_factor)))
     if args.epochs is None:
         args.epochs = args.frames * args.plot_every
     if args.seed is not None:
@@ -238,106 +290,129 @@ def setup_outdir(args, relpath_args=None):
     printlog(" ".join(sys.argv))
 
 
+# --------------------------------------------------------------------------------------------------
+# Per-epoch callback
+# --------------------------------------------------------------------------------------------------
+class EpochCallback:
+    """
+    `callback(state, epoch, pinfo)` for the optimizers.  Depending on the epoch it reports to the log, appends a
+    row to train.csv, plots a frame and writes a checkpoint; user hooks receive this object as their last argument
+    (`cbinfo` in the reference's examples) and may read `args problem pinfo history frame epoch walltime
+    time_start time_callback task_report task_history task_plot task_checkpoint`.
+
+    `walltime` counts optimizer time only: whatever is spent inside the callback (hooks included) is accumulated
+    in `time_callback` and subtracted.
+    """
+
+    def __init__(self, problem, args, epoch_func=None, report_func=None, history_func=None, checkpoint_func=None,
+                 plot_func=None):
+        self.problem, self.args = problem, args
+        self._hooks = dict(epoch=epoch_func, report=report_func, history=history_func, checkpoint=checkpoint_func,
+                           plot=plot_func)
+        self.walltime = 0        # optimizer wall time at the last report
+        self.epoch = 0           # epoch of the last report
+        self.time_callback = 0   # total time spent in here
+        self.time_start = time.time()
+        self.frame = 0
+        self.pinfo = None
+        self.throughput = 0.0
+        self.history = History(csvpath="train.csv", warmup=1) if args.history_every else None
+        self.task_report = self.task_history = self.task_plot = self.task_checkpoint = False
+        self.cbinfo = self  # `callback.cbinfo` of the reference
+
+    def _schedule(self, epoch):
+        a = self.args
+        self.task_report = a.report_every and epoch % a.report_every == 0
+        self.task_history = self.history is not None and (epoch % a.history_every == 0 or epoch < a.history_full)
+        self.task_plot = epoch % a.plot_every == 0 and (epoch or a.frames)
+        self.task_checkpoint = a.checkpoint_every and epoch % a.checkpoint_every == 0
+        return self.task_report or self.task_history or self.task_plot or self.task_checkpoint
+
+    @staticmethod
+    def _named_norms(pinfo):
+        if not pinfo or "norms" not in pinfo:
+            return []
+        return [(name or str(i), norm) for i, (norm, name) in enumerate(zip(pinfo["norms"], pinfo["names"]))]
+
+    def _report(self, state, epoch, walltime):
+        printlog("\nepoch={:05d}".format(epoch))
+        norms = self._named_norms(self.pinfo)
+        if norms:
+            printlog("residual: " + ", ".join("{}:{:.5g}".format(k, float(np.array(v))) for k, v in norms))
+        if self._hooks["report"] is not None:
+            self._hooks["report"](self.problem, state, epoch, self)
+        used, pool = get_gpu_memory_usage_kb()
+        printlog("memory: {:} MiB, gpu_used: {:} MiB, gpu_pool: {:} MiB".format(
+            get_memory_usage_kb() // 1024, used // 1024, pool // 1024))
+        per_epoch = (walltime - self.walltime) / (epoch - self.epoch) if epoch > self.epoch else 0
+        cells_per_s = np.prod(self.problem.domain.cshape) / per_epoch if per_epoch > 0 else 0
+        printlog("walltime: {:.3f} s, walltime+callback: {:.3f} s, walltime/epoch: {:.3f} ms".format(
+            walltime, walltime + self.time_callback, per_epoch * 1000))
+        printlog("throughput: {:.3f} Mcells/s".format(cells_per_s / 1e6))
+        self.walltime, self.epoch, self.throughput = walltime, epoch, cells_per_s / 1e6
+
+    def _record(self, state, epoch, walltime):
+        h, pinfo = self.history, self.pinfo
+        used, pool = get_gpu_memory_usage_kb()
+        h.append("epoch", epoch)
+        h.append("frame", self.frame)
+        for key, norm in self._named_norms(pinfo):
+            h.append("norm_" + key, np.array(norm))
+        if pinfo and "loss" in pinfo:
+            h.append("loss", np.array(pinfo["loss"]))
+        if getattr(self.args, "linsolver_history", 0) and pinfo and "linsolver" in pinfo:
+            for key, val in pinfo["linsolver"].items():
+                if isinstance(val, (int, float, str, np.floating)):
+                    h.append("lin_" + key, val)
+        h.append("walltime", np.round(walltime, 3))
+        h.append("memory", get_memory_usage_kb() // 1024)
+        h.append("gpu_used", used // 1024)
+        h.append("gpu_pool", pool // 1024)
+        if self._hooks["history"] is not None:
+            self._hooks["history"](self.problem, state, epoch, h, self)
+        h.write()
+
+    def _checkpoint(self, state, epoch):
+        if self._hooks["checkpoint"] is not None:
+            self._hooks["checkpoint"](self.problem, state, epoch, self)
+            return
+        from .core import checkpoint_save
+
+        path = "checkpoint_{:06d}.pickle".format(epoch)
+        printlog(path)
+        checkpoint_save(self.problem.domain, state, path)
+
+    def __call__(self, state, epoch, pinfo):
+        if self._schedule(epoch):
+            cuda = _cuda()
+            if cuda:
+                cuda.synchronize()  # queued epochs belong to the optimizer's time, not to the callback's
+        entered = time.time()
+        self.pinfo = pinfo
+        if isinstance(self.problem.tracers, dict):
+            self.problem.tracers["epoch"] = epoch
+        if self._hooks["epoch"] is not None:
+            self._hooks["epoch"](self.problem, state, epoch, self)
+        now = time.time()
+        self.time_callback += now - entered
+        walltime = now - self.time_start - self.time_callback
+        if self.task_report:
+            self._report(state, epoch, walltime)
+        if self.task_history:
+            self._record(state, epoch, walltime)
+        if self.task_plot:
+            if self._hooks["plot"] is not None:
+                self._hooks["plot"](self.problem, state, epoch, self.frame, self)
+            self.frame += 1
+        if self.task_checkpoint:
+            self._checkpoint(state, epoch)
+        self.time_callback += time.time() - now
+
+
 def make_callback(problem, args=None, epoch_func=None, report_func=None, history_func=None, checkpoint_func=None,
                   plot_func=None):
-    """
-    Returns callback(state, epoch, pinfo) doing report / history / plot / checkpoint by modulo
-    (util.py:337-466).  Time spent inside the callback is excluded from the walltime used for the
-    throughput line.
-    """
-    cb = argparse.Namespace(walltime=0, epoch=0, time_callback=0, time_start=time.time(), problem=problem, args=args,
-                            frame=0)
-    cb.history = History(csvpath="train.csv", warmup=1) if args.history_every else None
-
-    def device_sync():
-        try:
-            import torch
-
-            if torch.cuda.is_available():
-                torch.cuda.synchronize()
-        except Exception:
-            pass
-
-    def callback(state, epoch, pinfo):
-        problem, args, history = cb.problem, cb.args, cb.history
-        domain = problem.domain
-        cb.task_report = args.report_every and epoch % args.report_every == 0
-        cb.task_history = history is not None and (epoch % args.history_every == 0 or epoch < args.history_full)
-        cb.task_plot = epoch % args.plot_every == 0 and (epoch or args.frames)
-        cb.task_checkpoint = args.checkpoint_every and epoch % args.checkpoint_every == 0
-        if cb.task_report or cb.task_history or cb.task_plot or cb.task_checkpoint:
-            device_sync()  # the device runs ahead of the host; account its time before the callback's
-        t_prev = time.time()
-        cb.pinfo = pinfo
-        if isinstance(problem.tracers, dict):
-            problem.tracers["epoch"] = epoch
-        if epoch_func is not None:
-            epoch_func(problem, state, epoch, cb)
-        now = time.time()
-        cb.time_callback += now - t_prev
-        t_prev = now
-        walltime = now - cb.time_start - cb.time_callback
-
-        if cb.task_report:
-            printlog("\nepoch={:05d}".format(epoch))
-            if pinfo and "norms" in pinfo:
-                printlog("residual: " + ", ".join("{}:{:.5g}".format(name or str(i), float(np.array(norm)))
-                                                  for i, (norm, name) in enumerate(zip(pinfo["norms"], pinfo["names"]))))
-            if report_func is not None:
-                report_func(problem, state, epoch, cb)
-            gpu_used, gpu_pool = get_gpu_memory_usage_kb()
-            printlog("memory: {:} MiB, gpu_used: {:} MiB, gpu_pool: {:} MiB".format(
-                get_memory_usage_kb() // 1024, gpu_used // 1024, gpu_pool // 1024))
-            if epoch > cb.epoch:
-                wte = (walltime - cb.walltime) / (epoch - cb.epoch)
-                thr = np.prod(domain.cshape) / wte if wte > 0 else 0
-            else:
-                wte = thr = 0
-            printlog("walltime: {:.3f} s".format(walltime)
-                     + ", walltime+callback: {:.3f} s".format(walltime + cb.time_callback)
-                     + ", walltime/epoch: {:.3f} ms".format(wte * 1000))
-            printlog("throughput: {:.3f} Mcells/s".format(thr / 1e6))
-            cb.walltime = walltime
-            cb.epoch = epoch
-            cb.throughput = thr / 1e6
-
-        if cb.task_history:
-            gpu_used, gpu_pool = get_gpu_memory_usage_kb()
-            history.append("epoch", epoch)
-            history.append("frame", cb.frame)
-            if pinfo and "norms" in pinfo:
-                for i, (norm, name) in enumerate(zip(pinfo["norms"], pinfo["names"])):
-                    history.append("norm_{:}".format(name or str(i)), np.array(norm))
-            if pinfo and "loss" in pinfo:
-                history.append("loss", np.array(pinfo["loss"]))
-            if getattr(args, "linsolver_history", 0) and "linsolver" in pinfo:
-                for key, val in pinfo["linsolver"].items():
-                    if isinstance(val, (int, float, str, np.floating)):
-                        history.append("lin_" + key, val)
-            history.append("walltime", np.round(walltime, 3))
-            history.append("memory", get_memory_usage_kb() // 1024)
-            history.append("gpu_used", gpu_used // 1024)
-            history.append("gpu_pool", gpu_pool // 1024)
-            if history_func is not None:
-                history_func(problem, state, epoch, history, cb)
-            history.write()
-
-        if cb.task_plot:
-            if plot_func is not None:
-                plot_func(problem, state, epoch, cb.frame, cb)
-            cb.frame += 1
-
-        if cb.task_checkpoint:
-            if checkpoint_func is not None:
-                checkpoint_func(problem, state, epoch, cb)
-            else:
-                from .core import checkpoint_save
-
-                path = "checkpoint_{:06d}.pickle".format(epoch)
-                printlog(path)
-                checkpoint_save(domain, state, path)
-
-        cb.time_callback += time.time() - t_prev
-
-    callback.cbinfo = cb
-    return callback
+    """Callback for `optimize`: `report_func(problem, state, epoch, cbinfo)`, `history_func(problem, state, epoch,
+    history, cbinfo)`, `plot_func(problem, state, epoch, frame, cbinfo)`, `checkpoint_func` / `epoch_func(problem,
+    state, epoch, cbinfo)` are called when their task is due (util.py:337-466)."""
+    return EpochCallback(problem, args, epoch_func=epoch_func, report_func=report_func, history_func=history_func,
+                         checkpoint_func=checkpoint_func, plot_func=plot_func)

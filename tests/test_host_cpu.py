@@ -2,7 +2,9 @@
 CPU tests (no GPU): the tracing front-end and its lowering to stencil plans, the host-side API mirror,
 and the C-ABI library surface.  The plans are checked by interpreting them with the CPU oracle.
 """
+import argparse
 import os
+import sys
 import re
 
 import numpy as np
@@ -352,3 +354,100 @@ def test_star_worklist_tiles_the_slab_once(dtype, shape, variant, zchunk):
         assert np.all(work[:, 3] == 0) and np.all(work[:, 4] == 512)
     if zchunk:
         assert np.max(work[:, 4] - work[:, 3]) <= zchunk
+
+
+def test_cli_flags_match_the_reference():
+    """Every flag of the reference's `util.add_arguments` / `linsolver.add_arguments` exists here with the same
+    type, default and choices (tests/golden/io/cli_flags.json is produced by executing those two functions from the
+    reference sources); the only addition is the `cg_b200` linear solver."""
+    import argparse
+    import json
+
+    from tests.golden.make_io_goldens import describe_flags
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "io", "cli_flags.json")))
+    for module, add in (("util", odil.util.add_arguments), ("linsolver", odil.linsolver.add_arguments)):
+        parser = argparse.ArgumentParser()
+        add(parser)
+        mine = json.loads(json.dumps(describe_flags(parser)))
+        assert sorted(mine) == sorted(gold[module])
+        for flag, (typ, default, choices) in gold[module].items():
+            if flag == "linsolver":
+                assert mine[flag][:2] == [typ, default] and mine[flag][2] == choices + ["cg_b200"]
+            else:
+                assert mine[flag] == [typ, default, choices], flag
+
+
+def test_epoch_callback_schedule_log_and_history(tmp_path, monkeypatch):
+    """make_callback: which epochs report / record / plot / checkpoint, the log lines downstream tools parse, the
+    train.csv columns, the hooks' arguments, and that time spent in hooks is not counted as optimizer time."""
+    import argparse
+    import time
+
+    monkeypatch.chdir(tmp_path)
+    log = open(tmp_path / "train.log", "w")
+    odil.set_log_file(log, echo=0)
+    problem = argparse.Namespace(domain=argparse.Namespace(cshape=(8, 4)), tracers={})
+    args = argparse.Namespace(report_every=2, history_every=2, history_full=2, plot_every=4, frames=1,
+                              checkpoint_every=4, linsolver_history=1)
+    seen = {"report": [], "history": [], "plot": [], "checkpoint": [], "epoch": []}
+
+    def epoch_func(p, state, epoch, cb):
+        seen["epoch"].append(epoch)
+        time.sleep(0.02)
+
+    def report_func(p, state, epoch, cb):
+        seen["report"].append((epoch, cb.task_report, cb.pinfo["loss"], cb.args is args, cb.problem is problem))
+
+    def history_func(p, state, epoch, history, cb):
+        seen["history"].append(epoch)
+        history.append("extra", 2.0 * epoch)
+        assert history is cb.history
+
+    def plot_func(p, state, epoch, frame, cb):
+        seen["plot"].append((epoch, frame, cb.frame))
+
+    def checkpoint_func(p, state, epoch, cb):
+        seen["checkpoint"].append(epoch)
+
+    cb = odil.make_callback(problem, args, epoch_func=epoch_func, report_func=report_func, history_func=history_func,
+                            checkpoint_func=checkpoint_func, plot_func=plot_func)
+    assert cb.cbinfo.history is not None and cb.cbinfo.frame == 0
+    for epoch in range(0, 7):
+        pinfo = {"norms": [np.float64(0.5) ** epoch, 3.0], "names": ["fu", ""], "loss": 1.0 / (epoch + 1),
+                 "linsolver": {"niter": 3, "residual": 0.25, "skipped": [1, 2]}}
+        cb("state", epoch, pinfo)
+    odil.set_log_file(sys.stderr)
+    log.close()
+    assert seen["epoch"] == list(range(7)) and problem.tracers["epoch"] == 6
+    assert [r[0] for r in seen["report"]] == [0, 2, 4, 6] and all(r[1] and r[3] and r[4] for r in seen["report"])
+    assert seen["history"] == [0, 1, 2, 4, 6]            # every 2nd epoch, and every epoch below history_full
+    assert seen["plot"] == [(0, 0, 0), (4, 1, 1)] and cb.frame == 2
+    assert seen["checkpoint"] == [0, 4]
+    text = open(tmp_path / "train.log").read()
+    assert "\nepoch=00004\nresidual: fu:0.0625, 1:3\n" in text
+    assert text.count("throughput: ") == 4 and "walltime/epoch: " in text and "gpu_pool: " in text
+    assert "throughput: 0.000 Mcells/s" in text.split("epoch=00002")[0]   # first report has no interval yet
+    rows = open(tmp_path / "train.csv").read().strip().split("\n")
+    assert rows[0] == "epoch,frame,norm_fu,norm_1,loss,lin_niter,lin_residual,walltime,memory,gpu_used,gpu_pool,extra"
+    assert [r.split(",")[0] for r in rows[1:]] == ["0", "1", "2", "4", "6"]
+    assert rows[3].split(",")[1:7] == ["1", "0.25", "3.0", "0.3333333333333333", "3", "0.25"]
+    # 7 x 20 ms were spent in the epoch hook: they are callback time, not optimizer time
+    assert cb.time_callback >= 0.14 and cb.walltime < cb.time_callback
+    assert cb.throughput > 0 and cb.epoch == 6
+
+
+def test_epoch_callback_default_checkpoint_and_no_history(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    saved = []
+    monkeypatch.setattr(odil.core, "checkpoint_save", lambda domain, state, path: saved.append(path))
+    problem = argparse.Namespace(domain=argparse.Namespace(cshape=(4,)), tracers=None)
+    args = argparse.Namespace(report_every=0, history_every=0, history_full=0, plot_every=5, frames=0,
+                              checkpoint_every=3)
+    cb = odil.make_callback(problem, args)
+    assert cb.history is None
+    for epoch in range(7):
+        cb(None, epoch, None)
+    assert saved == ["checkpoint_000000.pickle", "checkpoint_000003.pickle", "checkpoint_000006.pickle"]
+    assert cb.frame == 1  # epoch 0 is not a frame when frames == 0; epoch 5 is
+    assert not os.path.exists(tmp_path / "train.csv")

@@ -97,3 +97,62 @@ def test_raw_xmf_round_trip(dtype, tmp_path, monkeypatch):
     assert meta["count"] == src.shape and u.dtype == dtype and np.array_equal(u, src)
     np.testing.assert_array_almost_equal(meta["spacing"], spacing, decimal=8)
     assert meta["name"] == "foo" and meta["precision"] == np.dtype(dtype).itemsize
+
+
+def test_history_matches_reference_bytes(tmp_path):
+    """train.csv, the saved pickle and the CSV written on reload after the scripted session of
+    tests/golden/make_io_goldens.py::history_session are byte-identical to what the reference's History leaves
+    (late series, skipped values, array scalars, error messages are asserted inside the session)."""
+    from tests.golden.make_io_goldens import history_session
+
+    for path in history_session(odil.History, str(tmp_path)):
+        with open(path, "rb") as f, open(os.path.join(GOLD, os.path.basename(path)), "rb") as g:
+            assert f.read() == g.read(), os.path.basename(path)
+
+
+def test_history_takes_device_style_scalars(tmp_path):
+    class Lazy:  # stands in for the lazily fetched loss of eval_loss_grad
+        def __array__(self, dtype=None, copy=None):
+            return np.array(0.25)
+
+    h = odil.History(csvpath=str(tmp_path / "t.csv"))
+    h.append("loss", Lazy())
+    h.write()
+    h.close()
+    assert open(tmp_path / "t.csv").read() == "loss\n0.25\n"
+    assert h.csvkeys == ["loss"] and h.csvcount == 1 and h.csvpath.endswith("t.csv")
+
+
+def test_plotutil_savefig_without_matplotlib(tmp_path, monkeypatch):
+    """`from odil import plotutil` works on hosts without matplotlib (it is loaded on first use); `savefig` writes one
+    file per extension, blanks the time stamps of vector formats, honours ODIL_EXTLIST and skip_existing."""
+    from odil import plotutil
+
+    class Fig:
+        def __init__(self):
+            self.calls = []
+
+        def savefig(self, path, metadata=None, **kw):
+            self.calls.append((os.path.basename(path), metadata, kw))
+            open(path, "w").close()
+
+    fig, said = Fig(), []
+    base = str(tmp_path / "u_00001")
+    plotutil.savefig(fig, base, extlist=["png", "pdf", "svg"], printf=said.append, pad_inches=0.01)
+    assert fig.calls == [("u_00001.png", {}, {"pad_inches": 0.01}),
+                         ("u_00001.pdf", {"CreationDate": None, "DateModified": None}, {"pad_inches": 0.01}),
+                         ("u_00001.svg", {"Date": None}, {"pad_inches": 0.01})]
+    assert said == [base + ".png", base + ".pdf", base + ".svg"]
+    plotutil.savefig(fig, base, extlist=["png"], skip_existing=True, printf=said.append)
+    assert len(fig.calls) == 3 and said[-1] == "skip existing '{}.png'".format(base)
+    monkeypatch.setenv("ODIL_EXTLIST", "pdf,svg")
+    plotutil.set_extlist()
+    plotutil.savefig(fig, str(tmp_path / "v"))
+    assert [c[0] for c in fig.calls[3:]] == ["v.pdf", "v.svg"]
+    monkeypatch.delenv("ODIL_EXTLIST")
+    plotutil.set_extlist()
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="needs matplotlib"):
+            plotutil.set_log_ticks(None)
