@@ -451,3 +451,114 @@ def test_epoch_callback_default_checkpoint_and_no_history(tmp_path, monkeypatch)
     assert saved == ["checkpoint_000000.pickle", "checkpoint_000003.pickle", "checkpoint_000006.pickle"]
     assert cb.frame == 1  # epoch 0 is not a frame when frames == 0; epoch 5 is
     assert not os.path.exists(tmp_path / "train.csv")
+
+
+def test_optimize_grad_glue(monkeypatch):
+    """util.optimize_grad around a stand-in optimizer: the initial state is reported as epoch `epoch_start` with its
+    own loss, flags map to optimizer keywords, epochs count from `epoch_start`, the state object follows the
+    optimizer's arrays, and `callback_update_state` hands arrays modified by the callback back to the optimizer."""
+    from odil_b200 import util
+
+    class Domain:
+        dtype = np.float64
+        mod = "mod"
+
+        def arrays_from_state(self, state):
+            return list(state["arrays"])
+
+        def arrays_to_state(self, arrays, state):
+            state["arrays"] = list(arrays)
+
+    class Problem:
+        domain = Domain()
+        evals = 0
+
+        def eval_loss_grad(self, state):
+            Problem.evals += 1
+            x = state["arrays"][0]
+            return float(np.sum(x ** 2)), [2 * x], [float(np.sum(x ** 2))], ["f"], [float(np.sqrt(np.sum(x ** 2)))]
+
+    made = {}
+
+    class FakeOpt:
+        displayname = "Fake"
+
+        def run(self, x0, loss_grad, epochs, callback, epoch_start, lr, **kw):
+            made["run"] = dict(epochs=epochs, epoch_start=epoch_start, lr=lr, kw=kw)
+            x = list(x0)
+            for epoch in range(epoch_start + 1, epoch_start + epochs + 1):
+                loss, grads, pinfo = loss_grad(x)
+                x[0] = x[0] - lr * grads[0]
+                if callback:
+                    callback(x, epoch, pinfo)
+            return x, argparse.Namespace(epochs=epochs, evals=epochs)
+
+    def fake_make(name, dtype=None, mod=None, **kw):
+        made["make"] = dict(name=name, dtype=dtype, mod=mod, kw=kw)
+        return FakeOpt()
+
+    monkeypatch.setattr(util, "make_optimizer", fake_make)
+    monkeypatch.setattr(util, "printlog", lambda *a: None)
+    seen = []
+
+    def callback(state, epoch, pinfo):
+        seen.append((epoch, pinfo["loss"], float(state["arrays"][0][0])))
+        if epoch == 12:
+            state["arrays"] = [np.array([10.0])]  # the callback resets the unknown
+
+    args = argparse.Namespace(epochs=14, epoch_start=10, lr=0.25, callback_update_state=1, bfgs_m=7, bfgs_pgtol=None,
+                              bfgs_maxls=None, adam_epsilon=1e-3, adam_beta_1=None, adam_beta_2=None)
+    state = {"arrays": [np.array([8.0])]}
+    arrays, info = util.optimize(args, "fake", Problem(), state, callback)
+    assert made["make"] == dict(name="fake", dtype=np.float64, mod="mod", kw={"m": 7, "epsilon": 1e-3})
+    assert made["run"] == dict(epochs=4, epoch_start=10, lr=0.25, kw={"m": 7, "epsilon": 1e-3})
+    # epoch 10 = initial state; x halves every epoch (x - 0.25 * 2x); the callback sees the updated x and the loss
+    # evaluated before the update; after epoch 12 the optimizer continues from the callback's 10.0
+    assert seen == [(10, 64.0, 8.0), (11, 64.0, 4.0), (12, 16.0, 2.0), (13, 100.0, 5.0), (14, 25.0, 2.5)]
+    assert float(arrays[0][0]) == 2.5 and float(state["arrays"][0][0]) == 2.5 and info.epochs == 4
+    # without a callback the engine is still warmed up by one evaluation before the optimizer runs
+    Problem.evals = 0
+    args.callback_update_state = 0
+    util.optimize_grad(args, "fake", Problem(), {"arrays": [np.array([1.0])]}, None)
+    assert Problem.evals == 1 + 4
+
+
+def test_optimize_newton_glue(monkeypatch):
+    """util.optimize_newton around a stand-in problem and solver: state += solve(J, -F) per epoch, the callback sees
+    the initial state first and the solver's status afterwards."""
+    from odil_b200 import linsolver, util
+
+    class Domain:
+        def pack_state(self, state):
+            return state["x"].copy()
+
+        def unpack_state(self, packed, state):
+            state["x"] = packed
+
+        def arrays_from_state(self, state):
+            return [state["x"]]
+
+    class Problem:
+        domain = Domain()
+
+        def linearize(self, state):  # F(x) = 3 x - 6
+            return 3 * state["x"] - 6, 3.0
+
+        def eval_loss_grad(self, state):
+            f = 3 * state["x"] - 6
+            return float(f @ f), None, [float(f @ f)], ["f"], [float(np.sqrt(f @ f))]
+
+    def fake_solve(matrix, rhs, args, status, name):
+        status.update(niter=1, solver=name)
+        return rhs / matrix
+
+    monkeypatch.setattr(linsolver, "solve", fake_solve)
+    monkeypatch.setattr(util, "printlog", lambda *a: None)
+    seen = []
+    args = argparse.Namespace(epochs=2, epoch_start=0, linsolver="direct", linsolver_verbose=1)
+    state = {"x": np.array([5.0, -1.0])}
+    arrays, info = util.optimize(args, "newton", Problem(), state,
+                                 lambda st, epoch, pinfo: seen.append((epoch, pinfo["loss"], pinfo.get("linsolver"))))
+    assert seen == [(0, 162.0, None), (1, 0.0, {"niter": 1, "solver": "direct"}),
+                    (2, 0.0, {"niter": 1, "solver": "direct"})]
+    assert np.array_equal(arrays[0], [2.0, 2.0]) and info.epochs == 2
