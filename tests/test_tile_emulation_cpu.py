@@ -1,0 +1,173 @@
+"""
+NumPy restatements of the INDEX LOGIC of the 2-D shared-memory tile kernels (odil_b200/csrc/tile2d.cuh fused mode,
+mg_tile2d.cuh synthesis and transpose): same tile sizes, halo widths, staging order, magic-number row split,
+wrap / clamp / reflect rules and closed-form pad fold, executed tile by tile on the host and compared with the
+oracle.  This is how the kernels' addressing was checked before they first ran on a GPU (they then passed their
+parity tests unchanged); it stays as a guard on the design -- the kernels themselves are tested in
+tests/test_kernels_gpu.py.
+"""
+import numpy as np
+import pytest
+
+from oracle import odil_oracle as orc
+
+TY, TX = 32, 64      # kT2Y, kT2X
+CY, CX = 16, 64      # kM2Y, kM2X
+
+
+def _wrap(i, n):     # t2_wrap: C remainder, then shift into range
+    if i < 0 or i >= n:
+        i = int(np.fmod(i, n))
+        if i < 0:
+            i += n
+    return i
+
+
+def _cls(i, n, r):   # t2_class
+    if i < r:
+        return i
+    d = n - 1 - i
+    return 2 * r - d if d < r else r
+
+
+def tile2d_fused(U, c, table, offs, R, scale):
+    N0, N1 = U.shape
+    noff = len(offs)
+    H0, H1 = max(abs(o[0]) for o in offs), max(abs(o[1]) for o in offs)
+    AH, AW, FH, FW = TY + 4 * H0, TX + 4 * H1, TY + 2 * H0, TX + 2 * H1
+    mA, mF = (1 << 32) // AW + 1, (1 << 32) // FW + 1
+    C1 = 2 * R[1] + 1
+    tab = table.reshape(-1, noff)
+    G, Fo, ss = np.full(U.shape, np.nan), np.full(U.shape, np.nan), 0.0
+    for ty0 in range(0, N0, TY):
+        for tx0 in range(0, N1, TX):
+            sA, sF, sC = np.zeros(AH * AW), np.zeros(FH * FW), np.zeros(FH * FW, dtype=int)
+            sDA = [o[0] * AW + o[1] for o in offs]
+            sDF = [o[0] * FW + o[1] for o in offs]
+            for e in range(AH * AW):
+                r = (e * mA) >> 32
+                assert r == e // AW
+                sA[e] = U[_wrap(ty0 - 2 * H0 + r, N0), _wrap(tx0 - 2 * H1 + e - r * AW, N1)]
+            for e in range(FH * FW):
+                r = (e * mF) >> 32
+                cc = e - r * FW
+                ly, lx = ty0 - H0 + r, tx0 - H1 + cc
+                gy, gx = _wrap(ly, N0), _wrap(lx, N1)
+                cl = _cls(gy, N0, R[0]) * C1 + _cls(gx, N1, R[1])
+                at = (r + H0) * AW + cc + H1
+                f = c[gy, gx] + sum(tab[cl, o] * sA[at + sDA[o]] for o in range(noff))
+                sF[e], sC[e] = f, cl
+                if H0 <= r < H0 + TY and H1 <= cc < H1 + TX and ly < N0 and lx < N1:
+                    ss += f * f
+                    Fo[ly, lx] = f
+            for e in range(TY * TX):
+                r, cc = divmod(e, TX)
+                y, x = ty0 + r, tx0 + cc
+                if y < N0 and x < N1:
+                    at = (r + H0) * FW + cc + H1
+                    G[y, x] = scale * sum(tab[sC[at - sDF[o]], o] * sF[at - sDF[o]] for o in range(noff))
+    return Fo, G, ss
+
+
+@pytest.mark.parametrize("shape,offs,R", [
+    ((16, 12), [(0, 0), (-1, 0), (-2, 0), (-1, -1), (-1, 1)], (2, 1)),
+    ((33, 70), [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1)], (2, 1)),
+    ((3, 5), [(0, 0), (2, -2), (-1, 1)], (1, 2)),
+    ((40, 66), [(0, 0), (3, 0), (0, -4), (-2, 2)], (0, 0)),
+])
+def test_tile2d_fused_addressing(shape, offs, R):
+    rng = np.random.default_rng(0)
+    table = rng.standard_normal(tuple(2 * r + 1 for r in R) + (len(offs),))
+    U, c = rng.standard_normal(shape), rng.standard_normal(shape)
+    F_ref = orc.stencil_forward(U, offs, table, R, c)
+    g_ref = orc.stencil_adjoint(F_ref, offs, table, R, 0.37)
+    Fo, G, ss = tile2d_fused(U, c, table, offs, R, 0.37)
+    assert np.abs(Fo - F_ref).max() < 1e-12 and np.abs(G - g_ref).max() < 1e-12
+    assert abs(ss - (F_ref ** 2).sum()) < 1e-9 * (F_ref ** 2).sum()
+
+
+def _clamp(q, n):
+    return 0 if q < 0 else (n - 1 if q > n - 1 else q)
+
+
+def _reflect(q, n):
+    return 1 if q < 0 else (n - 2 if q > n - 1 else q)
+
+
+def interp_add2t(coarse, term, cfac, ffac):
+    n0, n1 = coarse.shape
+    PW = CX + 2
+    out = np.full((2 * n0, 2 * n1), np.nan)
+    for cy0 in range(0, n0, CY):
+        for cx0 in range(0, n1, CX):
+            sP = np.zeros((CY + 2) * PW)
+            for e in range((CY + 2) * PW):
+                r, cc = divmod(e, PW)
+                qy, qx = min(cy0 - 1 + r, n0), min(cx0 - 1 + cc, n1)
+                sy, sx = _clamp(qy, n0), _clamp(qx, n1)
+                v = coarse[sy, sx]
+                if sy != qy or sx != qx:
+                    v = 2 * v - coarse[_reflect(qy, n0), _reflect(qx, n1)]
+                sP[e] = v
+            for vec in range(2 * CY * (CX // 2)):
+                fr, vx = divmod(vec, CX // 2)
+                I, a = fr >> 1, fr & 1
+                fy, lc = 2 * cy0 + fr, 2 * vx
+                fx = 2 * (cx0 + lc)
+                if fy >= 2 * n0 or fx >= 2 * n1:
+                    continue
+                near, far = (I + 1) * PW + lc, (I + 2 * a) * PW + lc
+                h = [3 * sP[near + k] + sP[far + k] for k in range(4)]
+                o = [3 * h[1] + h[0], 3 * h[1] + h[2], 3 * h[2] + h[1], 3 * h[2] + h[3]]
+                for k in range(4):
+                    out[fy, fx + k] = cfac * (o[k] / 16) + ffac * term[fy, fx + k]
+    return out
+
+
+def interp_adjoint2t(gf, n0, n1, scale):
+    FH, FW, GW = 2 * (CY + 4) + 2, 2 * (CX + 4) + 2, CX + 4
+    g = np.full((n0, n1), np.nan)
+    for cy0 in range(0, n0, CY):
+        for cx0 in range(0, n1, CX):
+            fy0, fx0 = 2 * (cy0 - 2) - 1, 2 * (cx0 - 2) - 1
+            sG = np.zeros(FH * FW)
+            for e in range(FH * FW):
+                r, cc = divmod(e, FW)
+                y, x = fy0 + r, fx0 + cc
+                if 0 <= y < 2 * n0 and 0 <= x < 2 * n1:
+                    sG[e] = gf[y, x]
+            gp = np.zeros((CY + 4) * GW)
+            w = (1, 3, 3, 1)
+            for e in range((CY + 4) * GW):
+                r, cc = divmod(e, GW)
+                qy, qx = cy0 - 2 + r, cx0 - 2 + cc
+                if -1 <= qy <= n0 and -1 <= qx <= n1:
+                    gp[e] = sum(w[i] * w[j] * sG[(2 * r + i) * FW + 2 * cc + j] for i in range(4) for j in range(4)) / 16
+            for e in range(CY * CX):
+                r, cc = divmod(e, CX)
+                cy, cx = cy0 + r, cx0 + cc
+                if cy >= n0 or cx >= n1:
+                    continue
+                b = (r + 2) * GW + cc + 2
+
+                def cl(at):
+                    return gp[at] + (gp[at - 1] if cx == 0 else 0) + (gp[at + 1] if cx == n1 - 1 else 0)
+
+                def rf(at):
+                    return gp[at] + (gp[at - 2] if cx == 1 else 0) + (gp[at + 2] if cx == n1 - 2 else 0)
+
+                scl = cl(b) + (cl(b - GW) if cy == 0 else 0) + (cl(b + GW) if cy == n0 - 1 else 0)
+                srf = rf(b) + (rf(b - 2 * GW) if cy == 1 else 0) + (rf(b + 2 * GW) if cy == n0 - 2 else 0)
+                g[cy, cx] = scale * (2 * scl - srf)
+    return g
+
+
+@pytest.mark.parametrize("cshape", [(2, 2), (3, 4), (17, 66), (5, 130)])
+def test_mg_tile2d_addressing_and_pad_fold(cshape):
+    rng = np.random.default_rng(1)
+    n0, n1 = cshape
+    u, t = rng.standard_normal(cshape), rng.standard_normal((2 * n0, 2 * n1))
+    ref = 0.7 * orc.interp_to_finer(u, "cc") + 1.3 * t
+    assert np.abs(interp_add2t(u, t, 0.7, 1.3) - ref).max() < 1e-13
+    aref = 0.9 * orc.interp_adjoint(t, "cc", cshape)
+    assert np.abs(interp_adjoint2t(t, n0, n1, 0.9) - aref).max() < 1e-13
