@@ -101,6 +101,8 @@ struct odil_b200_plan {
     mutable int work_cap, work_n, work_key[6];
     int use_tile2d;    // 1: k_tile2d for 2-D grids (default; env ODIL_B200_TILE2D=0 or an explicit variant disables)
     int h2[2];         // stencil radius per axis (2-D plans)
+    int use_tile3d;    // 1: k_tile3d for non-star 3-D plans (opt-in: variant 80 or ODIL_B200_TILE3D=1; not yet GPU-validated)
+    int h3[3];         // stencil radius per axis (3-D plans)
     int star_xu;       // z-/y-arm coefficients of the interior y/z classes do not depend on the x class
 };
 
@@ -990,6 +992,7 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2), ((TX / 4 + 2) * (TY +
 #include "star7.cuh"
 #include "star8.cuh"
 #include "tile2d.cuh"
+#include "tile3d.cuh"
 namespace odil {
 
 // ------------------------------------------------------------------------------------------------
@@ -1476,6 +1479,76 @@ static int launch_tile2d(const odil_b200_plan* plan, const T* A, const T* c, T s
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 3-D marching tile kernel for non-star plans (tile3d.cuh) -- opt-in
+// ------------------------------------------------------------------------------------------------
+static int tile3d_zchunk(const odil_b200_plan* plan) {
+    if (plan->zchunk > 0) return (int)std::min<int64_t>(plan->zchunk, plan->shape[0]);
+    // enough CTAs for a few waves of 148 SMs x 2-4 resident CTAs, chunks long enough to hide the 4*H0 lead-in planes
+    const int64_t tiles = ((plan->shape[1] + kT3Y - 1) / kT3Y) * ((plan->shape[2] + kT3X - 1) / kT3X);
+    int64_t zc = 64;
+    while (zc > 16 && tiles * ((plan->shape[0] + zc - 1) / zc) < 148 * 8) zc /= 2;
+    return (int)std::min<int64_t>(zc, plan->shape[0]);
+}
+
+static bool tile3d_ok(const odil_b200_plan* plan, const odil_b200_slab* slab) {
+    if (!plan->use_tile3d || plan->ndim != 3 || plan->kind != 0) return false;
+    if (slab->halo > 0 || slab->n0 != plan->shape[0] || slab->z0 != 0) return false;
+    for (int a = 0; a < 3; ++a)
+        if (plan->h3[a] > kT3MaxRadius || plan->shape[a] < 1 || plan->shape[a] >= (1 << 30)) return false;
+    if (plan->ncls > 255 || plan->shape[1] * plan->shape[2] >= (1ll << 31)) return false;
+    const int64_t gx = (plan->shape[2] + kT3X - 1) / kT3X, gy = (plan->shape[1] + kT3Y - 1) / kT3Y;
+    const int zc = tile3d_zchunk(plan);
+    const int64_t gz = (plan->shape[0] + zc - 1) / zc;
+    return gy <= 65535 && gz <= 65535 && gx * gy * gz <= kPartialCapacity;
+}
+
+template <typename T>
+static int launch_tile3d(const odil_b200_plan* plan, const T* U, const T* c, T scale, T* G, T* Fout, int* nparts,
+                         cudaStream_t st) {
+    Tile3Params<T> p;
+    p.U = U;
+    p.c = c;
+    p.G = G;
+    p.Fout = Fout;
+    p.table = (const T*)plan->table_dev;
+    p.partials = plan->partials;
+    p.scale = scale;
+    p.N0 = (int)plan->shape[0];
+    p.N1 = (int)plan->shape[1];
+    p.N2 = (int)plan->shape[2];
+    p.R0 = plan->R[0];
+    p.R1 = plan->R[1];
+    p.R2 = plan->R[2];
+    p.H0 = plan->h3[0];
+    p.H1 = plan->h3[1];
+    p.H2 = plan->h3[2];
+    p.noff = plan->noff;
+    p.ncls = plan->ncls;
+    p.zchunk = tile3d_zchunk(plan);
+    const Tile3Dims d = t3_dims(p.H0, p.H1, p.H2);
+    p.magicA = (unsigned)((1ull << 32) / (unsigned)d.AW + 1);
+    p.magicF = (unsigned)((1ull << 32) / (unsigned)d.FW + 1);
+    for (int o = 0; o < ODIL_B200_MAX_OFFSETS; ++o) {
+        p.dz[o] = o < plan->noff ? (signed char)plan->off[o][0] : 0;
+        p.dy[o] = o < plan->noff ? (signed char)plan->off[o][1] : 0;
+        p.dx[o] = o < plan->noff ? (signed char)plan->off[o][2] : 0;
+    }
+    const size_t smem = t3_smem_bytes<T>(p.H0, p.H1, p.H2, p.ncls, p.noff);
+    ODIL_REQUIRE(smem <= 227 * 1024, "tile3d: %zu bytes of shared memory needed", smem);
+    static size_t smem_set = 48 * 1024;  // per template instantiation
+    if (smem > smem_set) {
+        ODIL_CUDA(cudaFuncSetAttribute(k_tile3d<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    dim3 grid((p.N2 + kT3X - 1) / kT3X, (p.N1 + kT3Y - 1) / kT3Y, (p.N0 + p.zchunk - 1) / p.zchunk);
+    k_tile3d<T><<<grid, kT3Threads, smem, st>>>(p);
+    ODIL_LAUNCHED();
+    *nparts = (int)(grid.x * grid.y * grid.z);
+    return 0;
+}
+
 template <typename T>
 static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, const void* U, const void* c,
                      double scale, void* G, void* Fout, double* sumsq, cudaStream_t st) {
@@ -1491,6 +1564,12 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     int nparts = 0;
     if (tile2d_ok(plan, slab)) {
         if (int rc = launch_tile2d<T, 2>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)) return rc;
+        k_reduce_partials<<<1, 1024, 0, st>>>(plan->partials, nparts, sumsq);
+        ODIL_LAUNCHED();
+        return 0;
+    }
+    if (tile3d_ok(plan, slab)) {
+        if (int rc = launch_tile3d<T>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)) return rc;
         k_reduce_partials<<<1, 1024, 0, st>>>(plan->partials, nparts, sumsq);
         ODIL_LAUNCHED();
         return 0;
@@ -1861,6 +1940,12 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
         if (ndim == 2)
             for (int o = 0; o < noff; ++o)
                 for (int a = 0; a < 2; ++a) p->h2[a] = std::max(p->h2[a], std::abs(p->off[o][a]));
+        const char* e3 = getenv("ODIL_B200_TILE3D");
+        p->use_tile3d = (e3 && e3[0] == '1') ? 1 : 0;
+        p->h3[0] = p->h3[1] = p->h3[2] = 0;
+        if (ndim == 3)
+            for (int o = 0; o < noff; ++o)
+                for (int a = 0; a < 3; ++a) p->h3[a] = std::max(p->h3[a], std::abs(p->off[o][a]));
     }
     p->work_dev = nullptr;
     p->work_cap = 0;
@@ -1993,11 +2078,16 @@ int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant) {
     ODIL_REQUIRE((variant >= 0 && variant <= 3) || (variant >= 10 && variant <= 13) ||
                      (variant >= 20 && variant <= 23) || (variant >= 30 && variant <= 32) ||
                      (variant >= 40 && variant <= 42) || (variant >= 50 && variant <= 52) ||
-                     (variant >= 60 && variant <= 62) || variant == 70 || variant == 71 || variant == -1,
+                     (variant >= 60 && variant <= 62) || variant == 70 || variant == 71 || variant == 80 ||
+                     variant == 81 || variant == -1,
                  "variant=%d unknown", variant);
     plan->zchunk = zchunk;
     // 70 / 71: 2-D tile kernel on / off with the default 3-D choice; any explicit star variant also turns it off
     // (so the star kernels stay reachable on 2-D grids)
+    if (variant == 80 || variant == 81) {  // 3-D marching tile kernel for non-star plans on / off
+        plan->use_tile3d = variant == 80;
+        return 0;
+    }
     plan->use_tile2d = variant == 70 || variant == -1;
     if (variant >= 70) variant = -1;
     // -1 / 50..52: k_star8 (default; up to 14 / 12 / 8 rows per CTA); 60..62: same with per-cell z/y-arm

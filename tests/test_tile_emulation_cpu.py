@@ -1,6 +1,6 @@
 """
-NumPy restatements of the INDEX LOGIC of the 2-D shared-memory tile kernels (odil_b200/csrc/tile2d.cuh fused mode,
-mg_tile2d.cuh synthesis and transpose): same tile sizes, halo widths, staging order, magic-number row split,
+NumPy restatements of the INDEX LOGIC of the shared-memory tile kernels (odil_b200/csrc/tile2d.cuh fused mode,
+mg_tile2d.cuh synthesis and transpose, tile3d.cuh marching rings): same tile sizes, halo widths, staging order, magic-number row split,
 wrap / clamp / reflect rules and closed-form pad fold, executed tile by tile on the host and compared with the
 oracle.  This is how the kernels' addressing was checked before they first ran on a GPU (they then passed their
 parity tests unchanged); it stays as a guard on the design -- the kernels themselves are tested in
@@ -171,3 +171,83 @@ def test_mg_tile2d_addressing_and_pad_fold(cshape):
     assert np.abs(interp_add2t(u, t, 0.7, 1.3) - ref).max() < 1e-13
     aref = 0.9 * orc.interp_adjoint(t, "cc", cshape)
     assert np.abs(interp_adjoint2t(t, n0, n1, 0.9) - aref).max() < 1e-13
+
+
+# --------------------------------------------------------------------------------------------------
+# tile3d.cuh: 16 x 64 tiles marching along axis 0 with rings of 2*H0+1 U and F planes
+# --------------------------------------------------------------------------------------------------
+def _slot(p, nr):    # t3_slot
+    p = int(np.fmod(p, nr))
+    return p + nr if p < 0 else p
+
+
+def tile3d_fused(U, c, table, offs, R, scale, zchunk):
+    T3Y, T3X = 16, 64
+    N0, N1, N2 = U.shape
+    noff = len(offs)
+    H0, H1, H2 = (max(abs(o[a]) for o in offs) for a in range(3))
+    AH, AW, FH, FW, NR = T3Y + 4 * H1, T3X + 4 * H2, T3Y + 2 * H1, T3X + 2 * H2, 2 * H0 + 1
+    C1, C2 = 2 * R[1] + 1, 2 * R[2] + 1
+    tab = table.reshape(-1, noff)
+    G, Fo, ss = np.full(U.shape, np.nan), np.full(U.shape, np.nan), 0.0
+    for zs in range(0, N0, zchunk):
+        ze = min(zs + zchunk, N0)
+        for ty0 in range(0, N1, T3Y):
+            for tx0 in range(0, N2, T3X):
+                sU, sF = np.zeros((NR, AH * AW)), np.zeros((NR, FH * FW))
+                sC = np.zeros((NR, FH * FW), dtype=int)
+
+                def stage(pz):
+                    rows = [_wrap(ty0 - 2 * H1 + r, N1) for r in range(AH)]
+                    cols = [_wrap(tx0 - 2 * H2 + q, N2) for q in range(AW)]
+                    sU[_slot(pz, NR)] = U[_wrap(pz, N0)][np.ix_(rows, cols)].reshape(-1)
+
+                j0, j1 = zs - H0, ze - 1 + H0
+                for pz in range(j0 - H0, j0 + H0):
+                    stage(pz)
+                for j in range(j0, j1 + 1):
+                    k = j - H0
+                    stage(j + H0)
+                    oU = [(_slot(j + o[0], NR), o[1] * AW + o[2]) for o in offs]
+                    oF = [(_slot(k - o[0], NR), -(o[1] * FW + o[2])) for o in offs]
+                    gz, fs = _wrap(j, N0), _slot(j, NR)
+                    for e in range(FH * FW):
+                        r, cc = divmod(e, FW)
+                        ly, lx = ty0 - H1 + r, tx0 - H2 + cc
+                        gy, gx = _wrap(ly, N1), _wrap(lx, N2)
+                        cl = (_cls(gz, N0, R[0]) * C1 + _cls(gy, N1, R[1])) * C2 + _cls(gx, N2, R[2])
+                        at = (r + H1) * AW + cc + H2
+                        f = c[gz, gy, gx] + sum(tab[cl, o] * sU[oU[o][0], at + oU[o][1]] for o in range(noff))
+                        sF[fs, e], sC[fs, e] = f, cl
+                        if zs <= j < ze and H1 <= r < H1 + T3Y and H2 <= cc < H2 + T3X and ly < N1 and lx < N2:
+                            ss += f * f
+                            Fo[j, ly, lx] = f
+                    if k >= zs:
+                        for e in range(T3Y * T3X):
+                            r, cc = divmod(e, T3X)
+                            y, x = ty0 + r, tx0 + cc
+                            if y < N1 and x < N2:
+                                at = (r + H1) * FW + cc + H2
+                                G[k, y, x] = scale * sum(tab[sC[s, at + dd], o] * sF[s, at + dd]
+                                                         for o, (s, dd) in enumerate(oF))
+    return Fo, G, ss
+
+
+WAVE2 = [(0, 0, 0), (-1, 0, 0), (-2, 0, 0), (-1, -1, 0), (-1, 1, 0), (-1, 0, -1), (-1, 0, 1)]
+
+
+@pytest.mark.parametrize("shape,offs,R,zchunk", [
+    ((7, 10, 9), WAVE2, (2, 1, 1), 3),
+    ((5, 18, 70), WAVE2, (2, 1, 1), 64),
+    ((4, 5, 6), [(0, 0, 0), (1, 1, 1), (-2, 0, 2), (0, -1, 0)], (1, 1, 2), 2),   # planes wrap more than once
+    ((3, 4, 5), [(0, 0, 0), (0, 1, -1)], (0, 0, 0), 1),                           # no coupling along axis 0
+])
+def test_tile3d_ring_addressing(shape, offs, R, zchunk):
+    rng = np.random.default_rng(3)
+    table = rng.standard_normal(tuple(2 * r + 1 for r in R) + (len(offs),))
+    U, c = rng.standard_normal(shape), rng.standard_normal(shape)
+    F_ref = orc.stencil_forward(U, offs, table, R, c)
+    g_ref = orc.stencil_adjoint(F_ref, offs, table, R, 0.37)
+    Fo, G, ss = tile3d_fused(U, c, table, offs, R, 0.37, zchunk)
+    assert np.abs(Fo - F_ref).max() < 1e-12 and np.abs(G - g_ref).max() < 1e-12
+    assert abs(ss - (F_ref ** 2).sum()) < 1e-9 * (F_ref ** 2).sum()

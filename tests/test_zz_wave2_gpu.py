@@ -59,3 +59,59 @@ def test_wave2_lbfgs_converges():
     assert losses[-1] < 2e-2 * losses[0]
     u = problem.domain.arrays_from_state(state)[0].cpu().numpy()
     assert np.sqrt(np.mean((u - problem.extra.ref_u) ** 2)) < 0.2
+
+
+# --------------------------------------------------------------------------------------------------
+# k_tile3d (marching tile kernel for non-star 3-D plans): opt-in until it has run on a GPU once
+# --------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+from odil_b200 import native  # noqa: E402
+
+WAVE2 = [(0, 0, 0), (-1, 0, 0), (-2, 0, 0), (-1, -1, 0), (-1, 1, 0), (-1, 0, -1), (-1, 0, 1)]
+TILE3D_CASES = [
+    ((7, 10, 9), WAVE2, (2, 1, 1), 3),
+    ((40, 18, 70), WAVE2, (2, 1, 1), 0),
+    ((4, 5, 6), [(0, 0, 0), (1, 1, 1), (-2, 0, 2), (0, -1, 0)], (1, 1, 2), 2),
+    ((33, 16, 64), [(0, 0, 0), (0, 1, -1), (1, 0, 0)], (0, 0, 0), 8),
+    ((64, 48, 200), WAVE2, (2, 1, 1), 16),
+]
+
+
+@pytest.mark.skipif(os.environ.get("ODIL_B200_EXPERIMENTAL", "0") != "1",
+                    reason="k_tile3d has not run on a GPU yet: set ODIL_B200_EXPERIMENTAL=1 to include it")
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("case", range(len(TILE3D_CASES)))
+def test_tile3d_matches_oracle_and_generic(prec, case):
+    nd, td = (np.float64, torch.float64) if prec == "f64" else (np.float32, torch.float32)
+    shape, offsets, rr, zchunk = TILE3D_CASES[case]
+    rng = np.random.default_rng(700 + case)
+    tshape = tuple(2 * r + 1 for r in rr) + (len(offsets),)
+    table = rng.standard_normal(tshape)
+    U = rng.standard_normal(shape).astype(nd)
+    c = rng.standard_normal(shape).astype(nd)
+    scale = 2.0 / U.size
+    F_ref = orc.stencil_forward(U.astype(np.float64), offsets, table, rr, c.astype(np.float64))
+    g_ref = orc.stencil_adjoint(F_ref, offsets, table, rr, scale)
+    tol = (1e-11 if prec == "f64" else 2e-5) * 10
+    res = {}
+    for variant in (80, 81):  # 80: k_tile3d, 81: the per-cell generic kernel
+        plan = native.StencilPlan(shape, td, offsets, rr, table.reshape(-1, len(offsets)))
+        plan.tune(zchunk=zchunk, variant=variant)
+        dU, dc = torch.as_tensor(U, device="cuda"), torch.as_tensor(c, device="cuda")
+        G = torch.full_like(dU, float("nan"))
+        F = torch.full_like(dU, float("nan"))
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dU, dc, scale, G, ss, F_out=F)
+        G0 = torch.full_like(dU, float("nan"))
+        ss0 = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dU, None, scale, G0, ss0)
+        res[variant] = [t.cpu().numpy() for t in (F, G, ss, G0, ss0)]
+        F, G, ss, G0, ss0 = res[variant]
+        assert relerr(F, F_ref) < tol and relerr(G, g_ref) < tol
+        assert abs(ss[0] - np.sum(F_ref ** 2)) < tol * np.sum(F_ref ** 2)
+        F0 = orc.stencil_forward(U.astype(np.float64), offsets, table, rr, None)
+        assert abs(ss0[0] - np.sum(F0 ** 2)) < tol * np.sum(F0 ** 2)
+        assert relerr(G0, orc.stencil_adjoint(F0, offsets, table, rr, scale)) < tol
+    for a, b in zip(res[80][:2], res[81][:2]):
+        assert relerr(a, b) < 64 * np.finfo(nd).eps
