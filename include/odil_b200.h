@@ -100,7 +100,7 @@ int odil_b200_stencil_plan_kind(const odil_b200_plan* plan);
  * generation / tile shape of the star sweep (50-52, 60-62 current; 30-42, 20-23, 10-13, 0-3 earlier ones, kept as
  * measured history), 70 / 71 switch the 2-D tile kernel on / off (any explicit star variant also switches it off,
  * so the star kernels stay reachable on 2-D grids); 80 / 81 switch the marching tile kernel for non-star 3-D plans
- * on / off (off by default until it has been validated on a GPU; also ODIL_B200_TILE3D=1 at plan creation). */
+ * on / off (default on; ODIL_B200_TILE3D=0 at plan creation also switches it off). */
 int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant);
 
 /* sumsq_out[0] = sum x^2 (double accumulate).  Replaces mean(square(f)) of a materialised F

@@ -101,7 +101,7 @@ struct odil_b200_plan {
     mutable int work_cap, work_n, work_key[6];
     int use_tile2d;    // 1: k_tile2d for 2-D grids (default; env ODIL_B200_TILE2D=0 or an explicit variant disables)
     int h2[2];         // stencil radius per axis (2-D plans)
-    int use_tile3d;    // 1: k_tile3d for non-star 3-D plans (opt-in: variant 80 or ODIL_B200_TILE3D=1; not yet GPU-validated)
+    int use_tile3d;    // 1: k_tile3d for non-star 3-D plans (default; ODIL_B200_TILE3D=0 or variant 81 selects k_generic)
     int h3[3];         // stencil radius per axis (3-D plans)
     int star_xu;       // z-/y-arm coefficients of the interior y/z classes do not depend on the x class
 };
@@ -1481,7 +1481,7 @@ static int launch_tile2d(const odil_b200_plan* plan, const T* A, const T* c, T s
 
 
 // ------------------------------------------------------------------------------------------------
-// 3-D marching tile kernel for non-star plans (tile3d.cuh) -- opt-in
+// 3-D marching tile kernel for non-star plans (tile3d.cuh)
 // ------------------------------------------------------------------------------------------------
 static int tile3d_zchunk(const odil_b200_plan* plan) {
     if (plan->zchunk > 0) return (int)std::min<int64_t>(plan->zchunk, plan->shape[0]);
@@ -1941,7 +1941,7 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
             for (int o = 0; o < noff; ++o)
                 for (int a = 0; a < 2; ++a) p->h2[a] = std::max(p->h2[a], std::abs(p->off[o][a]));
         const char* e3 = getenv("ODIL_B200_TILE3D");
-        p->use_tile3d = (e3 && e3[0] == '1') ? 1 : 0;
+        p->use_tile3d = !(e3 && e3[0] == '0');
         p->h3[0] = p->h3[1] = p->h3[2] = 0;
         if (ndim == 3)
             for (int o = 0; o < noff; ++o)

@@ -47,7 +47,8 @@ def test_wave2_eval_loss_grad(cshape, prec):
                                           np.asarray(e.init_u, dtype=np.float64),
                                           np.asarray(e.init_ut, dtype=np.float64), 1.0)
         g_probe = orc.numerical_jacobian_T(fn, U.astype(np.float64), F_ref) * (2.0 / F_ref.size)
-        assert relerr(g_ref, g_probe) < 1e-9
+        # (the traced table carries dt, dx, dy in the domain dtype: its coefficients are fp32-rounded for f32)
+        assert relerr(g_ref, g_probe) < (1e-9 if prec == "f64" else 1e-6)
     assert relerr(grads[0].cpu().numpy(), g_ref) < tol
 
 
@@ -62,10 +63,8 @@ def test_wave2_lbfgs_converges():
 
 
 # --------------------------------------------------------------------------------------------------
-# k_tile3d (marching tile kernel for non-star 3-D plans): opt-in until it has run on a GPU once
+# k_tile3d (marching tile kernel for non-star 3-D plans; selected with plan_tune(variant=80))
 # --------------------------------------------------------------------------------------------------
-import os  # noqa: E402
-
 from odil_b200 import native  # noqa: E402
 
 WAVE2 = [(0, 0, 0), (-1, 0, 0), (-2, 0, 0), (-1, -1, 0), (-1, 1, 0), (-1, 0, -1), (-1, 0, 1)]
@@ -78,8 +77,6 @@ TILE3D_CASES = [
 ]
 
 
-@pytest.mark.skipif(os.environ.get("ODIL_B200_EXPERIMENTAL", "0") != "1",
-                    reason="k_tile3d has not run on a GPU yet: set ODIL_B200_EXPERIMENTAL=1 to include it")
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("case", range(len(TILE3D_CASES)))
 def test_tile3d_matches_oracle_and_generic(prec, case):
