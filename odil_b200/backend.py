@@ -563,7 +563,11 @@ class ModB200(ModBase):
 
     def stop_gradient(self, x):
         if isinstance(x, Affine):
-            return Affine(x.shape, x.dtype, {(k, o, True): c for (k, o, _), c in x.lin.items()}, x.const)
+            lin = {}
+            for (k, o, _), c in x.lin.items():
+                k2 = (k, o, True)  # a frozen and a live term of the same (key, offset) add up
+                lin[k2] = lin[k2].added(c) if k2 in lin else c.copy()
+            return Affine(x.shape, x.dtype, lin, x.const)
         return x
 
     def reshape(self, x, shape):

@@ -640,11 +640,18 @@ class Problem:
 
     def _engine(self, state):
         cache = self._cache_eval_loss_grad
+        if "func" in cache and cache["func"].tracer_view.stale(self.tracers):
+            # A tracer the operator read at trace time (e.g. tracers["epoch"] in an annealed weight) has changed:
+            # the affine path holds its value inside the coefficient tables, so lower the operator again.
+            old = cache.pop("func")
+            cache["buffers"] = getattr(old, "_buffers", None)
         if "func" not in cache:
             from .engine import ResidualEngine
 
             cache["state"] = state
             cache["func"] = ResidualEngine(self, state)
+            if cache.get("buffers"):
+                cache["func"]._buffers = cache.pop("buffers")  # work arrays of the previous lowering
             cache["names"] = cache["func"].names
         return cache["func"]
 
@@ -717,8 +724,21 @@ def _to_numpy(a):
     return np.array(a)
 
 
+def _global_numpy(domain, a):
+    """Host copy of one state array in the reference's (global, halo-free) layout; collective in slab runs."""
+    slab = getattr(domain, "slab", None)
+    if slab is not None and torch.is_tensor(a) and a.dim() >= 1 and a.dim() == domain.ndim:
+        return slab.gather(a).detach().cpu().numpy()
+    return _to_numpy(a)
+
+
 def checkpoint_save(domain, state, path):
-    fields = {key: [_to_numpy(a) for a in domain.arrays_from_field(f)] for key, f in state.fields.items()}
+    """Writes {fields: {key: [ndarray, ...]}} with GLOBAL arrays.  In slab-decomposed runs every rank takes part
+    in the gather of the owned planes and rank 0 alone writes the file."""
+    fields = {key: [_global_numpy(domain, a) for a in domain.arrays_from_field(f)] for key, f in state.fields.items()}
+    slab = getattr(domain, "slab", None)
+    if slab is not None and slab.rank != 0:
+        return
     with open(path, "wb") as f:
         pickle.dump({"fields": fields}, f)
 
@@ -726,6 +746,7 @@ def checkpoint_save(domain, state, path):
 def checkpoint_load(domain, state, path, skip_missing=True, keys=None):
     with open(path, "rb") as f:
         data = pickle.load(f).get("fields", dict())
+    slab = getattr(domain, "slab", None)
     for key in keys or state.fields.keys():
         if key not in data:
             if not skip_missing:
@@ -734,9 +755,20 @@ def checkpoint_load(domain, state, path, skip_missing=True, keys=None):
         arrays = data[key]
         if not isinstance(arrays, list):
             arrays = [arrays]
+        field = state.fields[key]
         if state.initialized:
-            arrays = [domain.mod.variable(a, dtype=domain.dtype) for a in arrays]
-        domain.arrays_to_field(arrays, state.fields[key])
+            current = domain.arrays_from_field(field)
+            assert_equal(len(arrays), len(current), f" arrays of field '{key}' in {path}")
+            loaded = []
+            for a, cur in zip(arrays, current):
+                t = domain.mod.variable(a, dtype=domain.dtype)
+                if slab is not None and isinstance(field, (Field, MultigridField)):
+                    t = slab.scatter(t)  # checkpoints hold global arrays; cut this rank's slab (halos filled)
+                if cur is not None and hasattr(cur, "shape"):
+                    assert_equal(tuple(t.shape), tuple(cur.shape), f" for field '{key}' in {path}")
+                loaded.append(t)
+            arrays = loaded
+        domain.arrays_to_field(arrays, field)
 
 
 # --------------------------------------------------------------------------------------------------

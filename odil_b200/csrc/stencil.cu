@@ -1004,9 +1004,12 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
     for (int o = 0; o < noff; ++o)
         for (int a = 0; a < ndim; ++a) {
             p->off[o][a] = offsets[o * ndim + a];
-            if (std::abs(p->off[o][a]) >= shape[a] && shape[a] > 1 && p->off[o][a] != 0) {
+            // The kernels wrap an index with ONE conditional add / subtract, so |offset| must stay below the
+            // axis size on every axis, size-1 axes included (the host folds offsets modulo the size first).
+            if (std::abs(p->off[o][a]) >= shape[a] && p->off[o][a] != 0) {
                 delete p;
-                return fail("offset %d axis %d = %d exceeds the grid size", o, a, p->off[o][a]);
+                return fail("offset %d axis %d = %d exceeds the grid size %lld", o, a, p->off[o][a],
+                            (long long)shape[a]);
             }
             if (a == 0) p->rmax0 = std::max(p->rmax0, std::abs(p->off[o][a]));
         }

@@ -135,6 +135,14 @@ def lower_block(shape, coefs):
     Raises NonAffineError if some coefficient varies in the interior (not region-typed).
     """
     nd = len(shape)
+    # roll() along an axis of size n is periodic with period n: reduce every offset to the shortest equivalent one
+    # (on a size-1 axis every shift is the identity) and merge offsets that became equal.
+    folded = {}
+    for off, co in coefs.items():
+        red = tuple(0 if shape[a] == 1 else int(o) - shape[a] * round(int(o) / shape[a]) if abs(int(o)) >= shape[a]
+                    else int(o) for a, o in enumerate(off))
+        folded[red] = folded[red].added(co) if red in folded else co.copy()
+    coefs = folded
     offsets = sorted(coefs.keys())
     rr = [0] * nd
     for off in offsets:
@@ -222,6 +230,39 @@ def synthesize_slab(slab, arrays, shapes, factors, loc, buffers=None, exchanged=
     return res
 
 
+class TracerView(dict):
+    """What the operator sees as `ctx.tracers` during the trace.  The reference passes tracers to the jitted
+    function as run-time arguments (core.py:1076-1110); the affine path bakes their values into the coefficient
+    tables, so every key that was READ is recorded with its value and `Problem` re-lowers the operator when one of
+    them changes (EpochCallback updates tracers["epoch"] every epoch, util.py:370-378)."""
+
+    def __init__(self, values):
+        super().__init__(values or {})
+        self.reads = {}
+
+    def __getitem__(self, key):
+        v = super().__getitem__(key)
+        self.reads[key] = v
+        return v
+
+    def get(self, key, default=None):
+        if key in self:
+            return self[key]
+        return default
+
+    def stale(self, current):
+        """True if a tracer the trace depended on now has another value."""
+        for key, v in self.reads.items():
+            c = (current or {}).get(key)
+            try:
+                same = bool(np.all(np.asarray(c) == np.asarray(v)))
+            except Exception:
+                same = c is v
+            if not same:
+                return True
+        return False
+
+
 class _Block:
     def __init__(self, key, frozen, plan):
         self.key, self.frozen, self.plan = key, frozen, plan
@@ -292,7 +333,9 @@ class ResidualEngine:
     # ----------------------------------------------------------------------------------------------
     def _trace(self, state):
         problem, domain = self.problem, self.domain
-        ctx = Context(domain, state, extra=problem.extra, tracers=problem.tracers)
+        self.tracer_view = TracerView(problem.tracers if isinstance(problem.tracers, dict) else None)
+        ctx = Context(domain, state, extra=problem.extra,
+                      tracers=self.tracer_view if isinstance(problem.tracers, dict) else problem.tracers)
         ff = problem.operator(ctx)
         assert isinstance(ff, (tuple, list)) and len(ff), "Operator must return a non-empty list"
         names = [f[0] if isinstance(f, tuple) else "" for f in ff]

@@ -144,6 +144,17 @@ class GdOptimizer(Optimizer):
         return x, Namespace(epochs=epochs, evals=self.evals)
 
 
+def _reject_slabs(name):
+    """L-BFGS makes its line-search and stopping decisions from rank-local dot products; on slab-decomposed
+    grids the ranks would disagree on the number of evaluations and dead-lock the halo exchange."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
+            and int(os.environ.get("ODIL_SLABS", "1")) != 0:
+        raise NotImplementedError(
+            f"optimizer '{name}' is not available on slab-decomposed (multi-rank) grids; use 'adam' or 'gd'")
+
+
 class LbfgsbOptimizer(Optimizer):
 
     def __init__(self, pgtol=1e-16, m=50, maxls=50, factr=0, dtype=None, mod=None, **kwargs):
@@ -158,6 +169,7 @@ class LbfgsbOptimizer(Optimizer):
     def run(self, x0, loss_grad, epochs=None, callback=None, epoch_start=0, **kwargs):
         from scipy import optimize
 
+        _reject_slabs(self.name)
         self.epoch = epoch_start
         tdtype = x0[0].dtype
         device = x0[0].device
@@ -208,6 +220,7 @@ class LbfgsDeviceOptimizer(Optimizer):
     def run(self, x0, loss_grad, epochs=None, callback=None, epoch_start=0, **kwargs):
         from . import lbfgs
 
+        _reject_slabs(self.name)
         self.epoch = epoch_start
         tdtype, device = x0[0].dtype, x0[0].device
         shapes = [tuple(a.shape) for a in x0]

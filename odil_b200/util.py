@@ -253,6 +253,16 @@ _ENV_KEYS = ("OMP_NUM_THREADS", "CUDA_VISIBLE_DEVICES", "ODIL_WARN", "ODIL_BACKE
              "ODIL_DTYPE")
 
 
+def _is_writer():
+    """False on ranks > 0 of a multi-process (slab) run."""
+    try:
+        import torch.distributed as dist
+
+        return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+    except Exception:
+        return True
+
+
 def get_env_config():
     return {k: os.environ.get(k, "") for k in _ENV_KEYS}
 
@@ -271,10 +281,15 @@ def setup_outdir(args, relpath_args=None):
     config.update(get_env_config())
     config.update(runtime_backend=runtime.backend_name, runtime_dtype=runtime.dtype_name,
                   runtime_jit=runtime.enable_jit, runtime_gpu=runtime.enable_gpu)
-    with open(os.path.join(args.outdir, "args.json"), "w") as f:
-        json.dump(config, f, sort_keys=True, indent=4)
+    if _is_writer():
+        with open(os.path.join(args.outdir, "args.json"), "w") as f:
+            json.dump(config, f, sort_keys=True, indent=4)
     os.chdir(args.outdir)
-    set_log_file(open("train.log", "w"), echo=args.echo)
+    # One process per GPU (slab runs): rank 0 owns args.json, train.log, train.csv and the checkpoints.
+    if _is_writer():
+        set_log_file(open("train.log", "w"), echo=args.echo)
+    else:
+        set_log_file(open(os.devnull, "w"), echo=0)
     for name in relpath_args or ():
         if getattr(args, name):
             setattr(args, name, os.path.relpath(getattr(args, name), start=args.outdir))
@@ -316,7 +331,8 @@ class EpochCallback:
         self.frame = 0
         self.pinfo = None
         self.throughput = 0.0
-        self.history = History(csvpath="train.csv", warmup=1) if args.history_every else None
+        self.history = History(csvpath="train.csv" if _is_writer() else os.devnull, warmup=1) \
+            if args.history_every else None
         self.task_report = self.task_history = self.task_plot = self.task_checkpoint = False
         self.cbinfo = self  # `callback.cbinfo` of the reference
 

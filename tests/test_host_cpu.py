@@ -562,3 +562,53 @@ def test_optimize_newton_glue(monkeypatch):
     assert seen == [(0, 162.0, None), (1, 0.0, {"niter": 1, "solver": "direct"}),
                     (2, 0.0, {"niter": 1, "solver": "direct"})]
     assert np.array_equal(arrays[0], [2.0, 2.0]) and info.epochs == 2
+
+
+# --------------------------------------------------------------------------------------------------
+# Round-2 advisor findings
+# --------------------------------------------------------------------------------------------------
+def test_stop_gradient_merges_frozen_and_live_terms():
+    """mod.stop_gradient(u + ctx.field(k, frozen=True)) must ADD the two coefficients of the same (key, offset)."""
+    from odil_b200.backend import Affine
+
+    domain = odil.Domain(cshape=(8,), dtype=np.float64, multigrid=False, mod=odil.backend.ModB200(device="cpu"))
+
+    u = Affine.symbol("u", (0,), (8,), np.float64, frozen=False, device="cpu")
+    uf = Affine.symbol("u", (0,), (8,), np.float64, frozen=True, device="cpu")
+    e = domain.mod.stop_gradient(u + uf)
+    assert list(e.lin) == [("u", (0,), True)]
+    assert float(e.lin[("u", (0,), True)].dense((1,), torch.float64, "cpu")[0]) == 2.0
+
+
+def test_lower_block_folds_offsets_on_size_one_axes():
+    """roll() along a size-1 axis is the identity: offsets there fold to 0 and merge (the kernels wrap an index
+    with a single conditional add, so an offset of 2 on a size-1 axis must never reach them)."""
+    from odil_b200.backend import Coef
+    from odil_b200.engine import lower_block
+
+    one = torch.ones((1, 1), dtype=torch.float64)
+    offsets, rr, table = lower_block((1, 8), {(2, 0): Coef([one]), (0, 0): Coef([3 * one]), (0, 1): Coef([one]),
+                                              (0, 9): Coef([one])})
+    assert sorted(map(tuple, offsets.tolist())) == [(0, 0), (0, 1)]
+    mine = {tuple(o): table[:, i] for i, o in enumerate(offsets.tolist())}
+    assert np.all(mine[(0, 0)] == 4.0) and np.all(mine[(0, 1)] == 2.0)
+
+
+def test_tracer_reads_are_recorded_and_invalidate_the_lowering():
+    """An affine operator whose weight depends on tracers['epoch'] is re-lowered when the tracer changes
+    (the reference passes tracers as run-time arguments of the jitted function, core.py:1076-1110)."""
+    def op(ctx):
+        k = 0.5 ** (ctx.tracers["epoch"] / 10)
+        return [(ctx.field("u") - 1.0) * k]
+
+    domain = odil.Domain(cshape=(8,), dtype=np.float64, multigrid=False, mod=odil.backend.ModB200(device="cpu"))
+    state = odil.State(fields={"u": odil.Field(torch.zeros(8, dtype=torch.float64))}, initialized=True)
+    problem = odil.Problem(op, domain, tracers={"epoch": 0, "unused": 7})
+    eng = ResidualEngine(problem, state, trace_only=True)
+    assert eng.tracer_view.reads == {"epoch": 0}
+    assert not eng.tracer_view.stale({"epoch": 0, "unused": 8})
+    assert eng.tracer_view.stale({"epoch": 10, "unused": 7})
+    problem.tracers["epoch"] = 10
+    eng2 = ResidualEngine(problem, state, trace_only=True)
+    t0, t1 = eng.outputs[0].blocks[0].spec["table"], eng2.outputs[0].blocks[0].spec["table"]
+    assert np.allclose(t0, 1.0) and np.allclose(t1, 0.5)
