@@ -14,6 +14,12 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    from tests import parity
+
+    parity.dump()
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np

@@ -367,6 +367,65 @@ def gen_wave(odil, wave, out):
                 out[f"{tag}_grad{i}"] = g
 
 
+def load_test_operators():
+    """tests/operators.py of this repository, imported with `odil` bound to the REFERENCE package: its operators are
+    written against the public ODIL API only, so the unmodified reference core.py can run them."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("repo_test_operators", os.path.join(OUT, "..", "operators.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    assert m.odil.__file__.startswith(REF)
+    return m
+
+
+def wave2_setup(odil, ops, cshape, dtype, seed):
+    modn = odil.backend.ModNumpy()
+    domain = odil.Domain(cshape=tuple(cshape), dimnames=("t", "x", "y"), lower=(0, -1, -1), upper=(1, 1, 1),
+                         dtype=dtype, multigrid=False, mod=modn)
+    t1, x1, y1 = domain.points_1d()
+    T, X, Y = np.meshgrid(t1, x1, y1, indexing="ij")
+    lo, hi = domain.lower, domain.upper
+    extra = make_ns(kimp=1.0)
+    extra.xlo = ops.wave2_exact(T[:, 0, :], lo[1], Y[:, 0, :])[0].astype(dtype)
+    extra.xhi = ops.wave2_exact(T[:, 0, :], hi[1], Y[:, 0, :])[0].astype(dtype)
+    extra.ylo = ops.wave2_exact(T[:, :, 0], X[:, :, 0], lo[2])[0].astype(dtype)
+    extra.yhi = ops.wave2_exact(T[:, :, 0], X[:, :, 0], hi[2])[0].astype(dtype)
+    u0, ut0 = ops.wave2_exact(lo[0], X[0], Y[0])
+    extra.init_u, extra.init_ut = u0.astype(dtype), ut0.astype(dtype)
+    terms = [np.random.default_rng(seed).standard_normal(cshape).astype(dtype)]
+    return domain, extra, terms
+
+
+def gen_wave2(odil, out):
+    """BASELINE configs[2]: the (t, x, y) wave operator of tests/operators.py::wave2_operator evaluated by the
+    unmodified reference core.py (Context / field / roll / where): forward under ModNumpy, loss + gradient under
+    the torch shim.  The input field is default_rng(4) N(0,1), as in tests/test_zz_wave2_gpu.py."""
+    ops = load_test_operators()
+    for name, cshape in {"w2_10x8x6": (10, 8, 6), "w2_20x16x24": (20, 16, 24)}.items():
+        for dt, tdt in [(np.float64, torch.float64), (np.float32, torch.float32)]:
+            tag = name + ("_f64" if dt == np.float64 else "_f32")
+            domain, extra, terms = wave2_setup(odil, ops, cshape, dt, seed=4)
+            state = state_from_terms(odil, domain, "u", terms)
+            ctx = odil.core.Context(domain, state, extra=extra, tracers={"epoch": 0})
+            F = np.asarray(ops.wave2_operator(ctx)[0][1])
+            loss, grads, tl, names, values = eval_loss_grad_torch(odil, ops.wave2_operator, domain, extra, terms,
+                                                                  "u", tdt)
+            if dt == np.float64:
+                assert abs(loss - np.mean(F ** 2)) <= 1e-12 * abs(loss)
+            out[tag + "_U"] = terms[0]
+            out[tag + "_F"] = F
+            out[tag + "_loss"] = np.asarray(loss)
+            out[tag + "_grad0"] = grads[0]
+    # L-BFGS-B (SciPy, the reference's optimizer class) from a zero start, m = 20, 60 iterations, fp64
+    domain, extra, terms = wave2_setup(odil, ops, (12, 12, 12), np.float64, seed=4)
+    losses, arrays = run_reference_optimizer(odil, "lbfgsb", ops.wave2_operator, domain, extra,
+                                             [t * 0 for t in terms], torch.float64, 60, lr=None, m=20)
+    out["w2_lbfgsb_12_f64_losses"] = losses
+    if arrays is not None:
+        out["w2_lbfgsb_12_f64_x0"] = arrays[0]
+
+
 def run_reference_optimizer(odil, optname, operator, domain_np, extra_np, terms0, tdtype, epochs, lr, **kw):
     """Runs the reference's own optimizer class (optimizer.py) on the torch-shim loss_grad."""
     import odil.optimizer as ropt
@@ -463,8 +522,12 @@ def main():
         "poisson": lambda o: gen_poisson(odil, poisson, o),
         "wave": lambda o: gen_wave(odil, wave, o),
         "optim": lambda o: gen_optimizers(odil, poisson, wave, o),
+        "wave2": lambda o: gen_wave2(odil, o),
     }
+    only = sys.argv[1:]
     for name, fn in groups.items():
+        if only and name not in only:
+            continue
         out = {}
         fn(out)
         path = os.path.join(OUT, name + ".npz")

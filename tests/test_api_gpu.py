@@ -12,6 +12,7 @@ import torch
 
 import odil
 from tests import operators as ops
+from tests import parity
 
 pytestmark = pytest.mark.gpu
 
@@ -52,18 +53,22 @@ def test_poisson_eval_loss_grad(golden, name, prec):
     terms, grads = golden_terms(g, tag)
     set_terms(problem.domain, state, terms)
     loss, gr, tl, names, norms = problem.eval_loss_grad(state)
-    tol = 1e-11 if prec == "f64" else 2e-4
+    f64 = prec == "f64"
     assert names == [""]
-    assert abs(float(loss) - g[tag + "_loss"]) < tol * abs(g[tag + "_loss"])
-    assert abs(float(norms[0]) - np.sqrt(g[tag + "_loss"])) < tol * np.sqrt(g[tag + "_loss"])
+    parity.check(f"api/poisson/{tag}/loss", abs(float(loss) - g[tag + "_loss"]) / abs(g[tag + "_loss"]),
+                 parity.F64_LOSS if f64 else parity.F32_LOSS)
+    parity.check(f"api/poisson/{tag}/norm", abs(float(norms[0]) - np.sqrt(g[tag + "_loss"])) / np.sqrt(g[tag + "_loss"]),
+                 parity.F64_LOSS if f64 else parity.F32_LOSS)
     assert np.array(loss).dtype == dt
-    for a, b in zip(gr, grads):
+    for i, (a, b) in enumerate(zip(gr, grads)):
         assert tuple(a.shape) == b.shape
-        assert relerr(a.cpu().numpy(), b) < tol
+        parity.check(f"api/poisson/{tag}/grad{i}", relerr(a.cpu().numpy(), b), parity.F64_GRAD if f64 else parity.F32_GRAD)
+        parity.check(f"api/poisson/{tag}/grad{i}_l2", parity.rel_l2(a.cpu().numpy(), b),
+                     parity.F64_GRAD if f64 else parity.F32_GRAD)
     U = np.asarray(problem.domain.field(state, "u"))
-    assert relerr(U, g[tag + "_U"]) < (1e-13 if prec == "f64" else 1e-5)
+    parity.check(f"api/poisson/{tag}/U", relerr(U, g[tag + "_U"]), 1e-13 if f64 else 2e-6)
     F = problem.eval_operator(state)[0][0]
-    assert relerr(np.asarray(F), g[tag + "_F"]) < tol
+    parity.check(f"api/poisson/{tag}/F", relerr(np.asarray(F), g[tag + "_F"]), parity.F64_GRAD if f64 else parity.F32_FIELD)
 
 
 @pytest.mark.parametrize("name,cshape,nlvl", [("w_16x12_L0", (16, 12), 0), ("w_16x8_L2", (16, 8), 2)])
@@ -76,11 +81,12 @@ def test_wave_eval_loss_grad(golden, name, cshape, nlvl, prec):
     terms, grads = golden_terms(g, tag)
     set_terms(problem.domain, state, terms)
     loss, gr, tl, names, norms = problem.eval_loss_grad(state)
-    tol = 1e-10 if prec == "f64" else 3e-4
+    f64 = prec == "f64"
     assert names == ["fu"]
-    assert abs(float(loss) - g[tag + "_loss"]) < tol * abs(g[tag + "_loss"])
-    for a, b in zip(gr, grads):
-        assert relerr(a.cpu().numpy(), b) < tol
+    parity.check(f"api/wave/{tag}/loss", abs(float(loss) - g[tag + "_loss"]) / abs(g[tag + "_loss"]),
+                 1e-10 if f64 else parity.F32_LOSS)
+    for i, (a, b) in enumerate(zip(gr, grads)):
+        parity.check(f"api/wave/{tag}/grad{i}", relerr(a.cpu().numpy(), b), 1e-10 if f64 else parity.F32_GRAD)
 
 
 def run_args(**kw):
@@ -114,10 +120,12 @@ def test_adam_trajectory_api(golden, prec):
     losses = run_optimizer(problem, state, "adam", run_args(epochs=20, lr=0.005))
     # callback rows: epoch_start (initial loss) then one per epoch; reference goldens hold the per-epoch rows
     assert len(losses) == 21 and losses[0] == losses[1]
-    tol = 1e-9 if prec == "f64" else 1e-4
-    assert np.max(np.abs(losses[1:] / g[tag + "_losses"] - 1)) < tol
+    # north star: "loss trajectory matching the reference to 1e-5 relative"
+    parity.check(f"api/adam20/{tag}/losses", np.max(np.abs(losses[1:] / g[tag + "_losses"] - 1)),
+                 1e-9 if prec == "f64" else 1e-5)
     for i, a in enumerate(problem.domain.arrays_from_state(state)):
-        assert relerr(a.cpu().numpy(), g[f"{tag}_x{i}"]) < (1e-8 if prec == "f64" else 2e-3)
+        parity.check(f"api/adam20/{tag}/x{i}", relerr(a.cpu().numpy(), g[f"{tag}_x{i}"]),
+                     1e-8 if prec == "f64" else 2e-3)
 
 
 @pytest.mark.parametrize("case", [((16, 16), 3), ((24, 16, 32), 2), ((256,), 100)])

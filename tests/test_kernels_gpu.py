@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle import odil_oracle as orc
+from tests import parity
 
 pytestmark = pytest.mark.gpu
 
@@ -249,12 +250,13 @@ def test_poisson_golden(golden, name, prec):
     offsets, table, rr = orc.poisson_plan(ndim, steps)
     plan = native.StencilPlan(cshape, td, offsets, rr, table)
     loss, gr, U = device_eval_loss_grad(terms, "c" * ndim, plan, dev(-g[tag + "_rhs"]), td)
-    tol = 1e-11 if prec == "f64" else 2e-4
-    assert relerr(U, g[tag + "_U"]) < (1e-13 if prec == "f64" else 1e-5)
-    assert abs(loss - g[tag + "_loss"]) < tol * abs(g[tag + "_loss"])
-    for a, b in zip(gr, grads):
+    f64 = prec == "f64"
+    parity.check(f"kernels/poisson/{tag}/U", relerr(U, g[tag + "_U"]), 1e-13 if f64 else 2e-6)
+    parity.check(f"kernels/poisson/{tag}/loss", abs(loss - g[tag + "_loss"]) / abs(g[tag + "_loss"]),
+                 parity.F64_LOSS if f64 else parity.F32_LOSS)
+    for i, (a, b) in enumerate(zip(gr, grads)):
         assert a.shape == b.shape
-        assert relerr(a, b) < tol
+        parity.check(f"kernels/poisson/{tag}/grad{i}", relerr(a, b), parity.F64_GRAD if f64 else parity.F32_GRAD)
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
@@ -315,8 +317,8 @@ def test_adam_trajectory_golden(golden):
             losses.append(ss.item() / 256)
             alpha, omb1, omb2 = orc.adam_scalars(0.005, 0.9, 0.999, t, nd)
             native.adam_step(x, m, v, grads, alpha, omb1, omb2, 1e-7)
-        tol = 1e-9 if prec == "f64" else 1e-4
-        assert np.max(np.abs(np.array(losses) / g[tag + "_losses"] - 1)) < tol
+        parity.check(f"kernels/adam20/{tag}/losses", np.max(np.abs(np.array(losses) / g[tag + "_losses"] - 1)),
+                     1e-9 if prec == "f64" else 1e-5)
         for i in range(3):
             assert relerr(x[i].cpu().numpy(), g[f"{tag}_x{i}"]) < (1e-8 if prec == "f64" else 2e-3)
 

@@ -136,6 +136,31 @@ def test_wave_loss_grad(golden, name, cshape):
         assert relerr(a, b) < 1e-10
 
 
+@pytest.mark.parametrize("cshape", [(10, 8, 6), (20, 16, 24)])
+def test_wave2_oracle_matches_reference_golden(golden, cshape):
+    """BASELINE configs[2]: the oracle's directly written (t, x, y) wave residual equals what the unmodified
+    reference core.py computes for tests/operators.py::wave2_operator (tests/golden/make_goldens.py::gen_wave2)."""
+    import argparse
+
+    g = golden("wave2")
+    tag = "w2_{}_f64".format("x".join(map(str, cshape)))
+    U = g[tag + "_U"]
+    nt, nx, ny = cshape
+    # boundary data exactly as tests/operators.py::make_wave2 builds it (NumPy only)
+    from tests import operators as ops
+
+    t1 = (np.arange(nt) + 0.5) / nt
+    x1 = -1 + (np.arange(nx) + 0.5) * 2 / nx
+    y1 = -1 + (np.arange(ny) + 0.5) * 2 / ny
+    T, X, Y = np.meshgrid(t1, x1, y1, indexing="ij")
+    bnd = dict(xlo=ops.wave2_exact(T[:, 0, :], -1.0, Y[:, 0, :])[0], xhi=ops.wave2_exact(T[:, 0, :], 1.0, Y[:, 0, :])[0],
+               ylo=ops.wave2_exact(T[:, :, 0], X[:, :, 0], -1.0)[0], yhi=ops.wave2_exact(T[:, :, 0], X[:, :, 0], 1.0)[0])
+    u0, ut0 = ops.wave2_exact(0.0, X[0], Y[0])
+    F = orc.wave2_residual(U, 1.0 / nt, 2.0 / nx, 2.0 / ny, bnd, u0, ut0, 1.0)
+    assert np.max(np.abs(F - g[tag + "_F"])) < 1e-10 * np.max(np.abs(F))
+    assert abs(np.mean(F ** 2) - g[tag + "_loss"]) < 1e-11 * g[tag + "_loss"]
+
+
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_adam_trajectory(golden, prec):
     g = golden("optim")

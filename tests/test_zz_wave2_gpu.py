@@ -1,8 +1,9 @@
 """
 BASELINE configs[2] as a parity case: the wave operator in two space dimensions on a (t, x, y) grid through the
 public API (7 offsets, 45 region classes; not a star, so the sweep runs in the general per-cell stencil kernel).
-Checked against the oracle's directly written residual (oracle/odil_oracle.py::wave2_residual) and the adjoint of
-the traced plan; the device L-BFGS drives the loss down from a zero start.  (File name sorts last on purpose: this
+Pinned to tests/golden/wave2.npz: loss, residual field and gradient produced by the UNMODIFIED reference core.py
+running this very operator (tests/golden/make_goldens.py::gen_wave2), plus the oracle's directly written residual
+and the adjoint of the traced plan; the device L-BFGS follows the reference's SciPy L-BFGS-B trajectory.  (File name sorts last on purpose: this
 case was added after the round's last GPU session.)
 """
 import numpy as np
@@ -11,6 +12,7 @@ import torch
 
 from oracle import odil_oracle as orc
 from tests import operators as ops
+from tests import parity
 from tests.test_api_gpu import relerr, run_args, run_optimizer, set_terms
 
 pytestmark = pytest.mark.gpu
@@ -18,13 +20,24 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("cshape", [(10, 8, 6), (20, 16, 24)])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_wave2_eval_loss_grad(cshape, prec):
+def test_wave2_eval_loss_grad(cshape, prec, golden):
     dt = np.float64 if prec == "f64" else np.float32
     problem, state = ops.make_wave2(cshape, dt)
     e = problem.extra
     U = np.random.default_rng(4).standard_normal(cshape).astype(dt)
     set_terms(problem.domain, state, [U])
     loss, grads, terms, names, norms = problem.eval_loss_grad(state)
+    # reference-generated golden (unmodified reference core.py + this operator)
+    g = golden("wave2")
+    tag = "w2_{}_{}".format("x".join(map(str, cshape)), prec)
+    assert np.array_equal(g[tag + "_U"], U)
+    e_loss = abs(float(loss) - float(g[tag + "_loss"])) / float(g[tag + "_loss"])
+    e_grad = relerr(grads[0].cpu().numpy(), g[tag + "_grad0"])
+    e_F = relerr(problem.eval_operator(state)[0][0].numpy(), g[tag + "_F"])
+    f64 = prec == "f64"
+    parity.check(f"api/wave2/{tag}/loss", e_loss, 1e-11 if f64 else parity.F32_LOSS)
+    parity.check(f"api/wave2/{tag}/grad", e_grad, 1e-11 if f64 else parity.F32_GRAD)
+    parity.check(f"api/wave2/{tag}/F", e_F, 1e-11 if f64 else parity.F32_FIELD)
     nt, nx, ny = cshape
     bnd = {k: np.asarray(getattr(e, k), dtype=np.float64) for k in ("xlo", "xhi", "ylo", "yhi")}
     F_ref = orc.wave2_residual(U.astype(np.float64), 1.0 / nt, 2.0 / nx, 2.0 / ny, bnd,
@@ -52,10 +65,18 @@ def test_wave2_eval_loss_grad(cshape, prec):
     assert relerr(grads[0].cpu().numpy(), g_ref) < tol
 
 
-def test_wave2_lbfgs_converges():
+def test_wave2_lbfgs_converges(golden):
     problem, state = ops.make_wave2((12, 12, 12), np.float64)
     losses = run_optimizer(problem, state, "lbfgsb", run_args(epochs=60, bfgs_m=20))
     assert losses is not None and len(losses) >= 30
+    # the reference's LbfgsbOptimizer (SciPy) on the same operator from the same zero start: first row of the
+    # callback is the initial loss here, the loss after iteration 1 there
+    ref = golden("wave2")["w2_lbfgsb_12_f64_losses"]
+    mine = np.asarray(losses[1:1 + len(ref)], dtype=np.float64)
+    n = min(len(mine), 10)
+    err = np.max(np.abs(mine[:n] - ref[:n]) / ref[:n])
+    parity.check("api/wave2/lbfgs_first10_losses", err, 1e-6)
+    assert abs(mine[len(ref) - 2] - ref[-2]) < 0.5 * ref[-2]
     # SciPy's L-BFGS-B on the oracle's plan goes 65.0 -> 0.17 in 60 iterations (m = 20), rms error 0.106
     assert losses[-1] < 2e-2 * losses[0]
     u = problem.domain.arrays_from_state(state)[0].cpu().numpy()
