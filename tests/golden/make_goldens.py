@@ -16,7 +16,6 @@ The .npz files it writes are committed; tests never import /root/reference.
 import argparse
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -26,154 +25,19 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 
 # ----------------------------------------------------------------------------------------------
-# Environment: import the reference package, stub what is absent in this image.
+# The reference is imported and driven through oracle/ref_shim.py (stubs for what the image lacks + the torch `mod`
+# shim); the same module drives the reference arm of bench.py.
 # ----------------------------------------------------------------------------------------------
-def _stub_module(name, **attrs):
-    m = types.ModuleType(name)
-    for k, v in attrs.items():
-        setattr(m, k, v)
-    sys.modules[name] = m
-    return m
+sys.path.insert(0, os.path.abspath(os.path.join(OUT, "..", "..")))
+from oracle import ref_shim  # noqa: E402
+
+TorchMod = ref_shim.TorchMod
 
 
 def import_reference():
-    # The repo ships its own `odil` package; make sure the reference wins in this process.
-    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != os.path.abspath(os.path.join(OUT, "..", ".."))]
-    sys.path.insert(0, os.path.join(REF, "src"))
-    mpl = _stub_module("matplotlib", use=lambda *a, **k: None)
-    mpl.style = types.SimpleNamespace(use=lambda *a, **k: None)
-    _stub_module("matplotlib.pyplot")
-    mpl.pyplot = sys.modules["matplotlib.pyplot"]
-    import odil  # noqa: F401
-
-    assert odil.__file__.startswith(REF), odil.__file__
-    _stub_module("odil.plotutil")
-    # examples do `from odil.runtime import tf`
-    fake_tf = types.SimpleNamespace(function=lambda f=None, **k: (f if f is not None else (lambda g: g)))
-    _stub_module("odil.runtime", tf=fake_tf, jax=None, mod=None, dtype=np.dtype("float64"), enable_jit=False,
-                 backend_name="numpy", dtype_name="float64", enable_gpu=False)
-    odil.runtime = sys.modules["odil.runtime"]
-    sys.path.insert(0, os.path.join(REF, "examples", "poisson"))
-    sys.path.insert(0, os.path.join(REF, "examples", "wave"))
-    import poisson
-    import wave as _w  # noqa: F401  (stdlib wave would shadow; load by path instead)
-    import importlib.util
-
-    spec = importlib.util.spec_from_file_location("odil_wave_example", os.path.join(REF, "examples", "wave", "wave.py"))
-    wave = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(wave)
-    return odil, poisson, wave
-
-
-# ----------------------------------------------------------------------------------------------
-# torch `mod` shim (own code): only the callables the reference core.py / operators touch.
-# ----------------------------------------------------------------------------------------------
-class TorchMod:
-    jax = None
-    tf = None
-    modsp = None
-
-    def __init__(self, dtype=torch.float64):
-        self.tdtype = dtype
-        self.float32 = np.float32
-        self.float64 = np.float64
-        self.random = types.SimpleNamespace(set_seed=lambda s: torch.manual_seed(s))
-
-    @staticmethod
-    def _tt(dtype):
-        if isinstance(dtype, torch.dtype):
-            return dtype
-        return {np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64,
-                np.dtype("int64"): torch.int64, np.dtype("int32"): torch.int32}[np.dtype(dtype)]
-
-    def cast(self, x, dtype):
-        tt = self._tt(dtype)
-        if torch.is_tensor(x):
-            return x.to(tt)
-        # Python/NumPy scalars must be rounded ONCE to the target dtype (as jnp.array(x, dtype) does),
-        # not via torch's float32 default.
-        return torch.as_tensor(np.asarray(x), dtype=tt) if not isinstance(x, (int, float)) else torch.tensor(x, dtype=tt)
-
-    array = staticmethod(lambda x, dtype=None: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x))
-    constant = staticmethod(lambda x: torch.as_tensor(x))
-
-    def variable(self, x, dtype=None):
-        t = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x)
-        return t.to(self._tt(dtype)) if dtype is not None else t
-
-    def zeros(self, shape, dtype=None):
-        return torch.zeros(tuple(int(s) for s in np.atleast_1d(shape)), dtype=self._tt(dtype or np.float64))
-
-    zeros_like = staticmethod(torch.zeros_like)
-    ones_like = staticmethod(torch.ones_like)
-    copy = staticmethod(lambda x: x.clone())
-    is_tensor = staticmethod(torch.is_tensor)
-    stop_gradient = staticmethod(lambda x: x.detach())
-    mean = staticmethod(torch.mean)
-    sum = staticmethod(torch.sum)
-    square = staticmethod(torch.square)
-    sqrt = staticmethod(lambda x: torch.sqrt(torch.as_tensor(x)))
-    exp = staticmethod(torch.exp)
-    tanh = staticmethod(torch.tanh)
-    abs = staticmethod(torch.abs)
-    max = staticmethod(torch.max)
-    stack = staticmethod(lambda xs, axis=0: torch.stack(list(xs), dim=axis))
-    reshape = staticmethod(lambda x, shape: torch.reshape(torch.as_tensor(x), tuple(int(s) for s in shape)))
-    flatten = staticmethod(lambda x: torch.reshape(x, (-1,)))
-    concatenate = staticmethod(lambda xs, axis=0: torch.cat(list(xs), dim=axis))
-    transpose = staticmethod(lambda x, perm: x.permute(*[int(p) for p in perm]))
-    matmul = staticmethod(torch.matmul)
-
-    @staticmethod
-    def where(c, a, b):
-        c = torch.as_tensor(c)
-        ref = a if torch.is_tensor(a) else b
-        if not torch.is_tensor(a):
-            a = torch.as_tensor(a, dtype=ref.dtype)
-        if not torch.is_tensor(b):
-            b = torch.as_tensor(b, dtype=ref.dtype)
-        return torch.where(c, a, b)
-
-    @staticmethod
-    def roll(x, shift, axis=None):
-        x = torch.as_tensor(x)
-        if np.ndim(shift) == 0:
-            return torch.roll(x, int(shift), int(axis))
-        return torch.roll(x, [int(s) for s in shift], [int(a) for a in axis])
-
-    @staticmethod
-    def meshgrid(*xx, indexing="ij"):
-        return torch.meshgrid(*[torch.as_tensor(x) for x in xx], indexing=indexing)
-
-    @staticmethod
-    def pad(x, pad_width, mode):
-        # numpy.pad semantics for modes used by core.py: reflect, symmetric, constant(0).
-        for ax, (lo, hi) in enumerate(pad_width):
-            if lo == 0 and hi == 0:
-                continue
-            n = x.shape[ax]
-            if mode == "constant":
-                shp = list(x.shape)
-                parts = []
-                if lo:
-                    shp[ax] = lo
-                    parts.append(torch.zeros(shp, dtype=x.dtype))
-                parts.append(x)
-                if hi:
-                    shp[ax] = hi
-                    parts.append(torch.zeros(shp, dtype=x.dtype))
-                x = torch.cat(parts, dim=ax)
-                continue
-            assert lo <= 1 and hi <= 1
-            if mode == "reflect":
-                left, right = [1], [n - 2]
-            elif mode == "symmetric":
-                left, right = [0], [n - 1]
-            else:
-                raise ValueError(mode)
-            idx = (left if lo else []) + list(range(n)) + (right if hi else [])
-            x = torch.index_select(x, ax, torch.as_tensor(idx))
-        return x
+    odil, mods, origin = ref_shim.import_reference(("poisson", "wave"))
+    assert origin == REF, origin   # goldens come from /root/reference itself, not from a staged copy
+    return odil, mods["poisson"], mods["wave"]
 
 
 def numpy_conv_valid(input, filters, strides, padding):

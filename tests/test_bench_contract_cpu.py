@@ -18,7 +18,7 @@ def run_bench(*argv):
 
 
 def test_reference_arm_json_line():
-    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu_size", "32")
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", "--size", "32", "--levels", "3")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -26,11 +26,11 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["unit"] == "Mcells/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["vs_baseline"] is None
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["scaling"] == "weak"
-    assert "3D Poisson" in d["metric"] and "multigrid" in d["metric"] and "workload" in d["config"]
+    assert "Mcells/s" in d["metric"] and "3D Poisson" in d["config"]["workload"]
     assert d["value"] > 0 and abs(d["ms_per_step"] - 32 ** 3 / d["value"] / 1e3) < 1e-6 * d["ms_per_step"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == "Mcells/s"
-    assert "32^3" in cb["sample"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == "Mcells/s"
+    assert "32x32x32" in cb["sample"] and "UNMODIFIED reference" in cb["sample"] and cb["same_grid_as_workload"]
     e = d["e2e"]
     assert e == {"value": d["value"], "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
