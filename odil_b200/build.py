@@ -42,12 +42,16 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = find_nvcc()
+    # ODIL_B200_LEGACY=1 also compiles the superseded generations of the fused sweep (k_star7, k_star_tma, k_star3d:
+    # 36 kernel instantiations kept as measured history, selectable with plan_tune); off by default.
+    legacy = ["-DODIL_B200_LEGACY"] if os.environ.get("ODIL_B200_LEGACY", "0") not in ("", "0") else []
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + legacy + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for cmd, p in procs:

@@ -303,6 +303,7 @@ __device__ __noinline__ Pack<T, VW> s7_slow_adj(const T* __restrict__ tab, S7Geo
     return g;
 }
 
+#ifdef ODIL_B200_LEGACY
 // State of one strip-warp thread over the sweep (all members resolve to registers: every index is a
 // compile-time constant once step<PH> / lean<PH> are inlined).
 template <typename T, int VW, int TY, bool XU>
@@ -759,5 +760,7 @@ __global__ void __launch_bounds__(Star7Cfg<T, VW, TY>::NT)
     const double sum = block_sum(acc2, red);
     if (tid == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sum;
 }
+
+#endif  // ODIL_B200_LEGACY
 
 }  // namespace odil

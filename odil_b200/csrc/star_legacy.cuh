@@ -10,6 +10,7 @@ namespace odil {
 // ------------------------------------------------------------------------------------------------
 // Tiled star kernel
 // ------------------------------------------------------------------------------------------------
+#ifdef ODIL_B200_LEGACY
 template <typename T>
 struct StarParams {
     const T* U;
@@ -205,6 +206,8 @@ __global__ void __launch_bounds__(NT) k_star3d(StarParams<T> p) {
 // lookup on the few threads/planes that touch them -- no separate shell pass.
 // Requires N2 % 4 == 0 (16-byte column groups).
 // ------------------------------------------------------------------------------------------------
+#endif  // ODIL_B200_LEGACY
+
 template <typename T>
 struct StarV3Params {
     const T* U;
@@ -529,6 +532,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
+#ifdef ODIL_B200_LEGACY
 template <typename T>
 struct StarTmaParams {
     T* G;
@@ -736,5 +740,7 @@ __global__ void __launch_bounds__((TX / 4 + 2) * (TY + 2), ((TX / 4 + 2) * (TY +
     const double sum = block_sum(acc2, red);
     if (tid == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sum;
 }
+
+#endif  // ODIL_B200_LEGACY
 
 }  // namespace odil

@@ -108,8 +108,8 @@ struct odil_b200_plan {
 };
 
 #include "generic.cuh"
-#include "star_legacy.cuh"
-#include "star7.cuh"
+#include "star_legacy.cuh"   // k_star_v3 always; k_star3d / k_star_tma only with ODIL_B200_LEGACY
+#include "star7.cuh"         // helpers shared with star8.cuh; the k_star7 kernel itself only with ODIL_B200_LEGACY
 #include "star8.cuh"
 #include "tile2d.cuh"
 #include "tile3d.cuh"
@@ -249,6 +249,7 @@ static int launch_generic(const odil_b200_plan* plan, const GenParams& p, const 
     return 0;
 }
 
+#ifdef ODIL_B200_LEGACY
 template <typename T, int TY, int TX, int NT>
 static int launch_star_cfg(const StarParams<T>& sp, dim3 grid, bool vec, cudaStream_t st) {
     const size_t smem = (size_t)4 * (TY + 2) * (TX + 8) * sizeof(T);
@@ -269,6 +270,8 @@ static int launch_star_cfg(const StarParams<T>& sp, dim3 grid, bool vec, cudaStr
     ODIL_LAUNCHED();
     return 0;
 }
+
+#endif  // ODIL_B200_LEGACY
 
 template <typename T, int TY, int TX>
 static int launch_star_v3(const StarV3Params<T>& sp, dim3 grid, cudaStream_t st) {
@@ -334,6 +337,7 @@ static int make_plane_map(CUtensorMap* map, const T* base, int64_t nplanes, int 
     return 0;
 }
 
+#ifdef ODIL_B200_LEGACY
 template <typename T, int TY, int TX>
 static int launch_star_tma(const CUtensorMap& tmU, const CUtensorMap& tmC, const StarTmaParams<T>& sp, dim3 grid,
                            cudaStream_t st) {
@@ -420,6 +424,8 @@ static int launch_star7(const odil_b200_plan* plan, const odil_b200_slab* slab, 
     *nparts = gx * gy * gz;
     return 0;
 }
+
+#endif  // ODIL_B200_LEGACY
 
 // Work list of k_star8: tiles of up to NR rows x TX columns times z-chunks, chosen so that the CTAs fill the
 // SMs in whole waves with equal work.  cost ~ waves * (planes per chunk + lead-in) * (rows per CTA + ring rows).
@@ -700,6 +706,9 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     const bool v3 = tiled && plan->use_v3 && (n2 % 4 == 0) && ((uintptr_t)U % 16 == 0) && ((uintptr_t)G % 16 == 0) &&
                     ((uintptr_t)c % 16 == 0) && ((uintptr_t)Fout % 16 == 0);
     bool tma = v3 && plan->use_tma && plan->wrap_free && get_encode_tiled() != nullptr;
+#ifndef ODIL_B200_LEGACY
+    tma = false;
+#endif
     if (tma) {  // the three plane rings must fit the 227 KB of shared memory of one SM
         static const int tys[4] = {16, 8, 12, 26};
         const size_t need = 128 + (size_t)10 * (((tys[(plan->variant < 0 ? 1 : plan->variant) & 3] + 4) * (128 + 8) + 31) / 32 * 32) * sizeof(T) + 512 * sizeof(T) + 128;
@@ -720,6 +729,7 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         }
 #undef ODIL_S8
         if (rc) return rc;
+#ifdef ODIL_B200_LEGACY
     } else if (star7) {
         int rc;
 #define ODIL_S7(TY_, XU_) launch_star7<T, VW7, TY_, XU_>(plan, slab, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)
@@ -799,6 +809,7 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         }
         if (rc) return rc;
         nparts = gx * gy * gz;
+#endif  // ODIL_B200_LEGACY
     } else if (v3) {
         StarV3Params<T> sp;
         sp.U = io.U;
@@ -856,6 +867,7 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         }
         if (rc) return rc;
         nparts = gx * gy * gz;
+#ifdef ODIL_B200_LEGACY
     } else if (tiled) {
         StarParams<T> sp;
         sp.U = io.U;
@@ -933,6 +945,7 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
         if (rc) return rc;
         ODIL_REQUIRE(nparts + nb <= kPartialCapacity, "partials workspace overflow");
         nparts += nb;
+#endif  // ODIL_B200_LEGACY
     } else {
         BoxList all;
         whole_box(plan, slab, all);
@@ -1204,6 +1217,11 @@ int odil_b200_stencil_plan_tune(odil_b200_plan* plan, int zchunk, int variant) {
                      (variant >= 60 && variant <= 62) || variant == 70 || variant == 71 || variant == 80 ||
                      variant == 81 || variant == -1,
                  "variant=%d unknown", variant);
+#ifndef ODIL_B200_LEGACY
+    ODIL_REQUIRE(!((variant >= 0 && variant <= 3) || (variant >= 10 && variant <= 13) || (variant >= 30 && variant <= 42)),
+                 "variant=%d selects a superseded kernel generation (k_star_tma / k_star3d / k_star7): rebuild with "
+                 "ODIL_B200_LEGACY=1", variant);
+#endif
     plan->zchunk = zchunk;
     // 70 / 71: 2-D tile kernel on / off with the default 3-D choice; any explicit star variant also turns it off
     // (so the star kernels stay reachable on 2-D grids)

@@ -176,6 +176,17 @@ def test_star_plans_use_tiled_kernel():
     assert kinds == [0, 0, 0, 1, 1, 1, 1, 1, 0]
 
 
+def tune_or_skip(plan, zchunk, variant):
+    """The superseded generations of the sweep (k_star_tma 0-3, k_star3d 10-13, k_star7 30-42) are only compiled with
+    ODIL_B200_LEGACY=1; the default library rejects those variants."""
+    try:
+        plan.tune(zchunk=zchunk, variant=variant)
+    except native.NativeError as e:
+        if "ODIL_B200_LEGACY" in str(e):
+            pytest.skip("library built without ODIL_B200_LEGACY")
+        raise
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 10, 11, 12, 13, 20, 21, 22, 23])
 @pytest.mark.parametrize("zchunk", [0, 1, 5, 64])
 @pytest.mark.parametrize("kind", ["random", "dirichlet"])
@@ -193,7 +204,7 @@ def test_star_variants(variant, zchunk, kind):
     U = rng.standard_normal(shape)
     c = rng.standard_normal(shape)
     plan = native.StencilPlan(shape, torch.float64, offsets, rr, table)
-    plan.tune(zchunk=zchunk, variant=variant)
+    tune_or_skip(plan, zchunk, variant)
     F_ref = orc.stencil_forward(U, offsets, table.reshape(3, 3, 3, 7), rr, c)
     g_ref = orc.stencil_adjoint(F_ref, offsets, table.reshape(3, 3, 3, 7), rr, 0.5)
     G = torch.empty(shape, dtype=torch.float64, device="cuda")
@@ -443,7 +454,7 @@ def test_star8_variants(variant, zchunk, shape):
         plan = native.StencilPlan(shape, td, offsets, rr, table)
         assert plan.kind == 1
         if variant >= 0:
-            plan.tune(zchunk=zchunk, variant=variant)
+            tune_or_skip(plan, zchunk, variant)
         elif zchunk:
             plan.tune(zchunk=zchunk, variant=-1)
         F_ref = orc.stencil_forward(U.astype(np.float64), offsets, table.reshape(tshape), rr, c.astype(np.float64))
