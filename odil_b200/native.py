@@ -158,8 +158,19 @@ def _plane_ptr(t, halo):
     return p
 
 
+_replayed = 0
+
+
+def note_replayed_launches(n):
+    """Kernels executed by a CUDA-graph replay do not pass through the library's launchers; whoever replays a
+    captured epoch reports how many of this library's kernel nodes the graph holds."""
+    global _replayed
+    _replayed += int(n)
+
+
 def launch_count():
-    return int(load().odil_b200_launch_count())
+    """Kernels of this library launched in this process: direct launches + kernel nodes of replayed graphs."""
+    return int(load().odil_b200_launch_count()) + _replayed
 
 
 class StencilPlan:

@@ -107,11 +107,13 @@ class AdamNativeOptimizer(Optimizer):
         _, omb1, omb2 = adam_scalars(lr, beta_1, beta_2, 1, dtype)
         held = list(x)  # the tensors whose addresses the graph holds
         g = torch.cuda.CUDAGraph()
+        n_before = native.launch_count()
         with torch.cuda.graph(g):
             torch.index_select(table, 0, step, out=alpha_dev)
             step.add_(1)
             loss, grads, pinfo = loss_grad(held)
             native.adam_step_dev(held, m, v, grads, alpha_dev, omb1, omb2, eps)
+        nodes = native.launch_count() - n_before  # library kernels captured into one replay
         fetch = getattr(loss, "_fetch", None)
         self._graph = g  # owns the memory pool of grads / sums that pinfo still points into after run()
         for epoch in range(first, last + 1):
@@ -121,6 +123,7 @@ class AdamNativeOptimizer(Optimizer):
                     held[i].copy_(x[i])
                     x[i] = held[i]
             g.replay()
+            native.note_replayed_launches(nodes)
             if fetch is not None:
                 fetch.rearm()
             if epoch > 0 and callback is not None:

@@ -6,16 +6,18 @@ tests can be justified by what the kernels actually achieve (DESIGN.md section 5
 
 fp32 bars: the reference's own fp32 run differs from its fp64 run by 0.5e-7 .. 3e-7 (loss, relative) and
 0.4e-7 .. 3e-7 (gradient, relative to max|g|) on the golden cases (tests/golden/*.npz hold both precisions of the
-same inputs), i.e. a few fp32 ulps.  The bars below allow one order of magnitude above that spread.
+same inputs), i.e. a few fp32 ulps.  Measured on B200 (profiles/r02_parity_errors_call1.json): the kernels are within
+4.3e-7 of the reference's fp32 gradients and 1.2e-7 of its fp32 losses on every golden case, i.e. inside the
+reference's own spread.  The bars below are ~5x the measured worst case.
 """
 import json
 import os
 
 import numpy as np
 
-F32_LOSS = 2e-6      # relative error of the loss
-F32_GRAD = 5e-6      # max |g - g_ref| / max |g_ref|
-F32_FIELD = 5e-6     # same measure for residual fields / synthesised U
+F32_LOSS = 1e-6      # relative error of the loss
+F32_GRAD = 2e-6      # max |g - g_ref| / max |g_ref|
+F32_FIELD = 2e-6     # same measure for residual fields / synthesised U
 F64_LOSS = 1e-11
 F64_GRAD = 1e-11
 

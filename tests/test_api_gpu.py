@@ -122,10 +122,10 @@ def test_adam_trajectory_api(golden, prec):
     assert len(losses) == 21 and losses[0] == losses[1]
     # north star: "loss trajectory matching the reference to 1e-5 relative"
     parity.check(f"api/adam20/{tag}/losses", np.max(np.abs(losses[1:] / g[tag + "_losses"] - 1)),
-                 1e-9 if prec == "f64" else 1e-5)
+                 1e-9 if prec == "f64" else 2e-6)
     for i, a in enumerate(problem.domain.arrays_from_state(state)):
         parity.check(f"api/adam20/{tag}/x{i}", relerr(a.cpu().numpy(), g[f"{tag}_x{i}"]),
-                     1e-8 if prec == "f64" else 2e-3)
+                     1e-8 if prec == "f64" else 5e-6)
 
 
 @pytest.mark.parametrize("case", [((16, 16), 3), ((24, 16, 32), 2), ((256,), 100)])

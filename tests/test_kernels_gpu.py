@@ -329,9 +329,9 @@ def test_adam_trajectory_golden(golden):
             alpha, omb1, omb2 = orc.adam_scalars(0.005, 0.9, 0.999, t, nd)
             native.adam_step(x, m, v, grads, alpha, omb1, omb2, 1e-7)
         parity.check(f"kernels/adam20/{tag}/losses", np.max(np.abs(np.array(losses) / g[tag + "_losses"] - 1)),
-                     1e-9 if prec == "f64" else 1e-5)
+                     1e-9 if prec == "f64" else 2e-6)
         for i in range(3):
-            assert relerr(x[i].cpu().numpy(), g[f"{tag}_x{i}"]) < (1e-8 if prec == "f64" else 2e-3)
+            assert relerr(x[i].cpu().numpy(), g[f"{tag}_x{i}"]) < (1e-8 if prec == "f64" else 5e-6)
 
 
 def test_reductions():
