@@ -192,6 +192,28 @@ int odil_b200_multi_dot(const void* V, int64_t ld, int k, const void* g, int64_t
 int odil_b200_multi_axpy(const void* V, int64_t ld, int k, const double* coef, double a0, const void* g, void* d,
                          int64_t count, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Run-time specialised kernels for operators that are not affine stencils.
+ *
+ * Replaces: the reference's per-operator XLA program -- `jax.jit(value_and_grad(eval_loss))` (core.py:1100-1107),
+ * `tf.function(jit_compile=True)` (core.py:1069-1071), the per-(key, shift) Jacobian diagonals of
+ * `_eval_operator_grad_tf` (core.py:1313-1361).  The host tracer (odil_b200/graph.py, codegen.py) writes CUDA C for
+ * the traced operator (residuals, loss partial sums, reverse-mode adjoint, Jacobian products); these entry points
+ * compile it with NVRTC to an sm_100a cubin and launch it.
+ *
+ *   jit_compile   source -> module (no device needed); jit_log() returns the compiler log of the calling thread
+ *   jit_cubin     the compiled image (inspection with cuobjdump, caching)
+ *   jit_kernel    handle of the `extern "C" __global__` function `name` (loads the image on first use)
+ *   jit_launch    1-D launch; the kernel's single by-value struct parameter is copied from params[0..nbytes)
+ * ------------------------------------------------------------------------------------------- */
+int odil_b200_jit_compile(const char* source, const char* const* options, int noptions, void** module_out);
+const char* odil_b200_jit_log(void);
+int odil_b200_jit_cubin(void* module, const void** data, uint64_t* size);
+int odil_b200_jit_kernel(void* module, const char* name, int max_dynamic_smem, void** kernel_out);
+int odil_b200_jit_launch(void* kernel, uint32_t grid, uint32_t block, uint32_t smem, const void* params, uint64_t nbytes,
+                         void* stream);
+int odil_b200_jit_destroy(void* module);
+
 #ifdef __cplusplus
 }
 #endif

@@ -207,6 +207,8 @@ def as_known(x, like=None):
     """Wraps scalars / numpy / torch as Known. Python floats adopt the dtype of `like` (weak typing)."""
     if isinstance(x, Known):
         return x
+    if isinstance(x, graph.Expr):
+        raise graph.GraphError("expected a value independent of the unknowns, got a traced expression")
     if isinstance(x, Affine):
         raise NonAffineError("expected a value independent of the unknown fields")
     dtype = None
@@ -372,14 +374,23 @@ def _affine_binary(op, a, b):
     raise NonAffineError(f"'{op}' on an expression of the unknown fields (data-dependent masks are not affine)")
 
 
+def _is_graph(*xs):
+    """True if any operand is a node of the general expression graph (odil_b200.graph)."""
+    return any(isinstance(x, graph.Expr) for x in xs)
+
+
 def _binary(op, a, b):
+    if _is_graph(a, b):
+        return graph.g_binary(op, a, b)
     if isinstance(a, Affine) or isinstance(b, Affine):
         return _affine_binary(op, a, b)
     return _known_binary(op, a, b)
 
 
-def _unary_known(fn):
+def _unary_known(fn, name=None):
     def f(x, *args, **kw):
+        if _is_graph(x):
+            return graph.g_unary(name or fn.__name__, x)
         if isinstance(x, Affine):
             raise NonAffineError(f"{fn.__name__} of an expression of the unknown fields")
         x = as_known(x)
@@ -411,7 +422,7 @@ class ModB200(ModBase):
         for name, fn in [("abs", torch.abs), ("cos", torch.cos), ("sin", torch.sin), ("exp", torch.exp),
                          ("sqrt", torch.sqrt), ("square", torch.square), ("log", torch.log), ("tanh", torch.tanh),
                          ("sigmoid", torch.sigmoid), ("floor", torch.floor), ("relu", torch.relu)]:
-            setattr(self, name, _unary_known(fn))
+            setattr(self, name, _unary_known(fn, name))
 
     # -- creation -------------------------------------------------------------------------------
     def _set_seed(self, seed):
@@ -426,6 +437,8 @@ class ModB200(ModBase):
         return Known((mean + stddev * u).to(torch_dtype(dtype)).to(self.device))
 
     def cast(self, x, dtype):
+        if _is_graph(x):
+            return graph.g_cast(x, dtype)
         if isinstance(x, Affine):
             if np.dtype(numpy_dtype(dtype)) == x.dtype:
                 return x
@@ -467,11 +480,15 @@ class ModB200(ModBase):
         return self.ones(shape, dtype or np.float32) * value
 
     def zeros_like(self, x):
+        if _is_graph(x):
+            return self.zeros(x.shape, x.dtype if x.kind == "f" else np.float64)
         if torch.is_tensor(x):
             return torch.zeros_like(x)
         return self.zeros(x.shape, x.dtype)
 
     def ones_like(self, x):
+        if _is_graph(x):
+            return self.ones(x.shape, x.dtype if x.kind == "f" else np.float64)
         if torch.is_tensor(x):
             return torch.ones_like(x)
         return self.ones(x.shape, x.dtype)
@@ -502,6 +519,8 @@ class ModB200(ModBase):
 
     # -- elementwise / structural ---------------------------------------------------------------
     def where(self, cond, a, b):
+        if _is_graph(cond, a, b):
+            return graph.g_where(cond, a, b)
         if isinstance(cond, Affine):
             raise NonAffineError("where() on a condition that depends on the unknown fields")
         cond = as_known(cond)
@@ -539,6 +558,8 @@ class ModB200(ModBase):
             shifts, axes = [int(shift)], [int(axis)]
         else:
             shifts, axes = [int(s) for s in shift], [int(a) for a in axis]
+        if _is_graph(x):
+            return graph.g_roll(x, shifts, axes)
         if isinstance(x, Affine):
             nd = len(x.shape)
             per_axis = [0] * nd
@@ -562,6 +583,8 @@ class ModB200(ModBase):
         return Known(torch.roll(x.t, sh, dims) if sh else x.t, x.shape)
 
     def stop_gradient(self, x):
+        if _is_graph(x):
+            return graph.g_stop_gradient(x)
         if isinstance(x, Affine):
             lin = {}
             for (k, o, _), c in x.lin.items():
@@ -571,6 +594,8 @@ class ModB200(ModBase):
         return x
 
     def reshape(self, x, shape):
+        if _is_graph(x):
+            return graph.g_reshape(x, shape)
         if isinstance(x, Affine):
             raise NonAffineError("reshape of a field expression")
         if torch.is_tensor(x):
@@ -581,9 +606,13 @@ class ModB200(ModBase):
         return self.reshape(x, [-1])
 
     def stack(self, xs, axis=0):
+        if _is_graph(*xs):
+            return graph.g_stack(list(xs), axis)
         return Known(torch.stack([as_known(x).full() for x in xs], dim=axis))
 
     def concatenate(self, xs, axis=0):
+        if _is_graph(*xs):
+            return graph.g_concat(list(xs), axis)
         if all(torch.is_tensor(x) for x in xs):
             return torch.cat(list(xs), dim=axis)
         return Known(torch.cat([as_known(x).full() for x in xs], dim=axis))
@@ -596,6 +625,8 @@ class ModB200(ModBase):
         return [Known(t) for t in torch.split(as_known(x).full(), [int(s) for s in sizes], dim=axis)]
 
     def transpose(self, x, perm=None):
+        if _is_graph(x):
+            return graph.g_transpose(x, perm)
         t = as_known(x).full()
         return Known(t.permute(*[int(p) for p in perm]) if perm is not None else t.T)
 
@@ -603,34 +634,51 @@ class ModB200(ModBase):
         return Known(torch.movedim(as_known(x).full(), src, dst))
 
     def broadcast_to(self, x, shape):
+        if _is_graph(x):
+            return graph.g_broadcast(x, shape)
         x = as_known(x)
         return Known(x.t, _bshape(x.shape, tuple(shape)))
 
     def pad(self, x, pad_width, mode="constant"):
+        if _is_graph(x):
+            return graph.g_pad(x, pad_width, mode)
         if isinstance(x, Affine):
             raise NonAffineError("pad of a field expression (loc change) is not on the fused path yet")
         return Known(_as_tensor(np.pad(as_known(x).numpy(), pad_width, mode=mode), self.device))
 
     def minimum(self, a, b):
+        if _is_graph(a, b):
+            return graph.g_binary("minimum", a, b)
         a, b = as_known(a, like=b if isinstance(b, Known) else None), as_known(b, like=a if isinstance(a, Known) else None)
         return Known(torch.minimum(*torch.broadcast_tensors(a.full(), b.full())))
 
     def maximum(self, a, b):
+        if _is_graph(a, b):
+            return graph.g_binary("maximum", a, b)
         a, b = as_known(a, like=b if isinstance(b, Known) else None), as_known(b, like=a if isinstance(a, Known) else None)
         return Known(torch.maximum(*torch.broadcast_tensors(a.full(), b.full())))
 
     def clip(self, x, lo, hi):
+        if _is_graph(x, lo, hi):
+            return graph.g_binary("minimum", graph.g_binary("maximum", x, lo), hi)
         return Known(torch.clamp(as_known(x).full(), lo, hi))
 
     def matmul(self, a, b):
+        if _is_graph(a, b):
+            raise graph.GraphError("matmul of traced expressions: use ctx.neural_net / elementwise products")
         return Known(torch.matmul(as_known(a).full(), as_known(b).full()))
 
     def gather_nd(self, u, idx):
+        if _is_graph(u, idx):
+            raise graph.GraphError("gather_nd of a traced expression is not supported")
         idx = as_known(idx).full().long()
         return Known(as_known(u).full()[tuple(torch.movedim(idx, -1, 0))])
 
     # -- reductions (Known only; reductions of field expressions are the loss, done by the engine) --
     def _reduce(self, fn, x, axis=None):
+        if _is_graph(x):
+            raise graph.GraphError("reductions of traced expressions inside an operator are not supported "
+                                   "(the loss reduction itself is done by the engine; see Context.Raw)")
         if isinstance(x, Affine):
             raise NonAffineError("reduction of a field expression inside the operator")
         t = as_known(x).full()
@@ -652,6 +700,9 @@ class ModB200(ModBase):
 
     def norm(self, x):
         return self._reduce(torch.linalg.vector_norm, x)
+
+
+from . import graph  # noqa: E402  (graph imports the classes above)
 
 
 class _ForeignBackend(ModBase):

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libodil_b200.so")
-SOURCES = ["stencil.cu", "multigrid.cu", "optim.cu"]
+SOURCES = ["stencil.cu", "multigrid.cu", "optim.cu", "jit.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import native
+from . import graph
 from .backend import Affine, Known, Lazy, ModB200, NonAffineError, as_known, torch_dtype
 
 
@@ -88,6 +89,8 @@ class State:
 # --------------------------------------------------------------------------------------------------
 def _device_array(u, mod, dtype=None):
     """Contiguous CUDA tensor from Known / numpy / torch."""
+    if isinstance(u, graph.Expr):
+        raise graph.GraphError("multigrid interpolation of a traced expression inside an operator is not supported")
     if isinstance(u, Affine):
         raise NonAffineError("multigrid transfer of a field expression inside an operator is not on the fused path")
     if isinstance(u, Known):
@@ -143,6 +146,8 @@ def restrict_to_coarser(u, loc=None, method=None, mod=None, depth=1):
     assert_equal(len(loc), len(u.shape))
     for l in loc:
         assert l in "cn.", "Invalid loc={}".format(loc)
+    if isinstance(u, graph.Expr):  # inside an operator (e.g. the `mgloss` outputs of examples/poisson/poisson.py:116-122)
+        return restrict_to_coarser(graph.g_restrict(u, loc), loc, method, mod, depth - 1)
     t = _device_array(u, mod)
     out = torch.empty(_coarse_shape(t.shape, loc), dtype=t.dtype, device=t.device)
     native.mg_restrict(tuple(t.shape), loc, t, out)
@@ -527,6 +532,15 @@ def eval_neural_net(net, inputs, mod, frozen=False):
     act = {"tanh": mod.tanh, "relu": mod.relu, "none": lambda x: x}[net.activation]
     if net.func_in is not None:
         inputs = net.func_in(*inputs)
+    if graph.any_expr(*inputs, *weights, *biases):
+        # traced evaluation (operator under ctx.neural_net): elementwise over the inputs' common shape
+        if frozen:
+            weights = [mod.stop_gradient(w) for w in weights]
+            biases = [mod.stop_gradient(b) for b in biases]
+        outputs = graph.g_mlp(weights, biases, list(inputs), net.activation)
+        if net.func_out is not None:
+            outputs = net.func_out(*outputs)
+        return outputs
     tmp = mod.stack(inputs, axis=0)
     nd = len(tmp.shape)
     tmp = mod.transpose(tmp, list(range(1, nd)) + [0])[..., None]
@@ -552,9 +566,12 @@ class Context:
         def __init__(self, value):
             self.value = value
 
-    def __init__(self, domain, state, watch_func=None, extra=None, tracers=None, distinct_shift=False):
+    def __init__(self, domain, state, watch_func=None, extra=None, tracers=None, distinct_shift=False, trace=None):
+        """trace: None = affine tracing (closed-form stencil symbols); an `engine_graph.GraphTrace` = general tracing,
+        where `state` is the trace's shadow state whose arrays are graph inputs."""
         self.domain = domain
         self.state = state
+        self.trace = trace
         self.watch_func = watch_func or (lambda _: None)
         self.extra = extra
         self.tracers = tracers
@@ -584,11 +601,15 @@ class Context:
         if isinstance(field, Array):
             if len(shift):
                 raise RuntimeError("Array requires an empty shift")
+            if self.trace is not None:
+                return self.mod.stop_gradient(field.array) if frozen else field.array
             shape = tuple(field.array.shape)
             return Affine.symbol(key, (0,) * len(shape), shape, self.dtype, frozen, device=self.mod.device)
         shift = tuple(int(s) for s in shift) or (0,) * domain.ndim
         if len(shift) != domain.ndim:
             raise RuntimeError("Expected {} shift components, got shift={}".format(domain.ndim, shift))
+        if self.trace is not None:
+            return self._field_graph(key, field, shift, loc or field.loc, frozen)
         if loc is not None and loc != field.loc:
             raise NonAffineError("ctx.field(loc=...) with a change of location is not on the fused path yet")
         desc = (key, shift, field.loc, frozen)
@@ -601,11 +622,33 @@ class Context:
             self.desc_to_array[desc] = Affine.symbol(key, shift, shape, self.dtype, frozen, device=self.mod.device)
         return self.desc_to_array[desc]
 
+    def _field_graph(self, key, field, shift, loc, frozen):
+        """General tracing of ctx.field, statement by statement as the reference does it (core.py:934-975): source
+        field -> zero pad (1, 0) where a cell-centred axis is read at nodes -> roll by -shift -> trim the last entry
+        where a node-centred axis is read at cells -> stop_gradient if frozen."""
+        mod, ndim = self.mod, self.domain.ndim
+        desc = (key, shift, loc)
+        if desc not in self.desc_to_array:
+            array = self.trace.regular(key)
+            pad_flag = [lf == "c" and l == "n" for lf, l in zip(field.loc, loc)]
+            if any(pad_flag):
+                array = mod.pad(array, pad_width=[(1, 0) if f else (0, 0) for f in pad_flag], mode="constant")
+            if any(shift):
+                array = mod.roll(array, np.negative(shift), range(ndim))
+            trim_flag = [lf == "n" and l == "c" for lf, l in zip(field.loc, loc)]
+            if any(trim_flag):
+                array = array[tuple(slice(0, -1 if f else None) for f in trim_flag)]
+            self.desc_to_array[desc] = array
+        array = self.desc_to_array[desc]
+        return mod.stop_gradient(array) if frozen else array
+
     def neural_net(self, key, frozen=False):
         net = self.state.fields[key]
         if not isinstance(net, NeuralNet):
             raise TypeError("Expected NeuralNet, got type {} for key='{}'".format(type(net).__name__, key))
-        raise NonAffineError("NeuralNet unknowns are not on the fused path yet (SURVEY.md 8f-3)")
+        if self.trace is None:
+            raise NonAffineError("NeuralNet unknowns are evaluated by the general (graph) engine")
+        return lambda *inputs: eval_neural_net(net, inputs, self.mod, frozen=frozen)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -649,7 +692,15 @@ class Problem:
             from .engine import ResidualEngine
 
             cache["state"] = state
-            cache["func"] = ResidualEngine(self, state)
+            try:
+                cache["func"] = ResidualEngine(self, state)
+            except NonAffineError:
+                # Not an affine stencil with region-typed coefficients (products / functions of fields, neural nets,
+                # location changes, per-cell coefficients, Raw terms ...): trace the operator again into the general
+                # expression graph and generate its kernels (odil_b200.engine_graph).
+                from .engine_graph import GraphEngine
+
+                cache["func"] = GraphEngine(self, state)
             if cache.get("buffers"):
                 cache["func"]._buffers = cache.pop("buffers")  # work arrays of the previous lowering
             cache["names"] = cache["func"].names
@@ -670,6 +721,10 @@ class Problem:
         from .newton import StencilJacobian
 
         engine = self._engine(state)
+        if hasattr(engine, "jacobian"):
+            raise NotImplementedError(
+                "eval_operator_grad of a non-affine operator: use Problem.linearize (matrix-free Jacobian products "
+                "and .tocsr()) -- the per-(key, shift) diagonals exist only for affine stencils")
         values = engine.operator_values(self.domain.arrays_from_state(state))
         jac = StencilJacobian(engine)
         grads = []
@@ -711,7 +766,10 @@ class Problem:
         from .newton import StencilJacobian, residual_vector
 
         engine = self._engine(state)
-        vector = residual_vector(engine, self.domain.arrays_from_state(state))
+        arrays = self.domain.arrays_from_state(state)
+        vector = residual_vector(engine, arrays)
+        if hasattr(engine, "jacobian"):  # general (graph) engine: generated forward- / reverse-mode kernels
+            return vector, engine.jacobian(arrays)
         return vector, StencilJacobian(engine)
 
 

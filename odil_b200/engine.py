@@ -29,10 +29,11 @@ MAX_REGION_WIDTH = 8
 class _Fetch:
     """One device->host copy shared by all scalars of an evaluation, done on first use."""
 
-    def __init__(self, sums, counts, dtype):
+    def __init__(self, sums, counts, dtype, raws=None):
         self.sums = sums
         self.counts = counts
         self.dtype = dtype
+        self.raws = raws or [False] * len(counts)  # Context.Raw outputs: term = mean(value), norm = the term itself
         self._terms = None
 
     def terms(self):
@@ -57,7 +58,7 @@ class LazyScalar:
         t = self._fetch.terms()
         if self._kind == "loss":
             return self._fetch.dtype.type(sum(t))
-        if self._kind == "term":
+        if self._kind == "term" or self._fetch.raws[self._index]:
             return t[self._index]
         return np.sqrt(t[self._index])
 

@@ -16,7 +16,7 @@ def solve(matr, rhs, args, status=None, linsolver="direct"):
     status = status if status is not None else dict()
     from .newton import StencilJacobian, cg_normal
 
-    if isinstance(matr, StencilJacobian):
+    if hasattr(matr, "rmatvec") and hasattr(matr, "tocsr") and not scipy.sparse.issparse(matr):
         import torch
 
         if linsolver in ("cg_b200", "cg"):

@@ -25,6 +25,8 @@ EXPORTS = [
     "odil_b200_mg_interp_adjoint", "odil_b200_mg_restrict", "odil_b200_adam_step", "odil_b200_gd_step",
     "odil_b200_axpby", "odil_b200_multi_dot", "odil_b200_multi_axpy", "odil_b200_cg_update_xr",
     "odil_b200_cg_update_p", "odil_b200_star_worklist", "odil_b200_adam_step_dev",
+    "odil_b200_jit_compile", "odil_b200_jit_log", "odil_b200_jit_cubin", "odil_b200_jit_kernel",
+    "odil_b200_jit_launch", "odil_b200_jit_destroy",
 ]
 
 
@@ -109,8 +111,15 @@ def load(build_if_missing=False):
     lib.odil_b200_cg_update_xr.argtypes = [i64, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.odil_b200_cg_update_p.argtypes = [i64, ctypes.c_int, vp, vp, vp, vp, vp]
     lib.odil_b200_star_worklist.argtypes = [ctypes.c_int, ctypes.c_int, i64, i64, i64, ctypes.c_int, P(i32), ctypes.c_int]
+    lib.odil_b200_jit_compile.argtypes = [ctypes.c_char_p, P(ctypes.c_char_p), ctypes.c_int, P(vp)]
+    lib.odil_b200_jit_log.restype = ctypes.c_char_p
+    lib.odil_b200_jit_cubin.argtypes = [vp, P(vp), P(ctypes.c_uint64)]
+    lib.odil_b200_jit_kernel.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, P(vp)]
+    lib.odil_b200_jit_launch.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p,
+                                         ctypes.c_uint64, vp]
+    lib.odil_b200_jit_destroy.argtypes = [vp]
     for name in EXPORTS:
-        if name not in ("odil_b200_last_error", "odil_b200_launch_count", "odil_b200_version"):
+        if name not in ("odil_b200_last_error", "odil_b200_launch_count", "odil_b200_version", "odil_b200_jit_log"):
             getattr(lib, name).restype = ctypes.c_int
     _lib = lib
     return lib
@@ -365,3 +374,46 @@ def multi_axpy(V, k, coef, a0, g, d):
     load()
     _check(_lib.odil_b200_multi_axpy(_ptr(V), V.stride(0), int(k), _ptr(coef), float(a0), _ptr(g), _ptr(d), d.numel(),
                                      dtype_code(d.dtype), _stream()))
+
+
+# --------------------------------------------------------------------------------------------------
+# Run-time specialised kernels (csrc/jit.cu): NVRTC -> sm_100a cubin -> driver launch
+# --------------------------------------------------------------------------------------------------
+class JitModule:
+    """CUDA C source compiled for sm_100a (compilation needs no device; `kernel` / `launch` do)."""
+
+    def __init__(self, source, options=()):
+        lib = load()
+        self.source = source
+        self.handle = ctypes.c_void_p()
+        opts = (ctypes.c_char_p * max(1, len(options)))(*[o.encode() for o in options])
+        rc = lib.odil_b200_jit_compile(source.encode(), opts, len(options), ctypes.byref(self.handle))
+        self.log = (lib.odil_b200_jit_log() or b"").decode(errors="replace").strip("\x00").strip()
+        if rc != 0:
+            raise NativeError(lib.odil_b200_last_error().decode() + "\n" + self.log[-4000:])
+        self._kernels = {}
+
+    def cubin(self):
+        data, size = ctypes.c_void_p(), ctypes.c_uint64()
+        _check(_lib.odil_b200_jit_cubin(self.handle, ctypes.byref(data), ctypes.byref(size)))
+        return ctypes.string_at(data.value, size.value)
+
+    def kernel(self, name, max_dynamic_smem=0):
+        k = self._kernels.get(name)
+        if k is None:
+            k = ctypes.c_void_p()
+            _check(_lib.odil_b200_jit_kernel(self.handle, name.encode(), int(max_dynamic_smem), ctypes.byref(k)))
+            self._kernels[name] = k
+        return k
+
+    def launch(self, name, grid, block, params, smem=0):
+        k = self.kernel(name)
+        _call("jit:" + name, lambda: _check(_lib.odil_b200_jit_launch(k, int(grid), int(block), int(smem), params,
+                                                                     len(params), _stream())))
+
+    def __del__(self):
+        try:
+            if _lib is not None and self.handle:
+                _lib.odil_b200_jit_destroy(self.handle)
+        except Exception:
+            pass

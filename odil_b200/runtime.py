@@ -23,8 +23,30 @@ backend_name = os.environ.get("ODIL_BACKEND", "") or "b200"
 if backend_name != "b200":
     raise ImportError(f"Unknown ODIL_BACKEND='{backend_name}', options are: b200")
 
-tf = None
-jax = None
+
+
+class _ForeignJit:
+    """`from odil.runtime import tf` / `jax`: the reference's example scripts import the backend module and decorate
+    helper functions with `@tf.function()` (examples/heat/heat.py:282).  There is no TensorFlow / JAX here; the
+    decorator is the identity (functions run eagerly on ModB200 values) and any other attribute fails loudly."""
+
+    def __init__(self, name):
+        self._name = name
+
+    def function(self, func=None, **kwargs):
+        return func if callable(func) else (lambda f: f)
+
+    jit = function
+
+    def __bool__(self):
+        return False
+
+    def __getattr__(self, attr):
+        raise AttributeError(f"odil.runtime.{self._name}.{attr}: the B200 backend has no {self._name} module")
+
+
+tf = _ForeignJit("tf")
+jax = _ForeignJit("jax")
 mod = ModB200()
 
 dtype_name = os.environ.get("ODIL_DTYPE", "float32")

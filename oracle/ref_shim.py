@@ -99,7 +99,10 @@ class TorchMod:
         self.tdtype = dtype
         self.float32 = np.float32
         self.float64 = np.float64
-        self.random = types.SimpleNamespace(set_seed=lambda s: torch.manual_seed(s))
+        self.random = types.SimpleNamespace(
+            set_seed=lambda s: torch.manual_seed(s),
+            uniform=lambda shape, minval, maxval, dtype: (minval + (maxval - minval) * torch.rand(
+                tuple(shape), dtype=torch.float64)).to(self._tt(dtype)))
 
     @staticmethod
     def _tt(dtype):
@@ -146,6 +149,19 @@ class TorchMod:
     concatenate = staticmethod(lambda xs, axis=0: torch.cat([torch.as_tensor(x) for x in xs], dim=axis))
     transpose = staticmethod(lambda x, perm: x.permute(*[int(p) for p in perm]))
     matmul = staticmethod(torch.matmul)
+
+    sin = staticmethod(torch.sin)
+    cos = staticmethod(torch.cos)
+    log = staticmethod(torch.log)
+
+    @staticmethod
+    def convolution(input, filters, strides, padding):
+        """Stand-in for jax.lax.conv as core.py:751 calls it (cross-correlation, VALID, one stride for all axes)."""
+        assert padding == "VALID"
+        nd = input.dim()
+        conv = {1: torch.nn.functional.conv1d, 2: torch.nn.functional.conv2d, 3: torch.nn.functional.conv3d}[nd]
+        w = torch.as_tensor(filters, dtype=input.dtype)
+        return conv(input[None, None], w[None, None], stride=int(strides))[0, 0]
 
     @staticmethod
     def where(c, a, b):

@@ -6,8 +6,8 @@ Stages the UNMODIFIED reference into oracle/_ref/ so that the reference arm of b
 The sanctioned route (`pip install --target ... /root/reference`) fails in this image: the reference builds with
 hatchling, which is neither installed nor in /opt/wheelhouse, and there is no network.  A pure-Python package
 installs as a verbatim copy of its files, so this recipe does exactly what the wheel would: it copies
-src/odil/*.py (the package) and examples/poisson/poisson.py (the operator of the benchmark configuration, which the
-package does not ship) into oracle/_ref/, and writes their SHA-256 digests next to them.  oracle/_ref/ is
+src/odil/*.py (the package), the example scripts (the operator of the benchmark configuration, which the package
+does not ship, and the operators of the parity cases) and the reference's own test scripts into oracle/_ref/, and writes their SHA-256 digests next to them.  oracle/_ref/ is
 git-ignored (nothing of the reference enters the history) but not gpurun-ignored, like a built .so.
 oracle/reference_manifest.json (committed) pins the digests: oracle/ref_shim.py refuses files that differ.
 
@@ -28,6 +28,16 @@ FILES = {
     "examples/poisson/poisson.py": "examples/poisson/poisson.py",
     "examples/wave/wave.py": "examples/wave/wave.py",
     "examples/heat/heat.py": "examples/heat/heat.py",
+    "examples/heat_tmax/heat_tmax.py": "examples/heat_tmax/heat_tmax.py",
+    "examples/infer_constant/infer_constant.py": "examples/infer_constant/infer_constant.py",
+    "examples/velocity_from_tracer/veltracer.py": "examples/velocity_from_tracer/veltracer.py",
+    "examples/basic/fields.py": "examples/basic/fields.py",
+    # the reference's own test scripts: run unmodified against this package by tests/test_reference_scripts_gpu.py
+    "tests/test_optimize.py": "tests/test_optimize.py",
+    "tests/test_newton.py": "tests/test_newton.py",
+    "tests/test_domain.py": "tests/test_domain.py",
+    "tests/test_mg_interp.py": "tests/test_mg_interp.py",
+    "tests/test_mg_restrict.py": "tests/test_mg_restrict.py",
 }
 
 
