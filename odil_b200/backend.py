@@ -196,6 +196,20 @@ class Known(Lazy):
     def astype(self, dtype):
         return Known(self.t.to(torch_dtype(dtype)), self.shape)
 
+    # a little of the tensor surface, so that host code may treat a Known like the device tensor it wraps
+    def cpu(self):
+        return self.full().detach().cpu()
+
+    def clone(self):
+        return Known(self.t.clone(), self.shape)
+
+    def numel(self):
+        return math.prod(self.shape)
+
+    @property
+    def device(self):
+        return self.t.device
+
     def flatten(self):
         return Known(self.full().reshape(-1))
 

@@ -460,7 +460,10 @@ class Domain:
         return offset
 
     def _pack(self, arrays):
-        return self.mod.concatenate([self.mod.flatten(a) for a in arrays], axis=0)
+        """Flat vector of all entries (core.py:427-441).  Returned as a Known so that host arithmetic written for
+        the reference (`packed + delta` with a NumPy `delta`, np.array(packed)) works on the device-resident data."""
+        parts = [a.reshape(-1) if torch.is_tensor(a) else as_known(a).full().reshape(-1) for a in arrays]
+        return Known(torch.cat(parts)) if parts else Known(torch.zeros(0))
 
     def pack_field(self, field):
         return self._pack(self.arrays_from_field(field))
@@ -469,9 +472,16 @@ class Domain:
         return self._pack(self.arrays_from_state(state))
 
     def _unpack(self, packed, arrays):
+        """Splits a flat vector (Known / tensor / ndarray) into storage arrays shaped like `arrays`."""
         sizes = [math.prod(a.shape) for a in arrays]
-        split = self.mod.split_by_sizes(packed[: sum(sizes)], sizes)
-        return [self.mod.reshape(s, a.shape) for s, a in zip(split, arrays)], sum(sizes)
+        flat = packed if torch.is_tensor(packed) else as_known(packed).full()
+        flat = flat.reshape(-1)[: sum(sizes)]
+        res, start = [], 0
+        for n, a in zip(sizes, arrays):
+            t = flat[start:start + n].reshape(tuple(a.shape))
+            res.append(self.mod.variable(t, dtype=self.dtype) if torch.is_tensor(a) else Known(t))
+            start += n
+        return res, sum(sizes)
 
     def unpack_field(self, packed, field):
         arrays, used = self._unpack(packed, self.arrays_from_field(field))
@@ -767,7 +777,7 @@ class Problem:
 
         engine = self._engine(state)
         arrays = self.domain.arrays_from_state(state)
-        vector = residual_vector(engine, arrays)
+        vector = Known(residual_vector(engine, arrays))  # np.array(vector) and `-vector` both work (core.py:1127-1138)
         if hasattr(engine, "jacobian"):  # general (graph) engine: generated forward- / reverse-mode kernels
             return vector, engine.jacobian(arrays)
         return vector, StencilJacobian(engine)

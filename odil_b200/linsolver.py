@@ -19,6 +19,9 @@ def solve(matr, rhs, args, status=None, linsolver="direct"):
     if hasattr(matr, "rmatvec") and hasattr(matr, "tocsr") and not scipy.sparse.issparse(matr):
         import torch
 
+        if hasattr(rhs, "full"):  # Known (what Problem.linearize returns)
+            rhs = rhs.full()
+
         if linsolver in ("cg_b200", "cg"):
             # matrix-free CG on the device; everything stays in HBM
             return cg_normal(matr, rhs, tol=getattr(args, "linsolver_tol", 1e-6),

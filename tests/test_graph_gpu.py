@@ -1,0 +1,126 @@
+"""
+GPU parity of the general (non-affine) path: the cases of tests/nonaffine_cases.py -- UNMODIFIED reference operators
+(heat with k(u) and with a neural net, velocity-from-tracer, heat_tmax, infer_constant, the operators of the
+reference's tests/test_optimize.py and tests/test_newton.py, Poisson with mgloss, a Context.Raw term) -- evaluated
+through the public API (Problem.eval_loss_grad / eval_operator / linearize) by the NVRTC-compiled kernels, against
+goldens produced by the unmodified reference (tests/golden/make_nonaffine_goldens.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+import odil
+from odil_b200 import linsolver
+from odil_b200.engine_graph import GraphEngine
+from tests import nonaffine_cases as cases
+from tests import parity, refsrc
+from tests.test_graph_cpu import build_case, golden_arrays, relerr
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refsrc.available(), reason="reference scripts absent")]
+
+
+def load_state(problem, state, g, key, dt):
+    domain = problem.domain
+    x = [domain.mod.variable(a, dtype=dt) for a in golden_arrays(g, key, "x")]
+    domain.arrays_to_state(x, state)
+    return x
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("case", cases.CASES)
+def test_eval_loss_grad_matches_reference_golden(golden, case, prec):
+    g = golden("nonaffine")
+    key = f"{case}_{prec}"
+    problem, state, dt = build_case(case, prec, device="cuda")
+    load_state(problem, state, g, key, dt)
+    loss, grads, terms, names, norms = problem.eval_loss_grad(state)
+    assert isinstance(problem._engine(state), GraphEngine)
+    assert names == [str(n) for n in g[key + "_names"]]
+    f64 = prec == "f64"
+    parity.check(f"graph/{key}/loss", abs(float(loss) - float(g[key + "_loss"])) / abs(float(g[key + "_loss"])),
+                 1e-11 if f64 else 2e-6)
+    parity.check(f"graph/{key}/terms", relerr([float(t) for t in terms], g[key + "_terms"]), 1e-11 if f64 else 2e-6)
+    raws = [bool(r) for r in g[key + "_raws"]]
+    for t, n, r in zip(g[key + "_terms"], norms, raws):
+        ref = t if r else np.sqrt(t)
+        assert abs(float(n) - ref) <= (1e-10 if f64 else 1e-5) * max(abs(ref), 1e-30)
+    for i, (gi, gr) in enumerate(zip(grads, golden_arrays(g, key, "g"))):
+        assert tuple(gi.shape) == gr.shape
+        parity.check(f"graph/{key}/grad{i}", relerr(gi.cpu().numpy(), gr), 1e-11 if f64 else 1e-5)
+    values, names2 = problem.eval_operator(state)
+    for i, (F, Fr) in enumerate(zip(values, golden_arrays(g, key, "F"))):
+        parity.check(f"graph/{key}/F{i}", relerr(np.asarray(F), Fr), 1e-11 if f64 else 5e-6)
+    # a second evaluation (buffers reused, gradients re-zeroed) gives the same numbers up to the atomic order
+    loss2, grads2, _, _, _ = problem.eval_loss_grad(state)
+    assert abs(float(loss2) - float(loss)) <= 1e-12 * abs(float(loss))
+    for a, b in zip(grads, grads2):
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < (1e-13 if f64 else 1e-5)
+
+
+@pytest.mark.parametrize("case", cases.NEWTON_CASES)
+def test_linearize_matches_reference_golden(golden, case):
+    g = golden("nonaffine")
+    key = f"{case}_f64"
+    problem, state, dt = build_case(case, "f64", device="cuda")
+    load_state(problem, state, g, key, dt)
+    vector, matrix = problem.linearize(state)
+    Jr = g[key + "_jac"]
+    F = np.concatenate([f.reshape(-1) for f in golden_arrays(g, key, "F")])
+    parity.check(f"graph/{key}/linearize_vector", relerr(vector.cpu().numpy(), F), 1e-11)
+    J = matrix.tocsr().toarray()
+    assert J.shape == Jr.shape == matrix.shape
+    parity.check(f"graph/{key}/linearize_csr", np.max(np.abs(J - Jr)) / np.max(np.abs(Jr)), 1e-11)
+    rng = np.random.default_rng(0)
+    v = torch.as_tensor(rng.standard_normal(J.shape[1]), device="cuda")
+    w = torch.as_tensor(rng.standard_normal(J.shape[0]), device="cuda")
+    parity.check(f"graph/{key}/jvp", relerr(matrix.matvec(v).cpu().numpy(), Jr @ v.cpu().numpy()), 1e-11)
+    parity.check(f"graph/{key}/vjp", relerr(matrix.rmatvec(w).cpu().numpy(), Jr.T @ w.cpu().numpy()), 1e-11)
+    # SciPy-matrix surface the reference's scripts rely on (tests/test_newton.py:117-120)
+    normal = matrix.T @ matrix
+    assert np.allclose(normal.toarray(), Jr.T @ Jr, rtol=1e-10, atol=1e-12 * np.max(np.abs(Jr)) ** 2)
+    assert np.allclose(matrix.T @ F, Jr.T @ F, rtol=1e-10, atol=1e-10)
+
+
+def test_newton_step_cg_matches_direct_solve(golden):
+    """One Newton step of the heat problem with k(u): matrix-free CG on the device (linsolver cg_b200) against the
+    reference's direct solve of the normal equations on the assembled matrix."""
+    import argparse
+
+    g = golden("nonaffine")
+    problem, state, dt = build_case("heat_k", "f64", device="cuda")
+    load_state(problem, state, g, "heat_k_f64", dt)
+    vector, matrix = problem.linearize(state)
+    args = argparse.Namespace(linsolver_tol=1e-13, linsolver_maxiter=2000, linsolver_damp=0, linsolver_dampdiag=0)
+    status = {}
+    d_cg = linsolver.solve(matrix, -vector, args, status, "cg_b200").cpu().numpy()
+    d_direct = linsolver.solve(matrix, -vector, args, {}, "direct").cpu().numpy()
+    parity.check("graph/heat_k_f64/newton_step_cg_vs_direct", relerr(d_cg, d_direct), 1e-6)
+
+
+def test_epoch_tracer_is_a_runtime_parameter(golden):
+    """tracers['epoch'] feeds annealed weights (heat.py:43,118): changing it changes the loss WITHOUT re-tracing."""
+    g = golden("nonaffine")
+    problem, state, dt = build_case("heat_k", "f64", device="cuda")
+    load_state(problem, state, g, "heat_k_f64", dt)
+    loss7 = float(problem.eval_loss_grad(state)[0])
+    engine = problem._engine(state)
+    problem.tracers["epoch"] = 0
+    loss0 = float(problem.eval_loss_grad(state)[0])
+    assert problem._engine(state) is engine
+    terms7 = g["heat_k_f64_terms"]
+    # xreg term: weight kxreg * 0.5 ** (epoch / 5) -> term scales by 0.5 ** (-2 * 7 / 5)
+    expect = float(g["heat_k_f64_loss"]) + terms7[2] * (0.5 ** (-14 / 5) - 1)
+    assert abs(loss7 - float(g["heat_k_f64_loss"])) < 1e-11 * loss7
+    assert abs(loss0 - expect) < 1e-10 * abs(expect)
+
+
+@pytest.mark.parametrize("opt,epochs", [("adam", 60), ("lbfgsb", 20)])
+def test_optimizers_drive_a_nonaffine_problem(opt, epochs, golden):
+    """The optimizers run on a non-affine problem (heat with a neural-net conductivity): the loss goes down."""
+    from tests.test_api_gpu import run_args, run_optimizer
+
+    g = golden("nonaffine")
+    problem, state, dt = build_case("heat_knet", "f64", device="cuda")
+    load_state(problem, state, g, "heat_knet_f64", dt)
+    losses = run_optimizer(problem, state, opt, run_args(epochs=epochs, lr=0.01))
+    assert losses is not None and losses[-1] < 0.7 * losses[0]

@@ -38,7 +38,7 @@ def make_two_field(cshape=(6, 5), dtype=np.float64):
 def probe_jacobian(problem, state):
     """Dense Jacobian by evaluating the (affine) operator on unit vectors."""
     domain = problem.domain
-    packed0 = domain.pack_state(state).clone()
+    packed0 = domain.pack_state(state).full().clone()
     n = packed0.numel()
 
     def F(p):
