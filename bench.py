@@ -35,6 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Mcells/s (residual+grad+optimizer epoch)"
+NEWTON_CG = 20  # CG iterations per Newton step in the configs[4] workload
 
 
 def parse():
@@ -82,8 +83,8 @@ def workload(args, world):
                          "u, u_t from an exact plane-wave solution, unknowns start at 0")
     N, dt = args.size or 256, args.dtype or "f64"
     return dict(kind="heat3", cshape=(N, N, N), levels=0, dtype=dt, opt="newton",
-                text=f"3D heat inverse (t,x,y) = {N}^3, k(u) = 0.02 exp(-20 (u-0.5)^2), Newton + matrix-free CG on the "
-                     f"normal equations, {dt}")
+                text=f"3D heat inverse (t,x,y) = {N}^3, k(u) = 0.02 exp(-20 (u-0.5)^2), Newton + {NEWTON_CG} "
+                     f"iterations of matrix-free CG on the normal equations per step, {dt}")
 
 
 def config_block(args, world, wl):
@@ -275,6 +276,16 @@ def make_problem(wl, lr):
 
         problem, state = ops.make_wave2(cshape, npdt)
         return problem, state, dict(bfgs_m=50)
+    if wl["kind"] == "heat3":
+        from tests import nonaffine_cases as cases
+
+        operator, domain, state, extra, tracers = cases.make_heat3(odil, odil.runtime.mod, npdt, cshape,
+                                                                   device_data=True)
+        problem = odil.Problem(operator, domain, extra, tracers=dict(tracers))
+        # one step = one Newton iteration: linearize (generated kernels) + NEWTON_CG iterations of matrix-free CG on
+        # the normal equations (two generated Jacobian-product kernels each) + state update + loss evaluation
+        return problem, state, dict(linsolver="cg_b200", linsolver_tol=0.0, linsolver_maxiter=NEWTON_CG,
+                                    linsolver_damp=0.0, linsolver_verbose=0, linsolver_history=0)
     raise SystemExit(f"workload {wl['kind']} is not available in this build")
 
 
@@ -328,7 +339,10 @@ class Stepper:
         a = run_args(epochs=warmup + steps, lr=self.lr, **self.extra)
         os.environ["ODIL_B200_GRAPH"] = "1" if graph else "0"
         try:
-            odil.util.optimize_grad(a, self.wl["opt"], self.problem, self.state, callback)
+            if self.wl["opt"] == "newton":
+                odil.util.optimize_newton(a, self.problem, self.state, callback)
+            else:
+                odil.util.optimize_grad(a, self.wl["opt"], self.problem, self.state, callback)
         except odil.EarlyStopError:
             pass
         if "e1" not in ev:
@@ -454,30 +468,44 @@ def run_b200(args):
     peak, peak_src = measured_peak()
     kern = m["kern"]
     alg_bytes = {"stencil_fused": 3 * es * ncells_local, "adam_step": 7 * es * nunk_local}
+    alg_note = {"stencil_fused": "3*s bytes per cell (read U, read c, write g)"}
+    if wl["kind"] == "heat3":
+        # generated kernels of the heat operator (one field u, constants imp_mask and imp_u, two outputs)
+        alg_bytes.update({"jit:k_g0_jvp": 6 * es * ncells_local, "jit:k_g0_vjp": 6 * es * ncells_local,
+                          "jit:k_g0_lossgrad": 4 * es * ncells_local, "jit:k_g0_values": 5 * es * ncells_local})
+        alg_note.update({"jit:k_g0_jvp": "6*s bytes per cell (read u, tangent, imp_mask, imp_u; write 2 outputs)",
+                         "jit:k_g0_vjp": "6*s bytes per cell (read u, 2 cotangents, imp_mask, imp_u; write g)",
+                         "jit:k_g0_lossgrad": "4*s bytes per cell (read u, imp_mask, imp_u; write g)",
+                         "jit:k_g0_values": "5*s bytes per cell (read u, imp_mask, imp_u; write 2 outputs)"})
     for name, k in kern.items():
         if name in alg_bytes and k["ms_per_step"] > 0:
             gbs = alg_bytes[name] / (k["ms_per_step"] / max(k["calls_per_step"], 1) * 1e-3) / 1e9
             k.update({"achieved_GBs": gbs, "frac": gbs / peak})
-    fused = kern.get("stencil_fused", {})
+    # the dominant kernel of the step among those with a byte model (the fused sweep for the Poisson / wave configs)
+    cand = [n for n in kern if n in alg_bytes and n != "adam_step"]
+    top = "stencil_fused" if "stencil_fused" in kern else (max(cand, key=lambda n: kern[n]["ms_per_step"]) if cand
+                                                             else "stencil_fused")
+    fused = kern.get(top, {})
     launches_first, clocks_first, loss_first = m["launches"], m["clocks"], m["loss"]
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("cells") == ncells_local and tj.get("dtype") == wl["dtype"]:
+        if tj.get("cells") == ncells_local and tj.get("dtype") == wl["dtype"] and top == "stencil_fused":
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
     roofline = {
         "bound": "hbm",
-        "kernel": "odil_b200_stencil_fused (residual + loss + adjoint gradient in one sweep, + reduce)",
+        "kernel": ("odil_b200_stencil_fused (residual + loss + adjoint gradient in one sweep, + reduce)"
+                   if top == "stencil_fused" else f"{top} (NVRTC-generated kernel of the traced operator)"),
         "achieved": fused.get("achieved_GBs"), "peak": peak, "unit": "GB/s", "frac": fused.get("frac"),
         "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": alg_bytes["stencil_fused"],
+        "algorithmic_bytes_per_launch": alg_bytes.get(top),
         "ms_per_launch": (fused.get("ms_per_step") or 0) / max(fused.get("calls_per_step", 1), 1) or None,
-        "note": "3*s bytes per cell (read U, read c, write g); time = CUDA events around the C-ABI call on the "
-                "launch stream, averaged over the timed steps (rank 0); traffic = dram bytes of one ncu --set full "
-                "capture of the same launch (profiles/fused_traffic.json)",
+        "note": alg_note.get(top, "") + "; time = CUDA events around the C-ABI call on the launch stream, averaged "
+                "over the timed steps (rank 0); traffic = dram bytes of one ncu --set full capture of the same launch "
+                "(profiles/fused_traffic.json)",
     }
 
     # e2e: every step the unknowns arrive from pinned host memory and the loss goes back to the host

@@ -41,7 +41,7 @@ def main():
     scripts = {name: load_by_path(os.path.join(REF, rel), "refscript_" + name) for name, rel in cases.SCRIPTS.items()}
     for m in scripts.values():
         assert m.odil is odil
-    cases.raw_operator.__globals__["odil"] = odil
+    sys.modules["odil"] = odil  # `import odil` inside the API-only operators of nonaffine_cases resolves to the reference
     out = {}
     for case in cases.CASES:
         for npdt, tdt, tag in [(np.float64, torch.float64, "f64"), (np.float32, torch.float32, "f32")]:

@@ -29,9 +29,9 @@ SCRIPTS = {
 }
 
 CASES = ["heat_k", "heat_k_mg", "heat_knet", "veltracer", "heat_tmax", "infer_constant", "optimize", "newton",
-         "poisson_mgloss", "raw_term"]
+         "poisson_mgloss", "raw_term", "heat3"]
 # cases whose Jacobian (Problem.linearize) is pinned as well; multigrid off
-NEWTON_CASES = ["heat_k", "newton", "infer_constant"]
+NEWTON_CASES = ["heat_k", "newton", "infer_constant", "heat3"]
 
 
 def _ns(**kw):
@@ -184,8 +184,96 @@ def _raw_term(odil, mod, dtype):
     return raw_operator, domain, state, _ns(), {"epoch": 3}
 
 
+def heat3_operator(ctx):
+    """BASELINE configs[4]: heat equation u_t = div(k(u) grad u) on a (t, x, y) grid with the conductivity of
+    examples/heat/heat.py:22-24, discretised like operator_odil (heat.py:36-137) with one more space dimension:
+    time-centred fluxes through the four faces of a cell, k evaluated at FROZEN face averages (heat.py:86-90), zero
+    Dirichlet walls by quadratic extrapolation, the initial condition imposed through the t-1 neighbours by linear
+    extrapolation, plus the imposed-data term of the inverse problem."""
+    import odil
+
+    mod, extra = ctx.mod, ctx.extra
+    dt, dx, dy = ctx.step()
+    it, ix, iy = ctx.indices()
+    nt, nx, ny = ctx.size()
+    zero = ctx.cast(0)
+
+    def stencil(frozen):
+        st = {}
+        for lvl in (0, -1):
+            for name, sh in [("c", (0, 0)), ("xm", (-1, 0)), ("xp", (1, 0)), ("ym", (0, -1)), ("yp", (0, 1))]:
+                st[(lvl, name)] = ctx.field("u", lvl, *sh, frozen=frozen)
+        # initial condition: value at the lower time level of the first layer, by linear extrapolation (heat.py:62-70)
+        u0 = extra.init_u
+        q0 = {"c": u0, "xm": mod.roll(u0, 1, axis=0), "xp": mod.roll(u0, -1, axis=0), "ym": mod.roll(u0, 1, axis=1),
+              "yp": mod.roll(u0, -1, axis=1)}
+        for name in ["c", "xm", "xp", "ym", "yp"]:
+            st[(-1, name)] = mod.where(it == 0, odil.core.extrap_linear(st[(0, name)], q0[name][None]), st[(-1, name)])
+        ex = odil.core.extrap_quadh
+        for lvl in (0, -1):
+            c = st[(lvl, "c")]
+            xm, xp, ym, yp = st[(lvl, "xm")], st[(lvl, "xp")], st[(lvl, "ym")], st[(lvl, "yp")]
+            st[(lvl, "xm")] = mod.where(ix == 0, ex(xp, c, 0), xm)
+            st[(lvl, "xp")] = mod.where(ix == nx - 1, ex(st[(lvl, "xm")], c, 0), xp)
+            st[(lvl, "ym")] = mod.where(iy == 0, ex(yp, c, 0), ym)
+            st[(lvl, "yp")] = mod.where(iy == ny - 1, ex(st[(lvl, "ym")], c, 0), yp)
+        return st
+
+    def conductivity(u):
+        return 0.02 * mod.exp(-((u - 0.5) ** 2) * 20)
+
+    q, qf = stencil(False), stencil(True)
+    mid = lambda s, name: s[(0, name)] + s[(-1, name)]
+    u_t = (q[(0, "c")] - q[(-1, "c")]) / dt
+    flux = 0
+    for name, h, sign in [("xm", dx, -1), ("xp", dx, 1), ("ym", dy, -1), ("yp", dy, 1)]:
+        grad = sign * (mid(q, name) - mid(q, "c")) / (2 * h)     # time-centred normal derivative at the face
+        k = conductivity((mid(qf, name) + mid(qf, "c")) * 0.25)  # frozen face value
+        flux = flux + sign * grad * k / h
+    fu = u_t - flux
+    res = [("fu", fu)]
+    kimp = extra.kimp * (np.prod(ctx.size()) / extra.imp_size) ** 0.5
+    res += [("imp", extra.imp_mask * (q[(0, "c")] - extra.imp_u) * kimp)]
+    return res
+
+
+def make_heat3(odil, mod, dtype, cshape, seed=3, device_data=False):
+    """Problem data of configs[4]: Gaussian initial profile, imposed values of a smooth field at ~2 % of the points."""
+    nt, nx, ny = cshape
+    domain = odil.Domain(cshape=tuple(cshape), dimnames=("t", "x", "y"), lower=(0, 0, 0), upper=(1, 1, 1), dtype=dtype,
+                         multigrid=False, mod=mod)
+    x1 = (np.arange(nx) + 0.5) / nx
+    y1 = (np.arange(ny) + 0.5) / ny
+    X, Y = np.meshgrid(x1, y1, indexing="ij")
+    extra = _ns(kimp=2.0)
+    extra.init_u = np.exp(-((X - 0.5) ** 2 + (Y - 0.5) ** 2) * 50).astype(dtype)
+    rng = np.random.default_rng(seed)
+    if device_data:  # large grids: build the data on the device (bench.py)
+        import torch
+
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        mask = (torch.rand(cshape, device="cuda", generator=gen) < 0.02).to(tdt)
+        extra.imp_size = int(mask.sum().item())
+        extra.imp_mask = odil.backend.Known(mask)
+        t1 = torch.linspace(0.5 / nt, 1 - 0.5 / nt, nt, device="cuda", dtype=tdt)
+        decay = torch.exp(-3 * t1)[:, None, None]
+        extra.imp_u = odil.backend.Known(decay * torch.as_tensor(extra.init_u, device="cuda")[None])
+    else:
+        mask = rng.random(cshape) < 0.2
+        extra.imp_size = int(mask.sum())
+        extra.imp_mask = mask.astype(dtype)
+        t1 = (np.arange(nt) + 0.5) / nt
+        extra.imp_u = (np.exp(-3 * t1)[:, None, None] * extra.init_u[None]).astype(dtype)
+    state = odil.State(fields={"u": odil.Field(np.zeros(cshape, dtype=dtype), loc="ccc")})
+    state = domain.init_state(state)
+    return heat3_operator, domain, state, extra, {"epoch": 0}
+
+
 def build(case, odil, mod, dtype, scripts):
     """Returns (operator, domain, state, extra, tracers)."""
+    if case == "heat3":
+        return make_heat3(odil, mod, dtype, (6, 5, 4))
     if case == "heat_k":
         return _heat(odil, mod, dtype, scripts["heat"], 0, False)
     if case == "heat_k_mg":
@@ -212,4 +300,4 @@ def build(case, odil, mod, dtype, scripts):
 def scripts_for(case):
     return {"heat_k": ["heat"], "heat_k_mg": ["heat"], "heat_knet": ["heat"], "veltracer": ["veltracer"],
             "heat_tmax": ["heat_tmax"], "infer_constant": ["infer_constant"], "optimize": ["test_optimize"],
-            "newton": ["test_newton"], "poisson_mgloss": ["poisson"], "raw_term": []}[case]
+            "newton": ["test_newton"], "poisson_mgloss": ["poisson"], "raw_term": [], "heat3": []}[case]
