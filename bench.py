@@ -337,7 +337,10 @@ class Stepper:
                 self.sync_all()
 
         a = run_args(epochs=warmup + steps, lr=self.lr, **self.extra)
-        os.environ["ODIL_B200_GRAPH"] = "1" if graph else "0"
+        if graph is None:
+            os.environ.pop("ODIL_B200_GRAPH", None)  # the package's own default (replay where launch-bound and safe)
+        else:
+            os.environ["ODIL_B200_GRAPH"] = "1" if graph else "0"
         try:
             if self.wl["opt"] == "newton":
                 odil.util.optimize_newton(a, self.problem, self.state, callback)
@@ -417,7 +420,9 @@ def run_b200(args):
         assert (domain.slab is not None) == (world > 1)
         ncells = int(np.prod(wl["cshape"]))
         stepper = Stepper(problem, state, wl, args.lr, extra, dist)
-        graph = bool(args.graph) if args.graph is not None else (args.config == 1 and world == 1)
+        from odil_b200 import optimizer as _opt
+
+        graph = bool(args.graph) if args.graph is not None else None
         timers = {}
 
         def timed(name, fn):
@@ -442,7 +447,8 @@ def run_b200(args):
         # enough for nvidia-smi to report clocks before and during the timed region
         ms0, _, _ = stepper.run(3, 5, graph=graph)
         stepper.run(1, int(min(400, max(10, 500.0 / max(ms0, 1e-3)))), graph=graph)
-        if with_kernels and not graph:
+        replayed = bool(_opt.LAST_RUN_INFO["graph"]) and wl["opt"] == "adam"
+        if with_kernels and not replayed:  # per-call CUDA events cannot be recorded inside a graph capture
             native.set_timer_hook(timed)
         ms, _, info = stepper.run(max(warmup, 3), steps, on_warm=on_warm, graph=graph)
         native.set_timer_hook(None)
@@ -457,7 +463,7 @@ def run_b200(args):
             per_step = sum(a.elapsed_time(b) for a, b in evs) / steps
             kern[name] = {"ms_per_step": per_step, "calls_per_step": len(evs) / steps}
         return dict(problem=problem, state=state, stepper=stepper, ms=ms, ncells=ncells, kern=kern, clocks=clocks,
-                    launches=n_launch, loss=float(info["pinfo"]["loss"]), graph=graph)
+                    launches=n_launch, loss=float(info["pinfo"]["loss"]), graph=replayed)
 
     m = measure(wl, args.steps, args.warmup, True)
     problem, state, ncells, ms = m["problem"], m["state"], m["ncells"], m["ms"]
@@ -486,7 +492,7 @@ def run_b200(args):
     top = "stencil_fused" if "stencil_fused" in kern else (max(cand, key=lambda n: kern[n]["ms_per_step"]) if cand
                                                              else "stencil_fused")
     fused = kern.get(top, {})
-    launches_first, clocks_first, loss_first = m["launches"], m["clocks"], m["loss"]
+    launches_first, clocks_first, loss_first, graph_first = m["launches"], m["clocks"], m["loss"], m["graph"]
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
@@ -567,6 +573,7 @@ def run_b200(args):
             "config": config_block(args, world, wl),
             "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_first, "clocks": clocks_first, "final_loss": loss_first,
+            "graph_replay": graph_first,
             "epoch_traffic_model": {"compulsory_bytes_per_cell": (6 * nunk_local / ncells_local + 1) * es,
                                     "epoch_frac_of_peak": (6 * nunk_local + ncells_local) * es / (ms * 1e-3) / 1e9 / peak},
         }

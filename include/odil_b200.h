@@ -214,6 +214,28 @@ int odil_b200_jit_launch(void* kernel, uint32_t grid, uint32_t block, uint32_t s
                          void* stream);
 int odil_b200_jit_destroy(void* module);
 
+/* ---------------------------------------------------------------------------------------------
+ * Slab communicator: halo exchange and scalar all-reduce between the GPUs of one node.
+ *
+ * The reference has no multi-device path.  One process per GPU; `comm_create` allocates this rank's communication
+ * block (flags + staging) and returns its 64-byte CUDA IPC handle; the host all-gathers the handles (any transport;
+ * torch.distributed here) and `comm_connect` maps the peers' blocks (NVLink / NVSwitch peer access).  The data plane
+ * is then pure device work on the caller's stream (two kernels per exchange, one per all-reduce), capturable in a
+ * CUDA graph.  Every rank must issue the same sequence of exchanges / all-reduces.
+ *
+ *   halo_exchange      ring exchange along axis 0 of `narrays` arrays: send_lo[i] / send_hi[i] = this rank's first /
+ *                      last nbytes[i] owned bytes (contiguous planes), recv_lo[i] / recv_hi[i] = its lower / upper halo
+ *   allreduce_scalars  in-place sum over ranks of count <= 16 doubles in device memory, summed in rank order
+ * ------------------------------------------------------------------------------------------- */
+typedef struct odil_b200_comm odil_b200_comm;
+int odil_b200_comm_create(int rank, int world, int64_t halo_bytes, odil_b200_comm** comm, void* ipc_handle_out);
+int odil_b200_comm_connect(odil_b200_comm* comm, const void* ipc_handles_in_rank_order);
+int64_t odil_b200_comm_capacity(const odil_b200_comm* comm);
+int odil_b200_halo_exchange(odil_b200_comm* comm, int narrays, const void* const* send_lo, const void* const* send_hi,
+                            void* const* recv_lo, void* const* recv_hi, const int64_t* nbytes, void* stream);
+int odil_b200_allreduce_scalars(odil_b200_comm* comm, double* dev_scalars, int count, void* stream);
+int odil_b200_comm_destroy(odil_b200_comm* comm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libodil_b200.so")
-SOURCES = ["stencil.cu", "multigrid.cu", "optim.cu", "jit.cu"]
+SOURCES = ["stencil.cu", "multigrid.cu", "optim.cu", "jit.cu", "comm.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

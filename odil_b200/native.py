@@ -27,6 +27,8 @@ EXPORTS = [
     "odil_b200_cg_update_p", "odil_b200_star_worklist", "odil_b200_adam_step_dev",
     "odil_b200_jit_compile", "odil_b200_jit_log", "odil_b200_jit_cubin", "odil_b200_jit_kernel",
     "odil_b200_jit_launch", "odil_b200_jit_destroy",
+    "odil_b200_comm_create", "odil_b200_comm_connect", "odil_b200_comm_capacity", "odil_b200_halo_exchange",
+    "odil_b200_allreduce_scalars", "odil_b200_comm_destroy",
 ]
 
 
@@ -118,8 +120,16 @@ def load(build_if_missing=False):
     lib.odil_b200_jit_launch.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p,
                                          ctypes.c_uint64, vp]
     lib.odil_b200_jit_destroy.argtypes = [vp]
+    lib.odil_b200_comm_create.argtypes = [ctypes.c_int, ctypes.c_int, i64, P(vp), ctypes.c_char_p]
+    lib.odil_b200_comm_connect.argtypes = [vp, ctypes.c_char_p]
+    lib.odil_b200_comm_capacity.argtypes = [vp]
+    lib.odil_b200_comm_capacity.restype = i64
+    lib.odil_b200_halo_exchange.argtypes = [vp, ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), vp]
+    lib.odil_b200_allreduce_scalars.argtypes = [vp, vp, ctypes.c_int, vp]
+    lib.odil_b200_comm_destroy.argtypes = [vp]
     for name in EXPORTS:
-        if name not in ("odil_b200_last_error", "odil_b200_launch_count", "odil_b200_version", "odil_b200_jit_log"):
+        if name not in ("odil_b200_last_error", "odil_b200_launch_count", "odil_b200_version", "odil_b200_jit_log",
+                        "odil_b200_comm_capacity"):
             getattr(lib, name).restype = ctypes.c_int
     _lib = lib
     return lib
@@ -417,3 +427,49 @@ class JitModule:
                 _lib.odil_b200_jit_destroy(self.handle)
         except Exception:
             pass
+
+
+# --------------------------------------------------------------------------------------------------
+# Slab communicator (csrc/comm.cu): halo exchange and scalar all-reduce over NVLink peer memory
+# --------------------------------------------------------------------------------------------------
+IPC_HANDLE_BYTES = 64
+
+
+class Comm:
+    """One per process (= per GPU).  `all_gather_bytes(bytes) -> [bytes per rank]` is the only thing asked of the host
+    plumbing (torch.distributed): it carries the 64-byte IPC handles once, at creation."""
+
+    def __init__(self, rank, world, halo_bytes, all_gather_bytes):
+        lib = load()
+        self.rank, self.world = int(rank), int(world)
+        self.handle = ctypes.c_void_p()
+        mine = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(lib.odil_b200_comm_create(self.rank, self.world, int(halo_bytes), ctypes.byref(self.handle), mine))
+        handles = all_gather_bytes(mine.raw)
+        assert len(handles) == self.world and all(len(h) == IPC_HANDLE_BYTES for h in handles)
+        _check(lib.odil_b200_comm_connect(self.handle, b"".join(handles)))
+        self.capacity = int(lib.odil_b200_comm_capacity(self.handle))
+
+    @staticmethod
+    def bytes_needed(nbytes_list):
+        return sum((n + 255) // 256 * 256 for n in nbytes_list)
+
+    def halo_exchange(self, send_lo, send_hi, recv_lo, recv_hi):
+        """Lists of contiguous CUDA tensor views (same length, pairwise equal sizes)."""
+        n = len(send_lo)
+        VP = ctypes.c_void_p * n
+        nbytes = (ctypes.c_int64 * n)(*[t.numel() * t.element_size() for t in send_lo])
+        args = [VP(*[_ptr(t).value for t in ts]) for ts in (send_lo, send_hi, recv_lo, recv_hi)]
+        _call("halo_exchange", lambda: _check(_lib.odil_b200_halo_exchange(self.handle, n, *args, nbytes, _stream())))
+
+    def allreduce_scalars(self, t):
+        """In-place sum over ranks of a small float64 CUDA tensor (deterministic: rank order)."""
+        if t.dtype != torch.float64:
+            raise NativeError("allreduce_scalars: float64 tensor expected")
+        _call("allreduce_scalars", lambda: _check(_lib.odil_b200_allreduce_scalars(self.handle, _ptr(t), t.numel(),
+                                                                                    _stream())))
+
+    def destroy(self):
+        if self.handle:
+            _lib.odil_b200_comm_destroy(self.handle)
+            self.handle = ctypes.c_void_p()

@@ -19,6 +19,9 @@ import torch
 from . import native
 
 
+LAST_RUN_INFO = {"graph": False}  # how the most recent optimizer run executed its epochs (read by bench.py)
+
+
 class Optimizer:
 
     def __init__(self, name=None, displayname=None, dtype=None):
@@ -76,12 +79,21 @@ class AdamNativeOptimizer(Optimizer):
         v = [torch.zeros_like(e) for e in x]
         eps = float(dtype.type(epsilon))
         if graph is None:
-            graph = os.environ.get("ODIL_B200_GRAPH", "0") not in ("", "0")
+            env = os.environ.get("ODIL_B200_GRAPH", "")
+            if env != "":
+                graph = env != "0"
+            else:
+                # default: replay where the epoch is launch-bound (small grids) and the caller vouches that nothing
+                # outside the captured kernels changes between epochs (`loss_grad.graph_safe`, set by optimize_grad:
+                # affine operator, no tracer baked into its tables, state arrays not swapped by the callback)
+                graph = bool(getattr(loss_grad, "graph_safe", False)) and sum(e.numel() for e in x) <= (1 << 24)
         if graph and torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size() > 1:
-            graph = False  # slab runs exchange halos through NCCL inside loss_grad: not captured (yet)
+                and torch.distributed.get_world_size() > 1 and os.environ.get("ODIL_B200_COMM", "peer") == "nccl":
+            graph = False  # NCCL groups issued through torch.distributed are not captured; the peer-memory
+            #                communicator (csrc/comm.cu) is plain kernels and replays
         first, last = epoch_start + 1, epoch_start + epochs
         eager_until = last if not graph else min(last, first + 1)
+        LAST_RUN_INFO["graph"] = bool(graph and eager_until < last)
         for epoch in range(first, eager_until + 1):
             self.evals += 1
             loss, grads, pinfo = loss_grad(x)

@@ -15,12 +15,20 @@ Per epoch the engine does ONE batched exchange of all multigrid terms (width 2),
 level on its extended range, runs the fused stencil kernel on its owned planes, and exchanges the
 gradient halo (width 1) once per multigrid level for the transposed interpolation.  Loss terms are
 summed with one tiny all-reduce.
+
+Data plane on GPUs: the library's own communicator (csrc/comm.cu, `native.Comm`): boundary planes are stored
+straight into the neighbours' staging areas over NVLink peer memory and flagged -- two small kernels per exchange,
+one per all-reduce, all on the compute stream and capturable in a CUDA graph.  torch.distributed (NCCL) only
+carries the 64-byte IPC handles at start-up.  ODIL_B200_COMM=nccl selects the round-1 arrangement (batched
+ncclSend/ncclRecv groups + ncclAllReduce through torch.distributed); CPU tensors (the gloo tests of the host
+logic) always take the torch.distributed route.
 """
 import os
 
 import torch
 
 HALO = 2
+_COMM = {}  # one peer-memory communicator per process: (rank, world) -> native.Comm
 
 
 class SlabInfo:
@@ -28,6 +36,37 @@ class SlabInfo:
     def __init__(self, rank, world, group=None, halo=HALO):
         self.rank, self.world, self.group = int(rank), int(world), group
         self.halo = int(halo)
+        self.use_peer = os.environ.get("ODIL_B200_COMM", "peer") != "nccl"
+
+    @property
+    def comm(self):
+        return _COMM.get((self.rank, self.world))
+
+    # -- peer-memory communicator -------------------------------------------------------------------
+    def _all_gather_bytes(self, raw):
+        import torch.distributed as dist
+
+        mine = torch.tensor(list(raw), dtype=torch.uint8, device="cuda")
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        return [bytes(p.cpu().tolist()) for p in parts]
+
+    def ensure_comm(self, nbytes):
+        """Communicator whose staging holds `nbytes` per direction (collective when it has to be (re)created: every
+        rank asks for the same size because every rank exchanges the same arrays)."""
+        from . import native
+
+        comm = self.comm
+        if comm is None or comm.capacity < nbytes:
+            if comm is not None:
+                import torch.distributed as dist
+
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)  # nobody may still be writing into the block that is about to go
+                comm.destroy()
+            comm = native.Comm(self.rank, self.world, max(int(nbytes * 1.25), 1 << 20), self._all_gather_bytes)
+            _COMM[(self.rank, self.world)] = comm
+        return comm
 
     @staticmethod
     def from_environment():
@@ -98,6 +137,20 @@ class SlabInfo:
                 a[H - width:H].copy_(a[H + n - width:H + n])
                 a[H + n:H + n + width].copy_(a[H:H + width])
             return
+        if self.use_peer and locals_ and all(a.is_cuda for a in locals_):
+            from . import native
+
+            send_lo, send_hi, recv_lo, recv_hi = [], [], [], []
+            for a in locals_:
+                H = self.halo
+                n = a.shape[0] - 2 * H
+                send_lo.append(a[H:H + width])
+                send_hi.append(a[H + n - width:H + n])
+                recv_lo.append(a[H - width:H])
+                recv_hi.append(a[H + n:H + n + width])
+            need = native.Comm.bytes_needed([t.numel() * t.element_size() for t in send_lo])
+            self.ensure_comm(need).halo_exchange(send_lo, send_hi, recv_lo, recv_hi)
+            return
         lo = (self.rank - 1) % self.world
         hi = (self.rank + 1) % self.world
         ops = []
@@ -119,5 +172,8 @@ class SlabInfo:
         import torch.distributed as dist
 
         if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            if self.use_peer and t.is_cuda and t.dtype == torch.float64 and t.numel() <= 16:
+                self.ensure_comm(0).allreduce_scalars(t)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t

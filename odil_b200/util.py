@@ -202,6 +202,14 @@ def optimize_grad(args, optname, problem, state, callback=None, **kwargs):
         if args.callback_update_state:
             arrays[:] = domain.arrays_from_state(state)
 
+    def graph_safe():
+        """True if replaying the captured epoch is equivalent to running it: the operator lowered to static stencil
+        plans (no tracer value inside its tables, no run-time parameters of generated kernels)."""
+        engine = getattr(problem, "_cache_eval_loss_grad", {}).get("func")
+        view = getattr(engine, "tracer_view", None)
+        return (engine is not None and not hasattr(engine, "jacobian") and view is not None and not view.reads
+                and not args.callback_update_state)
+
     for flag, name in _OPTIMIZER_FLAGS.items():
         if getattr(args, flag, None) is not None:
             kwargs[name] = getattr(args, flag)
@@ -212,6 +220,7 @@ def optimize_grad(args, optname, problem, state, callback=None, **kwargs):
         callback(state, args.epoch_start, loss_grad(arrays)[2])
     else:
         loss_grad(arrays)  # builds the engine before the optimizer's first timed epoch
+    loss_grad.graph_safe = graph_safe()
     arrays, optinfo = opt.run(arrays, loss_grad=loss_grad, epochs=args.epochs - args.epoch_start,
                               callback=on_epoch if callback else None, epoch_start=args.epoch_start, lr=args.lr,
                               **kwargs)
