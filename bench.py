@@ -446,6 +446,10 @@ def run_b200(args):
         # burn-in (untimed): traces the operator, builds plans and work lists, and keeps the device under load long
         # enough for nvidia-smi to report clocks before and during the timed region
         ms0, _, _ = stepper.run(3, 5, graph=graph)
+        if dist is not None:  # every rank must run the same number of epochs (halo exchanges are collective)
+            t_ = torch.tensor([ms0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms0 = t_.item()
         stepper.run(1, int(min(400, max(10, 500.0 / max(ms0, 1e-3)))), graph=graph)
         replayed = bool(_opt.LAST_RUN_INFO["graph"]) and wl["opt"] == "adam"
         if with_kernels and not replayed:  # per-call CUDA events cannot be recorded inside a graph capture

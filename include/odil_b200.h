@@ -192,6 +192,15 @@ int odil_b200_multi_dot(const void* V, int64_t ld, int k, const void* g, int64_t
 int odil_b200_multi_axpy(const void* V, int64_t ld, int k, const double* coef, double a0, const void* g, void* d,
                          int64_t count, int dtype, void* stream);
 
+/* Fusion across the optimizer seam: the transposed interpolation of the finest level streams the
+ * gradient g_fine of the finest multigrid term once and applies that term's Adam update (optimizer.py:311-319) on the
+ * way, instead of k_adam reading g_fine a second time.  alpha_dev (nullable): step size in device memory (CUDA-graph
+ * replay).  Returns 1 without doing anything when the arrays do not fit the marching kernel (caller: unfused pair). */
+int odil_b200_mg_interp_adjoint_adam(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* g_fine,
+                                     double scale, void* g_coarse, void* x, void* m, void* v, double alpha,
+                                     const double* alpha_dev, double one_minus_beta1, double one_minus_beta2,
+                                     double epsilon, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Run-time specialised kernels for operators that are not affine stencils.
  *

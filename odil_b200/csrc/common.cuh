@@ -87,4 +87,16 @@ struct alignas(16) Vec4 {
     T x, y, z, w;
 };
 
+// One Adam update (reference optimizer.py:311-319), shared by k_adam (optim.cu) and the transposed interpolation that
+// applies the update of the finest multigrid term while it streams the gradient (mg_march.cuh).
+template <typename T>
+__device__ __forceinline__ void adam_one(T& x, T& m, T& v, const T g, const T alpha, const T omb1, const T omb2,
+                                         const T eps) {
+    // Same operation order as the reference; no FMA contraction across the rounding points that
+    // matter (m and v updates are written as the reference writes them).
+    m = m + (g - m) * omb1;
+    v = v + (g * g - v) * omb2;
+    x = x - (m * alpha) / (sqrt(v) + eps);
+}
+
 }  // namespace odil

@@ -727,6 +727,50 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
     return 0;
 }
 
+// g_coarse = scale * I^T g_fine  AND  the Adam update of the fine array (x, m, v) with gradient g_fine, in one pass
+// over g_fine (whole arrays, single GPU).  Returns 1 -- nothing done -- when the geometry is not the one the marching
+// kernel handles (cell-centred 3-D, even coarse width, 16-byte aligned arrays): the caller then runs
+// odil_b200_mg_interp_adjoint and odil_b200_adam_step separately.
+int odil_b200_mg_interp_adjoint_adam(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* g_fine,
+                                     double scale, void* g_coarse, void* x, void* m_state, void* v_state, double alpha,
+                                     const double* alpha_dev, double one_minus_beta1, double one_minus_beta2,
+                                     double epsilon, void* stream) {
+    MgGeom g;
+    if (int rc = make_geom(ndim, cshape, loc, g)) return rc;
+    ODIL_REQUIRE(g_fine && g_coarse && x && m_state && v_state, "null array");
+    ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    Mg3 m;
+    bool cz = false;
+    if (!(fast3_geometry(g, m, cz) && march_ok(m, cz, ndim, g_fine, g_coarse, x) && (uintptr_t)m_state % 16 == 0 &&
+          (uintptr_t)v_state % 16 == 0))
+        return 1;
+    const int n0 = (int)g.cn[0];
+    const int zc = march_chunk(m, n0, 4);
+    dim3 block(32, 4, 1);
+    dim3 grid((m.n2 / 2 + 31) / 32, (m.n1 + 3) / 4, (unsigned)((n0 + zc - 1) / zc));
+    if (grid.y > 65535 || grid.z > 65535) return 1;
+    const int nfix = 16 * n0 + 16 * (m.n1 + m.n2);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ODIL_B200_F32) {
+        MgAdam<float> ad{(float*)x, (float*)m_state, (float*)v_state, (float)alpha, (float)one_minus_beta1,
+                         (float)one_minus_beta2, (float)epsilon, alpha_dev};
+        k_interp_adjoint3m_adam<float><<<grid, block, 0, st>>>(m, (const float*)g_fine, (float)scale, (float*)g_coarse, 0, n0,
+                                                               zc, ad);
+        k_adjoint_joint_fix<float><<<(nfix + 127) / 128, 128, 0, st>>>(m, (const float*)g_fine, (float)scale,
+                                                                       (float*)g_coarse, 0, n0, 0, 0);
+    } else {
+        MgAdam<double> ad{(double*)x, (double*)m_state, (double*)v_state, alpha, one_minus_beta1, one_minus_beta2, epsilon,
+                          alpha_dev};
+        k_interp_adjoint3m_adam<double><<<grid, block, 0, st>>>(m, (const double*)g_fine, scale, (double*)g_coarse, 0, n0, zc,
+                                                                ad);
+        k_adjoint_joint_fix<double><<<(nfix + 127) / 128, 128, 0, st>>>(m, (const double*)g_fine, scale, (double*)g_coarse, 0,
+                                                                        n0, 0, 0);
+    }
+    launch_counter()++;  // two launches
+    ODIL_LAUNCHED();
+    return 0;
+}
+
 int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* g_fine,
                                 double scale, void* g_coarse, const odil_b200_mg_adj_range* range, void* stream) {
     MgGeom g;

@@ -21,16 +21,6 @@ struct AdamBatch {
 };
 
 template <typename T>
-__device__ __forceinline__ void adam_one(T& x, T& m, T& v, const T g, const T alpha, const T omb1, const T omb2,
-                                         const T eps) {
-    // Same operation order as the reference; no FMA contraction across the rounding points that
-    // matter (m and v updates are written as the reference writes them).
-    m = m + (g - m) * omb1;
-    v = v + (g * g - v) * omb2;
-    x = x - (m * alpha) / (sqrt(v) + eps);
-}
-
-template <typename T>
 __global__ void __launch_bounds__(256) k_adam(AdamBatch<T> b) {
     const int t = blockIdx.y;
     const int64_t n = b.n[t];

@@ -476,16 +476,32 @@ class ResidualEngine:
             res, cfac = out, 1.0
         return res
 
+    def request_fused_adam(self, x, m, v, alpha, omb1, omb2, eps, alpha_dev=None):
+        """Asks the NEXT loss_grad() to apply the Adam update of the finest multigrid term itself, inside the
+        transposed interpolation that streams that term's gradient (odil_b200_mg_interp_adjoint_adam); the gradient
+        entry of an updated array comes back as None.  x, m, v: the optimizer's lists, aligned with `arrays`."""
+        self._fused_adam = dict(x=x, m=m, v=v, alpha=alpha, omb1=omb1, omb2=omb2, eps=eps, alpha_dev=alpha_dev)
+
     def _scatter_grad(self, unk, gU, grads):
         """Gradient of the regular field -> gradients of the stored arrays."""
         if unk.kind != "MultigridField":
             grads[unk.first] = gU
             return
         g = gU
+        fused = getattr(self, "_fused_adam", None)
         for lvl in range(unk.narrays):
             if lvl > 0:
                 gc = self._buf(("gV", unk.key, lvl), unk.shapes[lvl])
-                native.mg_interp_adjoint(unk.shapes[lvl], unk.mgloc, g, 1.0, gc)
+                done = False
+                if lvl == 1 and fused is not None and unk.factors[0] == 1 and self.slab is None:
+                    i = unk.first
+                    done = native.mg_interp_adjoint_adam(unk.shapes[1], unk.mgloc, g, 1.0, gc, fused["x"][i],
+                                                         fused["m"][i], fused["v"][i], fused["alpha"], fused["omb1"],
+                                                         fused["omb2"], fused["eps"], fused["alpha_dev"])
+                    if done:
+                        grads[i] = None  # already applied
+                if not done:
+                    native.mg_interp_adjoint(unk.shapes[lvl], unk.mgloc, g, 1.0, gc)
                 g = gc
             f = unk.factors[lvl]
             grads[unk.first + lvl] = g if f == 1 else g * f
@@ -522,11 +538,15 @@ class ResidualEngine:
                 blk.plan.adjoint(F, 2.0 / out.n, g if blk.key in gU else None, g)
                 gU[blk.key] = g
         grads = [None] * self.narrays
+        applied = set()
         for key, unk in self.unknowns.items():
             if key in gU:
                 self._scatter_grad(unk, gU[key], grads)
+                if grads[unk.first] is None:
+                    applied.add(unk.first)
+        self._fused_adam = None
         for i in range(self.narrays):
-            if grads[i] is None:
+            if grads[i] is None and i not in applied:
                 grads[i] = torch.zeros_like(arrays[i])
         fetch = _Fetch(sums, [o.n for o in self.outputs], self.dtype)
         loss = LazyScalar(fetch, "loss")

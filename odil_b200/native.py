@@ -25,6 +25,7 @@ EXPORTS = [
     "odil_b200_mg_interp_adjoint", "odil_b200_mg_restrict", "odil_b200_adam_step", "odil_b200_gd_step",
     "odil_b200_axpby", "odil_b200_multi_dot", "odil_b200_multi_axpy", "odil_b200_cg_update_xr",
     "odil_b200_cg_update_p", "odil_b200_star_worklist", "odil_b200_adam_step_dev",
+    "odil_b200_mg_interp_adjoint_adam",
     "odil_b200_jit_compile", "odil_b200_jit_log", "odil_b200_jit_cubin", "odil_b200_jit_kernel",
     "odil_b200_jit_launch", "odil_b200_jit_destroy",
     "odil_b200_comm_create", "odil_b200_comm_connect", "odil_b200_comm_capacity", "odil_b200_halo_exchange",
@@ -101,6 +102,8 @@ def load(build_if_missing=False):
                                             P(MgRange), vp]
     lib.odil_b200_mg_interp_adjoint.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, dbl, vp,
                                                 P(MgAdjRange), vp]
+    lib.odil_b200_mg_interp_adjoint_adam.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, dbl, vp, vp,
+                                                     vp, vp, dbl, vp, dbl, dbl, dbl, vp]
     lib.odil_b200_mg_restrict.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, vp, vp]
     lib.odil_b200_adam_step.argtypes = [ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), ctypes.c_int, dbl, dbl,
                                         dbl, dbl, vp]
@@ -285,6 +288,28 @@ def mg_interp_adjoint(cshape, loc, g_fine, scale, g_coarse, rng=None):
         _ptr(g_coarse), r, _stream())))
 
 
+def mg_interp_adjoint_adam(cshape, loc, g_fine, scale, g_coarse, x, m, v, alpha, omb1, omb2, eps, alpha_dev=None):
+    """g_coarse = scale * I^T g_fine and the Adam update of (x, m, v) with gradient g_fine in one pass over g_fine.
+    Returns False (nothing done) if the arrays do not fit the fused kernel."""
+    load()
+    for t in (x, m, v):
+        if t.dtype != g_fine.dtype or t.shape != g_fine.shape:
+            raise NativeError("fused Adam: x, m, v must match the fine gradient in dtype and shape")
+    res = {}
+
+    def run():
+        rc = _lib.odil_b200_mg_interp_adjoint_adam(
+            len(cshape), _cshape(cshape), loc.encode(), dtype_code(g_fine.dtype), _ptr(g_fine), float(scale),
+            _ptr(g_coarse), _ptr(x), _ptr(m), _ptr(v), float(alpha), _ptr(alpha_dev) if alpha_dev is not None else None,
+            float(omb1), float(omb2), float(eps), _stream())
+        if rc not in (0, 1):
+            _check(rc)
+        res["applied"] = rc == 0
+
+    _call("mg_interp_adjoint_adam", run)
+    return res["applied"]
+
+
 def mg_restrict(fshape, loc, fine, out):
     load()
     _check(_lib.odil_b200_mg_restrict(len(fshape), _cshape(fshape), loc.encode(), dtype_code(fine.dtype), _ptr(fine),
@@ -305,6 +330,8 @@ def _ptr_array(tensors, dtype=None, counts=None):
 def adam_step(x, m, v, g, alpha, omb1, omb2, eps):
     load()
     n = len(x)
+    if n == 0:
+        return
     cnt = [t.numel() for t in x]
     counts = (ctypes.c_int64 * n)(*cnt)
     dt = x[0].dtype
@@ -319,6 +346,8 @@ def adam_step_dev(x, m, v, g, alpha_dev, omb1, omb2, eps):
     if alpha_dev.dtype != torch.float64 or not alpha_dev.is_cuda or alpha_dev.numel() != 1:
         raise NativeError("adam_step_dev: alpha_dev must be a 1-element float64 CUDA tensor")
     n = len(x)
+    if n == 0:
+        return
     cnt = [t.numel() for t in x]
     counts = (ctypes.c_int64 * n)(*cnt)
     dt = x[0].dtype

@@ -94,11 +94,19 @@ class AdamNativeOptimizer(Optimizer):
         first, last = epoch_start + 1, epoch_start + epochs
         eager_until = last if not graph else min(last, first + 1)
         LAST_RUN_INFO["graph"] = bool(graph and eager_until < last)
+        # Fusion across the optimizer seam: an engine that can apply the update of the finest multigrid term while it
+        # streams that term's gradient (odil_b200_mg_interp_adjoint_adam) is told the step in advance and hands back
+        # None in place of the gradients it has consumed.
+        fuse = getattr(loss_grad, "fuse_adam", None)
         for epoch in range(first, eager_until + 1):
             self.evals += 1
-            loss, grads, pinfo = loss_grad(x)
             alpha, omb1, omb2 = adam_scalars(lr, beta_1, beta_2, epoch - epoch_start, dtype)
-            native.adam_step(x, m, v, grads, alpha, omb1, omb2, eps)
+            if fuse is not None:
+                fuse(x, m, v, alpha, omb1, omb2, eps)
+            loss, grads, pinfo = loss_grad(x)
+            rest = [i for i, g in enumerate(grads) if g is not None]
+            native.adam_step([x[i] for i in rest], [m[i] for i in rest], [v[i] for i in rest],
+                             [grads[i] for i in rest], alpha, omb1, omb2, eps)
             if epoch > 0 and callback is not None:
                 callback(x, epoch, pinfo)
         if eager_until < last:
@@ -123,8 +131,13 @@ class AdamNativeOptimizer(Optimizer):
         with torch.cuda.graph(g):
             torch.index_select(table, 0, step, out=alpha_dev)
             step.add_(1)
+            fuse = getattr(loss_grad, "fuse_adam", None)
+            if fuse is not None:
+                fuse(held, m, v, 0.0, omb1, omb2, eps, alpha_dev=alpha_dev)
             loss, grads, pinfo = loss_grad(held)
-            native.adam_step_dev(held, m, v, grads, alpha_dev, omb1, omb2, eps)
+            rest = [i for i, gr in enumerate(grads) if gr is not None]
+            native.adam_step_dev([held[i] for i in rest], [m[i] for i in rest], [v[i] for i in rest],
+                                 [grads[i] for i in rest], alpha_dev, omb1, omb2, eps)
         nodes = native.launch_count() - n_before  # library kernels captured into one replay
         fetch = getattr(loss, "_fetch", None)
         self._graph = g  # owns the memory pool of grads / sums that pinfo still points into after run()

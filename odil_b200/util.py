@@ -221,6 +221,10 @@ def optimize_grad(args, optname, problem, state, callback=None, **kwargs):
     else:
         loss_grad(arrays)  # builds the engine before the optimizer's first timed epoch
     loss_grad.graph_safe = graph_safe()
+    engine = getattr(problem, "_cache_eval_loss_grad", {}).get("func")
+    if hasattr(engine, "request_fused_adam") and not hasattr(engine, "jacobian") \
+            and os.environ.get("ODIL_B200_FUSE_ADAM", "1") != "0":
+        loss_grad.fuse_adam = engine.request_fused_adam
     arrays, optinfo = opt.run(arrays, loss_grad=loss_grad, epochs=args.epochs - args.epoch_start,
                               callback=on_epoch if callback else None, epoch_start=args.epoch_start, lr=args.lr,
                               **kwargs)
