@@ -51,8 +51,50 @@ def numpy_dtype(dtype):
     return np.dtype(dtype)
 
 
+HOST_NUMEL = 1 << 16  # Known values up to this size live on the host (see _as_tensor)
+
+
+def _codevice(*ts):
+    """The same tensors, the host-resident ones moved to the device of the others (if any is on a GPU)."""
+    dev = next((t.device for t in ts if torch.is_tensor(t) and t.is_cuda), None)
+    if dev is None:
+        return ts
+    return tuple(t.to(dev) if torch.is_tensor(t) and not t.is_cuda else t for t in ts)
+
+
 def _as_tensor(x, device=None, dtype=None):
-    """torch tensor from python scalar / numpy / torch, rounding python floats ONCE to `dtype`."""
+    """torch tensor from python scalar / numpy / torch, rounding python floats ONCE to `dtype`.
+
+    Values that do not come from the device and are small (index vectors, coordinates, masks, step sizes, boundary
+    data: the compact operands of the trace) stay on the HOST: the algebra of the trace (where / add / div on shapes
+    like (N, 1, 1)) then runs in host memory instead of launching hundreds of tiny library kernels, and only what
+    the kernels consume (dense constants, coefficient tables) is uploaded.  Large arrays go to `device`."""
+    device = device or default_device()
+    if torch.is_tensor(x):
+        t = x if (x.is_cuda or x.numel() <= HOST_NUMEL) else x.to(device)
+    elif isinstance(x, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        if t.numel() > HOST_NUMEL:
+            t = t.to(device)
+    elif isinstance(x, (bool, np.bool_)):
+        t = torch.tensor(bool(x))
+    elif isinstance(x, (int, np.integer)):
+        t = torch.tensor(int(x), dtype=torch_dtype(dtype) if dtype is not None else torch.int64)
+    elif isinstance(x, (float, np.floating)):
+        if dtype is None:
+            dtype = x.dtype if isinstance(x, np.floating) else np.float64
+        t = torch.tensor(float(x), dtype=torch_dtype(dtype))
+    else:
+        t = torch.from_numpy(np.asarray(x))
+        if t.numel() > HOST_NUMEL:
+            t = t.to(device)
+    if dtype is not None and t.dtype != torch_dtype(dtype):
+        t = t.to(torch_dtype(dtype))
+    return t
+
+
+def _as_tensor_on(x, device=None, dtype=None):
+    """As _as_tensor, but always on `device` (state storage)."""
     device = device or default_device()
     if torch.is_tensor(x):
         t = x.to(device)
@@ -251,7 +293,7 @@ def _known_binary(op, a, b):
     if not isinstance(b, Known):
         b = as_known(b, like=a)
     nd = max(len(a.shape), len(b.shape))
-    ta, tb = _align(a.t, nd), _align(b.t, nd)
+    ta, tb = _codevice(_align(a.t, nd), _align(b.t, nd))
     if ta.dtype != tb.dtype and ta.dtype.is_floating_point and tb.dtype.is_floating_point:
         # numpy promotion (float32 op float64 -> float64)
         pt = torch.promote_types(ta.dtype, tb.dtype)
@@ -272,6 +314,7 @@ class Coef:
     def add_term(self, t):
         for i, u in enumerate(self.terms):
             if u.shape == t.shape:
+                u, t = _codevice(u, t)
                 self.terms[i] = u + t
                 return
         self.terms.append(t)
@@ -284,14 +327,19 @@ class Coef:
 
     def scaled(self, k, divide=False):
         """Every term times (or divided by) compact tensor k."""
-        return Coef([(t / k) if divide else (t * k) for t in self.terms])
+        out = []
+        for t in self.terms:
+            t, kk = _codevice(t, k)
+            out.append((t / kk) if divide else (t * kk))
+        return Coef(out)
 
     def masked(self, cond, keep_true):
         z = None
         out = []
         for t in self.terms:
+            t, c = _codevice(t, cond)
             z = torch.zeros((), dtype=t.dtype, device=t.device)
-            out.append(torch.where(cond, t, z) if keep_true else torch.where(cond, z, t))
+            out.append(torch.where(c, t, z) if keep_true else torch.where(c, z, t))
         return Coef(out)
 
     def rolled(self, shifts):
@@ -311,7 +359,7 @@ class Coef:
     def dense(self, shape, dtype, device):
         r = torch.zeros(shape, dtype=dtype, device=device)
         for t in self.terms:
-            r += t.to(dtype)
+            r += t.to(device=device, dtype=dtype)
         return r
 
 
@@ -326,7 +374,7 @@ class Affine(Lazy):
 
     @staticmethod
     def symbol(key, shift, shape, dtype, frozen=False, device=None):
-        one = torch.ones((1,) * len(shape), dtype=torch_dtype(dtype), device=device or default_device())
+        one = torch.ones((1,) * len(shape), dtype=torch_dtype(dtype))  # coefficients are compact: host memory
         return Affine(shape, dtype, {(key, tuple(int(s) for s in shift), bool(frozen)): Coef([one])})
 
     def _coef_tensor(self, k):
@@ -444,11 +492,11 @@ class ModB200(ModBase):
 
     def _uniform(self, shape, minval, maxval, dtype):
         u = torch.rand(tuple(shape), generator=self._gen, dtype=torch.float64)
-        return Known((minval + (maxval - minval) * u).to(torch_dtype(dtype)).to(self.device))
+        return Known((minval + (maxval - minval) * u).to(torch_dtype(dtype)))
 
     def _normal(self, shape, mean=0, stddev=1, dtype=np.float32):
         u = torch.randn(tuple(shape), generator=self._gen, dtype=torch.float64)
-        return Known((mean + stddev * u).to(torch_dtype(dtype)).to(self.device))
+        return Known((mean + stddev * u).to(torch_dtype(dtype)))
 
     def cast(self, x, dtype):
         if _is_graph(x):
@@ -476,19 +524,19 @@ class ModB200(ModBase):
         """State storage: a plain device tensor (what the kernels and optimizers operate on)."""
         if isinstance(x, Known):
             x = x.full()
-        t = _as_tensor(x, self.device, dtype=dtype)
-        return t.contiguous().clone() if torch.is_tensor(x) else t.contiguous()
+        t = _as_tensor_on(x, self.device, dtype=dtype)
+        return t.contiguous().clone() if torch.is_tensor(x) and x.device == t.device else t.contiguous()
 
     def is_tensor(self, x):
         return torch.is_tensor(x) or isinstance(x, Lazy)
 
     def zeros(self, shape, dtype=np.float32):
         shape = (shape,) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
-        return Known(torch.zeros((1,) * len(shape), dtype=torch_dtype(dtype), device=self.device), shape)
+        return Known(torch.zeros((1,) * len(shape), dtype=torch_dtype(dtype)), shape)
 
     def ones(self, shape, dtype=np.float32):
         shape = (shape,) if np.ndim(shape) == 0 else tuple(int(s) for s in shape)
-        return Known(torch.ones((1,) * len(shape), dtype=torch_dtype(dtype), device=self.device), shape)
+        return Known(torch.ones((1,) * len(shape), dtype=torch_dtype(dtype)), shape)
 
     def full(self, shape, value, dtype=None):
         return self.ones(shape, dtype or np.float32) * value
@@ -559,11 +607,11 @@ class ModB200(ModBase):
         like = a if isinstance(a, Known) else (b if isinstance(b, Known) else None)
         a, b = as_known(a, like=like), as_known(b, like=like)
         nd = max(len(cond.shape), len(a.shape), len(b.shape))
-        ta, tb = _align(a.t, nd), _align(b.t, nd)
+        ta, tb, tc = _codevice(_align(a.t, nd), _align(b.t, nd), _align(cond.t, nd))
         if ta.dtype != tb.dtype:
             pt = torch.promote_types(ta.dtype, tb.dtype)
             ta, tb = ta.to(pt), tb.to(pt)
-        return Known(torch.where(_align(cond.t, nd).to(torch.bool), ta, tb), _bshape(cond.shape, a.shape, b.shape))
+        return Known(torch.where(tc.to(torch.bool), ta, tb), _bshape(cond.shape, a.shape, b.shape))
 
     def roll(self, x, shift, axis=None):
         if axis is None:
@@ -622,14 +670,14 @@ class ModB200(ModBase):
     def stack(self, xs, axis=0):
         if _is_graph(*xs):
             return graph.g_stack(list(xs), axis)
-        return Known(torch.stack([as_known(x).full() for x in xs], dim=axis))
+        return Known(torch.stack(list(_codevice(*[as_known(x).full() for x in xs])), dim=axis))
 
     def concatenate(self, xs, axis=0):
         if _is_graph(*xs):
             return graph.g_concat(list(xs), axis)
         if all(torch.is_tensor(x) for x in xs):
             return torch.cat(list(xs), dim=axis)
-        return Known(torch.cat([as_known(x).full() for x in xs], dim=axis))
+        return Known(torch.cat(list(_codevice(*[as_known(x).full() for x in xs])), dim=axis))
 
     hstack = concatenate
 
@@ -664,13 +712,13 @@ class ModB200(ModBase):
         if _is_graph(a, b):
             return graph.g_binary("minimum", a, b)
         a, b = as_known(a, like=b if isinstance(b, Known) else None), as_known(b, like=a if isinstance(a, Known) else None)
-        return Known(torch.minimum(*torch.broadcast_tensors(a.full(), b.full())))
+        return Known(torch.minimum(*torch.broadcast_tensors(*_codevice(a.full(), b.full()))))
 
     def maximum(self, a, b):
         if _is_graph(a, b):
             return graph.g_binary("maximum", a, b)
         a, b = as_known(a, like=b if isinstance(b, Known) else None), as_known(b, like=a if isinstance(a, Known) else None)
-        return Known(torch.maximum(*torch.broadcast_tensors(a.full(), b.full())))
+        return Known(torch.maximum(*torch.broadcast_tensors(*_codevice(a.full(), b.full()))))
 
     def clip(self, x, lo, hi):
         if _is_graph(x, lo, hi):
@@ -680,13 +728,13 @@ class ModB200(ModBase):
     def matmul(self, a, b):
         if _is_graph(a, b):
             raise graph.GraphError("matmul of traced expressions: use ctx.neural_net / elementwise products")
-        return Known(torch.matmul(as_known(a).full(), as_known(b).full()))
+        return Known(torch.matmul(*_codevice(as_known(a).full(), as_known(b).full())))
 
     def gather_nd(self, u, idx):
         if _is_graph(u, idx):
             raise graph.GraphError("gather_nd of a traced expression is not supported")
-        idx = as_known(idx).full().long()
-        return Known(as_known(u).full()[tuple(torch.movedim(idx, -1, 0))])
+        ut, idx = _codevice(as_known(u).full(), as_known(idx).full().long())
+        return Known(ut[tuple(torch.movedim(idx, -1, 0))])
 
     # -- reductions (Known only; reductions of field expressions are the loss, done by the engine) --
     def _reduce(self, fn, x, axis=None):

@@ -159,14 +159,13 @@ def lower_block(shape, coefs):
     cls_shape = tuple(2 * r + 1 for r in rr)
     table = np.zeros(cls_shape + (len(offsets),), dtype=np.float64)
     for o, off in enumerate(offsets):
-        acc = torch.zeros(cls_shape, dtype=torch.float64, device=coefs[off].terms[0].device if coefs[off].terms
-                          else "cpu")
+        acc = torch.zeros(cls_shape, dtype=torch.float64)
         for t in coefs[off].terms:
-            s = t.to(torch.float64)
+            s = t
             for a in range(nd):
                 if s.shape[a] != 1:
                     s = s.index_select(a, torch.as_tensor(reps[a], device=s.device))
-            acc = acc + s
+            acc = acc + s.to(torch.float64).cpu()
         table[..., o] = acc.cpu().numpy()
     keep = [o for o in range(len(offsets)) if np.any(table[..., o] != 0)]
     if not keep:
@@ -351,7 +350,7 @@ class ResidualEngine:
                 raise NonAffineError("Context.Raw loss terms are not on the fused path yet")
             if not isinstance(v, Affine):
                 v = as_known(v)
-                const = v.full().to(self.tdtype).contiguous()
+                const = v.full().to(device=self.device, dtype=self.tdtype).contiguous()
                 self.outputs.append(_Output(name, tuple(v.shape), const, []))
                 continue
             groups = {}

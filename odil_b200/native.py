@@ -181,6 +181,7 @@ def _plane_ptr(t, halo):
 
 
 _replayed = 0
+FUSED_ADAM_APPLIED = 0  # how many times odil_b200_mg_interp_adjoint_adam really ran (it declines unsuitable arrays)
 
 
 def note_replayed_launches(n):
@@ -307,6 +308,8 @@ def mg_interp_adjoint_adam(cshape, loc, g_fine, scale, g_coarse, x, m, v, alpha,
         res["applied"] = rc == 0
 
     _call("mg_interp_adjoint_adam", run)
+    global FUSED_ADAM_APPLIED
+    FUSED_ADAM_APPLIED += int(res["applied"])
     return res["applied"]
 
 
