@@ -55,6 +55,8 @@ def parse():
     p.add_argument("--cpu_budget_s", type=float, default=420.0, help="wall-time budget of the reference arm")
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--no_strong", action="store_true", help="skip the extra strong-scaling block at N > 1")
+    p.add_argument("--profile", action="store_true",
+                   help="short run for ncu: no burn-in, no clock sampler, no e2e / CPU / strong-scaling legs")
     p.add_argument("--graph", type=int, default=None, help="CUDA-graph replay of the Adam epoch (default: config 1)")
     return p.parse_args()
 
@@ -441,23 +443,24 @@ def run_b200(args):
             timers.clear()
             launches["n0"] = native.launch_count()
 
-        if rank == 0 and with_kernels:
+        if rank == 0 and with_kernels and not args.profile:
             sampler.start()
         # burn-in (untimed): traces the operator, builds plans and work lists, and keeps the device under load long
         # enough for nvidia-smi to report clocks before and during the timed region
-        ms0, _, _ = stepper.run(3, 5, graph=graph)
+        ms0, _, _ = stepper.run(1, 2, graph=graph) if args.profile else stepper.run(3, 5, graph=graph)
         if dist is not None:  # every rank must run the same number of epochs (halo exchanges are collective)
             t_ = torch.tensor([ms0], device="cuda", dtype=torch.float64)
             dist.all_reduce(t_, op=dist.ReduceOp.MAX)
             ms0 = t_.item()
-        stepper.run(1, int(min(400, max(10, 500.0 / max(ms0, 1e-3)))), graph=graph)
+        if not args.profile:
+            stepper.run(1, int(min(400, max(10, 500.0 / max(ms0, 1e-3)))), graph=graph)
         replayed = bool(_opt.LAST_RUN_INFO["graph"]) and wl["opt"] == "adam"
         if with_kernels and not replayed:  # per-call CUDA events cannot be recorded inside a graph capture
             native.set_timer_hook(timed)
-        ms, _, info = stepper.run(max(warmup, 3), steps, on_warm=on_warm, graph=graph)
+        ms, _, info = stepper.run(warmup if args.profile else max(warmup, 3), steps, on_warm=on_warm, graph=graph)
         native.set_timer_hook(None)
         n_launch = native.launch_count() - launches["n0"]
-        clocks = sampler.stop() if rank == 0 and with_kernels else None
+        clocks = sampler.stop() if rank == 0 and with_kernels and not args.profile else None
         if dist is not None:
             t_ = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t_, op=dist.ReduceOp.MAX)
@@ -520,7 +523,9 @@ def run_b200(args):
 
     # e2e: every step the unknowns arrive from pinned host memory and the loss goes back to the host
     e2e = None
-    if wl["opt"] == "adam":
+    if args.profile:
+        args.no_cpu_baseline = args.no_strong = True
+    elif wl["opt"] == "adam":
         host = [torch.empty(a.shape, dtype=a.dtype, pin_memory=True).copy_(a) for a in x]
         h2d = sum(a.numel() * a.element_size() for a in host)
         _, wall_ms, _ = m["stepper"].run(2, args.e2e_steps, e2e_host=host)
