@@ -222,8 +222,11 @@ def optimize_grad(args, optname, problem, state, callback=None, **kwargs):
         loss_grad(arrays)  # builds the engine before the optimizer's first timed epoch
     loss_grad.graph_safe = graph_safe()
     engine = getattr(problem, "_cache_eval_loss_grad", {}).get("func")
+    # Opt-in (ODIL_B200_FUSE_ADAM=1): the fused kernel is bit-identical to the pair it replaces but, measured at 512^3
+    # fp32 on B200, slower (0.874 ms vs 0.179 + 0.575 ms: at 168 registers it runs 12 warps per SM and is bound by
+    # latency, not by the 4 bytes per cell it saves) -- profiles/README.md, round 2.
     if hasattr(engine, "request_fused_adam") and not hasattr(engine, "jacobian") \
-            and os.environ.get("ODIL_B200_FUSE_ADAM", "1") != "0":
+            and os.environ.get("ODIL_B200_FUSE_ADAM", "0") not in ("", "0"):
         loss_grad.fuse_adam = engine.request_fused_adam
     arrays, optinfo = opt.run(arrays, loss_grad=loss_grad, epochs=args.epochs - args.epoch_start,
                               callback=on_epoch if callback else None, epoch_start=args.epoch_start, lr=args.lr,
