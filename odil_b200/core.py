@@ -649,6 +649,7 @@ class Context:
             if any(trim_flag):
                 array = array[tuple(slice(0, -1 if f else None) for f in trim_flag)]
             self.desc_to_array[desc] = array
+            self.trace.note_field(desc, field.loc, pad_flag, trim_flag)
         array = self.desc_to_array[desc]
         return mod.stop_gradient(array) if frozen else array
 
@@ -731,10 +732,9 @@ class Problem:
         from .newton import StencilJacobian
 
         engine = self._engine(state)
-        if hasattr(engine, "jacobian"):
-            raise NotImplementedError(
-                "eval_operator_grad of a non-affine operator: use Problem.linearize (matrix-free Jacobian products "
-                "and .tocsr()) -- the per-(key, shift) diagonals exist only for affine stencils")
+        if hasattr(engine, "jacobian"):  # general engine: diagonals read off the generated Jacobian rows
+            arrays = self.domain.arrays_from_state(state)
+            return engine.operator_values(arrays), engine.operator_grad(arrays), engine.names
         values = engine.operator_values(self.domain.arrays_from_state(state))
         jac = StencilJacobian(engine)
         grads = []

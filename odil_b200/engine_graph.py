@@ -59,6 +59,7 @@ class GraphTrace:
                 self.exprs.append(graph.g_input(len(self.shapes), shape, engine.dtype))
                 self.shapes.append(tuple(shape))
         self.regular_slot = {}
+        self.fields_read = {}  # (key, shift, loc) -> (source loc, pad flags, trim flags): what ctx.field() produced
         # shadow state: same containers, arrays replaced by graph inputs
         fields = {}
         for key, field in state.fields.items():
@@ -77,6 +78,24 @@ class GraphTrace:
                 fields[key] = NeuralNet(ex[:nw], ex[nw:], func_in=field.func_in, func_out=field.func_out,
                                         activation=field.activation)
         self.state = State(fields=fields, initialized=True)
+
+    def note_field(self, desc, src_loc, pad_flag, trim_flag):
+        self.fields_read[desc] = (src_loc, tuple(pad_flag), tuple(trim_flag))
+
+    def column_map(self, desc, col0):
+        """Packed-state column that ctx.field(*desc) reads in every cell of its result (-1 where it reads the zero
+        pad): the index array of the source field pushed through the same pad / roll / trim (core.py:956-969)."""
+        key, shift, loc = desc
+        unk = self.engine.unknowns[key]
+        src_loc, pad_flag, trim_flag = self.fields_read[desc]
+        idx = np.arange(math.prod(unk.shapes[0]), dtype=np.int64).reshape(unk.shapes[0]) + int(col0[unk.first])
+        if any(pad_flag):
+            idx = np.pad(idx, [(1, 0) if f else (0, 0) for f in pad_flag], mode="constant", constant_values=-1)
+        if any(shift):
+            idx = np.roll(idx, tuple(int(-s) for s in shift), axis=tuple(range(idx.ndim)))
+        if any(trim_flag):
+            idx = idx[tuple(slice(0, -1 if f else None) for f in trim_flag)]
+        return idx
 
     def regular(self, key):
         unk = self.engine.unknowns[key]
@@ -241,6 +260,46 @@ class GraphEngine(ResidualEngine):
     def jacobian(self, arrays):
         return GraphJacobian(self, arrays)
 
+    def operator_grad(self, arrays):
+        """Per output: {(key, shift, loc): dF/d(that shifted field), an array on the output's grid} for every
+        ctx.field() the operator made, and {(key, None, None): dense block} for Array unknowns -- what the reference's
+        `_eval_operator_grad_tf` returns (core.py:1313-1361), read off the rows the 'jac' kernels write."""
+        jac = GraphJacobian(self, arrays)
+        return diagonals_from_rows(self, jac.col0, jac.rows())
+
+
+def diagonals_from_rows(engine, col0, rows_per_output):
+    """rows_per_output[k] = (cell index, packed column, value) arrays of output k (COO rows of the Jacobian)."""
+    trace = engine.trace
+    maps = {desc: trace.column_map(desc, col0) for desc in trace.fields_read}
+    res = []
+    for k, out in enumerate(engine.outputs):
+        cell, col, val = rows_per_output[k]
+        d = {}
+        taken = np.zeros(len(cell), dtype=bool)
+        for desc, cmap in maps.items():
+            if tuple(cmap.shape) != tuple(out.shape):
+                continue
+            hit = (~taken) & (cmap.reshape(-1)[cell] == col)
+            g = np.zeros(out.n, dtype=np.float64)
+            np.add.at(g, cell[hit], val[hit])
+            taken |= hit
+            if np.any(g != 0) or desc[1] == (0,) * len(desc[1]):
+                d[desc] = Known(torch.as_tensor(g.reshape(out.shape), dtype=engine.tdtype))
+        for key, unk in engine.unknowns.items():
+            if unk.kind != "Array":
+                continue
+            lo, n = int(col0[unk.first]), math.prod(unk.shapes[0])
+            hit = (~taken) & (col >= lo) & (col < lo + n)
+            if np.any(hit):
+                block = np.zeros((out.n, n), dtype=np.float64)
+                np.add.at(block, (cell[hit], col[hit] - lo), val[hit])
+                d[(key, None, None)] = Known(torch.as_tensor(block.reshape(out.shape + tuple(unk.shapes[0])),
+                                                             dtype=engine.tdtype))
+                taken |= hit
+        res.append(d)
+    return res
+
 
 class GraphJacobian:
     """J = dF/d(packed state) at a fixed state: matrix-free products on the device (`matvec`, `rmatvec`: the
@@ -288,16 +347,14 @@ class GraphJacobian:
             return self.matvec(x)
         return self.tocsr().dot(x)
 
-    def tocsr(self):
-        import scipy.sparse
-
-        if self._csr is not None:
-            return self._csr
+    def rows(self):
+        """Per output k: (cell, column, value) of the non-zero Jacobian entries, from the 'jac' kernels."""
         eng = self.engine
         if self.shape[0] * 8 > 2 ** 31:
-            raise MemoryError("tocsr() is meant for small problems; use the matrix-free products (linsolver cg_b200)")
-        rows, cols, vals = [], [], []
+            raise MemoryError("explicit Jacobian rows are meant for small problems; use the matrix-free products")
         colbase = [int(c) for c in self.col0[:-1]]
+        empty = (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0))
+        res = [empty] * len(eng.outputs)
         for g, name, which in eng.gen.kernels("jac"):
             k = g.results[which][0]
             nl = eng.gen.nloads(g)
@@ -308,11 +365,22 @@ class GraphJacobian:
             eng._launch("jac", self.arrays, jcol=jcol, jval=jval, colbase=colbase, prm=self.prm, only=(g.gid, which))
             v = jval.cpu().numpy().astype(np.float64)
             c = jcol.cpu().numpy()
-            r = np.repeat(np.arange(g.ncell, dtype=np.int64), nl) + int(self.row0[k])
+            r = np.repeat(np.arange(g.ncell, dtype=np.int64), nl)
             keep = v != 0
-            rows.append(r[keep])
-            cols.append(c[keep])
-            vals.append(v[keep])
+            res[k] = (r[keep], c[keep], v[keep])
+        return res
+
+    def tocsr(self):
+        import scipy.sparse
+
+        if self._csr is not None:
+            return self._csr
+        rows, cols, vals = [], [], []
+        for k, (r, c, v) in enumerate(self.rows()):
+            if len(r):
+                rows.append(r + int(self.row0[k]))
+                cols.append(c)
+                vals.append(v)
         if rows:
             m = scipy.sparse.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                                         shape=self.shape)

@@ -124,3 +124,47 @@ def test_optimizers_drive_a_nonaffine_problem(opt, epochs, golden):
     load_state(problem, state, g, "heat_knet_f64", dt)
     losses = run_optimizer(problem, state, opt, run_args(epochs=epochs, lr=0.01))
     assert losses is not None and losses[-1] < 0.7 * losses[0]
+
+
+@pytest.mark.parametrize("case", ["newton", "heat_k", "heat3"])
+def test_eval_operator_grad_diagonals_match_reference_jacobian(golden, case):
+    """Problem.eval_operator_grad for non-affine operators: per output {(key, shift, loc): dF/d(shifted field)} like
+    `_eval_operator_grad_tf` (core.py:1313-1361) -- every entry of the reference-generated dense Jacobian that the
+    diagonals claim is reproduced, and together with the Array / NeuralNet columns they account for all of it."""
+    g = golden("nonaffine")
+    key = f"{case}_f64"
+    problem, state, dt = build_case(case, "f64", device="cuda")
+    load_state(problem, state, g, key, dt)
+    values, grads, names = problem.eval_operator_grad(state)
+    engine = problem._engine(state)
+    Jr = g[key + "_jac"].copy()
+    sizes = [a.numel() for a in problem.domain.arrays_from_state(state)]
+    col0 = np.concatenate([[0], np.cumsum(sizes)])
+    row0 = np.concatenate([[0], np.cumsum([o.n for o in engine.outputs])])
+    assert len(grads) == len(values) == len(names)
+    nfield = 0
+    for k, d in enumerate(grads):
+        for desc, coef in d.items():
+            coef = np.asarray(coef)
+            if desc[1] is None:  # Array unknown: dense block
+                unk = engine.unknowns[desc[0]]
+                lo = int(col0[unk.first])
+                blk = coef.reshape(engine.outputs[k].n, -1)
+                assert np.allclose(blk, Jr[row0[k]:row0[k + 1], lo:lo + blk.shape[1]], rtol=1e-11, atol=1e-13)
+                Jr[row0[k]:row0[k + 1], lo:lo + blk.shape[1]] = 0
+                continue
+            cmap = engine.trace.column_map(desc, col0).reshape(-1)
+            cells = np.arange(engine.outputs[k].n)
+            ok = cmap >= 0
+            ref = np.zeros(engine.outputs[k].n)
+            ref[ok] = Jr[row0[k] + cells[ok], cmap[ok]]
+            assert np.allclose(coef.reshape(-1), ref, rtol=1e-11, atol=1e-13), (case, k, desc)
+            Jr[row0[k] + cells[ok], cmap[ok]] = 0
+            nfield += 1
+    assert nfield > 0
+    # what is left of the Jacobian belongs to NeuralNet weights only
+    left = np.abs(Jr).sum(axis=0) > 0
+    for key_, unk in engine.unknowns.items():
+        if unk.kind != "NeuralNet":
+            for i in range(unk.first, unk.first + unk.narrays):
+                assert not left[col0[i]:col0[i + 1]].any(), key_
