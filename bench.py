@@ -563,9 +563,13 @@ def run_b200(args):
         a2 = argparse.Namespace(**vars(args))
         a2.scaling = "strong"
         wl2 = workload(a2, world)
-        m2 = measure(wl2, args.steps, args.warmup, False)
-        strong = {"value": m2["ncells"] / (m2["ms"] * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": m2["ms"],
-                  "workload": wl2["text"], "scaling": "strong", "final_loss": m2["loss"]}
+        try:
+            m2 = measure(wl2, args.steps, args.warmup, False)
+            strong = {"value": m2["ncells"] / (m2["ms"] * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": m2["ms"],
+                      "workload": wl2["text"], "scaling": "strong", "final_loss": m2["loss"],
+                      "graph_replay": m2["graph"]}
+        except Exception as exc:  # the extra block must never cost the headline line
+            strong = {"error": repr(exc)[:300], "workload": wl2["text"], "scaling": "strong"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and wl["kind"] == "poisson":

@@ -86,7 +86,7 @@ class AdamNativeOptimizer(Optimizer):
                 # default: replay where the epoch is launch-bound (small grids) and the caller vouches that nothing
                 # outside the captured kernels changes between epochs (`loss_grad.graph_safe`, set by optimize_grad:
                 # affine operator, no tracer baked into its tables, state arrays not swapped by the callback)
-                graph = bool(getattr(loss_grad, "graph_safe", False)) and sum(e.numel() for e in x) <= (1 << 24)
+                graph = bool(getattr(loss_grad, "graph_safe", False)) and sum(e.numel() for e in x) <= (1 << 25)
         if graph and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1 and os.environ.get("ODIL_B200_COMM", "peer") == "nccl":
             graph = False  # NCCL groups issued through torch.distributed are not captured; the peer-memory
