@@ -466,8 +466,8 @@ __device__ __forceinline__ void mg_adj_march(const Mg3& m, const T* __restrict__
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(128, 4) k_interp_adjoint3m(Mg3 m, const T* __restrict__ gf, T scale,
+template <typename T, int OCC = 4>
+__global__ void __launch_bounds__(128, OCC) k_interp_adjoint3m(Mg3 m, const T* __restrict__ gf, T scale,
                                                              T* __restrict__ gc, int cz_begin, int cz_end, int out_z0,
                                                              int fine_z0, int zc) {
     const int lane = threadIdx.x;

@@ -614,6 +614,16 @@ static int march_chunk(const Mg3& m, int ncz, int ctas_per_sm) {
     }
     return best_zc;
 }
+// resident CTAs per SM k_interp_adjoint3m<float> is compiled for: 4 (128 registers), 5 (96) or 6 (80, small spills)
+static int adj_occ() {
+    static const int occ = [] {
+        const char* e = getenv("ODIL_B200_ADJ_OCC");
+        const int v = e ? atoi(e) : 4;
+        return v == 5 || v == 6 ? v : 4;
+    }();
+    return occ;
+}
+
 static bool march_ok(const Mg3& m, bool cz, int ndim, const void* a, const void* b, const void* c) {
     if (8 * (int64_t)m.n0 * m.n1 * m.n2 >= (1ll << 31)) return false;  // 32-bit element offsets inside
     return cz && ndim == 3 && m.n2 % 2 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) &&
@@ -810,26 +820,29 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
         Mg3 m;
         bool cz = false;
         if (fast3_geometry(g, m, cz) && march_ok(m, cz, ndim, g_fine, g_coarse, nullptr)) {
-            const int zc = march_chunk(m, (int)(r.cz_end - r.cz_begin), 4);
+            const int occ = dtype == ODIL_B200_F32 ? adj_occ() : 4;
+            const int zc = march_chunk(m, (int)(r.cz_end - r.cz_begin), occ);
             dim3 block(32, 4, 1);
             dim3 grid((m.n2 / 2 + 31) / 32, (m.n1 + 3) / 4, (unsigned)((r.cz_end - r.cz_begin + zc - 1) / zc));
             const int nfix = 16 * (int)(r.cz_end - r.cz_begin) + 16 * (m.n1 + m.n2);
             if (grid.y <= 65535 && grid.z <= 65535) {
+#define ODIL_ADJ(T_, OCC_)                                                                                             \
+    k_interp_adjoint3m<T_, OCC_><<<grid, block, 0, st>>>(m, (const T_*)g_fine, (T_)scale, (T_*)g_coarse, (int)r.cz_begin, \
+                                                         (int)r.cz_end, (int)r.out_z0, (int)r.fine_z0, zc)
                 if (dtype == ODIL_B200_F32) {
-                    k_interp_adjoint3m<float><<<grid, block, 0, st>>>(m, (const float*)g_fine, (float)scale,
-                                                                      (float*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
-                                                                      (int)r.out_z0, (int)r.fine_z0, zc);
+                    if (occ == 5) ODIL_ADJ(float, 5);
+                    else if (occ == 6) ODIL_ADJ(float, 6);
+                    else ODIL_ADJ(float, 4);
                     k_adjoint_joint_fix<float><<<(nfix + 127) / 128, 128, 0, st>>>(
                         m, (const float*)g_fine, (float)scale, (float*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                         (int)r.out_z0, (int)r.fine_z0);
                 } else {
-                    k_interp_adjoint3m<double><<<grid, block, 0, st>>>(m, (const double*)g_fine, scale,
-                                                                       (double*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
-                                                                       (int)r.out_z0, (int)r.fine_z0, zc);
+                    ODIL_ADJ(double, 4);
                     k_adjoint_joint_fix<double><<<(nfix + 127) / 128, 128, 0, st>>>(
                         m, (const double*)g_fine, scale, (double*)g_coarse, (int)r.cz_begin, (int)r.cz_end,
                         (int)r.out_z0, (int)r.fine_z0);
                 }
+#undef ODIL_ADJ
                 launch_counter()++;  // two launches
                 ODIL_LAUNCHED();
                 return 0;
