@@ -62,6 +62,8 @@ class GroupProgram:
         self.tape = []          # ('load', z, slot, lin, guard, uniform) | ('op', z, [(arg, contrib, tcontrib)])
         self.memo = {}
         self.defs = {}          # expression string -> SSA name (ints / bools / loads)
+        self.fdefs = {}         # floating expression string -> SSA name (value numbering)
+        self.tape_index = {}    # SSA name -> its ('op', ...) tape entry
         self.n = 0
         self.uniform = {}       # (slot, lin) -> index of the register accumulator
         self.ncell = math.prod(self.shape)
@@ -156,9 +158,28 @@ class GroupProgram:
         return v
 
     def fvar(self, expr):
-        name = self.new("v")
-        self.lines.append(f"const T {name} = {expr};")
+        """SSA variable of a floating expression; identical expressions share one variable (value numbering: a frozen
+        copy of a stencil -- ctx.field(..., frozen=True) -- re-uses the arithmetic of the live one, only the adjoint
+        flow differs)."""
+        name = self.fdefs.get(expr)
+        if name is None:
+            name = self.new("v")
+            self.lines.append(f"const T {name} = {expr};")
+            self.fdefs[expr] = name
         return name
+
+    def record(self, z, parts):
+        """Adjoint rules of z: parts = [(argument position, argument variable, rule)].  One tape entry per variable,
+        created at its first ACTIVE use; later uses add the positions that were inactive before."""
+        entry = self.tape_index.get(z)
+        if entry is None:
+            entry = ("op", z, [])
+            self.tape.append(entry)
+            self.tape_index[z] = entry
+        have = {p[0] for p in entry[2]}
+        for part in parts:
+            if part[0] not in have:
+                entry[2].append(part)
 
     def as_float(self, v):
         if v.kind == "b":
@@ -196,9 +217,7 @@ class GroupProgram:
             return Val(self.defs[key], "f", True)
         if op == "stopgrad":
             x = self.emit(n.args[0], I, G)
-            if not x.active:
-                return x
-            return Val(self.fvar(x.name) if x.kind == "f" else x.name, x.kind, False)
+            return x if not x.active else Val(x.name, x.kind, False)  # same value, adjoint flow cut
         if op in ("broadcast",):
             return self.emit(n.args[0], self.bidx(n.args[0].shape, I, n.shape), G)
         if op == "roll":
@@ -293,15 +312,28 @@ class GroupProgram:
         return self.arith(op, n, args)
 
     def select(self, cond, x, y):
-        z = self.fvar(f"{cond} ? {self.as_float(x)} : {self.as_float(y)}")
+        xa, ya = self.as_float(x), self.as_float(y)
+        if xa == ya:
+            return Val(xa, "f", x.active or y.active)
+        z = self.fvar(f"{cond} ? {xa} : {ya}")
         parts = []
         if x.active:
-            parts.append((x.name, lambda d, c=cond: f"({c} ? {d} : T(0))"))
+            parts.append((0, x.name, lambda d, c=cond: f"({c} ? {d} : T(0))"))
         if y.active:
-            parts.append((y.name, lambda d, c=cond: f"({c} ? T(0) : {d})"))
+            parts.append((1, y.name, lambda d, c=cond: f"({c} ? T(0) : {d})"))
         if parts:
-            self.tape.append(("op", z, parts))
+            self.record(z, parts)
         return Val(z, "f", bool(parts))
+
+    @staticmethod
+    def _literal(text):
+        """Value of a `T(...)` literal operand, else None."""
+        if text.startswith("T(") and text.endswith(")"):
+            try:
+                return float(text[2:-1])
+            except ValueError:
+                return None
+        return None
 
     def arith(self, op, n, args):
         a = self.as_float(args[0])
@@ -309,6 +341,21 @@ class GroupProgram:
         lin = lambda p: (lambda d, p=p: f"{p} * {d}")
         one = lambda d: d
         neg = lambda d: f"-{d}"
+        # exact algebraic identities (x + 0, x * 1, x / 1) and division by a literal whose reciprocal is exact (a
+        # power of two): the quotient is bit-identical and costs one multiplication instead of a division sequence
+        la, lb = self._literal(a), (self._literal(b) if b is not None else None)
+        if op in ("add", "sub") and lb == 0.0:
+            return args[0] if args[0].kind == "f" else Val(a, "f", False)
+        if op == "add" and la == 0.0:
+            return args[1] if args[1].kind == "f" else Val(b, "f", False)
+        if op in ("mul", "div") and lb == 1.0:
+            return args[0] if args[0].kind == "f" else Val(a, "f", False)
+        if op == "mul" and la == 1.0:
+            return args[1] if args[1].kind == "f" else Val(b, "f", False)
+        if op == "div" and lb is not None and lb != 0.0 and math.isfinite(lb):
+            mant, _ = math.frexp(lb)
+            if abs(mant) == 0.5 and math.isfinite(1.0 / lb):
+                op, b = "mul", _lit(1.0 / lb, self.gen.real)
         if op == "add":
             expr, parts = f"{a} + {b}", [one, one]
         elif op == "sub":
@@ -362,14 +409,17 @@ class GroupProgram:
                 "floor": lambda: [None],
                 "abs": lambda: [lambda d: f"({a} > T(0) ? {d} : ({a} < T(0) ? -{d} : T(0)))"],
             }[op]()
-        active = [(x.name, p) for x, p in zip(args, parts) if x.active and p is not None]
+        active = [(i, x.name, p) for i, (x, p) in enumerate(zip(args, parts)) if x.active and p is not None]
         if active:
-            self.tape.append(("op", z, active))
+            self.record(z, active)
         return Val(z, "f", bool(active))
 
     # -- per-cell bodies ------------------------------------------------------------------------------
     def coords(self):
         out, rem = [], "cell"
+        if self.ncell < 2 ** 31:  # 32-bit divisions by constants (multiply-shift) instead of 64-bit ones
+            out.append("const unsigned cell32 = (unsigned)cell;")
+            rem = "cell32"
         nd = len(self.shape)
         strides = self.gen.c_strides(self.shape)
         for a in range(nd):
@@ -410,7 +460,7 @@ class GroupProgram:
             if e[0] == "op":
                 if z not in adj:
                     continue
-                for arg, contrib in e[2]:
+                for _, arg, contrib in e[2]:
                     add(arg, contrib(f"d_{z}"))
             else:
                 _, z, slot, lin, G, uniform = e
@@ -444,7 +494,7 @@ class GroupProgram:
                 out.append(f"const T t_{z} = {src};" if G is None else f"const T t_{z} = {G} ? {src} : T(0);")
                 tan[z] = True
             else:
-                terms = [contrib(f"t_{arg}") for arg, contrib in e[2] if arg in tan]
+                terms = [contrib(f"t_{arg}") for _, arg, contrib in e[2] if arg in tan]
                 if terms:
                     out.append(f"const T t_{z} = {' + '.join(terms)};")
                     tan[z] = True
@@ -597,7 +647,13 @@ class Generator:
 
     def const_slot(self, n):
         k = n.attrs["known"]
-        key = (k.t.data_ptr(), tuple(k.t.shape), tuple(k.shape), str(k.t.dtype))
+        if k.t.numel() <= (1 << 20):  # equal masks / coordinate arrays built twice by the operator share one slot
+            import hashlib
+
+            digest = hashlib.sha1(k.t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()
+        else:
+            digest = k.t.data_ptr()
+        key = (digest, tuple(k.t.shape), tuple(k.shape), str(k.t.dtype))
         if key not in self._const_of:
             t = k.t
             nd = len(k.shape)
