@@ -169,8 +169,9 @@ def _dcstep(stx, fx, dx, sty, fy, dy, stp, fp, dp, brackt, stpmin, stpmax):
 
 
 class _History:
-    """S and Y as rows of one device matrix V = [S; Y] (a ring: the oldest pair's rows are reused) plus
-    the small host matrices S^T Y and Y^T Y kept in age order."""
+    """S and Y as rows of one device matrix V (pair p occupies rows 2p and 2p+1; a ring: the oldest pair's rows are
+    reused) plus the small host matrices S^T Y and Y^T Y kept in age order.  Only the rows in use are streamed: while
+    the history is filling, the two passes per iteration cost 2 k vectors each, not 2 m."""
 
     def __init__(self, m, n, device):
         self.m, self.n = m, n
@@ -192,10 +193,10 @@ class _History:
 
     def dots(self, vec):
         """(S^T vec, Y^T vec) for the stored pairs in age order: one device pass over V, one sync."""
-        native.multi_dot(self.V, 2 * self.m, vec, self._out)
+        native.multi_dot(self.V, 2 * len(self.rows), vec, self._out)   # physical rows 0 .. 2 * col - 1 are in use
         h = self._out.cpu().numpy()
         idx = np.asarray(self.rows, dtype=int)
-        return h[idx].copy(), h[self.m + idx].copy()
+        return h[2 * idx].copy(), h[2 * idx + 1].copy()
 
     def push(self, s, y, sty, yty, Sty, Yty):
         """Appends the pair (s, y); Sty = S_old^T y, Yty = Y_old^T y (host, age order), sty = s.y, yty = y.y."""
@@ -208,8 +209,8 @@ class _History:
         else:
             row = len(self.rows)
         k = len(self.rows)
-        self.V[row].copy_(s)
-        self.V[m + row].copy_(y)
+        self.V[2 * row].copy_(s)
+        self.V[2 * row + 1].copy_(y)
         self.rows.append(row)
         self.sy[:k, k] = Sty
         self.sy[k, :k] = 0.0
@@ -231,10 +232,10 @@ class _History:
         u2 = -Rinv_p1
         coef = np.zeros(2 * self.m)
         idx = np.asarray(self.rows, dtype=int)
-        coef[idx] = -u1
-        coef[self.m + idx] = -gam * u2
+        coef[2 * idx] = -u1
+        coef[2 * idx + 1] = -gam * u2
         self._coef.copy_(torch.from_numpy(coef))
-        native.multi_axpy(self.V, 2 * self.m, self._coef, -gam, g, d)
+        native.multi_axpy(self.V, 2 * k, self._coef, -gam, g, d)
 
 
 def _dot(a, b, out):
