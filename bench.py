@@ -55,6 +55,9 @@ def parse():
     p.add_argument("--cpu_budget_s", type=float, default=420.0, help="wall-time budget of the reference arm")
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--no_strong", action="store_true", help="skip the extra strong-scaling block at N > 1")
+    p.add_argument("--extra_configs", type=str, default="1,4,2",
+                   help="N=1, default config only: also measure these BASELINE configs (own processes) and embed "
+                        "their summaries in the line; empty string disables")
     p.add_argument("--profile", action="store_true",
                    help="short run for ncu: no burn-in, no clock sampler, no e2e / CPU / strong-scaling legs")
     p.add_argument("--graph", type=int, default=None, help="CUDA-graph replay of the Adam epoch (default: config 1)")
@@ -391,6 +394,31 @@ def slab_parity(world, rank):
     return out
 
 
+def other_configs(which):
+    """The other single-GPU configurations of BASELINE.json, each measured by `bench.py --config C` in its own
+    process (isolated from the headline measurement) and summarised: secondary lines, not the contract line."""
+    steps = {1: ("200", "5"), 2: ("10", "5"), 4: ("3", "3")}
+    out = {}
+    for c in which:
+        if c not in steps:
+            continue
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--config", str(c), "--steps", steps[c][0], "--warmup",
+               steps[c][1], "--e2e_steps", "2", "--no_cpu_baseline", "--extra_configs", ""]
+        try:
+            r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=240)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            d = json.loads(lines[-1])
+            out[str(c)] = {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"],
+                           "ms_per_step": d["ms_per_step"], "steps": d["steps"], "dtype": d["dtype"],
+                           "graph_replay": d.get("graph_replay"), "gpu_launches": d.get("gpu_launches"),
+                           "dominant_kernel": d["roofline"]["kernel"], "dominant_kernel_frac": d["roofline"]["frac"],
+                           "e2e": d["e2e"]["value"] if d.get("e2e") else None, "clocks": d.get("clocks"),
+                           "final_loss": d.get("final_loss")}
+        except Exception as exc:
+            out[str(c)] = {"error": repr(exc)[:300]}
+    return out
+
+
 def run_b200(args):
     import torch
 
@@ -571,6 +599,10 @@ def run_b200(args):
         except Exception as exc:  # the extra block must never cost the headline line
             strong = {"error": repr(exc)[:300], "workload": wl2["text"], "scaling": "strong"}
 
+    others = None
+    if rank == 0 and world == 1 and args.config == 3 and args.extra_configs and not args.profile \
+            and args.size is None:
+        others = other_configs([int(c) for c in args.extra_configs.split(",") if c.strip()])
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and wl["kind"] == "poisson":
         try:
@@ -590,6 +622,8 @@ def run_b200(args):
             "epoch_traffic_model": {"compulsory_bytes_per_cell": (6 * nunk_local / ncells_local + 1) * es,
                                     "epoch_frac_of_peak": (6 * nunk_local + ncells_local) * es / (ms * 1e-3) / 1e9 / peak},
         }
+        if others is not None:
+            line["other_configs"] = others
         if parity is not None:
             line["parity"] = parity
         if strong is not None:
