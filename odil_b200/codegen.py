@@ -21,6 +21,7 @@ The same source compiles for the host when ODIL_HOST is defined (plain loops, `+
 check the generated programs against reference-generated goldens without a GPU.  The product path never does.
 """
 import math
+import os
 import struct
 
 import numpy as np
@@ -30,6 +31,7 @@ from .graph import BINARY, COMPARE, LOGICAL, GraphError, toposort
 
 BLOCK = 256
 MAX_GRID = 148 * 4
+EXACT_DIV = os.environ.get("ODIL_B200_EXACT_DIV", "0") not in ("", "0")
 
 
 def _lit(v, real):
@@ -352,9 +354,12 @@ class GroupProgram:
             return args[0] if args[0].kind == "f" else Val(a, "f", False)
         if op == "mul" and la == 1.0:
             return args[1] if args[1].kind == "f" else Val(b, "f", False)
-        if op == "div" and lb is not None and lb != 0.0 and math.isfinite(lb):
+        if op == "div" and lb is not None and lb != 0.0 and math.isfinite(lb) and math.isfinite(1.0 / lb):
             mant, _ = math.frexp(lb)
-            if abs(mant) == 0.5 and math.isfinite(1.0 / lb):
+            # Other literal divisors (the /3 of extrap_quadh, evaluated for every cell under a boundary `where`): the
+            # product with the rounded reciprocal differs from the quotient by at most one ulp -- far inside the parity
+            # bars -- and replaces a ~25-instruction fp64 division sequence; ODIL_B200_EXACT_DIV=1 keeps the division.
+            if abs(mant) == 0.5 or not EXACT_DIV:
                 op, b = "mul", _lit(1.0 / lb, self.gen.real)
         if op == "add":
             expr, parts = f"{a} + {b}", [one, one]
