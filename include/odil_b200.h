@@ -234,6 +234,9 @@ int odil_b200_jit_destroy(void* module);
  *
  *   halo_exchange      ring exchange along axis 0 of `narrays` arrays: send_lo[i] / send_hi[i] = this rank's first /
  *                      last nbytes[i] owned bytes (contiguous planes), recv_lo[i] / recv_hi[i] = its lower / upper halo
+ *   halo_accumulate    the transpose of halo_exchange: send_lo[i] / send_hi[i] = partial sums this rank computed for
+ *                      the planes just below / above its slab; they are ADDED to the owners' last / first owned planes
+ *                      (acc_hi / acc_lo on the receiving side), lower neighbour's contribution first (deterministic)
  *   allreduce_scalars  in-place sum over ranks of count <= 16 doubles in device memory, summed in rank order
  * ------------------------------------------------------------------------------------------- */
 typedef struct odil_b200_comm odil_b200_comm;
@@ -242,6 +245,8 @@ int odil_b200_comm_connect(odil_b200_comm* comm, const void* ipc_handles_in_rank
 int64_t odil_b200_comm_capacity(const odil_b200_comm* comm);
 int odil_b200_halo_exchange(odil_b200_comm* comm, int narrays, const void* const* send_lo, const void* const* send_hi,
                             void* const* recv_lo, void* const* recv_hi, const int64_t* nbytes, void* stream);
+int odil_b200_halo_accumulate(odil_b200_comm* comm, int narrays, const void* const* send_lo, const void* const* send_hi,
+                              void* const* acc_lo, void* const* acc_hi, const int64_t* nbytes, int dtype, void* stream);
 int odil_b200_allreduce_scalars(odil_b200_comm* comm, double* dev_scalars, int count, void* stream);
 int odil_b200_comm_destroy(odil_b200_comm* comm);
 

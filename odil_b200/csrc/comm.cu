@@ -153,6 +153,52 @@ static __global__ void __launch_bounds__(256) k_halo_pull(const HaloParams p) {
     }
 }
 
+// Consumer of a halo ACCUMULATION: what the lower / upper neighbour pushed is ADDED to this rank's first / last owned
+// planes (recv_lo / recv_hi point at them).  Used for the push-style transposed interpolation: every rank computes
+// partial sums for the coarse planes one beyond its slab and hands them to their owners once per epoch.
+template <typename T>
+static __global__ void __launch_bounds__(256) k_halo_pull_add(const HaloParams p) {
+    const unsigned int s = p.loc->halo_seq + 1;
+    const int par = s & 1;
+    CommShared* me = reinterpret_cast<CommShared*>(p.my_base);
+    if (threadIdx.x == 0) {
+        while ((int)(ld_acquire_sys(&me->halo_flag[0][par].v) - s) < 0) {
+        }
+        while ((int)(ld_acquire_sys(&me->halo_flag[1][par].v) - s) < 0) {
+        }
+    }
+    __syncthreads();
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    const char* from_lo = stage_ptr(p.my_base, p.stage_bytes, 0, par);
+    const char* from_hi = stage_ptr(p.my_base, p.stage_bytes, 1, par);
+    for (int i = 0; i < p.nitems; ++i) {
+        const long long n = p.it[i].nbytes / (long long)sizeof(T);
+        const T* a = reinterpret_cast<const T*>(from_lo + p.it[i].off);
+        const T* b = reinterpret_cast<const T*>(from_hi + p.it[i].off);
+        T* lo = reinterpret_cast<T*>(p.it[i].recv_lo);
+        T* hi = reinterpret_cast<T*>(p.it[i].recv_hi);
+        // fixed order: first the lower neighbour's contribution, then the upper one's (they may hit the same plane
+        // when a slab is one plane thick) -> deterministic sums
+        if (lo == hi) {
+            for (long long e = tid; e < n; e += nth) lo[e] = (lo[e] + a[e]) + b[e];
+        } else {
+            for (long long e = tid; e < n; e += nth) {
+                lo[e] += a[e];
+                hi[e] += b[e];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&p.loc->pull_done, 1u);
+        if (t == gridDim.x - 1) {
+            p.loc->pull_done = 0;
+            p.loc->halo_seq = s;
+        }
+    }
+}
+
 struct RedParams {
     int rank, world, count;
     char* base[kMaxWorld];
@@ -253,8 +299,8 @@ int64_t odil_b200_comm_capacity(const odil_b200_comm* c) { return c ? c->stage_b
 // Ring exchange of `narrays` arrays: send_lo[i] / send_hi[i] point at this rank's first / last `nbytes[i]` owned bytes,
 // recv_lo[i] / recv_hi[i] at its lower / upper halo.  Replaces the batched ncclSend/ncclRecv group of round 1
 // (odil_b200/slab.py exchange).  Asynchronous on `stream`; capturable.
-int odil_b200_halo_exchange(odil_b200_comm* c, int narrays, const void* const* send_lo, const void* const* send_hi,
-                            void* const* recv_lo, void* const* recv_hi, const int64_t* nbytes, void* stream) {
+static int halo_run(odil_b200_comm* c, int narrays, const void* const* send_lo, const void* const* send_hi,
+                    void* const* recv_lo, void* const* recv_hi, const int64_t* nbytes, int add_dtype, void* stream) {
     ODIL_REQUIRE(c && c->connected, "communicator is not connected");
     ODIL_REQUIRE(narrays >= 1 && narrays <= kMaxItems, "narrays=%d out of range (1..%d)", narrays, kMaxItems);
     HaloParams p;
@@ -283,9 +329,28 @@ int odil_b200_halo_exchange(odil_b200_comm* c, int narrays, const void* const* s
     cudaStream_t st = (cudaStream_t)stream;
     k_halo_push<<<blocks, 256, 0, st>>>(p);
     ODIL_LAUNCHED();
-    k_halo_pull<<<blocks, 256, 0, st>>>(p);
+    if (add_dtype == ODIL_B200_F32)
+        k_halo_pull_add<float><<<blocks, 256, 0, st>>>(p);
+    else if (add_dtype == ODIL_B200_F64)
+        k_halo_pull_add<double><<<blocks, 256, 0, st>>>(p);
+    else
+        k_halo_pull<<<blocks, 256, 0, st>>>(p);
     ODIL_LAUNCHED();
     return 0;
+}
+
+int odil_b200_halo_exchange(odil_b200_comm* c, int narrays, const void* const* send_lo, const void* const* send_hi,
+                            void* const* recv_lo, void* const* recv_hi, const int64_t* nbytes, void* stream) {
+    return halo_run(c, narrays, send_lo, send_hi, recv_lo, recv_hi, nbytes, -1, stream);
+}
+
+// Ring ACCUMULATION: send_lo[i] / send_hi[i] = this rank's partial sums for the plane(s) just below / above its slab
+// (owned by the lower / upper neighbour); acc_lo[i] / acc_hi[i] = this rank's first / last owned plane(s), to which the
+// lower / upper neighbour's partial sums are added.  dtype: element type of every array.
+int odil_b200_halo_accumulate(odil_b200_comm* c, int narrays, const void* const* send_lo, const void* const* send_hi,
+                              void* const* acc_lo, void* const* acc_hi, const int64_t* nbytes, int dtype, void* stream) {
+    ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    return halo_run(c, narrays, send_lo, send_hi, acc_lo, acc_hi, nbytes, dtype, stream);
 }
 
 // In-place sum over all ranks of `count` doubles in device memory (loss terms, dot products).  Replaces ncclAllReduce.

@@ -411,27 +411,43 @@ class ResidualEngine:
                     slab.exchange([U[u.key]], width=H)
             else:
                 U[u.key] = a[0]
+        # Gradient work arrays carry GH = 3 zero halo planes per side (the state arrays carry H = 2).  The transposed
+        # interpolation is done push-style: every rank computes the coarse planes of its slab AND the one plane beyond
+        # each end from its own fine planes only (planes it does not own read as zero -- GH = 3 keeps every such read
+        # inside the allocation), so those end planes and the first / last owned planes hold PARTIAL sums.  By
+        # linearity the partial sums can be carried through all levels; ONE halo accumulation at the end hands them to
+        # their owners (round 1 exchanged the gradient halo once per level: three more synchronisation points).
+        GH = max(3, H)
+        gshape = lambda shape: (slab.check(shape) + 2 * GH,) + tuple(shape[1:])
+        view = lambda g: g[GH - H: g.shape[0] - (GH - H)]  # the H-halo layout of the state arrays
         grads = [None] * self.narrays
+        acc_items = []
         for k, out in enumerate(self.outputs):
             blk = out.blocks[0]
             u = self.unknowns[blk.key]
             z0, n0 = slab.owned_range(out.shape)
-            g = self._buf(("gU", blk.key), slab.local_shape(out.shape), zero=True)
-            blk.plan.fused(U[blk.key], out.const_local, 2.0 / out.n, g, sums[k:k + 1], slab=(n0, z0, H))
+            g = self._buf(("gU", blk.key), gshape(out.shape), zero=True)
+            blk.plan.fused(U[blk.key], out.const_local, 2.0 / out.n, view(g), sums[k:k + 1], slab=(n0, z0, H))
             if u.kind != "MultigridField":
-                grads[u.first] = g
+                grads[u.first] = view(g)
                 continue
             gl = g
             for lvl in range(u.narrays):
                 if lvl > 0:
-                    slab.exchange([gl], width=1)
                     zc, nc = slab.owned_range(u.shapes[lvl])
                     zf, _ = slab.owned_range(u.shapes[lvl - 1])
-                    gc = self._buf(("gV", u.key, lvl), slab.local_shape(u.shapes[lvl]), zero=True)
-                    native.mg_interp_adjoint(u.shapes[lvl], u.mgloc, gl, 1.0, gc, rng=(zc, zc + nc, zc - H, zf - H))
+                    cb, ce = max(zc - 1, 0), min(zc + nc + 1, u.shapes[lvl][0])
+                    gc = self._buf(("gV", u.key, lvl), gshape(u.shapes[lvl]), zero=True)
+                    native.mg_interp_adjoint(u.shapes[lvl], u.mgloc, gl, 1.0, gc, rng=(cb, ce, zc - GH, zf - GH))
+                    acc_items.append((gc[GH - 1:GH], gc[GH + nc:GH + nc + 1], gc[GH:GH + 1], gc[GH + nc - 1:GH + nc]))
                     gl = gc
                 f = u.factors[lvl]
-                grads[u.first + lvl] = gl if f == 1 else gl * f
+                grads[u.first + lvl] = (view(gl), f)
+        slab.accumulate(acc_items)
+        for i in range(self.narrays):
+            if isinstance(grads[i], tuple):
+                gv, f = grads[i]
+                grads[i] = gv if f == 1 else gv * f
         for i in range(self.narrays):
             if grads[i] is None:
                 grads[i] = torch.zeros_like(arrays[i])

@@ -29,6 +29,7 @@ EXPORTS = [
     "odil_b200_jit_compile", "odil_b200_jit_log", "odil_b200_jit_cubin", "odil_b200_jit_kernel",
     "odil_b200_jit_launch", "odil_b200_jit_destroy",
     "odil_b200_comm_create", "odil_b200_comm_connect", "odil_b200_comm_capacity", "odil_b200_halo_exchange",
+    "odil_b200_halo_accumulate",
     "odil_b200_allreduce_scalars", "odil_b200_comm_destroy",
 ]
 
@@ -128,6 +129,7 @@ def load(build_if_missing=False):
     lib.odil_b200_comm_capacity.argtypes = [vp]
     lib.odil_b200_comm_capacity.restype = i64
     lib.odil_b200_halo_exchange.argtypes = [vp, ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), vp]
+    lib.odil_b200_halo_accumulate.argtypes = [vp, ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), ctypes.c_int, vp]
     lib.odil_b200_allreduce_scalars.argtypes = [vp, vp, ctypes.c_int, vp]
     lib.odil_b200_comm_destroy.argtypes = [vp]
     for name in EXPORTS:
@@ -493,6 +495,16 @@ class Comm:
         nbytes = (ctypes.c_int64 * n)(*[t.numel() * t.element_size() for t in send_lo])
         args = [VP(*[_ptr(t).value for t in ts]) for ts in (send_lo, send_hi, recv_lo, recv_hi)]
         _call("halo_exchange", lambda: _check(_lib.odil_b200_halo_exchange(self.handle, n, *args, nbytes, _stream())))
+
+    def halo_accumulate(self, send_lo, send_hi, acc_lo, acc_hi):
+        """Adds the neighbours' partial sums (their send_hi / send_lo planes) to this rank's first / last owned planes."""
+        n = len(send_lo)
+        VP = ctypes.c_void_p * n
+        nbytes = (ctypes.c_int64 * n)(*[t.numel() * t.element_size() for t in send_lo])
+        args = [VP(*[_ptr(t).value for t in ts]) for ts in (send_lo, send_hi, acc_lo, acc_hi)]
+        code = dtype_code(send_lo[0].dtype)
+        _call("halo_accumulate", lambda: _check(_lib.odil_b200_halo_accumulate(self.handle, n, *args, nbytes, code,
+                                                                                _stream())))
 
     def allreduce_scalars(self, t):
         """In-place sum over ranks of a small float64 CUDA tensor (deterministic: rank order)."""

@@ -168,6 +168,46 @@ class SlabInfo:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
+    def accumulate(self, items):
+        """
+        Transpose of `exchange`: items = [(send_lo, send_hi, acc_lo, acc_hi)] of contiguous plane views.  send_lo /
+        send_hi hold the partial sums this rank computed for the plane(s) just below / above its slab; the owners add
+        them: acc_lo (this rank's first owned planes) += the lower neighbour's send_hi, acc_hi (last owned planes) +=
+        the upper neighbour's send_lo -- in that order.  One call per epoch for all multigrid levels.
+        """
+        import torch.distributed as dist
+
+        if not items:
+            return
+        if self.world == 1:
+            for send_lo, send_hi, acc_lo, acc_hi in items:
+                lo, hi = send_hi.clone(), send_lo.clone()  # ring of one: my own partials wrap around
+                acc_lo.add_(lo)
+                acc_hi.add_(hi)
+            return
+        if self.use_peer and all(t.is_cuda for it in items for t in it):
+            from . import native
+
+            cols = list(zip(*items))
+            need = native.Comm.bytes_needed([t.numel() * t.element_size() for t in cols[0]])
+            self.ensure_comm(need).halo_accumulate(list(cols[0]), list(cols[1]), list(cols[2]), list(cols[3]))
+            return
+        lo = (self.rank - 1) % self.world
+        hi = (self.rank + 1) % self.world
+        ops, bufs = [], []
+        for send_lo, send_hi, acc_lo, acc_hi in items:
+            from_lo, from_hi = torch.empty_like(acc_lo), torch.empty_like(acc_hi)
+            bufs.append((from_lo, from_hi, acc_lo, acc_hi))
+            ops.append(dist.P2POp(dist.isend, send_hi.contiguous(), hi, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, from_lo, lo, group=self.group))
+            ops.append(dist.P2POp(dist.isend, send_lo.contiguous(), lo, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, from_hi, hi, group=self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for from_lo, from_hi, acc_lo, acc_hi in bufs:
+            acc_lo.add_(from_lo)
+            acc_hi.add_(from_hi)
+
     def all_reduce_sum(self, t):
         import torch.distributed as dist
 

@@ -47,6 +47,14 @@ def main():
             ref.exchange(b, width=width)
             for x, y in zip(a, b):
                 assert torch.equal(x, y), ("halo exchange differs from the NCCL exchange", it, x.shape)
+            # accumulate (transpose of the exchange): peer-memory kernels == isend / irecv + add
+            pa = [torch.randn(s, dtype=d, device="cuda", generator=gen) for s, d in zip(shapes, dts)]
+            pb = [t.clone() for t in pa]
+            items = lambda ts: [(t[0:1], t[-1:], t[1:2], t[-2:-1]) for t in ts]
+            slab.accumulate(items(pa))
+            ref.accumulate(items(pb))
+            for x, y in zip(pa, pb):
+                assert torch.equal(x, y), ("halo accumulation differs from the isend/irecv arrangement", it, x.shape)
             s1 = torch.randn(3 + it, dtype=torch.float64, device="cuda", generator=gen)
             s2 = s1.clone()
             slab.all_reduce_sum(s1)

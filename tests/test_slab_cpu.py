@@ -52,6 +52,17 @@ def _worker(rank, world, port, results):
         s = torch.tensor([float(rank + 1), 10.0])
         slab.all_reduce_sum(s)
         assert s.tolist() == [3.0, 20.0]
+        # accumulate = transpose of exchange: partial sums computed for the planes just outside the slab are added
+        # to their owners' first / last owned planes (ring)
+        p = torch.zeros(8 + 2 * 3, 2, dtype=torch.float64)           # gradient layout: 3 halo planes per side
+        p[3:11] = 1.0                                                 # owned planes
+        p[2] = 10.0 * (rank + 1)                                      # partial for the plane below (lower neighbour's)
+        p[11] = 100.0 * (rank + 1)                                    # partial for the plane above (upper neighbour's)
+        slab.accumulate([(p[2:3], p[11:12], p[3:4], p[10:11])])
+        other = 1 - rank                                              # world 2: both neighbours are the other rank
+        assert torch.all(p[3] == 1.0 + 100.0 * (other + 1))           # first owned += lower neighbour's upper partial
+        assert torch.all(p[10] == 1.0 + 10.0 * (other + 1))           # last owned  += upper neighbour's lower partial
+        assert torch.all(p[4:10] == 1.0)
         results[rank] = "ok"
     except Exception as e:  # pragma: no cover
         results[rank] = repr(e)
