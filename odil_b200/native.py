@@ -503,6 +503,8 @@ class Comm:
         nbytes = (ctypes.c_int64 * n)(*[t.numel() * t.element_size() for t in send_lo])
         args = [VP(*[_ptr(t).value for t in ts]) for ts in (send_lo, send_hi, acc_lo, acc_hi)]
         code = dtype_code(send_lo[0].dtype)
+        if any(t.dtype != send_lo[0].dtype for ts in (send_lo, send_hi, acc_lo, acc_hi) for t in ts):
+            raise NativeError("halo_accumulate: all arrays of one call must have the same dtype")
         _call("halo_accumulate", lambda: _check(_lib.odil_b200_halo_accumulate(self.handle, n, *args, nbytes, code,
                                                                                 _stream())))
 

@@ -48,7 +48,8 @@ def main():
             for x, y in zip(a, b):
                 assert torch.equal(x, y), ("halo exchange differs from the NCCL exchange", it, x.shape)
             # accumulate (transpose of the exchange): peer-memory kernels == isend / irecv + add
-            pa = [torch.randn(s, dtype=d, device="cuda", generator=gen) for s, d in zip(shapes, dts)]
+            one = dts[it % 2]  # one element type per call (odil_b200_halo_accumulate takes a single dtype)
+            pa = [torch.randn(s, dtype=one, device="cuda", generator=gen) for s in shapes]
             pb = [t.clone() for t in pa]
             items = lambda ts: [(t[0:1], t[-1:], t[1:2], t[-2:-1]) for t in ts]
             slab.accumulate(items(pa))
