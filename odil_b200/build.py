@@ -45,6 +45,8 @@ def build(force=False, verbose=False):
     # ODIL_B200_LEGACY=1 also compiles the superseded generations of the fused sweep (k_star7, k_star_tma, k_star3d:
     # 36 kernel instantiations kept as measured history, selectable with plan_tune); off by default.
     legacy = ["-DODIL_B200_LEGACY"] if os.environ.get("ODIL_B200_LEGACY", "0") not in ("", "0") else []
+    # extra defines for A/B builds, e.g. ODIL_B200_DEFINES="-DODIL_B200_NO_FFMA2" with ODIL_B200_LIB_OUT=<path>
+    legacy += os.environ.get("ODIL_B200_DEFINES", "").split()
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
     procs = []
@@ -60,9 +62,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+    out = os.environ.get("ODIL_B200_LIB_OUT") or LIB
+    cmd = [nvcc, "-shared", "-o", out] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -175,11 +175,59 @@ struct S7W<T, VW, true> {
     }
 };
 
+// Packed fp32 arithmetic (sm_100: FFMA2 / FMUL2, two IEEE fp32 operations per instruction and lane).  The sweep is
+// bound by instruction issue (ncu: 55 % issue slots at 4 warps per scheduler, FMA pipe 23 %): pairing the four cells of
+// a lane halves the issue slots of the multiply-adds.  Every cell keeps its own chain of operations in the same order,
+// so the results are bit-identical to the scalar form.
+#ifndef ODIL_B200_NO_FFMA2
+#define ODIL_B200_FFMA2 1
+#else
+#define ODIL_B200_FFMA2 0
+#endif
+
+__device__ __forceinline__ float2 s7_arm2(const S7W<float, 4, true>& w, int o, int) { return make_float2(w.a[o], w.a[o]); }
+__device__ __forceinline__ float2 s7_arm2(const S7W<float, 4, false>& w, int o, int h) {
+    return make_float2(w.a[o].v[2 * h], w.a[o].v[2 * h + 1]);
+}
+__device__ __forceinline__ float2 s7_pair(const Pack<float, 4>& a, int h) { return make_float2(a.v[2 * h], a.v[2 * h + 1]); }
+
+template <bool XU>
+__device__ __forceinline__ Pack<float, 4> s7_fwd_pk(const S7W<float, 4, XU>& w, const Pack<float, 4>& cc,
+                                                    const Pack<float, 4>& uc, const Pack<float, 4>& um,
+                                                    const Pack<float, 4>& up, const Pack<float, 4>& uym,
+                                                    const Pack<float, 4>& uyp, float ul, float ur) {
+    // aligned pairs (cells 0,1 and 2,3) for the centre and the z / y arms; the x arms read the neighbouring cell, whose
+    // pairs would have to be assembled with moves, so they stay scalar (same position in each cell's chain)
+    Pack<float, 4> f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float2 a = s7_pair(cc, h);
+        a = __ffma2_rn(s7_pair(w.c, h), s7_pair(uc, h), a);
+        a = __ffma2_rn(s7_arm2(w, 0, h), s7_pair(um, h), a);
+        a = __ffma2_rn(s7_arm2(w, 1, h), s7_pair(up, h), a);
+        a = __ffma2_rn(s7_arm2(w, 2, h), s7_pair(uym, h), a);
+        a = __ffma2_rn(s7_arm2(w, 3, h), s7_pair(uyp, h), a);
+        f.v[2 * h] = a.x;
+        f.v[2 * h + 1] = a.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float xl = j > 0 ? uc.v[j > 0 ? j - 1 : 0] : ul;
+        const float xr = j < 3 ? uc.v[j < 3 ? j + 1 : 0] : ur;
+        f.v[j] = fmaf(w.xm.v[j], xl, f.v[j]);
+        f.v[j] = fmaf(w.xp.v[j], xr, f.v[j]);
+    }
+    return f;
+}
+
 // F of VW consecutive cells of one row.
 template <typename T, int VW, bool XU>
 __device__ __forceinline__ Pack<T, VW> s7_fwd(const S7W<T, VW, XU>& w, const Pack<T, VW>& cc, const Pack<T, VW>& uc,
                                               const Pack<T, VW>& um, const Pack<T, VW>& up, const Pack<T, VW>& uym,
                                               const Pack<T, VW>& uyp, T ul, T ur) {
+#if ODIL_B200_FFMA2
+    if constexpr (sizeof(T) == 4 && VW == 4) return s7_fwd_pk<XU>(w, cc, uc, um, up, uym, uyp, ul, ur);
+#endif
     Pack<T, VW> f;
 #pragma unroll
     for (int j = 0; j < VW; ++j) {

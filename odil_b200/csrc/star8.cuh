@@ -135,12 +135,52 @@ struct S8Ring {
     __device__ __forceinline__ uint32_t next_par() const { return bar + 8 == 8 * NST ? par ^ 1u : par; }
 };
 
+// Packed fp32 form of s8_adj (FFMA2 / FMUL2; same chain of operations per cell, bit-identical results).
+template <bool XU>
+__device__ __forceinline__ Pack<float, 4> s8_adj_pk(const S7W<float, 4, XU>& w, const S7W<float, 4, XU>& wa, float wxpL,
+                                                    float wxmR, float scale, const Pack<float, 4>& fc,
+                                                    const Pack<float, 4>& fm, const Pack<float, 4>& fp,
+                                                    const Pack<float, 4>& fym, const Pack<float, 4>& fyp, float fl,
+                                                    float fr) {
+    Pack<float, 4> g;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float2 s = __fmul2_rn(s7_pair(w.c, h), s7_pair(fc, h));
+        s = __ffma2_rn(s7_arm2(w, 0, h), s7_pair(fp, h), s);
+        s = __ffma2_rn(s7_arm2(w, 1, h), s7_pair(fm, h), s);
+        s = __ffma2_rn(s7_arm2(wa, 2, h), s7_pair(fyp, h), s);
+        s = __ffma2_rn(s7_arm2(wa, 3, h), s7_pair(fym, h), s);
+        g.v[2 * h] = s.x;
+        g.v[2 * h + 1] = s.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // x arms: the neighbouring cell's row (scalar, see s7_fwd_pk)
+        const float xl = j > 0 ? fc.v[j > 0 ? j - 1 : 0] : fl;
+        const float xr = j < 3 ? fc.v[j < 3 ? j + 1 : 0] : fr;
+        const float axm = j < 3 ? w.xm.v[j < 3 ? j + 1 : 0] : wxmR;
+        const float axp = j > 0 ? w.xp.v[j > 0 ? j - 1 : 0] : wxpL;
+        g.v[j] = fmaf(axm, xr, g.v[j]);
+        g.v[j] = fmaf(axp, xl, g.v[j]);
+    }
+    const float2 sc2 = make_float2(scale, scale);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float2 s = __fmul2_rn(s7_pair(g, h), sc2);
+        g.v[2 * h] = s.x;
+        g.v[2 * h + 1] = s.y;
+    }
+    return g;
+}
+
 // g of VW consecutive cells; the y-arm coefficients come from the rows above / below (ayp: yp coefficient of
 // the cell at y-1, aym: ym coefficient of the cell at y+1), everything else from the own row.
 template <typename T, int VW, bool XU>
 __device__ __forceinline__ Pack<T, VW> s8_adj(const S7W<T, VW, XU>& w, const S7W<T, VW, XU>& wa, T wxpL, T wxmR, T scale,
                                               const Pack<T, VW>& fc, const Pack<T, VW>& fm, const Pack<T, VW>& fp,
                                               const Pack<T, VW>& fym, const Pack<T, VW>& fyp, T fl, T fr) {
+#if ODIL_B200_FFMA2
+    if constexpr (sizeof(T) == 4 && VW == 4) return s8_adj_pk<XU>(w, wa, wxpL, wxmR, scale, fc, fm, fp, fym, fyp, fl, fr);
+#endif
     Pack<T, VW> g;
 #pragma unroll
     for (int j = 0; j < VW; ++j) {

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libodil_b200.so")
+LIB_PATH = os.environ.get("ODIL_B200_LIB") or os.path.join(_HERE, "lib", "libodil_b200.so")  # override: A/B builds
 
 F32, F64 = 0, 1
 MAX_NDIM = 4
