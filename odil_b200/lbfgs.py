@@ -346,6 +346,14 @@ def minimize(func, x0, m=50, maxiter=15000, maxls=20, pgtol=1e-5, factr=1e7, cal
             Sty, Yty = hist.dots(r)
         else:
             Sty, Yty = np.zeros(0), np.zeros(0)
+        was_full = hist.col == hist.m
         hist.push(d, r, dr, rr, Sty, Yty)
-        Stg = Ytg = None                          # the new pair's products with g are computed next turn
+        # S^T g and Y^T g of the UPDATED history without another pass over it: the old pairs' products with the new
+        # gradient were just computed (Stg_new, Ytg_new; the oldest entry leaves with its pair), the new pair adds
+        # s.g = stp * (d.g) -- known from the line search -- and y.g (one dot product)
+        sg = gd * stp if stp != 1.0 else gd
+        yg = _dot(r, g, sc)
+        drop = 1 if was_full else 0
+        Stg = np.concatenate([Stg_new[drop:], [sg]])
+        Ytg = np.concatenate([Ytg_new[drop:], [yg]])
     return x, f, dict(warnflag=warnflag, task=task, funcalls=nfev, nit=nit)
