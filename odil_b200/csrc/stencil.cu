@@ -666,10 +666,15 @@ static int launch_tile3d(const odil_b200_plan* plan, const T* U, const T* c, T s
     static size_t smem_set = 48 * 1024;  // per template instantiation
     if (smem > smem_set) {
         ODIL_CUDA(cudaFuncSetAttribute(k_tile3d<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ODIL_CUDA(cudaFuncSetAttribute(k_tile3d8<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     dim3 grid((p.N2 + kT3X - 1) / kT3X, (p.N1 + kT3Y - 1) / kT3Y, (p.N0 + p.zchunk - 1) / p.zchunk);
-    k_tile3d<T><<<grid, kT3Threads, smem, st>>>(p);
+    static const bool old_kernel = getenv("ODIL_B200_TILE3D_OLD") != nullptr;
+    if (p.noff <= kT3N && !old_kernel)
+        k_tile3d8<T><<<grid, kT3Threads, smem, st>>>(p);  // unrolled offsets, interior cells from registers
+    else
+        k_tile3d<T><<<grid, kT3Threads, smem, st>>>(p);
     ODIL_LAUNCHED();
     *nparts = (int)(grid.x * grid.y * grid.z);
     return 0;
