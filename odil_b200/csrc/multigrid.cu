@@ -577,6 +577,7 @@ static bool fast3_geometry(const MgGeom& g, Mg3& m, bool& cz) {
 }  // namespace odil
 #include "mg_march.cuh"
 #include "mg_tile2d.cuh"
+#include "mg_adj_tma.cuh"
 namespace odil {
 
 // 2-D cell-centred whole-array transfers through the shared-memory tile kernels (mg_tile2d.cuh).
@@ -595,8 +596,11 @@ static bool tile2_ok(const MgGeom& g, bool whole, const void* a, const void* b, 
 // __launch_bounds__): the number of chunks is chosen so that the CTAs fill the 148 SMs in (nearly) whole waves --
 // the first version used 1792 CTAs on 888 slots = 2.02 waves, i.e. a third wave for 2 % of the work -- with
 // chunks of at least 8 coarse planes so that the 2-plane lead-in stays small.
+static int chunk_for_waves(int64_t layer, int ncz, int ctas_per_sm);
 static int march_chunk(const Mg3& m, int ncz, int ctas_per_sm) {
-    const int64_t layer = (int64_t)((m.n2 / 2 + 31) / 32) * ((m.n1 + 3) / 4);
+    return chunk_for_waves((int64_t)((m.n2 / 2 + 31) / 32) * ((m.n1 + 3) / 4), ncz, ctas_per_sm);
+}
+static int chunk_for_waves(int64_t layer, int ncz, int ctas_per_sm) {
     const int64_t slots = 148 * (int64_t)ctas_per_sm;
     int best_zc = ncz;
     double best = -1.0;
@@ -622,6 +626,14 @@ static int adj_occ() {
         return v == 5 || v == 6 ? v : 4;
     }();
     return occ;
+}
+
+// TMA-fed transposed interpolation: dense fine array whose rows are a multiple of 16 bytes (n2 even: guaranteed by
+// march_ok), a driver that exports cuTensorMapEncodeTiled; ODIL_B200_ADJ_TMA=0 keeps the LDG kernel.
+static bool adj_tma_ok(const Mg3& m) {
+    const char* e = getenv("ODIL_B200_ADJ_TMA");  // read per call: tests flip it to compare the two kernels
+    const bool off = e && atoi(e) == 0;
+    return !off && m.fs1 == 2 * (int64_t)m.n2 && m.fs0 == m.fs1 * 2 * m.n1 && get_encode_tiled() != nullptr;
 }
 
 static bool march_ok(const Mg3& m, bool cz, int ndim, const void* a, const void* b, const void* c) {
@@ -825,6 +837,37 @@ int odil_b200_mg_interp_adjoint(int ndim, const int64_t* cshape, const char* loc
             dim3 block(32, 4, 1);
             dim3 grid((m.n2 / 2 + 31) / 32, (m.n1 + 3) / 4, (unsigned)((r.cz_end - r.cz_begin + zc - 1) / zc));
             const int nfix = 16 * (int)(r.cz_end - r.cz_begin) + 16 * (m.n1 + m.n2);
+            if (dtype == ODIL_B200_F32 && adj_tma_ok(m)) {
+                // TMA-fed sweep (mg_adj_tma.cuh).  The tensor map covers exactly the fine planes the range may touch
+                // (the masks of k_interp_adjoint3m); everything outside reads as zero.
+                constexpr int NS = 4;
+                using Cfg = A3Cfg<float, NS>;
+                const int cb = (int)r.cz_begin, ce = (int)r.cz_end, nf0 = 2 * m.n0;
+                const int lo = cb == 1 ? 0 : std::max(2 * cb - 1, 0);
+                const int hi = ce - 1 == m.n0 - 2 ? nf0 - 1 : std::min(2 * ce, nf0 - 1);
+                CUtensorMap tm;
+                if (int rc = make_plane_map<float>(&tm, (const float*)g_fine + (int64_t)(lo - r.fine_z0) * m.fs0,
+                                                   hi - lo + 1, 2 * m.n1, 2 * m.n2, kA3BY, kA3BX, 2))
+                    return rc;
+                const int64_t layer = (int64_t)((m.n2 / 2 + 31) / 32) * ((m.n1 + kA3RJ - 1) / kA3RJ);
+                const int zt = chunk_for_waves(layer, ce - cb, 2);
+                dim3 gt((m.n2 / 2 + 31) / 32, (m.n1 + kA3RJ - 1) / kA3RJ, (unsigned)((ce - cb + zt - 1) / zt));
+                if (gt.y <= 65535 && gt.z <= 65535) {
+                    static bool attr_set = false;
+                    if (!attr_set) {
+                        ODIL_CUDA(cudaFuncSetAttribute(k_interp_adjoint3t<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       (int)Cfg::SMEM));
+                        attr_set = true;
+                    }
+                    k_interp_adjoint3t<NS><<<gt, kA3Threads, Cfg::SMEM, st>>>(tm, m, (float)scale, (float*)g_coarse, cb, ce,
+                                                                           (int)r.out_z0, lo, zt);
+                    k_adjoint_joint_fix<float><<<(nfix + 127) / 128, 128, 0, st>>>(
+                        m, (const float*)g_fine, (float)scale, (float*)g_coarse, cb, ce, (int)r.out_z0, (int)r.fine_z0);
+                    launch_counter()++;  // two launches
+                    ODIL_LAUNCHED();
+                    return 0;
+                }
+            }
             if (grid.y <= 65535 && grid.z <= 65535) {
 #define ODIL_ADJ(T_, OCC_)                                                                                             \
     k_interp_adjoint3m<T_, OCC_><<<grid, block, 0, st>>>(m, (const T_*)g_fine, (T_)scale, (T_*)g_coarse, (int)r.cz_begin, \

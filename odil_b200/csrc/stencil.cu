@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace odil {
 
@@ -113,6 +114,7 @@ struct odil_b200_plan {
 #include "star8.cuh"
 #include "tile2d.cuh"
 #include "tile3d.cuh"
+#include "tile3t.cuh"
 namespace odil {
 
 // ------------------------------------------------------------------------------------------------
@@ -300,41 +302,6 @@ static void star_v3_tile(int variant, int& TY, int& TX) {
         case 3: TY = 26; TX = 128; break;   // 1020 threads
         default: TY = 16; TX = 128; break;  // 680 threads
     }
-}
-
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_tiled() {
-    static PFN_encodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)ptr;
-    }
-    return fn;
-}
-
-// 3-D tensor map over a C-order (nplanes, N1, N2) array with a (1, BY, BX) box; zero fill outside.
-template <typename T>
-static int make_plane_map(CUtensorMap* map, const T* base, int64_t nplanes, int N1, int N2, int BY, int BX) {
-    PFN_encodeTiled enc = get_encode_tiled();
-    ODIL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
-    const cuuint64_t gdim[3] = {(cuuint64_t)N2, (cuuint64_t)N1, (cuuint64_t)nplanes};
-    const cuuint64_t gstr[2] = {(cuuint64_t)N2 * sizeof(T), (cuuint64_t)N1 * N2 * sizeof(T)};
-    const cuuint32_t box[3] = {(cuuint32_t)BX, (cuuint32_t)BY, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
-    const CUresult r = enc(map, dt, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ODIL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
-    return 0;
 }
 
 #ifdef ODIL_B200_LEGACY
@@ -630,9 +597,89 @@ static bool tile3d_ok(const odil_b200_plan* plan, const odil_b200_slab* slab) {
     return gy <= 65535 && gz <= 65535 && gx * gy * gz <= kPartialCapacity;
 }
 
+// k_tile3t (tile3t.cuh): TMA-fed version for wrap-free plans with at most 8 offsets; ODIL_B200_TILE3T=0 (read per
+// call, so that tests can compare the two) keeps k_tile3d.
+template <typename T>
+static bool tile3t_ok(const odil_b200_plan* plan, const T* U) {
+    const char* e = getenv("ODIL_B200_TILE3T");
+    if (e && atoi(e) == 0) return false;
+    return plan->wrap_free && plan->noff <= kT3tN && (plan->shape[2] * sizeof(T)) % 16 == 0 &&
+           (uintptr_t)U % 16 == 0 && get_encode_tiled() != nullptr;
+}
+
+// z-chunk of k_tile3t: whole waves of 148 x (resident CTAs per SM), counting the 4*H0 lead-in planes of every chunk
+static int tile3t_zchunk(const odil_b200_plan* plan, int ctas_per_sm) {
+    const int N0 = (int)plan->shape[0];
+    if (plan->zchunk > 0) return std::min(plan->zchunk, N0);
+    const int64_t tiles = ((plan->shape[1] + kT3tY - 1) / kT3tY) * ((plan->shape[2] + kT3tX - 1) / kT3tX);
+    const int64_t slots = 148 * (int64_t)std::max(ctas_per_sm, 1);
+    const int lead = 4 * plan->h3[0];
+    int best_zc = N0;
+    double best = -1.0;
+    for (int gz = 1; gz <= std::max(1, N0 / 8); ++gz) {
+        const int zc = (N0 + gz - 1) / gz;
+        const int gzr = (N0 + zc - 1) / zc;
+        if (gzr > 65535 || tiles * gzr > kPartialCapacity) break;
+        const int64_t waves = (tiles * gzr + slots - 1) / slots;
+        const double cost = (double)waves * (zc + lead);
+        if (best < 0 || cost < best * 0.999) {
+            best = cost;
+            best_zc = zc;
+        }
+    }
+    return best_zc;
+}
+
+template <typename T>
+static int launch_tile3t(const odil_b200_plan* plan, const T* U, const T* c, T scale, T* G, T* Fout, int* nparts,
+                         cudaStream_t st) {
+    Tile3tParams<T> p;
+    p.c = c;
+    p.G = G;
+    p.Fout = Fout;
+    p.table = (const T*)plan->table_dev;
+    p.partials = plan->partials;
+    p.scale = scale;
+    p.N0 = (int)plan->shape[0];
+    p.N1 = (int)plan->shape[1];
+    p.N2 = (int)plan->shape[2];
+    p.R0 = plan->R[0];
+    p.R1 = plan->R[1];
+    p.R2 = plan->R[2];
+    p.H0 = plan->h3[0];
+    p.H1 = plan->h3[1];
+    p.H2 = plan->h3[2];
+    p.noff = plan->noff;
+    p.ncls = plan->ncls;
+    const Tile3tDims d = t3t_dims<T>(p.H0, p.H1, p.H2, p.ncls, p.noff);
+    ODIL_REQUIRE(d.total <= 227 * 1024, "tile3t: %zu bytes of shared memory needed", d.total);
+    p.magicF = (unsigned)((1ull << 32) / (unsigned)d.FW + 1);
+    for (int o = 0; o < kT3tN; ++o) {
+        p.dz[o] = o < plan->noff ? (signed char)plan->off[o][0] : 0;
+        p.dy[o] = o < plan->noff ? (signed char)plan->off[o][1] : 0;
+        p.dx[o] = o < plan->noff ? (signed char)plan->off[o][2] : 0;
+    }
+    static size_t smem_set = 0;  // per template instantiation
+    static int occ = 1;
+    if (d.total > smem_set) {
+        ODIL_CUDA(cudaFuncSetAttribute(k_tile3t<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.total));
+        smem_set = d.total;
+    }
+    ODIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile3t<T>, kT3tThreads, d.total));
+    p.zchunk = tile3t_zchunk(plan, occ);
+    CUtensorMap tmU;
+    if (int rc = make_plane_map<T>(&tmU, U, p.N0, p.N1, p.N2, d.AH, d.AW)) return rc;
+    dim3 grid((p.N2 + kT3tX - 1) / kT3tX, (p.N1 + kT3tY - 1) / kT3tY, (p.N0 + p.zchunk - 1) / p.zchunk);
+    k_tile3t<T><<<grid, kT3tThreads, d.total, st>>>(tmU, p);
+    ODIL_LAUNCHED();
+    *nparts = (int)(grid.x * grid.y * grid.z);
+    return 0;
+}
+
 template <typename T>
 static int launch_tile3d(const odil_b200_plan* plan, const T* U, const T* c, T scale, T* G, T* Fout, int* nparts,
                          cudaStream_t st) {
+    if (tile3t_ok<T>(plan, U)) return launch_tile3t<T>(plan, U, c, scale, G, Fout, nparts, st);
     Tile3Params<T> p;
     p.U = U;
     p.c = c;
@@ -670,8 +717,9 @@ static int launch_tile3d(const odil_b200_plan* plan, const T* U, const T* c, T s
         smem_set = smem;
     }
     dim3 grid((p.N2 + kT3X - 1) / kT3X, (p.N1 + kT3Y - 1) / kT3Y, (p.N0 + p.zchunk - 1) / p.zchunk);
-    static const bool old_kernel = getenv("ODIL_B200_TILE3D_OLD") != nullptr;
-    if (p.noff <= kT3N && !old_kernel)
+    // k_tile3d8 measured SLOWER than k_tile3d on B200 (2.03 vs 1.50 ms at 256 x 512 x 512): opt-in for comparison only
+    static const bool unrolled = getenv("ODIL_B200_TILE3D8") != nullptr;
+    if (p.noff <= kT3N && unrolled)
         k_tile3d8<T><<<grid, kT3Threads, smem, st>>>(p);  // unrolled offsets, interior cells from registers
     else
         k_tile3d<T><<<grid, kT3Threads, smem, st>>>(p);

@@ -516,6 +516,37 @@ def test_marching_transfers(cshape, prec):
             assert relerr(gg.cpu().numpy(), g_ref[cb:ce]) < tol
 
 
+@pytest.mark.parametrize("cshape", [(4, 4, 4), (5, 7, 6), (9, 4, 34), (33, 17, 64), (6, 66, 130), (40, 72, 192)])
+def test_adjoint_tma_equals_ldg(cshape, monkeypatch):
+    """k_interp_adjoint3t (TMA-staged fine planes, the fp32 default) against k_interp_adjoint3m (LDG, ODIL_B200_ADJ_TMA=0):
+    the same operations per coarse cell, so the results are bit-identical -- whole arrays and slab-style plane ranges."""
+    rng = np.random.default_rng(11)
+    fshape = tuple(2 * s for s in cshape)
+    term = rng.standard_normal(fshape).astype(np.float32)
+    n0 = cshape[0]
+    ranges = [None] + ([(0, 2), (1, n0 - 1), (n0 - 2, n0), (2, 3)] if n0 >= 5 else [])
+    for r in ranges:
+        outs = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("ODIL_B200_ADJ_TMA", flag)
+            if r is None:
+                gc = torch.full(cshape, float("nan"), dtype=torch.float32, device="cuda")
+                native.mg_interp_adjoint(cshape, "ccc", dev(term), 0.9, gc)
+            else:
+                cb, ce = r
+                f_lo, f_hi = max(2 * cb - 2, 0), min(2 * ce + 2, fshape[0])
+                gc = torch.full((ce - cb,) + tuple(cshape[1:]), float("nan"), dtype=torch.float32, device="cuda")
+                native.mg_interp_adjoint(cshape, "ccc", dev(term[f_lo:f_hi]), 0.9, gc, rng=(cb, ce, cb, f_lo))
+            outs.append(gc.cpu().numpy())
+        assert np.array_equal(outs[0], outs[1]), (cshape, r, np.max(np.abs(outs[0] - outs[1])))
+    if ranges[0] is None:
+        g_ref = 0.9 * orc.interp_adjoint(term.astype(np.float64), "ccc", cshape)
+        monkeypatch.setenv("ODIL_B200_ADJ_TMA", "1")
+        gc = torch.full(cshape, float("nan"), dtype=torch.float32, device="cuda")
+        native.mg_interp_adjoint(cshape, "ccc", dev(term), 0.9, gc)
+        assert relerr(gc.cpu().numpy(), g_ref) < 100 * np.finfo(np.float32).eps
+
+
 # --------------------------------------------------------------------------------------------------
 # k_tile2d: any offset set of small radius on 2-D grids (the wave example's footprint), all three modes
 # --------------------------------------------------------------------------------------------------

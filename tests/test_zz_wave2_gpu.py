@@ -133,3 +133,72 @@ def test_tile3d_matches_oracle_and_generic(prec, case):
         assert relerr(G0, orc.stencil_adjoint(F0, offsets, table, rr, scale)) < tol
     for a, b in zip(res[80][:2], res[81][:2]):
         assert relerr(a, b) < 64 * np.finfo(nd).eps
+
+
+# --------------------------------------------------------------------------------------------------
+# k_tile3t (TMA-fed version of k_tile3d: the default for wrap-free non-star 3-D plans with <= 8 offsets)
+# --------------------------------------------------------------------------------------------------
+def wrap_free_table(rng, offsets, rr):
+    """Random region-typed table whose coefficients vanish wherever the neighbour would cross a face of the grid
+    (what every non-periodic operator lowers to; needs rr >= the stencil radius per axis)."""
+    tshape = tuple(2 * r + 1 for r in rr) + (len(offsets),)
+    table = rng.standard_normal(tshape)
+    for cls in np.ndindex(*tshape[:-1]):
+        for o, off in enumerate(offsets):
+            for a in range(3):
+                ci, r, d = cls[a], rr[a], off[a]
+                if (ci < r and ci + d < 0) or (ci > r and d > 2 * r - ci):
+                    table[cls + (o,)] = 0.0
+    return table
+
+
+TILE3T_CASES = [
+    ((7, 10, 12), WAVE2, (2, 1, 1), 3),
+    ((40, 18, 72), WAVE2, (2, 1, 1), 0),
+    ((9, 5, 8), [(0, 0, 0), (1, 1, 1), (-2, 0, 2), (0, -1, 0)], (2, 1, 2), 2),
+    ((33, 16, 64), [(0, 0, 0), (0, 1, -1), (1, 0, 0)], (1, 1, 1), 8),
+    ((64, 48, 200), WAVE2, (2, 1, 1), 16),
+    ((70, 50, 132), WAVE2, (2, 2, 2), 0),
+    ((20, 33, 260), [(0, 0, 0), (2, 0, 0), (-2, 0, 0), (0, 2, 0), (0, -2, 0), (0, 0, 2), (0, 0, -2), (1, 1, 1)],
+     (2, 2, 2), 0),
+]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("case", range(len(TILE3T_CASES)))
+def test_tile3t_matches_oracle_tile3d_and_generic(prec, case, monkeypatch):
+    nd, td = (np.float64, torch.float64) if prec == "f64" else (np.float32, torch.float32)
+    shape, offsets, rr, zchunk = TILE3T_CASES[case]
+    rng = np.random.default_rng(900 + case)
+    table = wrap_free_table(rng, offsets, rr)
+    U = rng.standard_normal(shape).astype(nd)
+    c = rng.standard_normal(shape).astype(nd)
+    scale = 2.0 / U.size
+    F_ref = orc.stencil_forward(U.astype(np.float64), offsets, table, rr, c.astype(np.float64))
+    g_ref = orc.stencil_adjoint(F_ref, offsets, table, rr, scale)
+    F0 = orc.stencil_forward(U.astype(np.float64), offsets, table, rr, None)
+    g0_ref = orc.stencil_adjoint(F0, offsets, table, rr, scale)
+    tol = (1e-11 if prec == "f64" else 2e-5) * 10
+    res = {}
+    for name, env, variant in (("tile3t", "1", 80), ("tile3d", "0", 80), ("generic", "0", 81)):
+        monkeypatch.setenv("ODIL_B200_TILE3T", env)
+        plan = native.StencilPlan(shape, td, offsets, rr, table.reshape(-1, len(offsets)))
+        plan.tune(zchunk=zchunk, variant=variant)
+        dU, dc = torch.as_tensor(U, device="cuda"), torch.as_tensor(c, device="cuda")
+        G = torch.full_like(dU, float("nan"))
+        F = torch.full_like(dU, float("nan"))
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dU, dc, scale, G, ss, F_out=F)
+        G0 = torch.full_like(dU, float("nan"))
+        ss0 = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dU, None, scale, G0, ss0)
+        res[name] = [t.cpu().numpy() for t in (F, G, G0, ss, ss0)]
+        F, G, G0, ss, ss0 = res[name]
+        assert relerr(F, F_ref) < tol and relerr(G, g_ref) < tol and relerr(G0, g0_ref) < tol, name
+        assert abs(ss[0] - np.sum(F_ref ** 2)) < tol * np.sum(F_ref ** 2), name
+        assert abs(ss0[0] - np.sum(F0 ** 2)) < tol * np.sum(F0 ** 2), name
+    # same operations per cell in the same order: F and g agree bit for bit (up to the sign of zero)
+    for a, b in zip(res["tile3t"][:3], res["tile3d"][:3]):
+        assert np.array_equal(a, b)
+    for a, b in zip(res["tile3t"][:3], res["generic"][:3]):
+        assert relerr(a, b) < 64 * np.finfo(nd).eps
