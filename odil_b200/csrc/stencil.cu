@@ -651,9 +651,8 @@ static int launch_tile3t(const odil_b200_plan* plan, const T* U, const T* c, T s
     p.H2 = plan->h3[2];
     p.noff = plan->noff;
     p.ncls = plan->ncls;
-    const Tile3tDims d = t3t_dims<T>(p.H0, p.H1, p.H2, p.ncls, p.noff);
+    const Tile3tDims d = t3t_dims<T>(p.H0, p.H1, p.ncls, p.noff);
     ODIL_REQUIRE(d.total <= 227 * 1024, "tile3t: %zu bytes of shared memory needed", d.total);
-    p.magicF = (unsigned)((1ull << 32) / (unsigned)d.FW + 1);
     for (int o = 0; o < kT3tN; ++o) {
         p.dz[o] = o < plan->noff ? (signed char)plan->off[o][0] : 0;
         p.dy[o] = o < plan->noff ? (signed char)plan->off[o][1] : 0;
@@ -668,7 +667,7 @@ static int launch_tile3t(const odil_b200_plan* plan, const T* U, const T* c, T s
     ODIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile3t<T>, kT3tThreads, d.total));
     p.zchunk = tile3t_zchunk(plan, occ);
     CUtensorMap tmU;
-    if (int rc = make_plane_map<T>(&tmU, U, p.N0, p.N1, p.N2, d.AH, d.AW)) return rc;
+    if (int rc = make_plane_map<T>(&tmU, U, p.N0, p.N1, p.N2, d.AH, kT3tAW)) return rc;
     dim3 grid((p.N2 + kT3tX - 1) / kT3tX, (p.N1 + kT3tY - 1) / kT3tY, (p.N0 + p.zchunk - 1) / p.zchunk);
     k_tile3t<T><<<grid, kT3tThreads, d.total, st>>>(tmU, p);
     ODIL_LAUNCHED();
