@@ -607,12 +607,15 @@ static bool tile3t_ok(const odil_b200_plan* plan, const T* U) {
            (uintptr_t)U % 16 == 0 && get_encode_tiled() != nullptr;
 }
 
-// z-chunk of k_tile3t: whole waves of 148 x (resident CTAs per SM), counting the 4*H0 lead-in planes of every chunk
+// z-chunk of k_tile3t.  The kernel is bound by instruction issue when the SMs are full (ncu: 50 % of the issue slots
+// with 2 CTAs per SM), so an SM's time is the SUM of the planes of the CTAs it runs, and by the per-plane barrier when
+// they are not: the chunk count minimises the larger of the two estimates, counting the 4*H0 lead-in planes.
 static int tile3t_zchunk(const odil_b200_plan* plan, int ctas_per_sm) {
     const int N0 = (int)plan->shape[0];
     if (plan->zchunk > 0) return std::min(plan->zchunk, N0);
     const int64_t tiles = ((plan->shape[1] + kT3tY - 1) / kT3tY) * ((plan->shape[2] + kT3tX - 1) / kT3tX);
-    const int64_t slots = 148 * (int64_t)std::max(ctas_per_sm, 1);
+    (void)ctas_per_sm;
+    const int64_t slots = 148;
     const int lead = 4 * plan->h3[0];
     int best_zc = N0;
     double best = -1.0;
@@ -620,8 +623,11 @@ static int tile3t_zchunk(const odil_b200_plan* plan, int ctas_per_sm) {
         const int zc = (N0 + gz - 1) / gz;
         const int gzr = (N0 + zc - 1) / zc;
         if (gzr > 65535 || tiles * gzr > kPartialCapacity) break;
-        const int64_t waves = (tiles * gzr + slots - 1) / slots;
-        const double cost = (double)waves * (zc + lead);
+        // measured at 256 x 512 x 512 and 128 x 256 x 256 (fp32, wave footprint): a plane costs ~1.13 us of an SM's
+        // issue slots and a pair of co-resident CTAs advances one plane per ~2.2 us (barrier / latency)
+        const int64_t ctas = tiles * gzr;
+        const double cost = std::max((double)((ctas + slots - 1) / slots) * 1.13, (double)((ctas + 2 * slots - 1) / (2 * slots)) * 2.2) *
+                            (zc + lead);
         if (best < 0 || cost < best * 0.999) {
             best = cost;
             best_zc = zc;
