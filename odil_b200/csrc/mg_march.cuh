@@ -167,8 +167,8 @@ __device__ __forceinline__ MgP<T> mg_plane(const Mg3& m, const T* __restrict__ c
 }
 
 // grid (ceil(n2 / 64), ceil(n1 / 4), z-chunks), block (32, 4): thread = coarse cells 2k, 2k+1 of coarse row J
-template <typename T>
-__global__ void __launch_bounds__(128, 5) k_interp_add3m(Mg3 m, const T* __restrict__ coarse, T cfac,
+template <typename T, bool PF = false>
+__global__ void __launch_bounds__(128, PF ? 4 : 5) k_interp_add3m(Mg3 m, const T* __restrict__ coarse, T cfac,
                                                       const T* __restrict__ term, T ffac, T* __restrict__ out,
                                                       int fz_begin, int fz_end, int out_z0, int coarse_z0, int zc) {
     const int k = blockIdx.x * 32 + threadIdx.x;
@@ -181,19 +181,38 @@ __global__ void __launch_bounds__(128, 5) k_interp_add3m(Mg3 m, const T* __restr
     MgP<T> Pc = mg_plane<T>(m, coarse, coarse_z0, Ibeg, J, k);
     const T s = cfac * T(1.0 / 64.0);
     const int64_t col = (int64_t)(2 * J) * m.fs1 + 4 * k;
+    // the four fine vectors of a step are loaded one step AHEAD (PF: twice the bytes in flight per warp; the kernel
+    // waits on memory -- ncu: 10 long-scoreboard stall cycles per issued instruction, 35 % of the issue slots used)
+    auto load_terms = [&](int I, MgVec4<T> (&t)[2][2]) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int fz = 2 * I + a;
+            const bool on = I < Iend && fz >= fz_begin && fz < fz_end;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int64_t lin = (int64_t)(fz - out_z0) * m.fs0 + col + (int64_t)b * m.fs1;
+                t[a][b] = (term && on) ? mg_ld4<T>(term + lin) : MgVec4<T>{T(0), T(0), T(0), T(0)};
+            }
+        }
+    };
+    MgVec4<T> tn[2][2];
+    if (PF) load_terms(Ibeg, tn);
     for (int I = Ibeg; I < Iend; ++I) {
-        // the four fine vectors of this step first (independent of the coarse loads below)
         MgVec4<T> t[2][2];
         bool on[2];
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const int fz = 2 * I + a;
             on[a] = fz >= fz_begin && fz < fz_end;
+        }
+        if (PF) {
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int64_t lin = (int64_t)(fz - out_z0) * m.fs0 + col + (int64_t)b * m.fs1;
-                t[a][b] = (term && on[a]) ? mg_ld4<T>(term + lin) : MgVec4<T>{T(0), T(0), T(0), T(0)};
-            }
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) t[a][b] = tn[a][b];
+            load_terms(I + 1, tn);
+        } else {
+            load_terms(I, t);
         }
         const MgP<T> Pp = mg_plane<T>(m, coarse, coarse_z0, I + 1, J, k);
 #pragma unroll

@@ -683,11 +683,19 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
         const bool pairs = (r.fz_begin % 2 == 0) && (r.fz_end % 2 == 0);
         if (fast3_geometry(g, m, cz) && march_ok(m, cz, ndim, coarse, fine_term, out) && r.fz_end > r.fz_begin) {
             const int ib = (int)(r.fz_begin >> 1), ie = (int)(((r.fz_end - 1) >> 1) + 1);
-            const int zc = march_chunk(m, ie - ib, 5);
+            // ODIL_B200_ADD_PF=1: the variant that loads the fine term one step ahead (4 CTAs per SM)
+            const char* epf = getenv("ODIL_B200_ADD_PF");
+            const bool pf = dtype == ODIL_B200_F32 && epf && atoi(epf) != 0;
+            const int zc = march_chunk(m, ie - ib, pf ? 4 : 5);
             dim3 block(32, 4, 1);
             dim3 grid((m.n2 / 2 + 31) / 32, (m.n1 + 3) / 4, (ie - ib + zc - 1) / zc);
             if (grid.y <= 65535 && grid.z <= 65535) {
-                if (dtype == ODIL_B200_F32) {
+                if (pf) {
+                    k_interp_add3m<float, true><<<grid, block, 0, st>>>(m, (const float*)coarse, (float)cfac,
+                                                                        (const float*)fine_term, (float)ffac, (float*)out,
+                                                                        (int)r.fz_begin, (int)r.fz_end, (int)r.out_z0,
+                                                                        (int)r.coarse_z0, zc);
+                } else if (dtype == ODIL_B200_F32) {
                     k_interp_add3m<float><<<grid, block, 0, st>>>(m, (const float*)coarse, (float)cfac,
                                                                   (const float*)fine_term, (float)ffac, (float*)out,
                                                                   (int)r.fz_begin, (int)r.fz_end, (int)r.out_z0,
