@@ -510,6 +510,12 @@ def run_b200(args):
     kern = m["kern"]
     alg_bytes = {"stencil_fused": 3 * es * ncells_local, "adam_step": 7 * es * nunk_local}
     alg_note = {"stencil_fused": "3*s bytes per cell (read U, read c, write g)"}
+    if "adam_synth" in kern:
+        # the finest multigrid term is updated by odil_b200_adam_synth (reads t0, m, v, g and 1/8 coarse value per cell,
+        # writes t0, m, v, U); odil_b200_adam_step then only covers the coarser terms
+        alg_bytes["adam_synth"] = (8 + 1 / 8) * es * ncells_local
+        alg_bytes["adam_step"] = 7 * es * max(nunk_local - ncells_local, 0)
+        alg_note["adam_synth"] = "(8 + 1/8)*s bytes per finest-level cell (read t0, m, v, g, coarse; write t0, m, v, U)"
     if wl["kind"] == "heat3":
         # generated kernels of the heat operator (one field u, constants imp_mask and imp_u, two outputs)
         alg_bytes.update({"jit:k_g0_jvp": 6 * es * ncells_local, "jit:k_g0_vjp": 6 * es * ncells_local,

@@ -578,6 +578,87 @@ static bool fast3_geometry(const MgGeom& g, Mg3& m, bool& cz) {
 #include "mg_march.cuh"
 #include "mg_tile2d.cuh"
 #include "mg_adj_tma.cuh"
+
+namespace odil {
+
+// ------------------------------------------------------------------------------------------------
+// k_adam_synth3 -- fusion across the optimizer seam, the other way round from k_interp_adjoint3m_adam: the Adam update
+// of the FINEST multigrid term t0 (optimizer.py:311-319) also produces the regular field of the NEXT evaluation,
+//     U = ffac * t0_new + cfac * I(V1)        (core.py:245-263; V1 = the already synthesised level 1),
+// so the synthesis of level 0 does not read t0 back from HBM: 32.5 instead of 36.5 bytes per fine cell for the pair
+// (k_adam of level 0 + k_interp_add3m of level 0).  A thread owns the fine vector (4 cells along x) of one fine row and
+// marches over kAsZC coarse planes (2 kAsZC fine planes), carrying the in-plane interpolation of three coarse planes in
+// registers; the interpolation uses mg_plane() and the plane combination of k_interp_add3m statement for statement, the
+// update is adam_one(): x, m, v and U are bit-identical to the unfused pair.  The coarse values (1/8 of the fine data)
+// come through L1 / L2.  (First version: one fine vector per thread, 131072 short-lived CTAs at 512^3: 0.78 ms = 86 %
+// of the measured HBM peak, no better than the unfused pair.)
+// grid (ceil(n2 / 128), ceil(2 n1 / 4), ceil(n0 / kAsZC)), block (64, 4).
+// ------------------------------------------------------------------------------------------------
+constexpr int kAsZC = 4;  // coarse planes (pairs of fine planes) per CTA
+
+template <typename T, int OCC>
+__global__ void __launch_bounds__(256, OCC) k_adam_synth3(Mg3 mm, const T* __restrict__ coarse, T cfac, T ffac, T* __restrict__ x,
+                                                     T* __restrict__ m, T* __restrict__ v, const T* __restrict__ g,
+                                                     T* __restrict__ out, T alpha_host, const double* __restrict__ alpha_dev,
+                                                     T omb1, T omb2, T eps) {
+    const int k = blockIdx.x * 64 + threadIdx.x;  // fine cells 4k .. 4k+3 = coarse cells 2k, 2k+1
+    const int fy = blockIdx.y * 4 + threadIdx.y;
+    if (2 * k >= mm.n2 || fy >= 2 * mm.n1) return;
+    const int J = fy >> 1, b = fy & 1;
+    const int Ibeg = blockIdx.z * kAsZC, Iend = min(Ibeg + kAsZC, mm.n0);
+    const T alpha = alpha_dev ? (T)__ldg(alpha_dev) : alpha_host;
+    const T s = cfac * T(1.0 / 64.0);
+    // in-plane interpolation of the coarse planes I-1, I, I+1 for the own fine row (row b of mg_plane's pair), carried
+    // along axis 0 like k_interp_add3m does
+    auto plane_row = [&](int zp, T (&p)[4]) {
+        const MgP<T> P = mg_plane<T>(mm, coarse, 0, zp, J, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) p[c] = b == 0 ? P.v[0][c] : P.v[1][c];
+    };
+    T Pm[4], Pc[4], Pp[4];
+    plane_row(Ibeg - 1, Pm);
+    plane_row(Ibeg, Pc);
+    int64_t lin = (int64_t)(2 * Ibeg) * mm.fs0 + (int64_t)fy * mm.fs1 + 4 * k;
+    for (int I = Ibeg; I < Iend; ++I) {
+        // the eight streams of the two fine planes first (independent of the coarse loads below)
+        MgVec4<T> xx[2], mv[2], vv[2], gg[2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            xx[a] = mg_ld4<T>(x + lin + a * mm.fs0);
+            mv[a] = mg_ld4<T>(m + lin + a * mm.fs0);
+            vv[a] = mg_ld4<T>(v + lin + a * mm.fs0);
+            gg[a] = mg_ld4<T>(g + lin + a * mm.fs0);
+        }
+        plane_row(I + 1, Pp);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            T r[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) r[c] = s * (a == 0 ? Pm[c] + T(3) * Pc[c] : T(3) * Pc[c] + Pp[c]);
+            adam_one(xx[a].x, mv[a].x, vv[a].x, gg[a].x, alpha, omb1, omb2, eps);
+            adam_one(xx[a].y, mv[a].y, vv[a].y, gg[a].y, alpha, omb1, omb2, eps);
+            adam_one(xx[a].z, mv[a].z, vv[a].z, gg[a].z, alpha, omb1, omb2, eps);
+            adam_one(xx[a].w, mv[a].w, vv[a].w, gg[a].w, alpha, omb1, omb2, eps);
+            r[0] = fma(ffac, xx[a].x, r[0]);
+            r[1] = fma(ffac, xx[a].y, r[1]);
+            r[2] = fma(ffac, xx[a].z, r[2]);
+            r[3] = fma(ffac, xx[a].w, r[3]);
+            const int64_t l = lin + a * mm.fs0;
+            mg_st4(out + l, MgVec4<T>{r[0], r[1], r[2], r[3]});
+            mg_st4(x + l, xx[a]);
+            mg_st4(m + l, mv[a]);
+            mg_st4(v + l, vv[a]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            Pm[c] = Pc[c];
+            Pc[c] = Pp[c];
+        }
+        lin += 2 * mm.fs0;
+    }
+}
+
+}  // namespace odil
 namespace odil {
 
 // 2-D cell-centred whole-array transfers through the shared-memory tile kernels (mg_tile2d.cuh).
@@ -753,6 +834,47 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
                                                            r.out_z0, r.coarse_z0);
     else
         return fail("dtype=%d unsupported", dtype);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
+// Adam update of the finest multigrid term (x, m, v with gradient g) AND out = ffac * x_new + cfac * I(coarse) in one pass
+// (k_adam_synth3).  Returns 1 -- nothing done -- when the geometry is not cell-centred 3-D with an even coarse width
+// and 16-byte aligned arrays: the caller then runs odil_b200_adam_step and odil_b200_mg_interp_add separately.
+int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* coarse, double cfac,
+                         double ffac, void* x, void* m_state, void* v_state, const void* g, void* out, double alpha,
+                         const double* alpha_dev, double one_minus_beta1, double one_minus_beta2, double epsilon,
+                         void* stream) {
+    MgGeom geo;
+    if (int rc = make_geom(ndim, cshape, loc, geo)) return rc;
+    ODIL_REQUIRE(coarse && x && m_state && v_state && g && out, "null array");
+    ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    Mg3 m;
+    bool cz = false;
+    if (!(fast3_geometry(geo, m, cz) && march_ok(m, cz, ndim, x, g, out) && (uintptr_t)m_state % 16 == 0 &&
+          (uintptr_t)v_state % 16 == 0 && (uintptr_t)coarse % 16 == 0))
+        return 1;
+    dim3 block(64, 4, 1);
+    dim3 grid((m.n2 / 2 + 63) / 64, (2 * m.n1 + 3) / 4, (unsigned)((m.n0 + kAsZC - 1) / kAsZC));
+    if (grid.y > 65535 || grid.z > 65535) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    // resident CTAs per SM the fp32 kernel is compiled for: 3 (80 registers, 16 bytes of spills; default) or 2 (128)
+    static const int occ = [] {
+        const char* e = getenv("ODIL_B200_SYNTH_OCC");
+        return e && atoi(e) == 2 ? 2 : 3;
+    }();
+#define ODIL_SYNTH_F32(OCC_)                                                                                              \
+    k_adam_synth3<float, OCC_><<<grid, block, 0, st>>>(m, (const float*)coarse, (float)cfac, (float)ffac, (float*)x,         \
+                                                       (float*)m_state, (float*)v_state, (const float*)g, (float*)out,       \
+                                                       (float)alpha, alpha_dev, (float)one_minus_beta1,                      \
+                                                       (float)one_minus_beta2, (float)epsilon)
+    if (dtype == ODIL_B200_F32) {
+        if (occ == 2) ODIL_SYNTH_F32(2);
+        else ODIL_SYNTH_F32(3);
+    } else
+        k_adam_synth3<double, 1><<<grid, block, 0, st>>>(m, (const double*)coarse, cfac, ffac, (double*)x, (double*)m_state,
+                                                      (double*)v_state, (const double*)g, (double*)out, alpha, alpha_dev,
+                                                      one_minus_beta1, one_minus_beta2, epsilon);
     ODIL_LAUNCHED();
     return 0;
 }

@@ -25,7 +25,7 @@ EXPORTS = [
     "odil_b200_mg_interp_adjoint", "odil_b200_mg_restrict", "odil_b200_adam_step", "odil_b200_gd_step",
     "odil_b200_axpby", "odil_b200_multi_dot", "odil_b200_multi_axpy", "odil_b200_cg_update_xr",
     "odil_b200_cg_update_p", "odil_b200_star_worklist", "odil_b200_adam_step_dev",
-    "odil_b200_mg_interp_adjoint_adam",
+    "odil_b200_mg_interp_adjoint_adam", "odil_b200_adam_synth",
     "odil_b200_jit_compile", "odil_b200_jit_log", "odil_b200_jit_cubin", "odil_b200_jit_kernel",
     "odil_b200_jit_launch", "odil_b200_jit_destroy",
     "odil_b200_comm_create", "odil_b200_comm_connect", "odil_b200_comm_capacity", "odil_b200_halo_exchange",
@@ -105,6 +105,8 @@ def load(build_if_missing=False):
                                                 P(MgAdjRange), vp]
     lib.odil_b200_mg_interp_adjoint_adam.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, dbl, vp, vp,
                                                      vp, vp, dbl, vp, dbl, dbl, dbl, vp]
+    lib.odil_b200_adam_synth.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, dbl, dbl, vp, vp, vp, vp,
+                                         vp, dbl, vp, dbl, dbl, dbl, vp]
     lib.odil_b200_mg_restrict.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, vp, vp]
     lib.odil_b200_adam_step.argtypes = [ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), ctypes.c_int, dbl, dbl,
                                         dbl, dbl, vp]
@@ -183,7 +185,9 @@ def _plane_ptr(t, halo):
 
 
 _replayed = 0
-FUSED_ADAM_APPLIED = 0  # how many times odil_b200_mg_interp_adjoint_adam really ran (it declines unsuitable arrays)
+FUSED_ADAM_APPLIED = 0
+ADAM_SYNTH_APPLIED = 0  # calls of odil_b200_adam_synth that ran the fused kernel
+# FUSED_ADAM_APPLIED: how many times odil_b200_mg_interp_adjoint_adam really ran (it declines unsuitable arrays)
 
 
 def note_replayed_launches(n):
@@ -312,6 +316,30 @@ def mg_interp_adjoint_adam(cshape, loc, g_fine, scale, g_coarse, x, m, v, alpha,
     _call("mg_interp_adjoint_adam", run)
     global FUSED_ADAM_APPLIED
     FUSED_ADAM_APPLIED += int(res["applied"])
+    return res["applied"]
+
+
+def adam_synth(cshape, loc, coarse, cfac, ffac, x, m, v, g, out, alpha, omb1, omb2, eps, alpha_dev=None):
+    """Adam update of the finest multigrid term (x, m, v with gradient g) and out = ffac * x_new + cfac * I(coarse) in one
+    pass (odil_b200_adam_synth).  Returns False (nothing done) if the arrays do not fit the fused kernel."""
+    load()
+    for t in (m, v, g, out):
+        if t.dtype != x.dtype or t.shape != x.shape:
+            raise NativeError("adam_synth: m, v, g, out must match x in dtype and shape")
+    res = {}
+
+    def run():
+        rc = _lib.odil_b200_adam_synth(
+            len(cshape), _cshape(cshape), loc.encode(), dtype_code(x.dtype), _ptr(coarse), float(cfac), float(ffac),
+            _ptr(x), _ptr(m), _ptr(v), _ptr(g), _ptr(out), float(alpha),
+            _ptr(alpha_dev) if alpha_dev is not None else None, float(omb1), float(omb2), float(eps), _stream())
+        if rc not in (0, 1):
+            _check(rc)
+        res["applied"] = rc == 0
+
+    _call("adam_synth", run)
+    global ADAM_SYNTH_APPLIED
+    ADAM_SYNTH_APPLIED += int(res["applied"])
     return res["applied"]
 
 

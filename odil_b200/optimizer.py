@@ -98,15 +98,22 @@ class AdamNativeOptimizer(Optimizer):
         # streams that term's gradient (odil_b200_mg_interp_adjoint_adam) is told the step in advance and hands back
         # None in place of the gradients it has consumed.
         fuse = getattr(loss_grad, "fuse_adam", None)
+        # The other fusion across the seam (the default where the engine offers it): the engine applies the whole
+        # update and, while it rewrites the finest multigrid term, synthesises the regular field of the next
+        # evaluation (odil_b200_adam_synth) -- same arithmetic, the finest term is read once per epoch instead of twice.
+        synth = getattr(loss_grad, "adam_synth", None) if fuse is None else None
         for epoch in range(first, eager_until + 1):
             self.evals += 1
             alpha, omb1, omb2 = adam_scalars(lr, beta_1, beta_2, epoch - epoch_start, dtype)
             if fuse is not None:
                 fuse(x, m, v, alpha, omb1, omb2, eps)
             loss, grads, pinfo = loss_grad(x)
-            rest = [i for i, g in enumerate(grads) if g is not None]
-            native.adam_step([x[i] for i in rest], [m[i] for i in rest], [v[i] for i in rest],
-                             [grads[i] for i in rest], alpha, omb1, omb2, eps)
+            if synth is not None:
+                synth(x, m, v, grads, alpha, omb1, omb2, eps)
+            else:
+                rest = [i for i, g in enumerate(grads) if g is not None]
+                native.adam_step([x[i] for i in rest], [m[i] for i in rest], [v[i] for i in rest],
+                                 [grads[i] for i in rest], alpha, omb1, omb2, eps)
             if epoch > 0 and callback is not None:
                 callback(x, epoch, pinfo)
         if eager_until < last:
@@ -135,9 +142,13 @@ class AdamNativeOptimizer(Optimizer):
             if fuse is not None:
                 fuse(held, m, v, 0.0, omb1, omb2, eps, alpha_dev=alpha_dev)
             loss, grads, pinfo = loss_grad(held)
-            rest = [i for i, gr in enumerate(grads) if gr is not None]
-            native.adam_step_dev([held[i] for i in rest], [m[i] for i in rest], [v[i] for i in rest],
-                                 [grads[i] for i in rest], alpha_dev, omb1, omb2, eps)
+            synth = getattr(loss_grad, "adam_synth", None) if fuse is None else None
+            if synth is not None:
+                synth(held, m, v, grads, 0.0, omb1, omb2, eps, alpha_dev=alpha_dev)
+            else:
+                rest = [i for i, gr in enumerate(grads) if gr is not None]
+                native.adam_step_dev([held[i] for i in rest], [m[i] for i in rest], [v[i] for i in rest],
+                                     [grads[i] for i in rest], alpha_dev, omb1, omb2, eps)
         nodes = native.launch_count() - n_before  # library kernels captured into one replay
         fetch = getattr(loss, "_fetch", None)
         self._graph = g  # owns the memory pool of grads / sums that pinfo still points into after run()

@@ -155,6 +155,44 @@ def test_adam_graph_replay_is_bit_identical(monkeypatch, case, prec):
     assert c0 <= c1 <= c0 + c0 // 8
 
 
+@pytest.mark.parametrize("case", [((32, 24, 40), 3), ((16, 20, 8), 2), ((64, 64, 64), 4), ((10, 8, 12), 2), ((16, 16), 3)])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("graph", ["0", "1"])
+def test_adam_fused_with_synthesis_is_bit_identical(monkeypatch, case, prec, graph):
+    """odil_b200_adam_synth (the default through optimize_grad): the Adam update of the finest multigrid term also writes
+    the regular field of the next evaluation, U = t0 + I(V1), so level 0 is not synthesised again.  Same arithmetic per
+    cell as k_adam and k_interp_add3m: loss trajectory and final state equal the unfused epoch (ODIL_B200_FUSE_SYNTH=0)
+    bit for bit, eagerly and under graph replay; 2-D grids take the unfused pair.  A state written by a torch operation
+    between two evaluations invalidates the cached field."""
+    dt = np.float64 if prec == "f64" else np.float32
+    cshape, nlvl = case
+    monkeypatch.setenv("ODIL_B200_GRAPH", graph)
+    out = []
+    for flag in ["0", "1"]:
+        monkeypatch.setenv("ODIL_B200_FUSE_SYNTH", flag)
+        problem, state = ops.make_poisson(cshape, nlvl, dt)
+        n0 = odil.native.ADAM_SYNTH_APPLIED
+        losses = run_optimizer(problem, state, "adam", run_args(epochs=8, lr=0.005))
+        arrays = problem.domain.arrays_from_state(state)
+        final = [a.cpu().numpy() for a in arrays]
+        # evaluation after the run: picks up the cached field (fused) or synthesises it (unfused) -- same numbers
+        loss_a, grads_a = problem.eval_loss_grad(state)[:2]
+        # ... and after a torch write to the state the cache must not be used
+        arrays[0].mul_(0.5)
+        loss_b, grads_b = problem.eval_loss_grad(state)[:2]
+        out.append((losses, final, odil.native.ADAM_SYNTH_APPLIED - n0, float(loss_a),
+                    [g.cpu().numpy() for g in grads_a], float(loss_b), [g.cpu().numpy() for g in grads_b]))
+    (l0, x0, s0, la0, ga0, lb0, gb0), (l1, x1, s1, la1, ga1, lb1, gb1) = out
+    assert s0 == 0
+    assert (s1 > 0) == (len(cshape) == 3)
+    assert np.array_equal(l0, l1)
+    for a, b in zip(x0, x1):
+        assert np.array_equal(a, b)
+    assert la0 == la1 and lb0 == lb1 and la0 != lb0
+    for a, b in zip(ga0 + gb0, ga1 + gb1):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("case", [((32, 24, 40), 3), ((16, 20, 8), 2), ((64, 64, 64), 4), ((16, 16), 3)])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("graph", ["0", "1"])
