@@ -205,11 +205,13 @@ int odil_b200_mg_interp_adjoint_adam(int ndim, const int64_t* cshape, const char
  * optimizer.py:311-319) also writes the regular field of the NEXT evaluation, out = ffac * t0_new + cfac * I(coarse)
  * (multigrid_to_regular, core.py:245-263; coarse = the synthesised level 1, cshape = its shape), so the synthesis of
  * level 0 does not read t0 back.  x, m, v and out are bit-identical to odil_b200_adam_step followed by
- * odil_b200_mg_interp_add.  Returns 1 without doing anything when the arrays do not fit (caller: unfused pair). */
+ * odil_b200_mg_interp_add.  range (nullable; slabs): even fine planes [fz_begin, fz_end) to update, out_z0 = global
+ * number of local plane 0 of x / m / v / g / out, coarse_z0 = that of `coarse` (as in odil_b200_mg_interp_add).
+ * Returns 1 without doing anything when the arrays do not fit (caller: unfused pair). */
 int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* coarse, double cfac,
                          double ffac, void* x, void* m, void* v, const void* g, void* out, double alpha,
                          const double* alpha_dev, double one_minus_beta1, double one_minus_beta2, double epsilon,
-                         void* stream);
+                         const odil_b200_mg_range* range, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Run-time specialised kernels for operators that are not affine stencils.

@@ -600,25 +600,29 @@ template <typename T, int OCC>
 __global__ void __launch_bounds__(256, OCC) k_adam_synth3(Mg3 mm, const T* __restrict__ coarse, T cfac, T ffac, T* __restrict__ x,
                                                      T* __restrict__ m, T* __restrict__ v, const T* __restrict__ g,
                                                      T* __restrict__ out, T alpha_host, const double* __restrict__ alpha_dev,
-                                                     T omb1, T omb2, T eps) {
+                                                     T omb1, T omb2, T eps, int cz_begin, int cz_end, int fine_z0,
+                                                     int coarse_z0) {
+    // cz_begin .. cz_end: coarse planes whose fine planes are updated (global numbers); fine_z0 / coarse_z0: global
+    // plane number of local plane 0 of the fine arrays / of `coarse` (slabs; 0 for whole arrays)
     const int k = blockIdx.x * 64 + threadIdx.x;  // fine cells 4k .. 4k+3 = coarse cells 2k, 2k+1
     const int fy = blockIdx.y * 4 + threadIdx.y;
     if (2 * k >= mm.n2 || fy >= 2 * mm.n1) return;
     const int J = fy >> 1, b = fy & 1;
-    const int Ibeg = blockIdx.z * kAsZC, Iend = min(Ibeg + kAsZC, mm.n0);
+    const int Ibeg = cz_begin + blockIdx.z * kAsZC, Iend = min(Ibeg + kAsZC, cz_end);
+    if (Ibeg >= Iend) return;
     const T alpha = alpha_dev ? (T)__ldg(alpha_dev) : alpha_host;
     const T s = cfac * T(1.0 / 64.0);
     // in-plane interpolation of the coarse planes I-1, I, I+1 for the own fine row (row b of mg_plane's pair), carried
     // along axis 0 like k_interp_add3m does
     auto plane_row = [&](int zp, T (&p)[4]) {
-        const MgP<T> P = mg_plane<T>(mm, coarse, 0, zp, J, k);
+        const MgP<T> P = mg_plane<T>(mm, coarse, coarse_z0, zp, J, k);
 #pragma unroll
         for (int c = 0; c < 4; ++c) p[c] = b == 0 ? P.v[0][c] : P.v[1][c];
     };
     T Pm[4], Pc[4], Pp[4];
     plane_row(Ibeg - 1, Pm);
     plane_row(Ibeg, Pc);
-    int64_t lin = (int64_t)(2 * Ibeg) * mm.fs0 + (int64_t)fy * mm.fs1 + 4 * k;
+    int64_t lin = (int64_t)(2 * Ibeg - fine_z0) * mm.fs0 + (int64_t)fy * mm.fs1 + 4 * k;
     for (int I = Ibeg; I < Iend; ++I) {
         // the eight streams of the two fine planes first (independent of the coarse loads below)
         MgVec4<T> xx[2], mv[2], vv[2], gg[2];
@@ -844,10 +848,15 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
 int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* coarse, double cfac,
                          double ffac, void* x, void* m_state, void* v_state, const void* g, void* out, double alpha,
                          const double* alpha_dev, double one_minus_beta1, double one_minus_beta2, double epsilon,
-                         void* stream) {
+                         const odil_b200_mg_range* range, void* stream) {
     MgGeom geo;
     if (int rc = make_geom(ndim, cshape, loc, geo)) return rc;
     ODIL_REQUIRE(coarse && x && m_state && v_state && g && out, "null array");
+    odil_b200_mg_range r{0, geo.fn[0], 0, 0};
+    if (range) r = *range;
+    ODIL_REQUIRE(r.fz_begin >= 0 && r.fz_end <= geo.fn[0] && r.fz_begin <= r.fz_end, "bad fine plane range");
+    if (r.fz_begin % 2 != 0 || r.fz_end % 2 != 0) return 1;
+    if (r.fz_begin == r.fz_end) return 0;
     ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
     Mg3 m;
     bool cz = false;
@@ -855,7 +864,8 @@ int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int d
           (uintptr_t)v_state % 16 == 0 && (uintptr_t)coarse % 16 == 0))
         return 1;
     dim3 block(64, 4, 1);
-    dim3 grid((m.n2 / 2 + 63) / 64, (2 * m.n1 + 3) / 4, (unsigned)((m.n0 + kAsZC - 1) / kAsZC));
+    const int cb = (int)(r.fz_begin / 2), ce = (int)(r.fz_end / 2), fz0 = (int)r.out_z0, cz0 = (int)r.coarse_z0;
+    dim3 grid((m.n2 / 2 + 63) / 64, (2 * m.n1 + 3) / 4, (unsigned)((ce - cb + kAsZC - 1) / kAsZC));
     if (grid.y > 65535 || grid.z > 65535) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     // resident CTAs per SM the fp32 kernel is compiled for: 3 (80 registers, 16 bytes of spills; default) or 2 (128)
@@ -867,14 +877,14 @@ int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int d
     k_adam_synth3<float, OCC_><<<grid, block, 0, st>>>(m, (const float*)coarse, (float)cfac, (float)ffac, (float*)x,         \
                                                        (float*)m_state, (float*)v_state, (const float*)g, (float*)out,       \
                                                        (float)alpha, alpha_dev, (float)one_minus_beta1,                      \
-                                                       (float)one_minus_beta2, (float)epsilon)
+                                                       (float)one_minus_beta2, (float)epsilon, cb, ce, fz0, cz0)
     if (dtype == ODIL_B200_F32) {
         if (occ == 2) ODIL_SYNTH_F32(2);
         else ODIL_SYNTH_F32(3);
     } else
         k_adam_synth3<double, 1><<<grid, block, 0, st>>>(m, (const double*)coarse, cfac, ffac, (double*)x, (double*)m_state,
                                                       (double*)v_state, (const double*)g, (double*)out, alpha, alpha_dev,
-                                                      one_minus_beta1, one_minus_beta2, epsilon);
+                                                      one_minus_beta1, one_minus_beta2, epsilon, cb, ce, fz0, cz0);
     ODIL_LAUNCHED();
     return 0;
 }

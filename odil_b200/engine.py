@@ -197,11 +197,13 @@ def wraps_axis0(shape, offsets, rwidth, table):
     return False
 
 
-def synthesize_slab(slab, arrays, shapes, factors, loc, buffers=None, exchanged=False):
+def synthesize_slab(slab, arrays, shapes, factors, loc, buffers=None, exchanged=False, stop_level=0):
     """
     Multigrid synthesis on local slabs: every level is produced on its EXTENDED range (owned planes
     plus the halo, clipped to the domain) from the level below, after one batched halo exchange of
     all terms.  `shapes` are the GLOBAL array shapes per level.  Returns the local U (with halos).
+    stop_level > 0: stop at that level and return (array, factor) of it (adam_synth_step: level 0 is produced by
+    odil_b200_adam_synth).
     """
     L = len(arrays)
     if not exchanged:
@@ -210,6 +212,11 @@ def synthesize_slab(slab, arrays, shapes, factors, loc, buffers=None, exchanged=
         return arrays[0] if factors[0] == 1 else arrays[0] * factors[0]
     H = slab.halo
     res, cfac = arrays[L - 1], float(factors[L - 1])
+    if stop_level > 0:
+        for lvl in range(L - 2, stop_level - 1, -1):
+            res = _synth_slab_level(slab, arrays, shapes, factors, loc, buffers, lvl, res, cfac)
+            cfac = 1.0
+        return res, cfac
     for lvl in range(L - 2, -1, -1):
         fshape, cshape = shapes[lvl], shapes[lvl + 1]
         zf, nf = slab.owned_range(fshape)
@@ -228,6 +235,26 @@ def synthesize_slab(slab, arrays, shapes, factors, loc, buffers=None, exchanged=
                              rng=(lo, hi, zf - H, zc - H))
         res, cfac = out, 1.0
     return res
+
+
+def _synth_slab_level(slab, arrays, shapes, factors, loc, buffers, lvl, res, cfac):
+    """One level of synthesize_slab: V_lvl = factors[lvl] * arrays[lvl] + cfac * I(res) on the extended range."""
+    H = slab.halo
+    fshape, cshape = shapes[lvl], shapes[lvl + 1]
+    zf, nf = slab.owned_range(fshape)
+    zc, _ = slab.owned_range(cshape)
+    key = ("V", lvl)
+    out = None if buffers is None else buffers.get(key)
+    if out is None or tuple(out.shape) != tuple(arrays[lvl].shape):
+        out = torch.zeros_like(arrays[lvl])
+        if buffers is not None:
+            buffers[key] = out
+    lo, hi = max(zf - H, 0), min(zf + nf + H, fshape[0])
+    if loc[0] == "c":
+        lo -= lo % 2
+        hi += hi % 2
+    native.mg_interp_add(cshape, loc, res, cfac, arrays[lvl], float(factors[lvl]), out, rng=(lo, hi, zf - H, zc - H))
+    return out
 
 
 class TracerView(dict):
@@ -399,12 +426,20 @@ class ResidualEngine:
         K = len(self.outputs)
         sums = torch.empty(K, dtype=torch.float64, device=self.device)
         used = [self.unknowns[k] for k in self.unknowns if k in self.used_keys]
-        # one batched halo exchange of every array of every used unknown
-        slab.exchange([arrays[u.first + i] for u in used for i in range(u.narrays)], width=H)
+        # regular fields left behind by adam_synth_step (computed from exactly these arrays, halos already exchanged)
+        hits = {}
+        for u in used:
+            cached = self._synth_cache.pop(u.key, None) if hasattr(self, "_synth_cache") else None
+            if cached is not None and cached[0] == self._signature(arrays[u.first: u.first + u.narrays]):
+                hits[u.key] = cached[1]
+        # one batched halo exchange of every array of every other used unknown
+        slab.exchange([arrays[u.first + i] for u in used if u.key not in hits for i in range(u.narrays)], width=H)
         U = {}
         for u in used:
             a = arrays[u.first: u.first + u.narrays]
-            if u.kind == "MultigridField":
+            if u.key in hits:
+                U[u.key] = hits[u.key]
+            elif u.kind == "MultigridField":
                 bufs = self._buffers.setdefault(("slabV", u.key), {})
                 U[u.key] = synthesize_slab(slab, a, u.shapes, u.factors, u.mgloc, bufs, exchanged=True)
                 if u.key in self.periodic_keys:
@@ -507,12 +542,10 @@ class ResidualEngine:
         finest term writes t0, m, v and U = t0 + I(V1).  The next loss_grad() on the same, untouched arrays picks U up
         instead of synthesising level 0 again.  Arrays the fused kernel does not fit take the plain update; results
         are bit-identical to native.adam_step followed by the usual synthesis."""
-        if self.slab is not None:
-            raise NotImplementedError("adam_synth_step on slab-decomposed grids")
         if not hasattr(self, "_synth_cache"):
             self._synth_cache = {}
-        cand = [u for k, u in self.unknowns.items()
-                if k in (self.used_keys | self._frozen_keys()) and u.kind == "MultigridField" and u.narrays >= 2]
+        keys = self.used_keys if self.slab is not None else (self.used_keys | self._frozen_keys())
+        cand = [u for k, u in self.unknowns.items() if k in keys and u.kind == "MultigridField" and u.narrays >= 2]
         first = {u.first for u in cand}
         rest = [i for i in range(len(x)) if i not in first and grads[i] is not None]
 
@@ -526,6 +559,37 @@ class ResidualEngine:
                 native.adam_step(*args, alpha, omb1, omb2, eps)
 
         plain(rest)
+        if self.slab is not None:
+            # slabs: the coarser terms' halos are exchanged, the coarse levels synthesised on their extended ranges, the
+            # finest term is updated on the OWNED planes (its halos are never needed again) and the halo of U is
+            # exchanged instead -- the same bytes as the exchange of the finest term it replaces
+            slab, H = self.slab, self.slab.halo
+            slab.exchange([x[u.first + i] for u in cand for i in range(1, u.narrays)], width=H)
+            done_u = []
+            for u in cand:
+                i0 = u.first
+                a = x[i0: i0 + u.narrays]
+                bufs = self._buffers.setdefault(("slabV", u.key), {})
+                res, cfac = synthesize_slab(slab, a, u.shapes, u.factors, u.mgloc, bufs, exchanged=True, stop_level=1)
+                out0 = bufs.get(("V", 0))
+                if out0 is None or tuple(out0.shape) != tuple(a[0].shape):
+                    out0 = bufs[("V", 0)] = torch.zeros_like(a[0])
+                zf, nf = slab.owned_range(u.shapes[0])
+                zc, _ = slab.owned_range(u.shapes[1])
+                done = grads[i0] is not None and u.key not in self.periodic_keys and native.adam_synth(
+                    u.shapes[1], u.mgloc, res, cfac, u.factors[0], x[i0], m[i0], v[i0], grads[i0], out0, alpha, omb1,
+                    omb2, eps, alpha_dev, rng=(zf, zf + nf, zf - H, zc - H))
+                if done:
+                    done_u.append((u, a, out0))
+                else:
+                    self._synth_cache.pop(u.key, None)
+                    if grads[i0] is not None:
+                        plain([i0])
+            if done_u:
+                slab.exchange([out0 for _, _, out0 in done_u], width=H)
+            for u, a, out0 in done_u:
+                self._synth_cache[u.key] = (self._signature(a), out0)
+            return
         for u in cand:
             i0, L = u.first, u.narrays
             a = x[i0: i0 + L]

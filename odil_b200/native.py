@@ -106,7 +106,7 @@ def load(build_if_missing=False):
     lib.odil_b200_mg_interp_adjoint_adam.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, dbl, vp, vp,
                                                      vp, vp, dbl, vp, dbl, dbl, dbl, vp]
     lib.odil_b200_adam_synth.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, dbl, dbl, vp, vp, vp, vp,
-                                         vp, dbl, vp, dbl, dbl, dbl, vp]
+                                         vp, dbl, vp, dbl, dbl, dbl, P(MgRange), vp]
     lib.odil_b200_mg_restrict.argtypes = [ctypes.c_int, P(i64), ctypes.c_char_p, ctypes.c_int, vp, vp, vp]
     lib.odil_b200_adam_step.argtypes = [ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), ctypes.c_int, dbl, dbl,
                                         dbl, dbl, vp]
@@ -319,10 +319,12 @@ def mg_interp_adjoint_adam(cshape, loc, g_fine, scale, g_coarse, x, m, v, alpha,
     return res["applied"]
 
 
-def adam_synth(cshape, loc, coarse, cfac, ffac, x, m, v, g, out, alpha, omb1, omb2, eps, alpha_dev=None):
+def adam_synth(cshape, loc, coarse, cfac, ffac, x, m, v, g, out, alpha, omb1, omb2, eps, alpha_dev=None, rng=None):
     """Adam update of the finest multigrid term (x, m, v with gradient g) and out = ffac * x_new + cfac * I(coarse) in one
-    pass (odil_b200_adam_synth).  Returns False (nothing done) if the arrays do not fit the fused kernel."""
+    pass (odil_b200_adam_synth).  rng = (fz_begin, fz_end, out_z0, coarse_z0) as in mg_interp_add (slabs).  Returns
+    False (nothing done) if the arrays do not fit the fused kernel."""
     load()
+    r = ctypes.byref(MgRange(*[int(q) for q in rng])) if rng is not None else None
     for t in (m, v, g, out):
         if t.dtype != x.dtype or t.shape != x.shape:
             raise NativeError("adam_synth: m, v, g, out must match x in dtype and shape")
@@ -332,7 +334,7 @@ def adam_synth(cshape, loc, coarse, cfac, ffac, x, m, v, g, out, alpha, omb1, om
         rc = _lib.odil_b200_adam_synth(
             len(cshape), _cshape(cshape), loc.encode(), dtype_code(x.dtype), _ptr(coarse), float(cfac), float(ffac),
             _ptr(x), _ptr(m), _ptr(v), _ptr(g), _ptr(out), float(alpha),
-            _ptr(alpha_dev) if alpha_dev is not None else None, float(omb1), float(omb2), float(eps), _stream())
+            _ptr(alpha_dev) if alpha_dev is not None else None, float(omb1), float(omb2), float(eps), r, _stream())
         if rc not in (0, 1):
             _check(rc)
         res["applied"] = rc == 0

@@ -130,6 +130,8 @@ class SlabInfo:
         import torch.distributed as dist
 
         width = self.halo if width is None else width
+        if not locals_:
+            return
         if self.world == 1:
             for a in locals_:
                 n = a.shape[0] - 2 * self.halo

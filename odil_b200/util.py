@@ -229,9 +229,9 @@ def optimize_grad(args, optname, problem, state, callback=None, **kwargs):
             and os.environ.get("ODIL_B200_FUSE_ADAM", "0") not in ("", "0"):
         loss_grad.fuse_adam = engine.request_fused_adam
     # Default (ODIL_B200_FUSE_SYNTH=0 disables): the Adam update of the finest multigrid term also writes the regular
-    # field of the next evaluation (engine.adam_synth_step, odil_b200_adam_synth).  Not with a callback that rewrites the
-    # state between epochs, not on slabs, not for the generated-kernel engine.
-    if hasattr(engine, "adam_synth_step") and not hasattr(engine, "jacobian") and getattr(engine, "slab", None) is None \
+    # field of the next evaluation (engine.adam_synth_step, odil_b200_adam_synth), also on slabs.  Not with a callback that
+    # rewrites the state between epochs, not for the generated-kernel engine.
+    if hasattr(engine, "adam_synth_step") and not hasattr(engine, "jacobian") \
             and not args.callback_update_state and os.environ.get("ODIL_B200_FUSE_SYNTH", "1") not in ("", "0"):
         loss_grad.adam_synth = engine.adam_synth_step
     arrays, optinfo = opt.run(arrays, loss_grad=loss_grad, epochs=args.epochs - args.epoch_start,

@@ -123,23 +123,36 @@ def main():
     if torch.cuda.is_available() and os.environ.get("ODIL_B200_COMM", "peer") != "nccl":
         import argparse
 
+        # ... and the fusion of the finest term's Adam update with the synthesis of the next regular field
+        # (odil_b200_adam_synth on the owned planes + one halo exchange of U) == the unfused epoch, on the owned planes
         finals = {}
-        for flag in ("0", "1"):
-            os.environ["ODIL_B200_GRAPH"] = flag
-            os.environ["ODIL_HALO"] = "2"
-            problem, state = ops.make_poisson((32 * world, 16, 24), 3, np.float32)
-            args = argparse.Namespace(epochs=12, epoch_start=0, lr=0.005, callback_update_state=0, bfgs_m=None,
-                                      bfgs_pgtol=None, bfgs_maxls=None, adam_epsilon=None, adam_beta_1=None,
-                                      adam_beta_2=None)
-            losses = []
-            odil.util.optimize_grad(args, "adam", problem, state, lambda st, ep, pinfo: losses.append(float(pinfo["loss"])))
-            finals[flag] = (losses, [a.clone() for a in problem.domain.arrays_from_state(state)])
+        for synth in ("0", "1"):
+            for flag in ("0", "1"):
+                os.environ["ODIL_B200_FUSE_SYNTH"] = synth
+                os.environ["ODIL_B200_GRAPH"] = flag
+                os.environ["ODIL_HALO"] = "2"
+                problem, state = ops.make_poisson((32 * world, 16, 24), 3, np.float32)
+                args = argparse.Namespace(epochs=12, epoch_start=0, lr=0.005, callback_update_state=0, bfgs_m=None,
+                                          bfgs_pgtol=None, bfgs_maxls=None, adam_epsilon=None, adam_beta_1=None,
+                                          adam_beta_2=None)
+                losses = []
+                n0 = native.ADAM_SYNTH_APPLIED
+                odil.util.optimize_grad(args, "adam", problem, state,
+                                        lambda st, ep, pinfo: losses.append(float(pinfo["loss"])))
+                sl = problem.domain.slab
+                finals[synth, flag] = (losses, [sl.owned(a).clone() for a in problem.domain.arrays_from_state(state)],
+                                       native.ADAM_SYNTH_APPLIED - n0)
         os.environ.pop("ODIL_B200_GRAPH")
-        assert finals["0"][0] == finals["1"][0], (finals["0"][0], finals["1"][0])
-        for a, b in zip(finals["0"][1], finals["1"][1]):
-            assert torch.equal(a, b)
+        os.environ.pop("ODIL_B200_FUSE_SYNTH")
+        ref = finals["0", "0"]
+        assert ref[2] == 0 and finals["1", "0"][2] > 0 and finals["1", "1"][2] > 0
+        for key, (losses, arrs, _) in finals.items():
+            assert losses == ref[0], (key, losses, ref[0])
+            for a, b in zip(arrs, ref[1]):
+                assert torch.equal(a, b), key
         if rank == 0:
             print("GRAPH_OK slab epoch replayed as a CUDA graph is bit-identical to eager epochs")
+            print("SYNTH_OK slab epoch with odil_b200_adam_synth is bit-identical to the unfused epoch")
     dist.barrier()
     if rank == 0:
         print(f"SLAB_WORKER_OK world={world} worst_f64_grad_relerr={worst:.3e}")
