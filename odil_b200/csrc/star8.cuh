@@ -86,6 +86,7 @@ struct Star8Params {
     int R0, R1, R2;
     T scale;
     int has_c;
+    int xr_async;  // x-ring warp re-arms the TMA stages without blocking on the other warps (ODIL_B200_S8_ASYNC)
 };
 
 // "published plane" words (one per working warp), release / acquire at CTA scope
@@ -620,9 +621,28 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
         int ph = 0;
         S8Ring<SLOT_U, SLOT_C, Cfg::NSU, Cfg::NST> ring;
         ring.init();
+        // Stage j >= NFL - 1 may be issued once every working warp has published plane max(j - NFL, 0) (it is then done
+        // with the U and c slots the stage overwrites).  Blocking form (default): wait for that right after publishing
+        // plane j - NFL, which makes this warp a per-plane meeting point of the CTA.  Non-blocking form (xr_async):
+        // poll once per plane, issue whatever has become possible, and block only before waiting on a stage that has
+        // not been issued yet -- the row warps are then coupled to their neighbouring rows only.
+        const bool xr_async = p.xr_async != 0;
+        int nxt = NFL - 1;  // next stage to issue (xr_async)
         for (int it = 0; it < niter; ++it) {
             const int zg = p.z0 + kf0 + it;
             const uint32_t ucur = uo + ring.ucur, unxt = uo + ring.unxt, oc = ring.c;
+            if (xr_async) {
+                uint32_t spins = 0;
+                while (nxt <= it) {  // stage `it` itself is still to be issued (nxt < niter here)
+                    const int mp = __reduce_min_sync(0xffffffffu, s8_peek(pub_w));
+                    if (mp >= max(nxt - NFL, 0)) {
+                        if (lane == 0) issue_stage(nxt);
+                        ++nxt;
+                    } else if (++spins > (1u << 26)) {
+                        __trap();
+                    }
+                }
+            }
             s7_mbar_wait(sbar + ring.bar, ring.par);
             ring.advance();
             const T up = s7_lds1(unxt, (T*)nullptr);
@@ -649,7 +669,13 @@ __global__ void __launch_bounds__(Star8Cfg<T, VW, NR>::NT) __maxnreg__((Star8Cfg
             if (lane == 0) s8_publish(pub_me, it);
             um = uc;
             uc = up;
-            if ((it == 0 && NFL - 1 < niter) || it + NFL < niter) {
+            if (xr_async) {
+                const int mp = min(it, __reduce_min_sync(0xffffffffu, s8_peek(pub_w)));  // this warp has published `it`
+                while (nxt < niter && mp >= max(nxt - NFL, 0)) {
+                    if (lane == 0) issue_stage(nxt);
+                    ++nxt;
+                }
+            } else if ((it == 0 && NFL - 1 < niter) || it + NFL < niter) {
                 // every other warp has published plane `it`: the U plane kf and the c plane kf are consumed
                 uint32_t spins = 0;
                 while (!__all_sync(0xffffffffu, s8_peek(pub_w) >= it))

@@ -115,6 +115,10 @@ struct odil_b200_plan {
 #include "tile2d.cuh"
 #include "tile3d.cuh"
 #include "tile3t.cuh"
+#include "tile2w.cuh"
+#ifndef ODIL_B200_TILE2W_DEFAULT
+#define ODIL_B200_TILE2W_DEFAULT 0  // k_tile2w is opt-in (ODIL_B200_TILE2W=1) until measured on the device
+#endif
 namespace odil {
 
 // ------------------------------------------------------------------------------------------------
@@ -459,6 +463,13 @@ static int launch_star8(const odil_b200_plan* plan, const odil_b200_slab* slab, 
     }
     sp.scale = scale;
     sp.has_c = c != nullptr;
+    {
+        static const int xr_async = [] {
+            const char* e = getenv("ODIL_B200_S8_ASYNC");
+            return e ? atoi(e) : 0;
+        }();
+        sp.xr_async = xr_async;
+    }
     const int key[6] = {sp.n0, sp.N1, sp.N2, NR, plan->zchunk, Cfg::TX};
     if (memcmp(key, plan->work_key, sizeof(key)) != 0) {
         std::vector<S8Work> work;
@@ -569,6 +580,84 @@ static int launch_tile2d(const odil_b200_plan* plan, const T* A, const T* c, T s
     k_tile2d<T, MODE><<<grid, kT2Threads, smem, st>>>(p);
     ODIL_LAUNCHED();
     if (nparts) *nparts = (int)(grid.x * grid.y);
+    return 0;
+}
+
+
+// k_tile2w (tile2w.cuh): warp-private marching version of the fused 2-D sweep for wrap-free plans with at most 8
+// offsets of radius <= 2; ODIL_B200_TILE2W=0 (read per call, so that tests can compare the two) keeps k_tile2d.
+template <typename T>
+static bool tile2w_fits(const odil_b200_plan* plan, const T* U, const T* c, const T* G, const T* Fout) {
+    return plan->wrap_free && plan->noff <= kT2wN && plan->h2[0] <= kT2wHM && plan->h2[1] <= kT2wHM &&
+           plan->shape[1] % kT2wVW == 0 && (uintptr_t)U % 16 == 0 && (uintptr_t)c % 16 == 0 && (uintptr_t)G % 16 == 0 &&
+           (uintptr_t)Fout % 16 == 0;
+}
+
+template <typename T>
+static bool tile2w_ok(const odil_b200_plan* plan, const T* U, const T* c, const T* G, const T* Fout) {
+    const char* e = getenv("ODIL_B200_TILE2W");
+    if (!(e ? atoi(e) != 0 : ODIL_B200_TILE2W_DEFAULT)) return false;
+    return tile2w_fits<T>(plan, U, c, G, Fout);
+}
+
+template <typename T>
+static int launch_tile2w(const odil_b200_plan* plan, const T* U, const T* c, T scale, T* G, T* Fout, int* nparts,
+                         cudaStream_t st) {
+    Tile2wParams<T> p;
+    p.U = U;
+    p.c = c;
+    p.G = G;
+    p.Fout = Fout;
+    p.table = (const T*)plan->table_dev;
+    p.partials = plan->partials;
+    p.scale = scale;
+    p.N0 = (int)plan->shape[0];
+    p.N1 = (int)plan->shape[1];
+    p.R0 = plan->R[0];
+    p.R1 = plan->R[1];
+    p.H0 = plan->h2[0];
+    p.H1 = plan->h2[1];
+    p.noff = plan->noff;
+    p.ncls = plan->ncls;
+    auto fdiv4 = [](int v) { return v >= 0 ? v / 4 : -((-v + 3) / 4); };  // floor(v / 4)
+    for (int o = 0; o < kT2wN; ++o) {
+        p.dy[o] = o < plan->noff ? (signed char)plan->off[o][0] : 0;
+        p.dx[o] = o < plan->noff ? (signed char)plan->off[o][1] : 0;
+        for (int j = 0; j < kT2wVW; ++j) {
+            const int a = j + p.dx[o], b = j - p.dx[o];
+            p.kU[o][j] = ((a - 4 * fdiv4(a)) * kT2wW + fdiv4(a)) * (int)sizeof(T);
+            p.kF[o][j] = ((b - 4 * fdiv4(b)) * kT2wW + fdiv4(b)) * (int)sizeof(T);
+        }
+    }
+    // enough warps for one full wave (148 SMs x 24 resident warps), chunks of 8 .. 64 rows (2*H0 lead-in rows each)
+    p.nstrips = (p.N1 + kT2wOwn - 1) / kT2wOwn;
+    const int64_t want = 148 * 24;
+    int rc = (int)(((int64_t)p.N0 * p.nstrips + want - 1) / want);
+    rc = std::min(64, std::max(8, (rc + 7) / 8 * 8));
+    int64_t nitems = (int64_t)p.nstrips * ((p.N0 + rc - 1) / rc);
+    while ((nitems + kT2wWarps - 1) / kT2wWarps > kPartialCapacity) {
+        rc *= 2;
+        nitems = (int64_t)p.nstrips * ((p.N0 + rc - 1) / rc);
+    }
+    p.rows_per_chunk = rc;
+    p.nitems = (int)nitems;
+    const size_t smem = t2w_smem_bytes<T>();
+    static bool attr_set = false;  // per element type
+    if (!attr_set && smem > 48 * 1024) {
+#define ODIL_T2W(N_) ODIL_CUDA(cudaFuncSetAttribute(k_tile2w<T, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+        ODIL_T2W(1); ODIL_T2W(2); ODIL_T2W(3); ODIL_T2W(4); ODIL_T2W(5); ODIL_T2W(6); ODIL_T2W(7); ODIL_T2W(8);
+#undef ODIL_T2W
+        attr_set = true;
+    }
+    const int grid = (int)((nitems + kT2wWarps - 1) / kT2wWarps);
+    switch (plan->noff) {
+#define ODIL_T2W(N_) case N_: k_tile2w<T, N_><<<grid, 32 * kT2wWarps, smem, st>>>(p); break
+        ODIL_T2W(1); ODIL_T2W(2); ODIL_T2W(3); ODIL_T2W(4); ODIL_T2W(5); ODIL_T2W(6); ODIL_T2W(7); ODIL_T2W(8);
+#undef ODIL_T2W
+        default: return fail("k_tile2w: %d offsets", plan->noff);
+    }
+    ODIL_LAUNCHED();
+    if (nparts) *nparts = grid;
     return 0;
 }
 
@@ -747,7 +836,17 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
     io.scale = (T)scale;
     int nparts = 0;
     if (tile2d_ok(plan, slab)) {
-        if (int rc = launch_tile2d<T, 2>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)) return rc;
+        {  // ODIL_B200_TILE2W=2: never fall back silently (tests)
+            const char* e = getenv("ODIL_B200_TILE2W");
+            if (e && atoi(e) == 2 && !tile2w_fits<T>(plan, io.U, io.c, io.out, io.Fout))
+                return fail("ODIL_B200_TILE2W=2: this plan does not fit k_tile2w (wrap-free, <= 8 offsets, radii <= 2, "
+                            "row length a multiple of 4, 16-byte aligned arrays)");
+        }
+        if (tile2w_ok<T>(plan, io.U, io.c, io.out, io.Fout)) {
+            if (int rc = launch_tile2w<T>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)) return rc;
+        } else if (int rc = launch_tile2d<T, 2>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)) {
+            return rc;
+        }
         k_reduce_partials<<<1, 1024, 0, st>>>(plan->partials, nparts, sumsq);
         ODIL_LAUNCHED();
         return 0;

@@ -15,6 +15,7 @@ boundary region (Poisson, wave, identity-type data terms) are supported; anythin
 NonAffineError at trace time (no silent fallback).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -547,6 +548,11 @@ class ResidualEngine:
         keys = self.used_keys if self.slab is not None else (self.used_keys | self._frozen_keys())
         cand = [u for k, u in self.unknowns.items() if k in keys and u.kind == "MultigridField" and u.narrays >= 2]
         first = {u.first for u in cand}
+        # ODIL_B200_SYNTH_CHAIN=1: the intermediate levels take the same fused kernel (Adam of t_l + V_l = t_l + I(V_l+1))
+        # instead of the multi-tensor Adam followed by mg_interp_add -- one pass over t_l instead of two
+        chain = self.slab is None and os.environ.get("ODIL_B200_SYNTH_CHAIN", "0") not in ("", "0")
+        if chain:
+            first |= {u.first + l for u in cand for l in range(1, u.narrays - 1)}
         rest = [i for i in range(len(x)) if i not in first and grads[i] is not None]
 
         def plain(idx):
@@ -596,7 +602,13 @@ class ResidualEngine:
             res, cfac = a[L - 1], u.factors[L - 1]
             for lvl in range(L - 2, 0, -1):
                 out = self._buf(("V", u.key, lvl), u.shapes[lvl])
-                native.mg_interp_add(u.shapes[lvl + 1], u.mgloc, res, cfac, a[lvl], u.factors[lvl], out)
+                i = i0 + lvl
+                if not (chain and grads[i] is not None and native.adam_synth(
+                        u.shapes[lvl + 1], u.mgloc, res, cfac, u.factors[lvl], x[i], m[i], v[i], grads[i], out, alpha,
+                        omb1, omb2, eps, alpha_dev)):
+                    if chain and grads[i] is not None:
+                        plain([i])
+                    native.mg_interp_add(u.shapes[lvl + 1], u.mgloc, res, cfac, a[lvl], u.factors[lvl], out)
                 res, cfac = out, 1.0
             out0 = self._buf(("V", u.key, 0), u.shapes[0])
             done = grads[i0] is not None and native.adam_synth(

@@ -670,6 +670,114 @@ def test_tile2d_large_wave_footprint_properties():
 
 
 # --------------------------------------------------------------------------------------------------
+# k_tile2w: the warp-private marching version of the fused 2-D sweep (wrap-free plans, <= 8 offsets, radii <= 2)
+# --------------------------------------------------------------------------------------------------
+TILE2W_CASES = [
+    # shape, offsets (None = star), rwidth
+    ((70, 152), [(0, 0), (-1, 0), (-2, 0), (-1, -1), (-1, 1)], (2, 1)),        # wave footprint (wave.py:38-46), 2 strips
+    ((32, 64), None, (1, 1)),
+    ((33, 68), None, (1, 1)),
+    ((5, 4), [(0, 0), (0, 1), (1, 0)], (1, 1)),                                # one lane of cells
+    ((96, 200), [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dy, dx) != (1, 1)], (1, 1)),  # 8 offsets
+    ((1, 300), [(0, 0), (0, -1), (0, 1)], (0, 1)),                             # single row
+    ((130, 8), [(0, 0), (1, 0), (-1, 0), (0, 1)], (3, 1)),                     # narrow, wide regions
+    ((257, 1024), None, (1, 1)),                                               # 9 strips x 33 chunks
+    ((64, 244), [(0, 0), (2, -2), (-1, 1), (1, 2), (-2, 0), (0, -1)], (2, 2)), # radius 2 on both axes
+    ((40, 120), [(0, 0), (1, 0), (0, -2), (-2, 2), (2, 1), (-1, -1), (0, 1), (1, -2)], (3, 2)),
+]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("case", range(len(TILE2W_CASES)))
+def test_tile2w_matches_oracle_and_tile2d(prec, case, monkeypatch):
+    """k_tile2w (ODIL_B200_TILE2W=2: refuse to fall back) against the oracle and against k_tile2d: same operations per
+    cell in the same order, so F and g are bit-identical; the loss sums differ by their summation order only."""
+    from tests.test_tile_emulation_cpu import wrap_free_table
+
+    nd, td = DT[prec]
+    shape, offsets, rr = TILE2W_CASES[case]
+    offsets = offsets or star_offsets(2)
+    rng = np.random.default_rng(700 + case)
+    table = wrap_free_table(rng.standard_normal(tuple(2 * r + 1 for r in rr) + (len(offsets),)), offsets, rr)
+    U = rng.standard_normal(shape).astype(nd)
+    c = rng.standard_normal(shape).astype(nd)
+    scale = 2.0 / U.size
+    F_ref = orc.stencil_forward(U.astype(np.float64), offsets, table, rr, c.astype(np.float64))
+    g_ref = orc.stencil_adjoint(F_ref, offsets, table, rr, scale)
+    F0 = orc.stencil_forward(U.astype(np.float64), offsets, table, rr, None)
+    g0 = orc.stencil_adjoint(F0, offsets, table, rr, scale)
+    tol = TOL[prec] * 10
+    res = {}
+    for flag in ("0", "2"):
+        monkeypatch.setenv("ODIL_B200_TILE2W", flag)
+        plan = native.StencilPlan(shape, td, offsets, rr, table.reshape(-1, len(offsets)))
+        dU, dc = dev(U), dev(c)
+        G = torch.full_like(dU, float("nan"))
+        F = torch.full_like(dU, float("nan"))
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dU, dc, scale, G, ss, F_out=F)
+        G1 = torch.full_like(dU, float("nan"))
+        ss1 = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dU, dc, scale, G1, ss1)
+        G3 = torch.full_like(dU, float("nan"))
+        ss0 = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(dU, None, scale, G3, ss0)
+        res[flag] = [t.cpu().numpy() for t in (F, G, G1, G3, ss, ss1, ss0)]
+        F, G, G1, G3, ss, ss1, ss0 = res[flag]
+        assert relerr(F, F_ref) < tol and relerr(G, g_ref) < tol and relerr(G3, g0) < tol
+        assert np.array_equal(G, G1)
+        assert abs(ss[0] - np.sum(F_ref ** 2)) < tol * np.sum(F_ref ** 2) and ss[0] == ss1[0]
+        assert abs(ss0[0] - np.sum(F0 ** 2)) < tol * np.sum(F0 ** 2)
+    for a, b in zip(res["0"][:4], res["2"][:4]):
+        assert np.array_equal(a, b)
+
+
+def test_tile2w_refuses_what_it_cannot_do(monkeypatch):
+    """ODIL_B200_TILE2W=2 turns the silent choice of k_tile2d (periodic plan, odd row length, 9 offsets) into an error;
+    ODIL_B200_TILE2W=1 falls back."""
+    rng = np.random.default_rng(3)
+    offsets, rr = star_offsets(2), (1, 1)
+    table = rng.standard_normal((9, 5))  # not wrap-free: the boundary classes couple across the periodic boundary
+    for shape, tab in (((16, 16), table), ((16, 18), None)):
+        if tab is None:
+            from tests.test_tile_emulation_cpu import wrap_free_table
+
+            tab = wrap_free_table(table.reshape(3, 3, 5), offsets, rr).reshape(9, 5)
+        U = torch.randn(shape, dtype=torch.float32, device="cuda")
+        G, ss = torch.empty_like(U), torch.zeros(1, dtype=torch.float64, device="cuda")
+        monkeypatch.setenv("ODIL_B200_TILE2W", "2")
+        plan = native.StencilPlan(shape, torch.float32, offsets, rr, tab)
+        with pytest.raises(native.NativeError):
+            plan.fused(U, None, 1.0, G, ss)
+        monkeypatch.setenv("ODIL_B200_TILE2W", "1")
+        plan.fused(U, None, 1.0, G, ss)
+        F = orc.stencil_forward(U.cpu().numpy().astype(np.float64), offsets, tab.reshape(3, 3, 5), rr, None)
+        assert relerr(G.cpu().numpy(), orc.stencil_adjoint(F, offsets, tab.reshape(3, 3, 5), rr, 1.0)) < 1e-5
+
+
+def test_tile2w_large_wave_footprint_equals_tile2d(monkeypatch):
+    """2048 x 4096 fp32 with the wave footprint: k_tile2w and k_tile2d agree bit for bit on g, to rounding on the loss."""
+    from tests.test_tile_emulation_cpu import wrap_free_table
+
+    shape, rr = (2048, 4096), (2, 1)
+    offsets = [(0, 0), (-1, 0), (-2, 0), (-1, -1), (-1, 1)]
+    rng = np.random.default_rng(9)
+    table = wrap_free_table(rng.standard_normal((5, 3, 5)), offsets, rr).reshape(15, 5)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    U = torch.randn(shape, dtype=torch.float32, device="cuda", generator=gen)
+    c = torch.randn(shape, dtype=torch.float32, device="cuda", generator=gen)
+    out = {}
+    for flag in ("0", "2"):
+        monkeypatch.setenv("ODIL_B200_TILE2W", flag)
+        plan = native.StencilPlan(shape, torch.float32, offsets, rr, table)
+        G, ss = torch.full_like(U, float("nan")), torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.fused(U, c, 0.5, G, ss)
+        out[flag] = (G, ss.item())
+    assert torch.equal(out["0"][0], out["2"][0])
+    assert abs(out["0"][1] - out["2"][1]) < 1e-6 * out["0"][1]
+
+
+# --------------------------------------------------------------------------------------------------
 # 2-D cell-centred transfers through shared-memory tiles (k_interp_add2t / k_interp_adjoint2t)
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cshape", [(2, 2), (3, 4), (16, 64), (17, 66), (5, 130), (40, 2), (33, 128), (64, 200),

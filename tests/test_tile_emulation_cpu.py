@@ -251,3 +251,143 @@ def test_tile3d_ring_addressing(shape, offs, R, zchunk):
     Fo, G, ss = tile3d_fused(U, c, table, offs, R, 0.37, zchunk)
     assert np.abs(Fo - F_ref).max() < 1e-12 and np.abs(G - g_ref).max() < 1e-12
     assert abs(ss - (F_ref ** 2).sum()) < 1e-9 * (F_ref ** 2).sum()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# k_tile2w (tile2w.cuh): one warp per (strip of 120 columns, chunk of rows), marching down the rows with two private
+# rings stored cell-major; lanes 0 and 31 carry the halo columns.  The emulation runs warp by warp with the lanes as a
+# vector of 32, the rings as arrays [8 slots][4 cell planes][34 words], the byte-offset tables kU / kF of the launcher
+# (in words here), the two fast paths and the table paths.
+# --------------------------------------------------------------------------------------------------------------------
+W2_VW, W2_OWN, W2_W, W2_NS = 4, 120, 34, 8
+
+
+def _fdiv4(v):
+    return v // 4  # Python floors; the launcher spells it out for C++
+
+
+def wrap_free_table(table, offs, R):
+    """Zeroes every (class, offset) entry whose neighbour would cross the boundary -- the rule of plan_create
+    (stencil.cu: wrap_free)."""
+    t = table.copy()
+    nd = len(R)
+    for cl in np.ndindex(*t.shape[:-1]):
+        for o, off in enumerate(offs):
+            for a in range(nd):
+                d, r, c = off[a], R[a], cl[a]
+                if d == 0:
+                    continue
+                crosses = (c + d < 0) if c < r else ((2 * r - c) < d if c > r else abs(d) > r)
+                if crosses:
+                    t[cl + (o,)] = 0.0
+    return t
+
+
+def tile2w_fused(U, c, table, offs, R, scale, rows_per_chunk):
+    N0, N1 = U.shape
+    assert N1 % 4 == 0
+    noff = len(offs)
+    H0, H1 = max(abs(o[0]) for o in offs), max(abs(o[1]) for o in offs)
+    assert H0 <= 2 and H1 <= 2 and noff <= 8
+    C1 = 2 * R[1] + 1
+    tab = table.reshape(-1, noff)
+    CI = R[0] * C1 + R[1]
+    kU = [[((j + o[1]) - 4 * _fdiv4(j + o[1])) * W2_W + _fdiv4(j + o[1]) for j in range(4)] for o in offs]
+    kF = [[((j - o[1]) - 4 * _fdiv4(j - o[1])) * W2_W + _fdiv4(j - o[1]) for j in range(4)] for o in offs]
+    nstrips = (N1 + W2_OWN - 1) // W2_OWN
+    nchunks = (N0 + rows_per_chunk - 1) // rows_per_chunk
+    G, Fo, ss = np.full(U.shape, np.nan), np.full(U.shape, np.nan), 0.0
+    lanes = np.arange(32)
+    for item in range(nstrips * nchunks):
+        strip, chunk = item % nstrips, item // nstrips
+        ys, ye = chunk * rows_per_chunk, min((chunk + 1) * rows_per_chunk, N0)
+        x0 = strip * W2_OWN + W2_VW * (lanes - 1)
+        xin = (x0 >= 0) & (x0 < N1)
+        own = xin & (lanes >= 1) & (lanes <= 30)
+        ccls = np.array([[(_cls(x0[l] + j, N1, R[1]) if xin[l] else 0) for j in range(4)] for l in range(32)])
+        fastXF = bool(np.all(~xin | ((x0 >= R[1]) & (x0 + 3 < N1 - R[1]))))
+        fastXG = bool(np.all(~own | ((x0 >= R[1] + H1) & (x0 + 3 < N1 - R[1] - H1))))
+        ringU = np.zeros(W2_NS * 4 * W2_W)
+        ringF = np.zeros(W2_NS * 4 * W2_W)
+        base = lanes + 1  # word of (slot 0, plane 0, own lane)
+
+        def load(A, r, extra=True):
+            out = np.zeros((32, 4))
+            if 0 <= r < N0 and extra:
+                for l in range(32):
+                    if xin[l]:
+                        out[l] = A[r, x0[l]: x0[l] + 4]
+            return out
+
+        for ru in range(ys - 2 * H0, ye + 2 * H0):
+            ucur = load(U, ru)
+            su = (ru & 7) * 4 * W2_W
+            for j in range(4):
+                ringU[su + j * W2_W + base] = ucur[:, j]
+            jf = ru - H0
+            if ru >= ys:
+                f = load(c, jf, jf < ye + H0)
+                rin = 0 <= jf < N0
+                if rin:
+                    so = [((jf + o[0]) & 7) * 4 * W2_W for o in offs]
+                    if fastXF and R[0] <= jf < N0 - R[0]:
+                        for o in range(noff):
+                            for j in range(4):
+                                f[:, j] += tab[CI, o] * ringU[so[o] + kU[o][j] + base]
+                    else:
+                        rc = _cls(jf, N0, R[0]) * C1
+                        for o in range(noff):
+                            for j in range(4):
+                                f[:, j] += tab[rc + ccls[:, j], o] * ringU[so[o] + kU[o][j] + base]
+                if not rin:
+                    f[:] = 0
+                f[~xin] = 0
+                if ys <= jf < ye:
+                    ss += float((f[own] ** 2).sum())
+                    for l in lanes[own]:
+                        Fo[jf, x0[l]: x0[l] + 4] = f[l]
+                sf = (jf & 7) * 4 * W2_W
+                for j in range(4):
+                    ringF[sf + j * W2_W + base] = f[:, j]
+            k = ru - 2 * H0
+            if k >= ys:
+                g = np.zeros((32, 4))
+                so = [((k - o[0]) & 7) * 4 * W2_W for o in offs]
+                if fastXG and R[0] + H0 <= k < N0 - R[0] - H0:
+                    for o in range(noff):
+                        for j in range(4):
+                            g[:, j] += tab[CI, o] * ringF[so[o] + kF[o][j] + base]
+                else:
+                    for o, off in enumerate(offs):
+                        sy = k - off[0]
+                        if not 0 <= sy < N0:
+                            continue
+                        rc = _cls(sy, N0, R[0]) * C1
+                        for j in range(4):
+                            sx = x0 + j - off[1]
+                            cx = np.array([(_cls(v, N1, R[1]) if 0 <= v < N1 else 0) for v in sx])
+                            g[:, j] += tab[rc + cx, o] * ringF[so[o] + kF[o][j] + base]
+                for l in lanes[own]:
+                    G[k, x0[l]: x0[l] + 4] = g[l] * scale
+    return Fo, G, ss
+
+
+@pytest.mark.parametrize("shape,offs,R,rpc", [
+    ((16, 12), [(0, 0), (-1, 0), (-2, 0), (-1, -1), (-1, 1)], (2, 1), 8),      # wave footprint (wave.py:38-46)
+    ((33, 124), [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1)], (1, 1), 8),        # 5-point star, two strips
+    ((9, 248), [(0, 0), (2, -2), (-1, 1), (1, 2), (-2, 0), (0, -1)], (2, 2), 16),
+    ((40, 120), [(0, 0), (1, 0), (0, -2), (-2, 2), (2, 1), (-1, -1), (0, 1), (1, -2)], (3, 2), 24),
+    ((5, 4), [(0, 0), (0, 1), (1, 0)], (1, 1), 8),
+    ((24, 368), [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1)], (0, 0), 8),         # no boundary classes at all
+])
+def test_tile2w_fused_addressing(shape, offs, R, rpc):
+    rng = np.random.default_rng(1)
+    table = wrap_free_table(rng.standard_normal(tuple(2 * r + 1 for r in R) + (len(offs),)), offs, R)
+    if R == (0, 0):  # every cell has the interior class: only offsets that never leave the array are wrap-free
+        offs, table = [(0, 0)], table[..., :1]
+    U, c = rng.standard_normal(shape), rng.standard_normal(shape)
+    F_ref = orc.stencil_forward(U, offs, table, R, c)
+    g_ref = orc.stencil_adjoint(F_ref, offs, table, R, 0.37)
+    Fo, G, ss = tile2w_fused(U, c, table, offs, R, 0.37, rpc)
+    assert np.abs(Fo - F_ref).max() < 1e-12 and np.abs(G - g_ref).max() < 1e-12
+    assert abs(ss - (F_ref ** 2).sum()) < 1e-9 * (F_ref ** 2).sum()
