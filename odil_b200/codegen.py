@@ -12,6 +12,10 @@ cells in a grid-stride loop and, per cell, executes a straight-line SSA program:
   jvp       forward-mode tangent  (J v)_k[cell]               (Newton: matrix-free Jacobian products)
   vjp       reverse mode with a given cotangent  J^T w
   jac       per cell and per load: column index and dF/d(load) (COO rows of the Jacobian, core.py:1144-1171)
+  jacd      per cell: dF_k/d(load) of every structurally connected (output, load) pair, one array per pair -- the
+            reference's per-(key, shift, loc) Jacobian "diagonals" (core.py:1341-1350) kept on the device
+  jvpd/vjpd the Jacobian products of a Newton step's CG iterations from those stored diagonals: J v = sum_l D_l * v[col_l],
+            J^T w scattered likewise -- no re-evaluation of the operator's arithmetic (exp, divisions) per product
 
 Index arithmetic (roll, slicing, pad, concatenate, reshape, transpose, broadcasting) is resolved symbolically per cell:
 `emit(node, index tuple, guard)` returns the SSA value of `node` at that index; integer literals are folded at
@@ -487,6 +491,94 @@ class GroupProgram:
                     out.append(f"if ({G}) ATOMIC_ADD(&a.gin[{slot}][{lin}], d_{z});")
         return out
 
+    def loads(self):
+        return [e for e in self.tape if e[0] == "load"]
+
+    def pairs(self):
+        """[(result position j, load position l)] whose derivative d result_j / d load_l is not structurally zero, for
+        loads of slots that receive gradients; None if such a load has a cell-independent address (network weights,
+        elements of Array unknowns: those take the plain jvp / vjp kernels)."""
+        if not hasattr(self, "_pairs"):
+            loads = self.loads()
+            pairs = []
+            for j, (k, v, raw) in enumerate(self.results):
+                if not v.active:
+                    continue
+                reach = {v.name}
+                for e in reversed(self.tape):
+                    if e[0] == "op" and e[1] in reach:
+                        reach.update(arg for _, arg, _c in e[2])
+                for l, e in enumerate(loads):
+                    if e[1] in reach and self.gen.slot_has_grad(e[2]):
+                        if e[5]:
+                            pairs = None
+                            break
+                        pairs.append((j, l))
+                if pairs is None:
+                    break
+            self._pairs = pairs
+        return self._pairs
+
+    def diagonal_store(self):
+        """Reverse sweep per result with seed 1; the adjoint of every connected load goes to its pair's array."""
+        out = []
+        loads = self.loads()
+        pairs = self.pairs()
+        for j, (k, v, raw) in enumerate(self.results):
+            mine = {l: pi for pi, (jj, l) in enumerate(pairs) if jj == j}
+            if not mine:
+                continue
+            out.append("{")
+            adj = {}
+
+            def add(var, expr):
+                if var in adj:
+                    out.append(f"d_{var} += {expr};")
+                else:
+                    out.append(f"T d_{var} = {expr};")
+                    adj[var] = True
+
+            add(v.name, "T(1)")
+            for e in reversed(self.tape):
+                z = e[1]
+                if e[0] == "op":
+                    if z in adj:
+                        for _, arg, contrib in e[2]:
+                            add(arg, contrib(f"d_{z}"))
+                else:
+                    l = loads.index(e)
+                    if l in mine:
+                        G = e[4]
+                        val = f"d_{z}" if z in adj else "T(0)"
+                        g = "" if G is None else f"!{G} ? T(0) : "
+                        out.append(f"a.jval[{mine[l]}ll * a.ncell + cell] = {g}{val};")
+            out.append("}")
+        return out
+
+    def diagonal_products(self, mode):
+        out = []
+        loads = self.loads()
+        pairs = self.pairs()
+        used = sorted({l for _, l in pairs})
+        D = lambda pi: f"a.jval[{pi}ll * a.ncell + cell]"
+        if mode == "jvpd":
+            for l in used:
+                _, z, slot, lin, G, _u = loads[l]
+                src = f"a.tin[{slot}][{lin}]"
+                out.append(f"const T t_{z} = {src};" if G is None else f"const T t_{z} = {G} ? {src} : T(0);")
+            for j, (k, v, raw) in enumerate(self.results):
+                terms = [f"{D(pi)} * t_{loads[l][1]}" for pi, (jj, l) in enumerate(pairs) if jj == j]
+                out.append(f"a.out[{k}][cell] = {' + '.join(terms) if terms else 'T(0)'};")
+        else:
+            for j in sorted({j for j, _ in pairs}):
+                out.append(f"const T s_{j} = a.seed[{self.results[j][0]}][cell];")
+            for l in used:
+                _, z, slot, lin, G, _u = loads[l]
+                terms = [f"{D(pi)} * s_{jj}" for pi, (jj, ll) in enumerate(pairs) if ll == l]
+                stmt = f"ATOMIC_ADD(&a.gin[{slot}][{lin}], {' + '.join(terms)});"
+                out.append(stmt if G is None else f"if ({G}) {stmt}")
+        return out
+
     def forward_tangent(self):
         out, tan = [], {}
         for e in self.tape:
@@ -537,6 +629,11 @@ class GroupProgram:
         elif mode == "jac":
             k, v, raw = self.results[which]
             lines += self.backward({v.name: "T(1)"} if v.active else {}, "jac")
+        elif mode == "jacd":
+            lines += self.diagonal_store()
+        elif mode in ("jvpd", "vjpd"):
+            # only the index arithmetic of the forward statements is live here; the compiler drops the rest
+            lines += self.diagonal_products(mode)
         else:
             raise ValueError(mode)
         return lines, nloads
@@ -764,3 +861,7 @@ class Generator:
 
     def nloads(self, g):
         return len([e for e in g.tape if e[0] == "load"])
+
+    def dia_ok(self):
+        """Every group can keep its Jacobian as per-cell diagonals (no cell-independent load receives a gradient)."""
+        return all(g.pairs() is not None for g in self.groups)

@@ -14,6 +14,7 @@ Supported unknowns: Field, MultigridField (through its synthesised regular field
 NeuralNet.  Not decomposed into slabs.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -320,6 +321,25 @@ class GraphJacobian:
         self.row0 = np.concatenate([[0], np.cumsum([o.n for o in engine.outputs])]).astype(np.int64)
         self.shape = (int(self.row0[-1]), int(self.col0[-1]))
         self._csr = None
+        self._dia = None  # per group: stored diagonals [npairs * ncell], built on the first product
+
+    def _diagonals(self):
+        """Per group the arrays D[pair][cell] = dF_k/d(load) at the fixed state (codegen mode 'jacd'), or False when the
+        operator does not allow it / they would not fit (ODIL_B200_NEWTON_DIA=0 disables, ODIL_B200_NEWTON_DIA_GB caps the
+        memory, default 24).  A Newton step evaluates the operator's arithmetic once here instead of once per CG product."""
+        if self._dia is None:
+            eng = self.engine
+            self._dia = False
+            if os.environ.get("ODIL_B200_NEWTON_DIA", "1") not in ("", "0") and eng.gen.dia_ok():
+                sizes = {g.gid: len(g.pairs()) * g.ncell for g in eng.gen.groups}
+                cap = float(os.environ.get("ODIL_B200_NEWTON_DIA_GB", "24")) * 2 ** 30
+                if sum(sizes.values()) * self.arrays[0].element_size() <= cap:
+                    dia = {}
+                    for g in eng.gen.groups:
+                        dia[g.gid] = torch.empty(max(1, sizes[g.gid]), dtype=self.dtype, device=self.device)
+                        eng._launch("jacd", self.arrays, jval=dia[g.gid], prm=self.prm, only=(g.gid, None))
+                    self._dia = dia
+        return self._dia
 
     def _split(self, x, starts, shapes):
         return [x[int(starts[i]): int(starts[i + 1])].view(shapes[i]) for i in range(len(shapes))]
@@ -330,7 +350,12 @@ class GraphJacobian:
         tin = self._split(x, self.col0, [tuple(a.shape) for a in self.arrays])
         y = torch.empty(self.shape[0], dtype=self.dtype, device=self.device)
         out = self._split(y, self.row0, [o.shape for o in eng.outputs])
-        eng._launch("jvp", self.arrays, tin=tin, out=out, prm=self.prm)
+        dia = self._diagonals()
+        if dia:
+            for g in eng.gen.groups:
+                eng._launch("jvpd", self.arrays, tin=tin, out=out, jval=dia[g.gid], prm=self.prm, only=(g.gid, None))
+        else:
+            eng._launch("jvp", self.arrays, tin=tin, out=out, prm=self.prm)
         return y
 
     def rmatvec(self, y):
@@ -339,7 +364,12 @@ class GraphJacobian:
         seed = self._split(y, self.row0, [o.shape for o in eng.outputs])
         x = torch.zeros(self.shape[1], dtype=self.dtype, device=self.device)
         gin = self._split(x, self.col0, [tuple(a.shape) for a in self.arrays])
-        eng._launch("vjp", self.arrays, gin=gin, seed=seed, prm=self.prm)
+        dia = self._diagonals()
+        if dia:
+            for g in eng.gen.groups:
+                eng._launch("vjpd", self.arrays, gin=gin, seed=seed, jval=dia[g.gid], prm=self.prm, only=(g.gid, None))
+        else:
+            eng._launch("vjp", self.arrays, gin=gin, seed=seed, prm=self.prm)
         return x
 
     def dot(self, x):

@@ -202,11 +202,45 @@ def launch_count():
     return int(load().odil_b200_launch_count()) + _replayed
 
 
+# Handles whose destructor ran while a CUDA graph was being captured: destroying them frees device memory (cudaFree /
+# cuModuleUnload), which invalidates a capture in progress.  Python's cyclic collector may run a destructor at any
+# allocation, so `__del__` parks the handle here and the next creation or `flush_deferred()` releases it.
+_deferred = []
+
+
+def _capturing():
+    try:
+        import torch
+
+        return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    except Exception:
+        return False
+
+
+def _release(destroy, handle):
+    if _capturing():
+        _deferred.append((destroy, handle))
+    else:
+        destroy(handle)
+
+
+def flush_deferred():
+    """Destroys the handles parked by destructors that ran during a graph capture (no-op while capturing)."""
+    if _deferred and not _capturing():
+        while _deferred:
+            destroy, handle = _deferred.pop()
+            try:
+                destroy(handle)
+            except Exception:
+                pass
+
+
 class StencilPlan:
     """Region-typed affine stencil (include/odil_b200.h: odil_b200_stencil_plan_create)."""
 
     def __init__(self, shape, dtype, offsets, rwidth, table):
         lib = load()
+        flush_deferred()
         self.shape = tuple(int(s) for s in shape)
         self.ndim = len(self.shape)
         self.dtype = dtype
@@ -230,7 +264,7 @@ class StencilPlan:
     def __del__(self):
         try:
             if getattr(self, "handle", None) and _lib is not None:
-                _lib.odil_b200_stencil_plan_destroy(self.handle)
+                _release(_lib.odil_b200_stencil_plan_destroy, self.handle)
                 self.handle = None
         except Exception:
             pass
@@ -488,7 +522,8 @@ class JitModule:
     def __del__(self):
         try:
             if _lib is not None and self.handle:
-                _lib.odil_b200_jit_destroy(self.handle)
+                _release(_lib.odil_b200_jit_destroy, self.handle)
+                self.handle = None
         except Exception:
             pass
 

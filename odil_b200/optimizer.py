@@ -134,6 +134,12 @@ class AdamNativeOptimizer(Optimizer):
         _, omb1, omb2 = adam_scalars(lr, beta_1, beta_2, 1, dtype)
         held = list(x)  # the tensors whose addresses the graph holds
         g = torch.cuda.CUDAGraph()
+        # A destructor that frees device memory (a dropped stencil plan, a torch tensor of an earlier problem held in a
+        # reference cycle) must not run inside the capture: collect what is collectable now; native handles whose
+        # destructor still runs during the capture are parked (native._release) and freed after it.
+        import gc
+
+        gc.collect()
         n_before = native.launch_count()
         with torch.cuda.graph(g):
             torch.index_select(table, 0, step, out=alpha_dev)
@@ -149,6 +155,7 @@ class AdamNativeOptimizer(Optimizer):
                 rest = [i for i, gr in enumerate(grads) if gr is not None]
                 native.adam_step_dev([held[i] for i in rest], [m[i] for i in rest], [v[i] for i in rest],
                                      [grads[i] for i in rest], alpha_dev, omb1, omb2, eps)
+        native.flush_deferred()
         nodes = native.launch_count() - n_before  # library kernels captured into one replay
         fetch = getattr(loss, "_fetch", None)
         self._graph = g  # owns the memory pool of grads / sums that pinfo still points into after run()

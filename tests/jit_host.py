@@ -142,3 +142,33 @@ class HostTwin:
         gin = [torch.zeros(a.shape, dtype=self.tdtype) for a in arrays]
         self.run("vjp", [a.contiguous() for a in arrays], gin=gin, seed=seed)
         return np.concatenate([g.numpy().reshape(-1) for g in gin]).astype(np.float64)
+
+    def diagonals(self, arrays):
+        """Per group the stored diagonals of mode 'jacd' (D[pair][cell])."""
+        ins = [a.contiguous() for a in arrays]
+        dia = {}
+        for g in self.gen.groups:
+            dia[g.gid] = torch.zeros(max(1, len(g.pairs()) * g.ncell), dtype=self.tdtype)
+            self.run("jacd", ins, jval=dia[g.gid], only=(g.gid, None))
+        return dia
+
+    def jvpd(self, arrays, x, dia):
+        eng = self.engine
+        sizes = [a.numel() for a in arrays]
+        col0 = np.concatenate([[0], np.cumsum(sizes)])
+        tin = [torch.as_tensor(x[col0[i]:col0[i + 1]], dtype=self.tdtype).reshape(arrays[i].shape).contiguous()
+               for i in range(len(arrays))]
+        out = [torch.zeros(o.shape, dtype=self.tdtype) for o in eng.outputs]
+        for g in self.gen.groups:
+            self.run("jvpd", [a.contiguous() for a in arrays], tin=tin, out=out, jval=dia[g.gid], only=(g.gid, None))
+        return np.concatenate([o.numpy().reshape(-1) for o in out]).astype(np.float64)
+
+    def vjpd(self, arrays, y, dia):
+        eng = self.engine
+        row0 = np.concatenate([[0], np.cumsum([o.n for o in eng.outputs])])
+        seed = [torch.as_tensor(y[row0[k]:row0[k + 1]], dtype=self.tdtype).reshape(o.shape).contiguous()
+                for k, o in enumerate(eng.outputs)]
+        gin = [torch.zeros(a.shape, dtype=self.tdtype) for a in arrays]
+        for g in self.gen.groups:
+            self.run("vjpd", [a.contiguous() for a in arrays], gin=gin, seed=seed, jval=dia[g.gid], only=(g.gid, None))
+        return np.concatenate([g.numpy().reshape(-1) for g in gin]).astype(np.float64)

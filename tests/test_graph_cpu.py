@@ -77,6 +77,13 @@ def test_host_twin_jacobian_matches_reference_golden(golden, case):
     v, w = rng.standard_normal(J.shape[1]), rng.standard_normal(J.shape[0])
     assert relerr(tw.jvp(x, v), Jr @ v) < 1e-11
     assert relerr(tw.vjp(x, w), Jr.T @ w) < 1e-11
+    # the same products from stored per-cell diagonals (modes jacd / jvpd / vjpd: what a Newton step's CG uses)
+    if tw.gen.dia_ok():
+        dia = tw.diagonals(x)
+        assert relerr(tw.jvpd(x, v, dia), Jr @ v) < 1e-11
+        assert relerr(tw.vjpd(x, w, dia), Jr.T @ w) < 1e-11
+    else:
+        assert case in ("newton", "infer_constant", "heat_k")  # network weights / Array elements among the unknowns
 
 
 @pytest.mark.parametrize("case", cases.CASES)
@@ -85,6 +92,8 @@ def test_generated_sources_compile_for_sm100a(case):
     problem, state, dt = build_case(case, "f32")
     tw = HostTwin(problem, state)
     modes = ["lossgrad", "values"] + (["jvp", "vjp", "jac"] if case in cases.NEWTON_CASES else [])
+    if case in cases.NEWTON_CASES and tw.gen.dia_ok():
+        modes += ["jacd", "jvpd", "vjpd"]
     for mode in modes:
         m = native.JitModule(tw.engine.source(mode))
         assert len(m.cubin()) > 1000

@@ -58,7 +58,11 @@ def test_eval_loss_grad_matches_reference_golden(golden, case, prec):
 
 
 @pytest.mark.parametrize("case", cases.NEWTON_CASES)
-def test_linearize_matches_reference_golden(golden, case):
+@pytest.mark.parametrize("dia", ["0", "1"])
+def test_linearize_matches_reference_golden(golden, case, dia, monkeypatch):
+    """dia = 1 (default): the Jacobian products come from per-cell diagonals stored once per linearisation (generated
+    kernels 'jacd' / 'jvpd' / 'vjpd') where the operator allows it; dia = 0: from the forward- / reverse-mode kernels."""
+    monkeypatch.setenv("ODIL_B200_NEWTON_DIA", dia)
     g = golden("nonaffine")
     key = f"{case}_f64"
     problem, state, dt = build_case(case, "f64", device="cuda")
@@ -73,8 +77,12 @@ def test_linearize_matches_reference_golden(golden, case):
     rng = np.random.default_rng(0)
     v = torch.as_tensor(rng.standard_normal(J.shape[1]), device="cuda")
     w = torch.as_tensor(rng.standard_normal(J.shape[0]), device="cuda")
-    parity.check(f"graph/{key}/jvp", relerr(matrix.matvec(v).cpu().numpy(), Jr @ v.cpu().numpy()), 1e-11)
-    parity.check(f"graph/{key}/vjp", relerr(matrix.rmatvec(w).cpu().numpy(), Jr.T @ w.cpu().numpy()), 1e-11)
+    tag = "d" if dia == "1" and matrix.engine.gen.dia_ok() else ""
+    parity.check(f"graph/{key}/jvp{tag}", relerr(matrix.matvec(v).cpu().numpy(), Jr @ v.cpu().numpy()), 1e-11)
+    parity.check(f"graph/{key}/vjp{tag}", relerr(matrix.rmatvec(w).cpu().numpy(), Jr.T @ w.cpu().numpy()), 1e-11)
+    assert bool(matrix._dia) == (tag == "d")
+    if case == "heat3":
+        assert tag == ("d" if dia == "1" else "")
     # SciPy-matrix surface the reference's scripts rely on (tests/test_newton.py:117-120)
     normal = matrix.T @ matrix
     assert np.allclose(normal.toarray(), Jr.T @ Jr, rtol=1e-10, atol=1e-12 * np.max(np.abs(Jr)) ** 2)
