@@ -16,6 +16,8 @@ cells in a grid-stride loop and, per cell, executes a straight-line SSA program:
             reference's per-(key, shift, loc) Jacobian "diagonals" (core.py:1341-1350) kept on the device
   jvpd/vjpd the Jacobian products of a Newton step's CG iterations from those stored diagonals: J v = sum_l D_l * v[col_l],
             J^T w scattered likewise -- no re-evaluation of the operator's arithmetic (exp, divisions) per product
+  vjpg      J^T w GATHERED per input cell (no atomics) when every connected load is a pure roll: ctx.field(key, *shift)
+            without a location change -- the common case
 
 Index arithmetic (roll, slicing, pad, concatenate, reshape, transpose, broadcasting) is resolved symbolically per cell:
 `emit(node, index tuple, guard)` returns the SSA value of `node` at that index; integer literals are folded at
@@ -72,6 +74,9 @@ class GroupProgram:
         self.tape_index = {}    # SSA name -> its ('op', ...) tape entry
         self.n = 0
         self.uniform = {}       # (slot, lin) -> index of the register accumulator
+        self.shift = {}         # index variable -> (axis, k): its value is (c_axis + k) mod shape[axis]
+        self.load_shift = {}    # load variable -> per-axis k if the load reads cell (c + k) mod shape of an array of the
+                                # group's shape (a pure roll), else None
         self.ncell = math.prod(self.shape)
         nd = len(self.shape)
         self.I0 = tuple(f"c{a}" if self.shape[a] > 1 else 0 for a in range(nd))
@@ -220,6 +225,19 @@ class GroupProgram:
                 self.defs[key] = name
                 uniform = isinstance(l, int)
                 self.tape.append(("load", name, slot, l, G, uniform))
+                ks = None
+                if G is None and tuple(n.shape) == self.shape:
+                    ks = []
+                    for a, i in enumerate(I):
+                        if isinstance(i, int):
+                            ks.append(0 if self.shape[a] == 1 and i == 0 else None)
+                        elif i == f"c{a}":
+                            ks.append(0)
+                        else:
+                            sh = self.shift.get(i)
+                            ks.append(sh[1] if sh is not None and sh[0] == a else None)
+                    ks = None if any(k is None for k in ks) else tuple(ks)
+                self.load_shift[name] = ks
             return Val(self.defs[key], "f", True)
         if op == "stopgrad":
             x = self.emit(n.args[0], I, G)
@@ -235,7 +253,13 @@ class GroupProgram:
                 elif isinstance(i, int):
                     J.append((i - s) % m)
                 else:
-                    J.append(self.ivar(f"{i} >= {s} ? {i} - {s} : {i} + {m - s}"))
+                    v = self.ivar(f"{i} >= {s} ? {i} - {s} : {i} + {m - s}")
+                    base = self.shift.get(i)
+                    if base is None and i.startswith("c") and i[1:].isdigit():
+                        base = (int(i[1:]), 0)
+                    if base is not None and m == self.shape[base[0]]:
+                        self.shift[v] = (base[0], (base[1] - s) % m)
+                    J.append(v)
             return self.emit(x, tuple(J), G)
         if op == "index":
             J = []
@@ -579,6 +603,56 @@ class GroupProgram:
                 out.append(stmt if G is None else f"if ({G}) {stmt}")
         return out
 
+    def gather_ok(self):
+        """Every connected load is a pure roll of an array of the group's shape: J^T w can be GATHERED per input cell
+        (no atomics, no zero fill of the result beyond the caller's)."""
+        pairs = self.pairs()
+        if pairs is None:
+            return False
+        loads = self.loads()
+        return all(self.load_shift.get(loads[l][1]) is not None for _, l in pairs)
+
+    def diagonal_gather(self):
+        """vjpg: g[slot][cell] += sum over loads l of that slot and results j of D[j,l][src] * seed_j[src], where src is
+        the cell whose load l reads `cell`: src_a = (c_a - k_a) mod n_a."""
+        out = []
+        loads = self.loads()
+        pairs = self.pairs()
+        strides = self.gen.c_strides(self.shape)
+        srcs = {}
+        accs = {}
+        for l in sorted({l for _, l in pairs}):
+            _, z, slot, lin, G, _u = loads[l]
+            ks = self.load_shift[z]
+            if ks not in srcs:
+                q = len(srcs)
+                terms = []
+                for a, k in enumerate(ks):
+                    n = self.shape[a]
+                    if n == 1:
+                        continue
+                    if k == 0:
+                        v = f"c{a}"
+                    else:
+                        v = f"q{q}_{a}"
+                        out.append(f"const int {v} = c{a} >= {k} ? c{a} - {k} : c{a} + {n - k};")
+                    big = self.ncell >= 2 ** 31
+                    terms.append(v if strides[a] == 1 else (f"(long long){v} * {strides[a]}" if big else f"{v} * {strides[a]}"))
+                out.append(f"const {'long long' if self.ncell >= 2 ** 31 else 'int'} s{q} = "
+                           f"{' + '.join(terms) if terms else '0'};")
+                srcs[ks] = f"s{q}"
+            src = srcs[ks]
+            terms = [f"a.jval[{pi}ll * a.ncell + {src}] * a.seed[{self.results[jj][0]}][{src}]"
+                     for pi, (jj, ll) in enumerate(pairs) if ll == l]
+            if slot not in accs:
+                accs[slot] = f"g{slot}"
+                out.append(f"T g{slot} = {' + '.join(terms)};")
+            else:
+                out.append(f"g{slot} += {' + '.join(terms)};")
+        for slot, name in accs.items():
+            out.append(f"a.gin[{slot}][cell] += {name};")
+        return out
+
     def forward_tangent(self):
         out, tan = [], {}
         for e in self.tape:
@@ -631,6 +705,8 @@ class GroupProgram:
             lines += self.backward({v.name: "T(1)"} if v.active else {}, "jac")
         elif mode == "jacd":
             lines += self.diagonal_store()
+        elif mode == "vjpg":
+            return list(self.coords()) + self.diagonal_gather(), nloads
         elif mode in ("jvpd", "vjpd"):
             # only the index arithmetic of the forward statements is live here; the compiler drops the rest
             lines += self.diagonal_products(mode)
@@ -861,6 +937,10 @@ class Generator:
 
     def nloads(self, g):
         return len([e for e in g.tape if e[0] == "load"])
+
+    def gather_ok(self):
+        """J^T w of every group can be gathered per input cell from the stored diagonals (mode 'vjpg')."""
+        return self.dia_ok() and all(g.gather_ok() for g in self.groups)
 
     def dia_ok(self):
         """Every group can keep its Jacobian as per-cell diagonals (no cell-independent load receives a gradient)."""

@@ -117,7 +117,7 @@ struct odil_b200_plan {
 #include "tile3t.cuh"
 #include "tile2w.cuh"
 #ifndef ODIL_B200_TILE2W_DEFAULT
-#define ODIL_B200_TILE2W_DEFAULT 0  // k_tile2w is opt-in (ODIL_B200_TILE2W=1) until measured on the device
+#define ODIL_B200_TILE2W_DEFAULT 1  // k_tile2w where the plan fits it (never slower than k_tile2d: profiles/README.md)
 #endif
 namespace odil {
 
@@ -600,6 +600,27 @@ static bool tile2w_ok(const odil_b200_plan* plan, const T* U, const T* c, const 
     return tile2w_fits<T>(plan, U, c, G, Fout);
 }
 
+// one instantiation per offset count (2 rows in flight, 4 warps per CTA: the other combinations measured slower, see
+// profiles/README.md)
+template <typename T, int NOFF>
+static int launch_tile2w_n(const Tile2wParams<T>& p, int64_t nitems, int* grid_out, cudaStream_t st) {
+    constexpr int PF = 2, WARPS = kT2wWarps;
+    // registers: at most 64 per thread for fp32 (32 resident warps per SM), 128 for fp64
+    constexpr int MINB = (sizeof(T) == 4 ? 1024 : 512) / (32 * WARPS);
+    const int grid = (int)((nitems + WARPS - 1) / WARPS);
+    const size_t smem = t2w_smem_bytes<T>(WARPS, p.H0);
+    *grid_out = grid;
+    static size_t smem_set = 48 * 1024;  // per instantiation
+    if (smem > smem_set) {
+        ODIL_CUDA(cudaFuncSetAttribute(k_tile2w<T, NOFF, PF, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        smem_set = smem;
+    }
+    k_tile2w<T, NOFF, PF, WARPS, MINB><<<grid, 32 * WARPS, smem, st>>>(p);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
 template <typename T>
 static int launch_tile2w(const odil_b200_plan* plan, const T* U, const T* c, T scale, T* G, T* Fout, int* nparts,
                          cudaStream_t st) {
@@ -628,12 +649,21 @@ static int launch_tile2w(const odil_b200_plan* plan, const T* U, const T* c, T s
             p.kU[o][j] = ((a - 4 * fdiv4(a)) * kT2wW + fdiv4(a)) * (int)sizeof(T);
             p.kF[o][j] = ((b - 4 * fdiv4(b)) * kT2wW + fdiv4(b)) * (int)sizeof(T);
         }
+        p.rU[o] = p.dy[o] - p.H0;
+        p.rF[o] = -p.H0 - p.dy[o];
     }
-    // enough warps for one full wave (148 SMs x 24 resident warps), chunks of 8 .. 64 rows (2*H0 lead-in rows each)
+    auto env_int = [](const char* name, int dflt) {
+        const char* e = getenv(name);
+        return e ? atoi(e) : dflt;
+    };
+    // A warp's march is a serial chain (~8 cycles per instruction when it runs alone), so the sweep wants MANY warps:
+    // about four waves of 148 SMs x 32 resident warps, in chunks of max(4, 4*H0) .. 64 rows (each pays 2*H0 lead-in
+    // rows).  Measured (profiles/README.md): 1024^2 star -> 4 rows, 2048 x 4096 wave footprint -> 8, 4096^2 star -> 8
     p.nstrips = (p.N1 + kT2wOwn - 1) / kT2wOwn;
-    const int64_t want = 148 * 24;
+    const int64_t want = 4 * 148 * 32;
     int rc = (int)(((int64_t)p.N0 * p.nstrips + want - 1) / want);
-    rc = std::min(64, std::max(8, (rc + 7) / 8 * 8));
+    rc = std::min(64, std::max(std::max(4, 4 * p.H0), (rc + 3) / 4 * 4));
+    rc = std::max(1, env_int("ODIL_B200_T2W_ROWS", rc));  // measurement knob
     int64_t nitems = (int64_t)p.nstrips * ((p.N0 + rc - 1) / rc);
     while ((nitems + kT2wWarps - 1) / kT2wWarps > kPartialCapacity) {
         rc *= 2;
@@ -641,22 +671,14 @@ static int launch_tile2w(const odil_b200_plan* plan, const T* U, const T* c, T s
     }
     p.rows_per_chunk = rc;
     p.nitems = (int)nitems;
-    const size_t smem = t2w_smem_bytes<T>();
-    static bool attr_set = false;  // per element type
-    if (!attr_set && smem > 48 * 1024) {
-#define ODIL_T2W(N_) ODIL_CUDA(cudaFuncSetAttribute(k_tile2w<T, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-        ODIL_T2W(1); ODIL_T2W(2); ODIL_T2W(3); ODIL_T2W(4); ODIL_T2W(5); ODIL_T2W(6); ODIL_T2W(7); ODIL_T2W(8);
-#undef ODIL_T2W
-        attr_set = true;
-    }
-    const int grid = (int)((nitems + kT2wWarps - 1) / kT2wWarps);
+    int grid = 0, rcode = 0;
     switch (plan->noff) {
-#define ODIL_T2W(N_) case N_: k_tile2w<T, N_><<<grid, 32 * kT2wWarps, smem, st>>>(p); break
+#define ODIL_T2W(N_) case N_: rcode = launch_tile2w_n<T, N_>(p, nitems, &grid, st); break
         ODIL_T2W(1); ODIL_T2W(2); ODIL_T2W(3); ODIL_T2W(4); ODIL_T2W(5); ODIL_T2W(6); ODIL_T2W(7); ODIL_T2W(8);
 #undef ODIL_T2W
         default: return fail("k_tile2w: %d offsets", plan->noff);
     }
-    ODIL_LAUNCHED();
+    if (rcode) return rcode;
     if (nparts) *nparts = grid;
     return 0;
 }

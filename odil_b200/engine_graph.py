@@ -366,8 +366,10 @@ class GraphJacobian:
         gin = self._split(x, self.col0, [tuple(a.shape) for a in self.arrays])
         dia = self._diagonals()
         if dia:
+            mode = "vjpg" if eng.gen.gather_ok() and os.environ.get("ODIL_B200_NEWTON_GATHER", "1") not in ("", "0") \
+                else "vjpd"
             for g in eng.gen.groups:
-                eng._launch("vjpd", self.arrays, gin=gin, seed=seed, jval=dia[g.gid], prm=self.prm, only=(g.gid, None))
+                eng._launch(mode, self.arrays, gin=gin, seed=seed, jval=dia[g.gid], prm=self.prm, only=(g.gid, None))
         else:
             eng._launch("vjp", self.arrays, gin=gin, seed=seed, prm=self.prm)
         return x

@@ -239,7 +239,7 @@ class LbfgsbOptimizer(Optimizer):
         def on_iteration(flat):
             self.epoch += 1
             if callback:
-                callback(to_arrays(flat), self.epoch, self.pinfo)
+                callback(to_arrays(flat, fresh=True), self.epoch, self.pinfo)  # the callback may keep them
 
         x, f, info = optimize.fmin_l_bfgs_b(func=func, x0=to_flat(x0), maxiter=epochs, pgtol=self.pgtol, m=self.m,
                                             maxls=self.maxls, factr=self.factr, maxfun=np.inf,
@@ -273,16 +273,26 @@ class LbfgsDeviceOptimizer(Optimizer):
         sizes = [int(np.prod(s)) for s in shapes]
         bounds = np.cumsum([0] + sizes)
 
-        def to_arrays(flat):
-            return [flat[bounds[i]:bounds[i + 1]].reshape(shapes[i]).to(tdtype).contiguous()
-                    for i in range(len(sizes))]
+        # The optimizer's vector is fp64 (SciPy's L-BFGS-B is fp64 end to end, optimizer.py:63-73,81-88); the operator
+        # works in the problem dtype.  One conversion pass each way per evaluation, into buffers allocated once: the
+        # unknowns into `work` (what loss_grad reads), the gradients into the flat fp64 vector `g64` -- no torch.cat,
+        # no intermediate copies.
+        work = [torch.empty(shapes[i], dtype=tdtype, device=device) for i in range(len(sizes))]
+        g64 = torch.empty(int(bounds[-1]), dtype=torch.float64, device=device)
+
+        def to_arrays(flat, fresh=False):
+            out = [torch.empty_like(w) for w in work] if fresh else work
+            for i, w in enumerate(out):
+                w.view(-1).copy_(flat[bounds[i]:bounds[i + 1]])
+            return out
 
         def func(flat):
             self.evals += 1
             loss, grads, pinfo = loss_grad(to_arrays(flat))
             self.pinfo = pinfo
-            g = torch.cat([a.reshape(-1).to(torch.float64) for a in grads])
-            return float(loss), g
+            for i, a in enumerate(grads):
+                g64[bounds[i]:bounds[i + 1]].copy_(a.reshape(-1))
+            return float(loss), g64
 
         def on_iteration(flat):
             self.epoch += 1
@@ -296,7 +306,7 @@ class LbfgsDeviceOptimizer(Optimizer):
         if optinfo.warnflag not in [0, 1] or optinfo.epochs < epochs:
             raise EarlyStopError(", ".join("{:}={:}".format(k, info.get(k, ""))
                                            for k in ["warnflag", "task", "funcalls", "nit"]), optinfo)
-        return to_arrays(x), optinfo
+        return to_arrays(x, fresh=True), optinfo
 
 
 def make_optimizer(name, dtype=None, mod=None, **kwargs):

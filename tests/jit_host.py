@@ -163,12 +163,15 @@ class HostTwin:
             self.run("jvpd", [a.contiguous() for a in arrays], tin=tin, out=out, jval=dia[g.gid], only=(g.gid, None))
         return np.concatenate([o.numpy().reshape(-1) for o in out]).astype(np.float64)
 
-    def vjpd(self, arrays, y, dia):
+    def vjpg(self, arrays, y, dia):
+        return self.vjpd(arrays, y, dia, mode="vjpg")
+
+    def vjpd(self, arrays, y, dia, mode="vjpd"):
         eng = self.engine
         row0 = np.concatenate([[0], np.cumsum([o.n for o in eng.outputs])])
         seed = [torch.as_tensor(y[row0[k]:row0[k + 1]], dtype=self.tdtype).reshape(o.shape).contiguous()
                 for k, o in enumerate(eng.outputs)]
         gin = [torch.zeros(a.shape, dtype=self.tdtype) for a in arrays]
         for g in self.gen.groups:
-            self.run("vjpd", [a.contiguous() for a in arrays], gin=gin, seed=seed, jval=dia[g.gid], only=(g.gid, None))
+            self.run(mode, [a.contiguous() for a in arrays], gin=gin, seed=seed, jval=dia[g.gid], only=(g.gid, None))
         return np.concatenate([g.numpy().reshape(-1) for g in gin]).astype(np.float64)

@@ -82,6 +82,10 @@ def test_host_twin_jacobian_matches_reference_golden(golden, case):
         dia = tw.diagonals(x)
         assert relerr(tw.jvpd(x, v, dia), Jr @ v) < 1e-11
         assert relerr(tw.vjpd(x, w, dia), Jr.T @ w) < 1e-11
+        if tw.gen.gather_ok():  # every load a pure roll: J^T w gathered per input cell
+            assert relerr(tw.vjpg(x, w, dia), Jr.T @ w) < 1e-11
+        else:
+            assert case != "heat3"
     else:
         assert case in ("newton", "infer_constant", "heat_k")  # network weights / Array elements among the unknowns
 
@@ -93,7 +97,7 @@ def test_generated_sources_compile_for_sm100a(case):
     tw = HostTwin(problem, state)
     modes = ["lossgrad", "values"] + (["jvp", "vjp", "jac"] if case in cases.NEWTON_CASES else [])
     if case in cases.NEWTON_CASES and tw.gen.dia_ok():
-        modes += ["jacd", "jvpd", "vjpd"]
+        modes += ["jacd", "jvpd", "vjpd"] + (["vjpg"] if tw.gen.gather_ok() else [])
     for mode in modes:
         m = native.JitModule(tw.engine.source(mode))
         assert len(m.cubin()) > 1000

@@ -259,7 +259,7 @@ def test_tile3d_ring_addressing(shape, offs, R, zchunk):
 # vector of 32, the rings as arrays [8 slots][4 cell planes][34 words], the byte-offset tables kU / kF of the launcher
 # (in words here), the two fast paths and the table paths.
 # --------------------------------------------------------------------------------------------------------------------
-W2_VW, W2_OWN, W2_W, W2_NS = 4, 120, 34, 8
+W2_VW, W2_OWN, W2_W = 4, 120, 34
 
 
 def _fdiv4(v):
@@ -289,11 +289,15 @@ def tile2w_fused(U, c, table, offs, R, scale, rows_per_chunk):
     noff = len(offs)
     H0, H1 = max(abs(o[0]) for o in offs), max(abs(o[1]) for o in offs)
     assert H0 <= 2 and H1 <= 2 and noff <= 8
+    NR = 2 * H0 + 1                       # rows per ring
+    SLOT = 4 * W2_W
     C1 = 2 * R[1] + 1
     tab = table.reshape(-1, noff)
     CI = R[0] * C1 + R[1]
     kU = [[((j + o[1]) - 4 * _fdiv4(j + o[1])) * W2_W + _fdiv4(j + o[1]) for j in range(4)] for o in offs]
     kF = [[((j - o[1]) - 4 * _fdiv4(j - o[1])) * W2_W + _fdiv4(j - o[1]) for j in range(4)] for o in offs]
+    rU = [o[0] - H0 for o in offs]        # ring slot relative to the newest row
+    rF = [-H0 - o[0] for o in offs]
     nstrips = (N1 + W2_OWN - 1) // W2_OWN
     nchunks = (N0 + rows_per_chunk - 1) // rows_per_chunk
     G, Fo, ss = np.full(U.shape, np.nan), np.full(U.shape, np.nan), 0.0
@@ -307,8 +311,8 @@ def tile2w_fused(U, c, table, offs, R, scale, rows_per_chunk):
         ccls = np.array([[(_cls(x0[l] + j, N1, R[1]) if xin[l] else 0) for j in range(4)] for l in range(32)])
         fastXF = bool(np.all(~xin | ((x0 >= R[1]) & (x0 + 3 < N1 - R[1]))))
         fastXG = bool(np.all(~own | ((x0 >= R[1] + H1) & (x0 + 3 < N1 - R[1] - H1))))
-        ringU = np.zeros(W2_NS * 4 * W2_W)
-        ringF = np.zeros(W2_NS * 4 * W2_W)
+        ringU = np.zeros(NR * SLOT)
+        ringF = np.zeros(NR * SLOT)
         base = lanes + 1  # word of (slot 0, plane 0, own lane)
 
         def load(A, r, extra=True):
@@ -319,40 +323,47 @@ def tile2w_fused(U, c, table, offs, R, scale, rows_per_chunk):
                         out[l] = A[r, x0[l]: x0[l] + 4]
             return out
 
-        for ru in range(ys - 2 * H0, ye + 2 * H0):
-            ucur = load(U, ru)
-            su = (ru & 7) * 4 * W2_W
+        def stage(u, slot):
             for j in range(4):
-                ringU[su + j * W2_W + base] = ucur[:, j]
+                ringU[slot * SLOT + j * W2_W + base] = u[:, j]
+
+        def slot_of(cu, rel):
+            t = cu + rel
+            assert -NR <= t < NR
+            return t + NR if t < 0 else t
+
+        for q in range(2 * H0):           # prologue
+            stage(load(U, ys - 2 * H0 + q), q)
+        cu = NR - 1
+        for ru in range(ys, ye + 2 * H0):
+            stage(load(U, ru), cu)
             jf = ru - H0
-            if ru >= ys:
-                f = load(c, jf, jf < ye + H0)
-                rin = 0 <= jf < N0
-                if rin:
-                    so = [((jf + o[0]) & 7) * 4 * W2_W for o in offs]
-                    if fastXF and R[0] <= jf < N0 - R[0]:
-                        for o in range(noff):
-                            for j in range(4):
-                                f[:, j] += tab[CI, o] * ringU[so[o] + kU[o][j] + base]
-                    else:
-                        rc = _cls(jf, N0, R[0]) * C1
-                        for o in range(noff):
-                            for j in range(4):
-                                f[:, j] += tab[rc + ccls[:, j], o] * ringU[so[o] + kU[o][j] + base]
-                if not rin:
-                    f[:] = 0
-                f[~xin] = 0
-                if ys <= jf < ye:
-                    ss += float((f[own] ** 2).sum())
-                    for l in lanes[own]:
-                        Fo[jf, x0[l]: x0[l] + 4] = f[l]
-                sf = (jf & 7) * 4 * W2_W
-                for j in range(4):
-                    ringF[sf + j * W2_W + base] = f[:, j]
+            f = load(c, jf, jf < ye + H0)
+            rin = 0 <= jf < N0
+            if rin:
+                so = [slot_of(cu, r) * SLOT for r in rU]
+                if fastXF and R[0] <= jf < N0 - R[0]:
+                    for o in range(noff):
+                        for j in range(4):
+                            f[:, j] += tab[CI, o] * ringU[so[o] + kU[o][j] + base]
+                else:
+                    rc = _cls(jf, N0, R[0]) * C1
+                    for o in range(noff):
+                        for j in range(4):
+                            f[:, j] += tab[rc + ccls[:, j], o] * ringU[so[o] + kU[o][j] + base]
+            if not rin:
+                f[:] = 0
+            f[~xin] = 0
+            if ys <= jf < ye:
+                ss += float((f[own] ** 2).sum())
+                for l in lanes[own]:
+                    Fo[jf, x0[l]: x0[l] + 4] = f[l]
+            for j in range(4):
+                ringF[cu * SLOT + j * W2_W + base] = f[:, j]
             k = ru - 2 * H0
             if k >= ys:
                 g = np.zeros((32, 4))
-                so = [((k - o[0]) & 7) * 4 * W2_W for o in offs]
+                so = [slot_of(cu, r) * SLOT for r in rF]
                 if fastXG and R[0] + H0 <= k < N0 - R[0] - H0:
                     for o in range(noff):
                         for j in range(4):
@@ -369,6 +380,7 @@ def tile2w_fused(U, c, table, offs, R, scale, rows_per_chunk):
                             g[:, j] += tab[rc + cx, o] * ringF[so[o] + kF[o][j] + base]
                 for l in lanes[own]:
                     G[k, x0[l]: x0[l] + 4] = g[l] * scale
+            cu = 0 if cu + 1 == NR else cu + 1
     return Fo, G, ss
 
 
