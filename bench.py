@@ -50,7 +50,7 @@ def parse():
     p.add_argument("--levels", type=int, default=None)
     p.add_argument("--dtype", type=str, default=None, choices=["f32", "f64"])
     p.add_argument("--lr", type=float, default=0.005)
-    p.add_argument("--e2e_steps", type=int, default=10)
+    p.add_argument("--e2e_steps", type=int, default=5)
     p.add_argument("--cpu_steps", type=int, default=2)
     p.add_argument("--cpu_budget_s", type=float, default=420.0, help="wall-time budget of the reference arm")
     p.add_argument("--no_cpu_baseline", action="store_true")
@@ -330,40 +330,9 @@ class Stepper:
                 if epoch > warmup:
                     info["loss"] = float(pinfo["loss"])  # the finished step's result goes back to the host
                 if epoch < warmup + steps:
-                    # The next step's inputs arrive from pinned host memory.  Input pipeline: the host->device copy of
-                    # step n + 1 runs on a copy stream into one of two staging sets while step n computes; at the step
-                    # boundary the staged set is copied into the optimizer's arrays on the compute stream.  Every step's
-                    # inputs cross PCIe inside the timed region (the first copy is issued after the start event).
-                    pipe = ev.setdefault("pipe", None)
-                    if pipe is None:
-                        arrays0 = domain.arrays_from_state(state)
-                        pipe = ev["pipe"] = {
-                            "stream": torch.cuda.Stream(),
-                            "bufs": [[torch.empty_like(a) for a in arrays0] for _ in range(2)],
-                            "ready": [torch.cuda.Event(), torch.cuda.Event()],
-                            "free": [torch.cuda.Event(), torch.cuda.Event()],
-                            "staged": set(),
-                        }
-
-                    def stage(n):  # inputs of the step after boundary n -> staging set n % 2 (copy stream)
-                        b = n % 2
-                        with torch.cuda.stream(pipe["stream"]):
-                            if n - 2 >= warmup:
-                                pipe["stream"].wait_event(pipe["free"][b])  # its previous content has been consumed
-                            for sbuf, h in zip(pipe["bufs"][b], e2e_host):
-                                sbuf.copy_(h, non_blocking=True)
-                            pipe["ready"][b].record(pipe["stream"])
-                        pipe["staged"].add(n)
-
-                    if epoch not in pipe["staged"]:
-                        stage(epoch)
-                    b = epoch % 2
-                    torch.cuda.current_stream().wait_event(pipe["ready"][b])
-                    for d, sbuf in zip(domain.arrays_from_state(state), pipe["bufs"][b]):
-                        d.copy_(sbuf, non_blocking=True)
-                    pipe["free"][b].record(torch.cuda.current_stream())
-                    if epoch + 1 < warmup + steps:
-                        stage(epoch + 1)
+                    # the next step's inputs arrive from pinned host memory
+                    for d, h in zip(domain.arrays_from_state(state), e2e_host):
+                        d.copy_(h, non_blocking=True)
             if epoch == warmup + steps:
                 ev["e1"] = torch.cuda.Event(enable_timing=True)
                 ev["e1"].record()
@@ -608,8 +577,7 @@ def run_b200(args):
         e2e = {"value": ncells / (wall_ms * 1e-3) / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": 8 * world, "ms_per_step": wall_ms,
                "note": "wall clock through odil.util.optimize_grad; per step and rank: H2D of all multigrid terms from "
-                       "pinned host memory (copy stream, double-buffered staging: the copy of step n+1 overlaps the "
-                       "epoch of step n) + device copy into the optimizer's arrays + epoch + D2H of the loss"}
+                       "pinned host memory + epoch + D2H of the loss"}
         del host
     else:
         # the optimizer owns its iterate: whole job from host arrays to a host result
