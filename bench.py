@@ -527,9 +527,10 @@ def run_b200(args):
         # Jacobian products from the diagonals stored once per Newton step (11 structurally non-zero (output, load)
         # pairs: 10 for the heat residual, 1 for the imposed-data term)
         alg_bytes.update({"jit:k_g0_jvpd": 14 * es * ncells_local, "jit:k_g0_vjpd": 14 * es * ncells_local,
-                          "jit:k_g0_jacd": 14 * es * ncells_local})
+                          "jit:k_g0_vjpg": 14 * es * ncells_local, "jit:k_g0_jacd": 14 * es * ncells_local})
         alg_note.update({"jit:k_g0_jvpd": "14*s bytes per cell (read 11 stored diagonals and the tangent; write 2 outputs)",
                          "jit:k_g0_vjpd": "14*s bytes per cell (read 11 stored diagonals and 2 cotangents; accumulate g)",
+                         "jit:k_g0_vjpg": "14*s bytes per cell (read 11 stored diagonals and 2 cotangents; write g)",
                          "jit:k_g0_jacd": "14*s bytes per cell (read u, imp_mask, imp_u; write 11 diagonals)"})
     for name, k in kern.items():
         if name in alg_bytes and k["ms_per_step"] > 0:
