@@ -243,6 +243,11 @@ def _dot(a, b, out):
     return out.item()
 
 
+def _maxabs(g):
+    """max |g_i| in one pass over g (g.abs().max() makes a temporary and reads it back)."""
+    return torch.linalg.vector_norm(g, ord=float("inf")).item()
+
+
 def minimize(func, x0, m=50, maxiter=15000, maxls=20, pgtol=1e-5, factr=1e7, callback=None):
     """
     func(x) -> (f, g): x, g flat fp64 device tensors (g may be overwritten by the caller on the next call).
@@ -260,7 +265,7 @@ def minimize(func, x0, m=50, maxiter=15000, maxls=20, pgtol=1e-5, factr=1e7, cal
     g = g.clone()
     nfev, nit = 1, 0
     task, warnflag = None, 0
-    sbgnrm = g.abs().max().item()
+    sbgnrm = _maxabs(g)
     if sbgnrm <= pgtol:
         return x, f, dict(warnflag=0, task="CONVERGENCE: NORM_OF_PROJECTED_GRADIENT_<=_PGTOL", funcalls=nfev, nit=0)
     Stg = Ytg = None
@@ -276,9 +281,9 @@ def minimize(func, x0, m=50, maxiter=15000, maxls=20, pgtol=1e-5, factr=1e7, cal
         dnorm = np.sqrt(_dot(d, d, sc))
         stp = min(1.0 / dnorm, BIG) if nit == 0 else 1.0
         t.copy_(x)
-        r.copy_(g)
+        g, r = r, g   # r = previous gradient (kept for y = g_new - g_old and for a failed search); g is overwritten below
         fold = f
-        gd = _dot(g, d, sc)
+        gd = _dot(r, d, sc)
         gdold = gd
         ls = _Search()
         info = 0
@@ -317,7 +322,7 @@ def minimize(func, x0, m=50, maxiter=15000, maxls=20, pgtol=1e-5, factr=1e7, cal
         nit += 1
         if callback is not None:
             callback(x)
-        sbgnrm = g.abs().max().item()
+        sbgnrm = _maxabs(g)
         if sbgnrm <= pgtol:
             task = "CONVERGENCE: NORM_OF_PROJECTED_GRADIENT_<=_PGTOL"
             break
