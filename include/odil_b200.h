@@ -166,6 +166,13 @@ int odil_b200_adam_step(int ntensors, void* const* x, void* const* m, void* cons
 int odil_b200_adam_step_dev(int ntensors, void* const* x, void* const* m, void* const* v, const void* const* g,
                             const int64_t* counts, int dtype, const double* alpha_dev, double one_minus_beta1,
                             double one_minus_beta2, double epsilon, void* stream);
+
+/* Step-size table of a replayed run: out[0] = table[step[0]], then step[0] += 1 (one launch).  The host tabulates
+ * alpha(epoch) = lr * sqrt(1 - beta2^t) / (1 - beta1^t) in the array dtype for every epoch of the run
+ * (optimizer.py:307-309) once; the captured epoch starts with this call and feeds `out` to odil_b200_adam_step_dev /
+ * odil_b200_adam_synth as alpha_dev. */
+int odil_b200_table_pick(const double* table, int64_t* step, double* out, void* stream);
+
 int odil_b200_gd_step(int ntensors, void* const* x, const void* const* g, const int64_t* counts, int dtype,
                       double lr, void* stream);
 /* y = a*x + b*y  (L-BFGS building block; also used for scaling). */

@@ -843,8 +843,9 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
 }
 
 // Adam update of the finest multigrid term (x, m, v with gradient g) AND out = ffac * x_new + cfac * I(coarse) in one pass
-// (k_adam_synth3).  Returns 1 -- nothing done -- when the geometry is not cell-centred 3-D with an even coarse width
-// and 16-byte aligned arrays: the caller then runs odil_b200_adam_step and odil_b200_mg_interp_add separately.
+// (k_adam_synth3; k_adam_synth2t on 2-D grids).  Returns 1 -- nothing done -- when the geometry is not cell-centred 3-D /
+// 2-D with an even coarse width and 16-byte aligned arrays: the caller then runs odil_b200_adam_step and
+// odil_b200_mg_interp_add separately.
 int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* coarse, double cfac,
                          double ffac, void* x, void* m_state, void* v_state, const void* g, void* out, double alpha,
                          const double* alpha_dev, double one_minus_beta1, double one_minus_beta2, double epsilon,
@@ -858,6 +859,23 @@ int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int d
     if (r.fz_begin % 2 != 0 || r.fz_end % 2 != 0) return 1;
     if (r.fz_begin == r.fz_end) return 0;
     ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    // 2-D cell-centred grids: the tile kernel of the synthesis with the update in front of it (k_adam_synth2t)
+    if (tile2_ok(geo, r.fz_begin == 0 && r.fz_end == geo.fn[0] && r.out_z0 == 0 && r.coarse_z0 == 0, coarse, x, out) &&
+        (uintptr_t)m_state % 16 == 0 && (uintptr_t)v_state % 16 == 0 && (uintptr_t)g % 16 == 0) {
+        const int n0 = (int)geo.cn[0], n1 = (int)geo.cn[1];
+        dim3 grid2((n1 + kM2X - 1) / kM2X, (n0 + kM2Y - 1) / kM2Y);
+        if (dtype == ODIL_B200_F32)
+            k_adam_synth2t<float><<<grid2, kM2Threads, 0, st>>>(
+                (const float*)coarse, (float)cfac, (float)ffac, (float*)x, (float*)m_state, (float*)v_state, (const float*)g,
+                (float*)out, (float)alpha, alpha_dev, (float)one_minus_beta1, (float)one_minus_beta2, (float)epsilon, n0, n1);
+        else
+            k_adam_synth2t<double><<<grid2, kM2Threads, 0, st>>>(
+                (const double*)coarse, cfac, ffac, (double*)x, (double*)m_state, (double*)v_state, (const double*)g,
+                (double*)out, alpha, alpha_dev, one_minus_beta1, one_minus_beta2, epsilon, n0, n1);
+        ODIL_LAUNCHED();
+        return 0;
+    }
     Mg3 m;
     bool cz = false;
     if (!(fast3_geometry(geo, m, cz) && march_ok(m, cz, ndim, x, g, out) && (uintptr_t)m_state % 16 == 0 &&
@@ -867,7 +885,6 @@ int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int d
     const int cb = (int)(r.fz_begin / 2), ce = (int)(r.fz_end / 2), fz0 = (int)r.out_z0, cz0 = (int)r.coarse_z0;
     dim3 grid((m.n2 / 2 + 63) / 64, (2 * m.n1 + 3) / 4, (unsigned)((ce - cb + kAsZC - 1) / kAsZC));
     if (grid.y > 65535 || grid.z > 65535) return 1;
-    cudaStream_t st = (cudaStream_t)stream;
     // resident CTAs per SM the fp32 kernel is compiled for: 3 (80 registers, 16 bytes of spills; default) or 2 (128)
     static const int occ = [] {
         const char* e = getenv("ODIL_B200_SYNTH_OCC");

@@ -272,6 +272,21 @@ int odil_b200_adam_step(int ntensors, void* const* x, void* const* m, void* cons
     return fail("dtype=%d unsupported", dtype);
 }
 
+// Head of a replayed Adam epoch: out[0] = table[step[0]]; step[0] += 1 -- the per-epoch step size (optimizer.py:307-309)
+// picked from a device table in ONE launch, so that a captured epoch reads nothing from the host.
+static __global__ void k_table_pick(const double* __restrict__ table, long long* __restrict__ step, double* __restrict__ out) {
+    const long long s = step[0];
+    out[0] = table[s];
+    step[0] = s + 1;
+}
+
+int odil_b200_table_pick(const double* table, int64_t* step, double* out, void* stream) {
+    ODIL_REQUIRE(table && step && out, "table_pick: null pointer");
+    k_table_pick<<<1, 1, 0, (cudaStream_t)stream>>>(table, reinterpret_cast<long long*>(step), out);
+    ODIL_LAUNCHED();
+    return 0;
+}
+
 int odil_b200_adam_step_dev(int ntensors, void* const* x, void* const* m, void* const* v, const void* const* g,
                             const int64_t* counts, int dtype, const double* alpha_dev, double one_minus_beta1,
                             double one_minus_beta2, double epsilon, void* stream) {

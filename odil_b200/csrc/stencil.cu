@@ -623,8 +623,10 @@ static int launch_tile2w_n(const Tile2wParams<T>& p, int64_t nitems, int* grid_o
 
 template <typename T>
 static int launch_tile2w(const odil_b200_plan* plan, const T* U, const T* c, T scale, T* G, T* Fout, int* nparts,
-                         cudaStream_t st) {
+                         double* sumsq, cudaStream_t st) {
     Tile2wParams<T> p;
+    p.sumsq = sumsq;  // the last CTA to finish sums the partials (fixed order): no separate reduction launch
+    p.counter = reinterpret_cast<unsigned*>(plan->partials + kPartialCapacity);
     p.U = U;
     p.c = c;
     p.G = G;
@@ -864,11 +866,9 @@ static int run_fused(const odil_b200_plan* plan, const odil_b200_slab* slab, con
                 return fail("ODIL_B200_TILE2W=2: this plan does not fit k_tile2w (wrap-free, <= 8 offsets, radii <= 2, "
                             "row length a multiple of 4, 16-byte aligned arrays)");
         }
-        if (tile2w_ok<T>(plan, io.U, io.c, io.out, io.Fout)) {
-            if (int rc = launch_tile2w<T>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)) return rc;
-        } else if (int rc = launch_tile2d<T, 2>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)) {
-            return rc;
-        }
+        if (tile2w_ok<T>(plan, io.U, io.c, io.out, io.Fout))
+            return launch_tile2w<T>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, sumsq, st);
+        if (int rc = launch_tile2d<T, 2>(plan, io.U, io.c, io.scale, io.out, io.Fout, &nparts, st)) return rc;
         k_reduce_partials<<<1, 1024, 0, st>>>(plan->partials, nparts, sumsq);
         ODIL_LAUNCHED();
         return 0;
@@ -1336,7 +1336,9 @@ int odil_b200_stencil_plan_create(int ndim, const int64_t* shape, int dtype, int
                 e = cudaMemcpy(p->table_dev, p->table.data(), esz * p->table.size(), cudaMemcpyHostToDevice);
             }
         }
-        if (e == cudaSuccess) e = cudaMalloc((void**)&p->partials, sizeof(double) * kPartialCapacity);
+        // + 2 doubles behind the partials: the "blocks done" counter of kernels that reduce their own partials (k_tile2w)
+        if (e == cudaSuccess) e = cudaMalloc((void**)&p->partials, sizeof(double) * (kPartialCapacity + 2));
+        if (e == cudaSuccess) e = cudaMemset(p->partials + kPartialCapacity, 0, 2 * sizeof(double));
         if (e == cudaSuccess && !star.empty()) {
             e = cudaMalloc(&p->star_table, esz * star.size());
             if (e == cudaSuccess) {

@@ -45,6 +45,8 @@ struct Tile2wParams {
     T* Fout;           // nullable
     const T* table;    // [ncls][noff]
     double* partials;  // one per CTA
+    double* sumsq;     // sum of the partials, written by the last CTA to finish
+    unsigned* counter; // CTAs done (zero between launches: the last CTA's atomicInc wraps it)
     T scale;
     int N0, N1;
     int R0, R1;
@@ -280,7 +282,22 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_tile2w(const __grid_consta
         }
     }
     const double s = block_sum(acc, red);
-    if (threadIdx.x == 0) p.partials[blockIdx.x] = s;
+    // Second stage inside the same launch: every CTA publishes its partial, the last one to arrive sums them all in a
+    // fixed order (thread t takes partials t, t + 128, ...; then the block tree) -- deterministic, no extra launch.
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        p.partials[blockIdx.x] = s;
+        __threadfence();
+        last = atomicInc(p.counter, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double v = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 32 * WARPS) v += __ldcg(p.partials + i);
+        v = block_sum(v, red);
+        if (threadIdx.x == 0) p.sumsq[0] = v;
+    }
 }
 
 }  // namespace odil

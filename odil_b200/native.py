@@ -24,7 +24,7 @@ EXPORTS = [
     "odil_b200_stencil_plan_tune", "odil_b200_sum_squares", "odil_b200_dot", "odil_b200_mg_interp_add",
     "odil_b200_mg_interp_adjoint", "odil_b200_mg_restrict", "odil_b200_adam_step", "odil_b200_gd_step",
     "odil_b200_axpby", "odil_b200_multi_dot", "odil_b200_multi_axpy", "odil_b200_cg_update_xr",
-    "odil_b200_cg_update_p", "odil_b200_star_worklist", "odil_b200_adam_step_dev",
+    "odil_b200_cg_update_p", "odil_b200_star_worklist", "odil_b200_adam_step_dev", "odil_b200_table_pick",
     "odil_b200_mg_interp_adjoint_adam", "odil_b200_adam_synth",
     "odil_b200_jit_compile", "odil_b200_jit_log", "odil_b200_jit_cubin", "odil_b200_jit_kernel",
     "odil_b200_jit_launch", "odil_b200_jit_destroy",
@@ -112,6 +112,7 @@ def load(build_if_missing=False):
                                         dbl, dbl, vp]
     lib.odil_b200_adam_step_dev.argtypes = [ctypes.c_int, P(vp), P(vp), P(vp), P(vp), P(i64), ctypes.c_int, vp, dbl,
                                             dbl, dbl, vp]
+    lib.odil_b200_table_pick.argtypes = [vp, vp, vp, vp]
     lib.odil_b200_gd_step.argtypes = [ctypes.c_int, P(vp), P(vp), P(i64), ctypes.c_int, dbl, vp]
     lib.odil_b200_axpby.argtypes = [i64, ctypes.c_int, dbl, vp, dbl, vp, vp]
     lib.odil_b200_multi_dot.argtypes = [vp, i64, ctypes.c_int, vp, i64, ctypes.c_int, vp, vp]
@@ -407,6 +408,14 @@ def adam_step(x, m, v, g, alpha, omb1, omb2, eps):
     _call("adam_step", lambda: _check(_lib.odil_b200_adam_step(
         n, _ptr_array(x, dt), _ptr_array(m, dt, cnt), _ptr_array(v, dt, cnt), _ptr_array(g, dt, cnt), counts,
         dtype_code(x[0].dtype), float(alpha), float(omb1), float(omb2), float(eps), _stream())))
+
+
+def table_pick(table, step, out):
+    """out[0] = table[step[0]]; step[0] += 1 on the device (float64 table, 1-element int64 `step`, 1-element float64 `out`)."""
+    load()
+    if table.dtype != torch.float64 or out.dtype != torch.float64 or step.dtype != torch.int64 or not table.is_cuda:
+        raise NativeError("table_pick: float64 CUDA table / out and an int64 CUDA step counter")
+    _call("table_pick", lambda: _check(_lib.odil_b200_table_pick(_ptr(table), _ptr(step), _ptr(out), _stream())))
 
 
 def adam_step_dev(x, m, v, g, alpha_dev, omb1, omb2, eps):

@@ -142,8 +142,7 @@ class AdamNativeOptimizer(Optimizer):
         gc.collect()
         n_before = native.launch_count()
         with torch.cuda.graph(g):
-            torch.index_select(table, 0, step, out=alpha_dev)
-            step.add_(1)
+            native.table_pick(table, step, alpha_dev)  # alpha_dev = table[step]; step += 1 (one launch)
             fuse = getattr(loss_grad, "fuse_adam", None)
             if fuse is not None:
                 fuse(held, m, v, 0.0, omb1, omb2, eps, alpha_dev=alpha_dev)
