@@ -70,67 +70,6 @@ __global__ void __launch_bounds__(kM2Threads) k_interp_add2t(const T* __restrict
     }
 }
 
-// k_adam_synth2t: the 2-D counterpart of k_adam_synth3 (multigrid.cu) -- the Adam update of the FINEST multigrid term
-// (optimizer.py:311-319, adam_one) and, from the updated values, the regular field of the next evaluation
-// out = ffac * x_new + cfac * I(coarse) (core.py:245-263).  The interpolation is k_interp_add2t statement for statement,
-// so x, m, v and out are bit-identical to k_adam followed by k_interp_add2t; one launch and one pass over the term less
-// per epoch (configs[1] is launch-bound: ~10 kernels of 3-17 us per epoch).
-template <typename T>
-__global__ void __launch_bounds__(kM2Threads) k_adam_synth2t(const T* __restrict__ coarse, T cfac, T ffac,
-                                                             T* __restrict__ x, T* __restrict__ m, T* __restrict__ v,
-                                                             const T* __restrict__ g, T* __restrict__ out, T alpha_host,
-                                                             const double* __restrict__ alpha_dev, T omb1, T omb2, T eps,
-                                                             int n0, int n1) {
-    __shared__ T sP[(kM2Y + 2) * kM2PW];
-    const int tid = threadIdx.x;
-    const int cy0 = blockIdx.y * kM2Y, cx0 = blockIdx.x * kM2X;
-    const T alpha = alpha_dev ? (T)__ldg(alpha_dev) : alpha_host;
-    for (int e = tid; e < (kM2Y + 2) * kM2PW; e += kM2Threads) {
-        const int r = e / kM2PW, cc = e % kM2PW;
-        const int qy = min(cy0 - 1 + r, n0), qx = min(cx0 - 1 + cc, n1);
-        const int sy = m2_clamp(qy, n0), sx = m2_clamp(qx, n1);
-        T val = __ldg(coarse + (int64_t)sy * n1 + sx);
-        if (sy != qy || sx != qx) val = T(2) * val - __ldg(coarse + (int64_t)m2_reflect(qy, n0) * n1 + m2_reflect(qx, n1));
-        sP[e] = val;
-    }
-    __syncthreads();
-    const int fn1 = 2 * n1;
-    constexpr int VPR = kM2X / 2;
-    for (int vec = tid; vec < 2 * kM2Y * VPR; vec += kM2Threads) {
-        const int fr = vec / VPR, vx = vec % VPR;
-        const int I = fr >> 1, a = fr & 1;
-        const int fy = 2 * cy0 + fr, lc = 2 * vx, fx = 2 * (cx0 + lc);
-        if (fy >= 2 * n0 || fx >= fn1) continue;
-        const int64_t lin = (int64_t)fy * fn1 + fx;
-        Vec4<T> t = *reinterpret_cast<const Vec4<T>*>(x + lin);
-        Vec4<T> mv = *reinterpret_cast<const Vec4<T>*>(m + lin);
-        Vec4<T> vv = *reinterpret_cast<const Vec4<T>*>(v + lin);
-        const Vec4<T> gv = *reinterpret_cast<const Vec4<T>*>(g + lin);
-        adam_one(t.x, mv.x, vv.x, gv.x, alpha, omb1, omb2, eps);
-        adam_one(t.y, mv.y, vv.y, gv.y, alpha, omb1, omb2, eps);
-        adam_one(t.z, mv.z, vv.z, gv.z, alpha, omb1, omb2, eps);
-        adam_one(t.w, mv.w, vv.w, gv.w, alpha, omb1, omb2, eps);
-        *reinterpret_cast<Vec4<T>*>(x + lin) = t;
-        *reinterpret_cast<Vec4<T>*>(m + lin) = mv;
-        *reinterpret_cast<Vec4<T>*>(v + lin) = vv;
-        const T* near = sP + (I + 1) * kM2PW + lc;
-        const T* far = sP + (I + 2 * a) * kM2PW + lc;
-        const T h0 = T(3) * near[0] + far[0], h1 = T(3) * near[1] + far[1];
-        const T h2 = T(3) * near[2] + far[2], h3 = T(3) * near[3] + far[3];
-        const T k = T(0.0625);
-        Vec4<T> res;
-        res.x = cfac * ((T(3) * h1 + h0) * k);
-        res.y = cfac * ((T(3) * h1 + h2) * k);
-        res.z = cfac * ((T(3) * h2 + h1) * k);
-        res.w = cfac * ((T(3) * h2 + h3) * k);
-        res.x += ffac * t.x;
-        res.y += ffac * t.y;
-        res.z += ffac * t.z;
-        res.w += ffac * t.w;
-        *reinterpret_cast<Vec4<T>*>(out + lin) = res;
-    }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(kM2Threads) k_interp_adjoint2t(const T* __restrict__ gf, T scale,
                                                                  T* __restrict__ gc, int n0, int n1) {

@@ -843,9 +843,10 @@ int odil_b200_mg_interp_add(int ndim, const int64_t* cshape, const char* loc, in
 }
 
 // Adam update of the finest multigrid term (x, m, v with gradient g) AND out = ffac * x_new + cfac * I(coarse) in one pass
-// (k_adam_synth3; k_adam_synth2t on 2-D grids).  Returns 1 -- nothing done -- when the geometry is not cell-centred 3-D /
-// 2-D with an even coarse width and 16-byte aligned arrays: the caller then runs odil_b200_adam_step and
-// odil_b200_mg_interp_add separately.
+// (k_adam_synth3).  Returns 1 -- nothing done -- when the geometry is not cell-centred 3-D with an even coarse width
+// and 16-byte aligned arrays: the caller then runs odil_b200_adam_step and odil_b200_mg_interp_add separately.  (A 2-D
+// version, k_interp_add2t with the update in front of it, measured slower than the pair on configs[1] -- 47.1 vs 45.5 us
+// per epoch -- and was removed.)
 int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int dtype, const void* coarse, double cfac,
                          double ffac, void* x, void* m_state, void* v_state, const void* g, void* out, double alpha,
                          const double* alpha_dev, double one_minus_beta1, double one_minus_beta2, double epsilon,
@@ -860,22 +861,6 @@ int odil_b200_adam_synth(int ndim, const int64_t* cshape, const char* loc, int d
     if (r.fz_begin == r.fz_end) return 0;
     ODIL_REQUIRE(dtype == ODIL_B200_F32 || dtype == ODIL_B200_F64, "dtype=%d unsupported", dtype);
     cudaStream_t st = (cudaStream_t)stream;
-    // 2-D cell-centred grids: the tile kernel of the synthesis with the update in front of it (k_adam_synth2t)
-    if (tile2_ok(geo, r.fz_begin == 0 && r.fz_end == geo.fn[0] && r.out_z0 == 0 && r.coarse_z0 == 0, coarse, x, out) &&
-        (uintptr_t)m_state % 16 == 0 && (uintptr_t)v_state % 16 == 0 && (uintptr_t)g % 16 == 0) {
-        const int n0 = (int)geo.cn[0], n1 = (int)geo.cn[1];
-        dim3 grid2((n1 + kM2X - 1) / kM2X, (n0 + kM2Y - 1) / kM2Y);
-        if (dtype == ODIL_B200_F32)
-            k_adam_synth2t<float><<<grid2, kM2Threads, 0, st>>>(
-                (const float*)coarse, (float)cfac, (float)ffac, (float*)x, (float*)m_state, (float*)v_state, (const float*)g,
-                (float*)out, (float)alpha, alpha_dev, (float)one_minus_beta1, (float)one_minus_beta2, (float)epsilon, n0, n1);
-        else
-            k_adam_synth2t<double><<<grid2, kM2Threads, 0, st>>>(
-                (const double*)coarse, cfac, ffac, (double*)x, (double*)m_state, (double*)v_state, (const double*)g,
-                (double*)out, alpha, alpha_dev, one_minus_beta1, one_minus_beta2, epsilon, n0, n1);
-        ODIL_LAUNCHED();
-        return 0;
-    }
     Mg3 m;
     bool cz = false;
     if (!(fast3_geometry(geo, m, cz) && march_ok(m, cz, ndim, x, g, out) && (uintptr_t)m_state % 16 == 0 &&

@@ -546,35 +546,9 @@ def test_adam_synth_equals_adam_then_interp(cshape, prec):
     xd, md, vd = x0.clone(), m0.clone(), v0.clone()
     native.adam_step_dev([xd], [md], [vd], [g], alpha_dev, omb1, omb2, eps)
     assert torch.equal(xc, xd) and torch.equal(mc, md) and torch.equal(vc, vd)
-    # unsupported geometry (odd coarse width): nothing is touched
-    assert not native.adam_synth((8, 9), "cc", dev(np.zeros((8, 9), npd)), 1.0, 1.0, *(dev(np.zeros((16, 18), npd)) for _ in range(5)),
+    # unsupported geometry: nothing is touched
+    assert not native.adam_synth((8, 8), "cc", dev(np.zeros((8, 8), npd)), 1.0, 1.0, *(dev(np.zeros((16, 16), npd)) for _ in range(5)),
                                  alpha, omb1, omb2, eps)
-
-
-@pytest.mark.parametrize("cshape", [(2, 2), (16, 64), (17, 66), (5, 130), (40, 2), (33, 128), (512, 512)])
-@pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_adam_synth_2d_equals_adam_then_interp(cshape, prec):
-    """k_adam_synth2t (2-D grids) against odil_b200_adam_step followed by odil_b200_mg_interp_add: x, m, v and the
-    synthesised field bit for bit, with the step size from the host and from device memory."""
-    npd, td = DT[prec]
-    rng = np.random.default_rng(6)
-    fshape = tuple(2 * s for s in cshape)
-    coarse = dev(rng.standard_normal(cshape).astype(npd))
-    mk = lambda: dev(rng.standard_normal(fshape).astype(npd))
-    x0, m0, g = mk(), mk(), mk()
-    v0 = dev(rng.random(fshape).astype(npd))
-    alpha, omb1, omb2, eps = 0.0123, 0.1, 0.001, 1e-7
-    xa, ma, va = x0.clone(), m0.clone(), v0.clone()
-    native.adam_step([xa], [ma], [va], [g], alpha, omb1, omb2, eps)
-    ua = torch.full(fshape, float("nan"), dtype=td, device="cuda")
-    native.mg_interp_add(cshape, "cc", coarse, 0.7, xa, 1.3, ua)
-    alpha_dev = torch.tensor([float(npd(alpha))], dtype=torch.float64, device="cuda")
-    for kw in (dict(), dict(alpha_dev=alpha_dev)):
-        xb, mb, vb = x0.clone(), m0.clone(), v0.clone()
-        ub = torch.full(fshape, float("nan"), dtype=td, device="cuda")
-        assert native.adam_synth(cshape, "cc", coarse, 0.7, 1.3, xb, mb, vb, g, ub, 0.0 if kw else alpha, omb1, omb2, eps, **kw)
-        for a, b in ((xa, xb), (ma, mb), (va, vb), (ua, ub)):
-            assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("cshape", [(4, 4, 4), (5, 7, 6), (9, 4, 34), (33, 17, 64), (6, 66, 130), (40, 72, 192)])
