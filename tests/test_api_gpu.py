@@ -150,9 +150,10 @@ def test_adam_graph_replay_is_bit_identical(monkeypatch, case, prec):
     assert np.array_equal(l0, l1)
     for a, b in zip(x0, x1):
         assert np.array_equal(a, b)
-    # launch_count() = direct launches + kernel nodes of replayed graphs: both paths execute the same kernels (the
-    # capture itself is counted once more although it executes nothing)
-    assert c0 <= c1 <= c0 + c0 // 8
+    # launch_count() = direct launches + kernel nodes of replayed graphs: both paths execute the same kernels, plus
+    # odil_b200_table_pick at the head of every replayed epoch (the capture itself is counted once more although it
+    # executes nothing)
+    assert c0 <= c1 <= c0 + c0 // 8 + 16
 
 
 @pytest.mark.parametrize("case", [((32, 24, 40), 3), ((16, 20, 8), 2), ((64, 64, 64), 4), ((10, 8, 12), 2), ((16, 16), 3)])
