@@ -612,3 +612,23 @@ def test_tracer_reads_are_recorded_and_invalidate_the_lowering():
     eng2 = ResidualEngine(problem, state, trace_only=True)
     t0, t1 = eng.outputs[0].blocks[0].spec["table"], eng2.outputs[0].blocks[0].spec["table"]
     assert np.allclose(t0, 1.0) and np.allclose(t1, 0.5)
+
+
+def test_native_handles_are_not_destroyed_during_a_graph_capture(monkeypatch):
+    """A destructor that runs while a CUDA graph is being captured (Python's cyclic collector can run one at any
+    allocation) must not free device memory: `native._release` parks the handle and `flush_deferred` destroys it
+    once the capture has ended."""
+    from odil_b200 import native
+
+    destroyed = []
+    state = {"capturing": True}
+    monkeypatch.setattr(native, "_capturing", lambda: state["capturing"])
+    monkeypatch.setattr(native, "_deferred", [])
+    native._release(destroyed.append, 11)
+    native.flush_deferred()            # still capturing: nothing happens
+    assert destroyed == [] and len(native._deferred) == 1
+    state["capturing"] = False
+    native._release(destroyed.append, 12)  # outside a capture: destroyed at once
+    assert destroyed == [12]
+    native.flush_deferred()
+    assert destroyed == [12, 11] and native._deferred == []
