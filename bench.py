@@ -94,7 +94,8 @@ def workload(args, world):
 
 def config_block(args, world, wl):
     return {"workload": wl["text"],
-            "l2": "inputs exceed L2 (no explicit flush)" if np.prod(wl["cshape"]) * 4 > 2 ** 28 else
+            "l2": "inputs exceed L2 (one field is larger than the 126 MB L2; no explicit flush)"
+                  if np.prod(wl["cshape"]) * (4 if wl["dtype"] == "f32" else 8) > 126e6 else
                   "working set is L2-resident (126 MB L2): launch-latency-bound, HBM fraction not meaningful",
             "api": "odil.Domain / odil.Problem(operator) / odil.util.optimize_grad (optimize_newton for config 4)",
             "parallelism": f"slab{world}" if world > 1 else "single",
