@@ -13,8 +13,6 @@ in SciPy (`lbfgsb.f`: mainlb / lnsrlb / matupd) restricted to the unconstrained 
 is a transcription of MINPACK-2 `dcsrch` / `dcstep` (More-Thuente) with L-BFGS-B's constants
 ftol=1e-3, gtol=0.9, xtol=0.1, first step min(1/|d|, stpmx), later steps 1.
 """
-import os
-
 import numpy as np
 import torch
 
@@ -245,9 +243,6 @@ def _dot(a, b, out):
     return out.item()
 
 
-_COPY_PREVIOUS = os.environ.get("ODIL_B200_LBFGS_COPY", "0") not in ("", "0")  # measurement: copy instead of swapping
-
-
 def _maxabs(g):
     """max |g_i| in one pass over g (g.abs().max() makes a temporary and reads it back)."""
     return torch.linalg.vector_norm(g, ord=float("inf")).item()
@@ -286,10 +281,7 @@ def minimize(func, x0, m=50, maxiter=15000, maxls=20, pgtol=1e-5, factr=1e7, cal
         dnorm = np.sqrt(_dot(d, d, sc))
         stp = min(1.0 / dnorm, BIG) if nit == 0 else 1.0
         t.copy_(x)
-        if _COPY_PREVIOUS:
-            r.copy_(g)
-        else:
-            g, r = r, g   # r = previous gradient (kept for y = g_new - g_old and for a failed search); g is overwritten below
+        g, r = r, g   # r = previous gradient (kept for y = g_new - g_old and for a failed search); g is overwritten below
         fold = f
         gd = _dot(r, d, sc)
         gdold = gd
