@@ -1,7 +1,7 @@
 """Traces the device L-BFGS run of configs[2] (bench.py's workload): after every function evaluation one line with the
 iteration, bitwise checksums (int64 wrap-around sums of the bit patterns) of x and of the returned gradient, and the
-loss.  Two runs (e.g. ODIL_B200_LBFGS_COPY=0 / 1) are compared line by line to find the first operation whose result
-differs.  Usage: python tools/trace_lbfgs.py out.txt [iterations] [size]"""
+loss.  Two runs (different builds, ODIL_B200_TILE3T=0 / 1, ...) are compared line by line to find the first operation
+whose result differs.  Usage: python tools/trace_lbfgs.py out.txt [iterations] [size]"""
 import argparse
 import sys
 
