@@ -102,3 +102,29 @@ def test_generated_sources_compile_for_sm100a(case):
         m = native.JitModule(tw.engine.source(mode))
         assert len(m.cubin()) > 1000
         assert "error" not in m.log.lower()
+
+
+@pytest.mark.parametrize("case", cases.CASES)
+def test_stored_diagonals_reproduce_the_forward_and_reverse_products(golden, case):
+    """For every example operator whose unknowns allow it: the Jacobian products from the stored per-cell diagonals
+    (modes jacd + jvpd / vjpd, and the gathered vjpg where every load is a pure roll) equal the forward- / reverse-mode
+    products (jvp / vjp) at the golden state -- pads, trims, strided slices (mgloss), Raw terms and where() included."""
+    g = golden("nonaffine")
+    key = f"{case}_f64"
+    problem, state, dt = build_case(case, "f64")
+    tw = HostTwin(problem, state)
+    if not tw.gen.dia_ok():
+        pytest.skip("cell-independent loads among the unknowns (network weights / Array elements)")
+    x = [torch.as_tensor(a) for a in golden_arrays(g, key, "x")]
+    if any(u.kind == "MultigridField" and u.narrays > 1 for u in tw.engine.unknowns.values()):
+        pytest.skip("Newton needs multigrid off")
+    ncol = sum(a.numel() for a in x)
+    nrow = sum(o.n for o in tw.engine.outputs)
+    rng = np.random.default_rng(1)
+    v, w = rng.standard_normal(ncol), rng.standard_normal(nrow)
+    dia = tw.diagonals(x)
+    jv, jtw = tw.jvp(x, v), tw.vjp(x, w)
+    assert relerr(tw.jvpd(x, v, dia), jv) < 1e-12
+    assert relerr(tw.vjpd(x, w, dia), jtw) < 1e-12
+    if tw.gen.gather_ok():
+        assert relerr(tw.vjpg(x, w, dia), jtw) < 1e-12
