@@ -207,9 +207,29 @@ def launch_count():
 # cuModuleUnload), which invalidates a capture in progress.  Python's cyclic collector may run a destructor at any
 # allocation, so `__del__` parks the handle here and the next creation or `flush_deferred()` releases it.
 _deferred = []
+_capture_depth = 0  # captures announced by capture_guard(): seen by destructors that run on ANY thread
+
+
+class capture_guard:
+    """`with native.capture_guard(): with torch.cuda.graph(g): ...` -- while it is open, destructors of native handles on
+    every thread park their handle (a collector pass triggered on another thread, e.g. a sampler thread, does not see
+    the capturing stream as its current stream); leaving it releases what was parked."""
+
+    def __enter__(self):
+        global _capture_depth
+        _capture_depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _capture_depth
+        _capture_depth -= 1
+        flush_deferred()
+        return False
 
 
 def _capturing():
+    if _capture_depth > 0:
+        return True
     try:
         import torch
 

@@ -141,7 +141,7 @@ class AdamNativeOptimizer(Optimizer):
 
         gc.collect()
         n_before = native.launch_count()
-        with torch.cuda.graph(g):
+        with native.capture_guard(), torch.cuda.graph(g):
             native.table_pick(table, step, alpha_dev)  # alpha_dev = table[step]; step += 1 (one launch)
             fuse = getattr(loss_grad, "fuse_adam", None)
             if fuse is not None:

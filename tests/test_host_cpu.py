@@ -632,3 +632,20 @@ def test_native_handles_are_not_destroyed_during_a_graph_capture(monkeypatch):
     assert destroyed == [12]
     native.flush_deferred()
     assert destroyed == [12, 11] and native._deferred == []
+
+
+def test_capture_guard_parks_destructors_of_other_threads(monkeypatch):
+    """capture_guard announces a capture to destructors on every thread (the collector may run on a sampler thread whose
+    current stream is not the capturing one) and releases what was parked when it closes."""
+    import threading
+
+    from odil_b200 import native
+
+    destroyed = []
+    monkeypatch.setattr(native, "_deferred", [])
+    with native.capture_guard():
+        t = threading.Thread(target=lambda: native._release(destroyed.append, 7))
+        t.start()
+        t.join()
+        assert destroyed == [] and len(native._deferred) == 1
+    assert destroyed == [7] and native._deferred == [] and native._capture_depth == 0
