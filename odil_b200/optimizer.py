@@ -238,7 +238,7 @@ class LbfgsbOptimizer(Optimizer):
         def on_iteration(flat):
             self.epoch += 1
             if callback:
-                callback(to_arrays(flat, fresh=True), self.epoch, self.pinfo)  # the callback may keep them
+                callback(to_arrays(flat), self.epoch, self.pinfo)
 
         x, f, info = optimize.fmin_l_bfgs_b(func=func, x0=to_flat(x0), maxiter=epochs, pgtol=self.pgtol, m=self.m,
                                             maxls=self.maxls, factr=self.factr, maxfun=np.inf,
@@ -296,7 +296,7 @@ class LbfgsDeviceOptimizer(Optimizer):
         def on_iteration(flat):
             self.epoch += 1
             if callback:
-                callback(to_arrays(flat), self.epoch, self.pinfo)
+                callback(to_arrays(flat, fresh=True), self.epoch, self.pinfo)  # the callback may keep them
 
         flat0 = torch.cat([a.reshape(-1).to(torch.float64) for a in x0]).to(device)
         x, f, info = lbfgs.minimize(func, flat0, m=self.m, maxiter=epochs, maxls=self.maxls, pgtol=self.pgtol,

@@ -649,3 +649,41 @@ def test_capture_guard_parks_destructors_of_other_threads(monkeypatch):
         t.join()
         assert destroyed == [] and len(native._deferred) == 1
     assert destroyed == [7] and native._deferred == [] and native._capture_depth == 0
+
+
+def test_lbfgs_optimizers_host_glue(monkeypatch):
+    """LbfgsbOptimizer (SciPy on the host) and LbfgsDeviceOptimizer (vector algebra replaced by torch-CPU stand-ins
+    here) behind the optimizer seam: same minimiser, arrays in the problem dtype and shape, one callback per iteration
+    with arrays the callback may keep (they are not the optimizer's conversion buffers)."""
+    from odil_b200 import native
+    from odil_b200.optimizer import LbfgsbOptimizer, LbfgsDeviceOptimizer
+
+    monkeypatch.setattr(native, "multi_dot", lambda V, k, g, out: out.__setitem__(slice(0, k), V[:k] @ g))
+    monkeypatch.setattr(native, "multi_axpy", lambda V, k, coef, a0, g, d: d.copy_(a0 * g + coef[:k] @ V[:k]))
+    monkeypatch.setattr(native, "dot", lambda a, b, out: out.__setitem__(0, torch.dot(a, b)))
+    monkeypatch.setattr(native, "axpby", lambda a, x, b, y: y.copy_(a * x + (b * y if b != 0 else 0)))
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((12, 12))
+    A = torch.as_tensor(A @ A.T + 0.5 * np.eye(12))
+    b = torch.as_tensor(rng.standard_normal(12))
+
+    def loss_grad(arrays):
+        x = torch.cat([a.reshape(-1) for a in arrays]).to(torch.float64)
+        r = A @ x - b
+        g = (A.T @ r).to(arrays[0].dtype)
+        return 0.5 * float(r @ r), [g[:8].reshape(2, 4), g[8:].reshape(4)], {"loss": 0.5 * float(r @ r)}
+
+    results = {}
+    for cls in (LbfgsbOptimizer, LbfgsDeviceOptimizer):
+        seen = []
+        x0 = [torch.zeros(2, 4, dtype=torch.float64), torch.zeros(4, dtype=torch.float64)]
+        arrays, info = cls(m=5, dtype=np.float64).run(x0, loss_grad, epochs=6,
+                                                      callback=lambda arr, epoch, pinfo: seen.append((epoch, arr)))
+        assert [e for e, _ in seen] == [1, 2, 3, 4, 5, 6] and info.epochs == 6
+        assert [tuple(a.shape) for a in arrays] == [(2, 4), (4,)] and arrays[0].dtype == torch.float64
+        # the arrays of successive callbacks are distinct objects holding distinct iterates
+        assert len({a[0].data_ptr() for _, a in seen}) == 6
+        assert not torch.equal(seen[0][1][0], seen[5][1][0])
+        assert torch.equal(seen[5][1][0], arrays[0]) and torch.equal(seen[5][1][1], arrays[1])
+        results[cls.__name__] = torch.cat([a.reshape(-1) for a in arrays])
+    assert torch.allclose(results["LbfgsbOptimizer"], results["LbfgsDeviceOptimizer"], rtol=1e-7, atol=1e-9)
